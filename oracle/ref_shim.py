@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE ONLY - never imported by the product package.
+
+Loads the reference's own hot-path Python files *unmodified* from
+/root/reference (read-only, only present in the build container, never on the
+GPU box) so that
+
+  * oracle/sst_oracle.py (the portable CPU restatement) can be pinned against
+    the real reference code, and
+  * oracle/make_golden.py can emit the fixtures under tests/golden/.
+
+Nothing is copied: the reference modules are imported in place.  The reference
+depends on mmcv / mmdet / torch_scatter / TorchEx(ingroup_indices) / ipdb which
+are absent from this image, so `sys.modules` is pre-seeded with minimal stubs
+(SURVEY.md Appendix A).  The two third-party *arithmetic* dependencies are
+restated here because their sources are not under /root/reference:
+
+  torch_scatter 2.0.9 (docs/overall_instructions.md:36) -> `scatter`,
+      `scatter_max`: call sites mmdet3d/ops/sst/sst_ops.py:173-175.
+  TorchEx `ingroup_indices.forward` (no version pinned; docs link only) ->
+      rank of every element inside its group; specification recovered from the
+      in-tree equivalents sst_input_layer.py:200-208 (`_slow`, stable order)
+      and sst_ops.py:194-242.  Parity for both is "unpinned" by the
+      reference's own tests.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF_ROOT = os.environ.get("SST_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "mmdet3d"))
+
+
+# --------------------------------------------------------------------------
+# third-party restatements (CPU, torch)
+# --------------------------------------------------------------------------
+def _ts_scatter(src, index, dim=0, reduce="sum", dim_size=None):
+    assert dim == 0
+    n = int(index.max()) + 1 if dim_size is None else dim_size
+    out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype)
+    idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    if reduce in ("sum", "add"):
+        return out.scatter_reduce(0, idx, src, "sum", include_self=False)
+    if reduce == "mean":
+        return out.scatter_reduce(0, idx, src, "mean", include_self=False)
+    if reduce == "max":
+        return out.scatter_reduce(0, idx, src, "amax", include_self=False)
+    raise NotImplementedError(reduce)
+
+
+def _ts_scatter_max(src, index, dim=0, dim_size=None):
+    out = _ts_scatter(src, index, dim, "max", dim_size)
+    # argmax: first (lowest) point index attaining the max, like torch_scatter
+    n = out.shape[0]
+    P = src.shape[0]
+    hit = src == out[index]
+    cand = torch.where(hit, torch.arange(P).view(-1, *([1] * (src.dim() - 1))).expand_as(src),
+                       torch.full_like(src, P, dtype=torch.long))
+    arg = torch.full(out.shape, P, dtype=torch.long)
+    idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    arg = arg.scatter_reduce(0, idx, cand, "amin", include_self=True)
+    return out, arg
+
+
+def _ingroup_forward(group_inds, out_inds):
+    """Stable rank-in-group == get_inner_win_inds_slow (sst_input_layer.py:200-208)."""
+    order = torch.sort(group_inds, stable=True).indices
+    g = group_inds[order]
+    n = g.numel()
+    if n == 0:
+        return
+    start = torch.ones(n, dtype=torch.bool)
+    start[1:] = g[1:] != g[:-1]
+    seg_start = torch.cummax(torch.where(start, torch.arange(n), torch.zeros(n, dtype=torch.long)), 0).values
+    out_inds[order] = torch.arange(n) - seg_start
+
+
+class _Registry:
+    def __init__(self):
+        self.d = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def deco(cls):
+            self.d[name or cls.__name__] = cls
+            return cls
+        return deco
+
+    def build(self, cfg, *a, **k):
+        cfg = dict(cfg)
+        return self.d[cfg.pop("type")](**cfg)
+
+
+def _build_norm_layer(cfg, num_features, postfix=""):
+    cfg = dict(cfg)
+    t = cfg.pop("type")
+    cfg.pop("requires_grad", None)
+    if t == "LN":
+        return "ln", nn.LayerNorm(num_features, **cfg)
+    if t in ("BN1d", "naiveSyncBN1d", "BN"):
+        return "bn", nn.BatchNorm1d(num_features, **cfg)
+    if t in ("BN2d", "naiveSyncBN2d"):
+        return "bn", nn.BatchNorm2d(num_features, **cfg)
+    raise NotImplementedError(t)
+
+
+def _build_conv_layer(cfg, *args, **kwargs):
+    cfg = dict(cfg or dict(type="Conv2d"))
+    t = cfg.pop("type")
+    assert t in ("Conv2d", "Conv")
+    return nn.Conv2d(*args, **kwargs, **cfg)
+
+
+def _passthrough_deco(*dargs, **dkwargs):
+    def deco(fn):
+        return fn
+    return deco
+
+
+_LOADED = None
+
+
+def load():
+    """Import the reference hot-path modules; returns a namespace of classes."""
+    global _LOADED
+    if _LOADED is not None:
+        return _LOADED
+    assert available(), f"reference tree not found at {REF_ROOT}"
+    reg = _Registry()
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("ipdb", set_trace=lambda *a, **k: None)
+    mod("mmcv")
+    mod("mmcv.runner", auto_fp16=_passthrough_deco, force_fp32=_passthrough_deco, BaseModule=nn.Module)
+    mod("mmcv.cnn", build_norm_layer=_build_norm_layer, build_conv_layer=_build_conv_layer,
+        NORM_LAYERS=_Registry())
+    mod("mmdet")
+    mod("mmdet.models", BACKBONES=reg)
+    mod("torch_scatter", scatter=_ts_scatter, scatter_max=_ts_scatter_max)
+    mod("ingroup_indices", forward=_ingroup_forward)
+
+    def pkg(name, rel):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF_ROOT, rel)]
+        sys.modules[name] = m
+        return m
+
+    pkg("mmdet3d", "mmdet3d")
+    ops = pkg("mmdet3d.ops", "mmdet3d/ops")
+    pkg("mmdet3d.ops.sst", "mmdet3d/ops/sst")
+    sp = pkg("mmdet3d.ops.spconv", "mmdet3d/ops/spconv")
+    sp.IS_SPCONV2_AVAILABLE = False
+    ops.spconv = sp
+    pkg("mmdet3d.models", "mmdet3d/models")
+    bld = mod("mmdet3d.models.builder", MIDDLE_ENCODERS=reg, VOXEL_ENCODERS=reg, BACKBONES=reg,
+              build_voxel_encoder=reg.build, build_fusion_layer=None)
+    sys.modules["mmdet3d.models"].builder = bld
+    for sub in ("middle_encoders", "backbones", "sst", "voxel_encoders"):
+        pkg(f"mmdet3d.models.{sub}", f"mmdet3d/models/{sub}")
+
+    sst_ops = importlib.import_module("mmdet3d.ops.sst.sst_ops")
+    for k in dir(sst_ops):
+        if not k.startswith("_"):
+            setattr(ops, k, getattr(sst_ops, k))
+    ops.make_sparse_convmodule = None
+
+    # DynamicScatter on CPU: the reference has no CPU dynamic_point_to_voxel
+    # (voxelization.h:96-108) -> use the oracle's restatement of
+    # scatter_points_cuda.cu:183-234 wrapped in the reference's own per-sample
+    # loop semantics (scatter_points.py:78-99).
+    from oracle import sst_oracle as O
+
+    class DynamicScatter(nn.Module):
+        def __init__(self, voxel_size, point_cloud_range, average_points):
+            super().__init__()
+            self.average_points = average_points
+
+        def forward(self, points, coors):
+            return O.dynamic_scatter_module(points, coors, self.average_points)
+
+    ops.DynamicScatter = DynamicScatter
+
+    ve_utils = importlib.import_module("mmdet3d.models.voxel_encoders.utils")
+    ve = importlib.import_module("mmdet3d.models.voxel_encoders.voxel_encoder")
+    il2 = importlib.import_module("mmdet3d.models.middle_encoders.sst_input_layer_v2")
+    blk = importlib.import_module("mmdet3d.models.sst.sst_basic_block_v2")
+    sstv2 = importlib.import_module("mmdet3d.models.backbones.sst_v2")
+    sir = importlib.import_module("mmdet3d.models.backbones.sir")
+    cos = importlib.import_module("mmdet3d.models.sst.cosine_msa")
+
+    ns = types.SimpleNamespace(
+        sst_ops=sst_ops, voxel_encoder=ve, ve_utils=ve_utils, input_layer_v2=il2, block_v2=blk,
+        sst_v2=sstv2, sir=sir, cosine_msa=cos, registry=reg,
+        DynamicVFE=ve.DynamicVFE, DynamicScatterVFE=ve.DynamicScatterVFE, SIRLayer=ve.SIRLayer,
+        SSTInputLayerV2=il2.SSTInputLayerV2, SSTv2=sstv2.SSTv2, SIR=sir.SIR,
+        EncoderLayer=blk.EncoderLayer, WindowAttention=blk.WindowAttention,
+    )
+    _LOADED = ns
+    return ns
