@@ -1,0 +1,311 @@
+"""Python face of the op surface the reference exports from `mmdet3d.ops`
+(mmdet3d/ops/__init__.py:23-30), backed by libsstb200 (CUDA, sm_100a).  Same names, argument meaning
+and error behaviour; no CPU path - CPU tensors raise.
+
+    Voxelization / voxelization       ops/voxel/voxelize.py:11-130          (dynamic branch only, V1)
+    DynamicScatter / dynamic_scatter  ops/voxel/scatter_points.py:9-110      (V2, V3)
+    scatter_v2                        ops/sst/sst_ops.py:151-182             (V5)
+    get_inner_win_inds                ops/sst/sst_ops.py:244-264             (B2)
+    get_window_coors, make_continuous_inds, get_flat2win_inds(_v2), flat2window(_v2), window2flat(_v2)
+                                      ops/sst/sst_ops.py:27-149,266-331      (B1, B4, B6)
+    build_mlp, get_activation(_layer) ops/sst/sst_ops.py:334-392             (S3)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib as L
+
+_REDUCE = {"sum": 0, "mean": 1, "max": 2}
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.SSTB200Error("sst_b200 ops need CUDA tensors (B200); there is no CPU implementation")
+
+
+# ----------------------------------------------------------------------------------------------
+# V1 voxelization
+# ----------------------------------------------------------------------------------------------
+def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
+    """voxel_layer.dynamic_voxelize (ops/voxel/src/voxelization.h:72-88): fills caller-allocated `coors`."""
+    assert NDim == 3
+    _need_cuda(points, coors)
+    assert points.dtype == torch.float32 and coors.dtype == torch.int32
+    assert points.is_contiguous() and coors.is_contiguous(), "points/coors must be contiguous"
+    c = L.ctx(points.device)
+    L.check(c, L.lib().sstb200_dynamic_voxelize(
+        c, points.data_ptr(), points.shape[0], points.shape[1], L.arr(C.c_float, [float(v) for v in voxel_size]),
+        L.arr(C.c_float, [float(v) for v in coors_range]), coors.data_ptr()))
+
+
+class _Voxelization(Function):
+    @staticmethod
+    def forward(ctx, points, voxel_size, coors_range, max_points=35, max_voxels=20000):
+        if max_points == -1 or max_voxels == -1:
+            coors = points.new_zeros(size=(points.size(0), 3), dtype=torch.int)
+            dynamic_voxelize(points.contiguous(), coors, voxel_size, coors_range, 3)
+            return coors
+        raise NotImplementedError("hard voxelization is outside the hot path (SURVEY.md 8f next-4)")
+
+
+voxelization = _Voxelization.apply
+
+
+class Voxelization(nn.Module):
+    """ops/voxel/voxelize.py:77-130."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000):
+        super().__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.max_num_points = max_num_points
+        self.max_voxels = max_voxels if isinstance(max_voxels, tuple) else (max_voxels, max_voxels)
+        pcr = torch.tensor(point_cloud_range, dtype=torch.float32)
+        grid = torch.round((pcr[3:] - pcr[:3]) / torch.tensor(voxel_size, dtype=torch.float32)).long()
+        self.grid_size = grid
+        self.pcd_shape = [*grid[:2], 1][::-1]
+
+    def forward(self, input):
+        mv = self.max_voxels[0] if self.training else self.max_voxels[1]
+        return voxelization(input, self.voxel_size, self.point_cloud_range, self.max_num_points, mv)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(voxel_size={self.voxel_size}, point_cloud_range="
+                f"{self.point_cloud_range}, max_num_points={self.max_num_points}, max_voxels={self.max_voxels})")
+
+
+# ----------------------------------------------------------------------------------------------
+# V2/V3 DynamicScatter
+# ----------------------------------------------------------------------------------------------
+def dynamic_point_to_voxel_forward(feats, coors, reduce_type, coor_bounds=None):
+    """voxel_layer.dynamic_point_to_voxel_forward -> [reduced_feats, out_coors, coors_map, reduce_count].
+    `coor_bounds` = (lo[3], hi[3]) of the valid coordinates if the caller knows the grid (saves one reduction
+    + sync); otherwise they are measured from `coors`."""
+    _need_cuda(feats, coors)
+    assert feats.dtype == torch.float32, "fp32 feats only"
+    assert coors.dtype == torch.int32 and coors.dim() == 2 and coors.shape[1] == 3
+    assert feats.is_contiguous() and coors.is_contiguous(), "feats/coors must be contiguous"
+    P, Cc = feats.shape
+    dev = feats.device
+    if P == 0:
+        return [feats.clone().detach(), coors.clone().detach(), coors.new_empty((0,), dtype=torch.int32),
+                coors.new_empty((0,), dtype=torch.int32)]
+    if coor_bounds is None:
+        hi = coors.amax(0).clamp(min=0).tolist()
+        lo = [0, 0, 0]
+    else:
+        lo, hi = coor_bounds
+    reduced = torch.empty((P, Cc), dtype=torch.float32, device=dev)
+    out_coors = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    cmap = torch.empty((P,), dtype=torch.int32, device=dev)
+    count = torch.empty((P,), dtype=torch.int32, device=dev)
+    num_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+    num_host = C.c_int32(0)
+    c = L.ctx(dev)
+    L.check(c, L.lib().sstb200_dynamic_point_to_voxel_forward(
+        c, feats.data_ptr(), coors.data_ptr(), P, Cc, _REDUCE[reduce_type], L.arr(C.c_int32, [int(v) for v in lo]),
+        L.arr(C.c_int32, [int(v) for v in hi]), reduced.data_ptr(), out_coors.data_ptr(), cmap.data_ptr(),
+        count.data_ptr(), num_dev.data_ptr(), C.byref(num_host)))
+    M = num_host.value
+    return [reduced[:M], out_coors[:M], cmap, count[:M]]
+
+
+def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map, reduce_count,
+                                    reduce_type):
+    """voxel_layer.dynamic_point_to_voxel_backward: fills caller-allocated grad_feats."""
+    _need_cuda(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map, reduce_count)
+    for t in (grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map, reduce_count):
+        assert t.is_contiguous()
+    c = L.ctx(feats.device)
+    L.check(c, L.lib().sstb200_dynamic_point_to_voxel_backward(
+        c, grad_feats.data_ptr(), grad_reduced_feats.data_ptr(), feats.data_ptr(), reduced_feats.data_ptr(),
+        coors_map.data_ptr(), reduce_count.data_ptr(), feats.shape[0], reduced_feats.shape[0], feats.shape[1],
+        _REDUCE[reduce_type]))
+
+
+class _dynamic_scatter(Function):
+    """ops/voxel/scatter_points.py:9-49."""
+
+    @staticmethod
+    def forward(ctx, feats, coors, reduce_type="max"):
+        voxel_feats, voxel_coors, point2voxel_map, voxel_points_count = dynamic_point_to_voxel_forward(
+            feats, coors, reduce_type)
+        ctx.reduce_type = reduce_type
+        ctx.save_for_backward(feats, voxel_feats, point2voxel_map, voxel_points_count)
+        ctx.mark_non_differentiable(voxel_coors)
+        return voxel_feats, voxel_coors
+
+    @staticmethod
+    def backward(ctx, grad_voxel_feats, grad_voxel_coors=None):
+        feats, voxel_feats, point2voxel_map, voxel_points_count = ctx.saved_tensors
+        grad_feats = torch.empty_like(feats)
+        dynamic_point_to_voxel_backward(grad_feats, grad_voxel_feats.contiguous(), feats, voxel_feats.contiguous(),
+                                        point2voxel_map, voxel_points_count.contiguous(), ctx.reduce_type)
+        return grad_feats, None, None
+
+
+dynamic_scatter = _dynamic_scatter.apply
+
+
+class DynamicScatter(nn.Module):
+    """ops/voxel/scatter_points.py:52-110."""
+
+    def __init__(self, voxel_size, point_cloud_range, average_points: bool):
+        super().__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.average_points = average_points
+
+    def forward_single(self, points, coors):
+        reduce = "mean" if self.average_points else "max"
+        return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce)
+
+    def forward(self, points, coors):
+        if coors.size(-1) == 3:
+            return self.forward_single(points, coors)
+        batch_size = int(coors[-1, 0]) + 1
+        voxels, voxel_coors = [], []
+        for i in range(batch_size):
+            inds = torch.where(coors[:, 0] == i)
+            voxel, voxel_coor = self.forward_single(points[inds], coors[inds][:, 1:])
+            voxel_coors.append(nn.functional.pad(voxel_coor, (1, 0), mode="constant", value=i))
+            voxels.append(voxel)
+        return torch.cat(voxels, dim=0), torch.cat(voxel_coors, dim=0)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(voxel_size={self.voxel_size}, point_cloud_range="
+                f"{self.point_cloud_range}, average_points={self.average_points})")
+
+
+# ----------------------------------------------------------------------------------------------
+# V5 scatter_v2
+# ----------------------------------------------------------------------------------------------
+def unique_rows(coors, return_counts=False, bounds=None):
+    """torch.unique(coors, dim=0, return_inverse=True[, return_counts=True]) for int64 [P,k<=4] rows."""
+    _need_cuda(coors)
+    assert coors.dtype == torch.int64 and coors.dim() == 2 and coors.shape[1] <= 4
+    coors = coors.contiguous()
+    P, k = coors.shape
+    dev = coors.device
+    if P == 0:
+        e = coors.new_empty((0,))
+        return (coors.clone(), e, e.int()) if return_counts else (coors.clone(), e)
+    if bounds is None:
+        lo, hi = coors.amin(0).tolist(), coors.amax(0).tolist()
+    else:
+        lo, hi = bounds
+    new_coors = torch.empty((P, k), dtype=torch.int64, device=dev)
+    inv = torch.empty((P,), dtype=torch.int64, device=dev)
+    cnt = torch.empty((P,), dtype=torch.int32, device=dev) if return_counts else None
+    num_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+    num_host = C.c_int32(0)
+    c = L.ctx(dev)
+    L.check(c, L.lib().sstb200_unique_rows_i64(
+        c, coors.data_ptr(), P, k, L.arr(C.c_int64, [int(v) for v in lo]), L.arr(C.c_int64, [int(v) for v in hi]),
+        new_coors.data_ptr(), inv.data_ptr(), L.ptr(cnt), num_dev.data_ptr(), C.byref(num_host)))
+    M = num_host.value
+    if return_counts:
+        return new_coors[:M], inv, cnt[:M].long()
+    return new_coors[:M], inv
+
+
+class _SegmentReduce(Function):
+    """torch_scatter.scatter / scatter_max, dim=0 (forward + backward)."""
+
+    @staticmethod
+    def forward(ctx, src, index, num_segments, mode):
+        _need_cuda(src, index)
+        assert src.dtype == torch.float32 and index.dtype == torch.int64
+        src = src.contiguous()
+        index = index.contiguous()
+        P, Cc = src.shape
+        out = torch.empty((num_segments, Cc), dtype=torch.float32, device=src.device)
+        arg = torch.empty((num_segments, Cc), dtype=torch.int64, device=src.device) if mode == "max" else None
+        c = L.ctx(src.device)
+        L.check(c, L.lib().sstb200_segment_reduce(c, src.data_ptr(), index.data_ptr(), P, Cc, num_segments,
+                                                  _REDUCE[mode], out.data_ptr(), L.ptr(arg)))
+        ctx.mode = mode
+        ctx.P = P
+        ctx.save_for_backward(index, arg if arg is not None else index)
+        if arg is not None:
+            ctx.mark_non_differentiable(arg)
+            return out, arg
+        return out, index.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, g, _=None):
+        index, arg = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.mode == "max":
+            gs = g.new_zeros((ctx.P + 1, g.shape[1]))
+            gs.scatter_(0, arg, g)
+            return gs[:ctx.P], None, None, None
+        gv = g[index]
+        if ctx.mode == "mean":
+            cnt = torch.bincount(index, minlength=g.shape[0]).clamp(min=1)
+            gv = gv / cnt[index][:, None].to(g.dtype)
+        return gv, None, None, None
+
+
+def segment_reduce(src, index, mode, num_segments=None):
+    if num_segments is None:
+        num_segments = int(index.max()) + 1 if index.numel() else 0
+    out, arg = _SegmentReduce.apply(src, index, num_segments, mode)
+    return out, (arg if mode == "max" else None)
+
+
+def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, new_coors=None):
+    """ops/sst/sst_ops.py:151-182."""
+    assert feat.size(0) == coors.size(0)
+    if mode == "avg":
+        mode = "mean"
+    if mode not in ("max", "mean", "sum"):
+        raise NotImplementedError
+    if unq_inv is None:
+        new_coors, unq_inv, unq_cnt = unique_rows(coors.long(), return_counts=True)
+    else:
+        assert new_coors is not None, "please pass new_coors for interface consistency"
+    if min_points > 0:
+        cnt_per_point = unq_cnt[unq_inv]
+        valid_mask = cnt_per_point >= min_points
+        feat = feat[valid_mask]
+        coors = coors[valid_mask]
+        new_coors, unq_inv, unq_cnt = unique_rows(coors.long(), return_counts=True)
+    new_feat, _ = segment_reduce(feat, unq_inv, mode, new_coors.shape[0])
+    if not return_inv:
+        return new_feat, new_coors
+    return new_feat, new_coors, unq_inv
+
+
+# ----------------------------------------------------------------------------------------------
+# B2 get_inner_win_inds
+# ----------------------------------------------------------------------------------------------
+class IngroupIndicesFunction(Function):
+    """ops/sst/sst_ops.py:244-262."""
+
+    @staticmethod
+    def forward(ctx, group_inds):
+        _need_cuda(group_inds)
+        assert group_inds.dtype == torch.int64 and group_inds.dim() == 1
+        group_inds = group_inds.contiguous()
+        out_inds = torch.zeros_like(group_inds) - 1
+        n = group_inds.numel()
+        if n:
+            assert int(group_inds.min()) >= 0, "group ids must be non-negative"
+            c = L.ctx(group_inds.device)
+            L.check(c, L.lib().sstb200_ingroup_indices(c, group_inds.data_ptr(), n, int(group_inds.max()),
+                                                       out_inds.data_ptr()))
+        ctx.mark_non_differentiable(out_inds)
+        return out_inds
+
+    @staticmethod
+    def backward(ctx, g):
+        return None
+
+
+get_inner_win_inds = IngroupIndicesFunction.apply
