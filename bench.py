@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py - LiDAR frames/sec of the SST hot path (BASELINE.json metric) on N B200s of one node.
+
+A "step" = one forward of BASELINE config 2 per GPU: 1 synthetic Waymo-shaped sweep (150k pts, 0.32 m pillars,
+~30k non-empty) through dynamic voxelisation -> DynamicVFE -> SSTInputLayerV2 -> SSTv2 (6 blocks = 12 SRA
+layers, d=128, h=8, ff=256), sparse output (to_bev=False, no attached convs).  Frames shard over GPUs
+(weak scaling, no data-path collective: inference has none).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # CPU port of the reference path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_POINTS = 150000
+METRIC = "lidar_frames_per_sec_sst6_fwd_150k"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_BEST_THREADS = None
+
+
+def pick_threads():
+    """Intra-op thread count that makes the CPU path fastest on this host (many small ops: all cores is not
+    always best).  Tried: 8, 16, 32, all; measured on a 20k-point frame; cached."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    from oracle import sst_oracle as O
+    from sst_b200 import flagship as fl
+    ncpu = os.cpu_count() or 1
+    cands = sorted({min(ncpu, t) for t in (8, 16, 32, ncpu)})
+    cfg = fl.sst_cfg(num_blocks=2)
+    vfe, il, bb = fl.build_sst(cfg)
+    wv, wb = dict(vfe.state_dict()), dict(bb.state_dict())
+    pts = O.synth_frame(1, 40000)
+    best = (1e30, ncpu)
+    with torch.no_grad():
+        for t in cands:
+            torch.set_num_threads(t)
+            for rep in range(2):
+                t0 = time.perf_counter()
+                co = torch.nn.functional.pad(O.dynamic_voxelize(pts, fl.VOXEL_SIZE, fl.PC_RANGE), (1, 0), value=0)
+                vf, vc = O.dynamic_vfe_forward(pts, co, wv, fl.VOXEL_SIZE, fl.PC_RANGE, 2)
+                info = O.input_layer_v2(vf, vc, fl.DROP_TEST, fl.WINDOW_SHAPE, (468, 468, 1))
+                O.sstv2_forward(info, wb, cfg['backbone']['nhead'], 2)
+                dt = time.perf_counter() - t0
+            best = min(best, (dt, t))
+    _BEST_THREADS = best[1]
+    return _BEST_THREADS
+
+
+def cpu_oracle_frames(n_frames, warmup, threads=None):
+    """The reference's own CPU path (restated in oracle/, see oracle/sst_oracle.py header) on the host cores."""
+    from oracle import sst_oracle as O
+    from sst_b200 import flagship as fl
+    threads = threads or pick_threads()
+    torch.set_num_threads(threads)
+    cfg = fl.sst_cfg()
+    vfe, il, bb = fl.build_sst(cfg)
+    wv, wb = dict(vfe.state_dict()), dict(bb.state_dict())
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_frames):
+            pts = O.synth_frame(1000 + i, P_POINTS)
+            t0 = time.perf_counter()
+            co = torch.nn.functional.pad(O.dynamic_voxelize(pts, fl.VOXEL_SIZE, fl.PC_RANGE), (1, 0), value=0)
+            vf, vc = O.dynamic_vfe_forward(pts, co, wv, fl.VOXEL_SIZE, fl.PC_RANGE, 2)
+            info = O.input_layer_v2(vf, vc, fl.DROP_TEST, fl.WINDOW_SHAPE, (468, 468, 1))
+            out = O.sstv2_forward(info, wb, cfg['backbone']['nhead'], cfg['backbone']['num_blocks'])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, threads, out.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    times, threads, M = cpu_oracle_frames(steps, min(args.warmup, 1))
+    tot = sum(times)
+    v = steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: SST-6 fwd, 150k-pt Waymo-shaped sweep, 0.32m pillars, d=128 h=8 ff=256, batch 1, sparse output"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} frames (each = full config-2 forward) on {threads} host threads, torch CPU fp32; "
+                                   "the reference itself is Python and cannot travel to the GPU box, so its restatement oracle/sst_oracle.py (validated bit-exact against it) is timed"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SSTB200_PRECISION", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+
+    from oracle import sst_oracle as O   # only for the synthetic frame generator + the cpu_baseline leg
+    from sst_b200 import build, flagship as fl
+    build.build()
+    from sst_b200.engine import SSTEngine
+
+    cfg = fl.sst_cfg()
+    vfe, il, bb = fl.build_sst(cfg)
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16"
+    eng = SSTEngine(fl.VOXEL_SIZE, fl.PC_RANGE, vfe.to(dev), il, bb.to(dev), max_points=P_POINTS, batch_size=1,
+                    precision=precision, device=dev)
+
+    NF = 4  # distinct resident frames per rank
+    frames_h = [O.synth_frame(1000 + rank * 64 + i, P_POINTS) for i in range(NF)]
+    frames_d = [f.to(dev) for f in frames_h]
+    offs_d = torch.tensor([0, P_POINTS], dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = eng.stream
+
+    def step(i):
+        eng.load_frames_device(frames_d[i % NF], offs_d)
+        return eng.run()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    for i in range(args.steps):
+        with torch.cuda.stream(st):
+            flush.zero_()               # evict L2 between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+        step(i)
+        with torch.cuda.stream(st):
+            e1.record(st)
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * args.steps / (total_ms / 1e3)
+
+    # ---- e2e through the public engine API with HOST buffers (H2D + D2H inside the timed region) -------------
+    pin = [f.pin_memory() for f in frames_h]
+    offs_pin = torch.tensor([0, P_POINTS], dtype=torch.int32).pin_memory()
+    out_f = torch.empty((P_POINTS, eng.d), dtype=torch.float32).pin_memory()
+    out_c = torch.empty((P_POINTS, 4), dtype=torch.int32).pin_memory()
+    M = 0
+    for i in range(3):
+        M = eng.forward_host(pin[i % NF], offs_pin, out_f, out_c)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        M = eng.forward_host(pin[i % NF], offs_pin, out_f, out_c)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(t.item())
+    h2d = P_POINTS * eng.F * 4 + 8
+    d2h = M * eng.d * 4 + M * 16 + 4
+
+    # ---- roofline of the dominant kernel group: one SRA encoder layer -------------------------------------------
+    roof = None
+    if rank == 0:
+        import ctypes as C
+        from sst_b200 import _lib as L
+        feats, coors, num = step(0)
+        torch.cuda.synchronize()
+        Mv = int(num.item())
+        offs = eng.plans[0]["win_offsets"]
+        R = int(eng.plans[0]["counters"][0].item())
+        nw = (offs[1:R + 1] - offs[:R]).double()
+        sum_n2 = float((nw * nw).sum().item())
+        d, ff = eng.d, cfg['backbone']['dim_feedforward'][0]
+        flops = Mv * (8 * d * d + 4 * d * ff) + 4 * d * sum_n2
+        ls, shift = eng._layers[0]
+        lib = L.lib()
+        ts = []
+        with torch.cuda.stream(st):
+            c = L.ctx(dev)
+            for it in range(8):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                L.check(c, lib.sstb200_sra_layer_forward(c, C.byref(ls), C.byref(eng._plan_structs[shift]), eng.vf.data_ptr(),
+                                                         eng.x[0].data_ptr(), eng.cap, eng.num.data_ptr(),
+                                                         {"fp32": 0, "bf16": 1}[precision]))
+                b.record(st)
+                ts.append((a, b))
+        torch.cuda.synchronize()
+        lt = sorted(x.elapsed_time(y) for x, y in ts[2:])
+        layer_ms = lt[len(lt) // 2]
+        pk = peaks()
+        ach = flops / (layer_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"SRA encoder layer ({precision} path, all launches of one layer)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel runs inside a 12-layer step)",
+                "flops_per_launch": flops, "ms_per_launch": layer_ms, "M": Mv, "sum_n2": sum_n2,
+                "layer_share_of_step": 12 * layer_ms / (total_ms / args.steps)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, threads, _ = cpu_oracle_frames(2, 1)
+        cpu = {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{len(times)} frames of the same workload after 1 warm-up (oracle/sst_oracle.py, torch CPU fp32, "
+                         f"{threads} threads)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "config2: SST-6 fwd, 150k-pt Waymo-shaped sweep, 0.32m pillars, d=128 h=8 ff=256, batch 1 per GPU, sparse output",
+                       "precision": precision, "voxels": int(M), "l2": "flushed between timed iterations (512 MB memset)",
+                       "parallelism": f"dp{world} (frames sharded, no collective)"},
+            "clocks": clocks, "gpu_launches": int(eng.launches_per_frame or 0) * args.steps,
+            "gpu_launches_per_step": int(eng.launches_per_frame or 0),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,151 @@ int sstb200_segment_reduce(sstb200_ctx* ctx, const float* src, const int64_t* in
 int sstb200_ingroup_indices(sstb200_ctx* ctx, const int64_t* group_inds, int num, int64_t max_group_id,
                             int64_t* out_inds);
 
+/* B1+B2+B3(levels)+B4  window partition and bucketing for ONE shift (do_shift = 0 | 1), fused.
+ *   get_window_coors            ops/sst/sst_ops.py:266-314
+ *   get_inner_win_inds          ops/sst/sst_ops.py:244-264 (stable order, sst_input_layer.py:200-208)
+ *   level assignment            models/middle_encoders/sst_input_layer_v2.py:128-150
+ *   make_continuous_inds + get_flat2win_inds   ops/sst/sst_ops.py:316-331, 27-64
+ * coors [n,4] (b,z,y,x).  n may also be given on the device (n_dev != NULL, n = capacity).
+ * token_level (int64 [n], may be NULL): drop level carried over from a preceding drop phase; when NULL the
+ * level of a window follows from its token count.  All outputs caller-allocated with capacity n
+ * (win_offsets n+1); pointers marked "opt" may be NULL. */
+typedef struct {
+  int32_t sparse_shape[3]; /* x, y, z */
+  int32_t window_shape[3]; /* x, y, z (z = sparse z for 2-D windows) */
+  int32_t batch_size;      /* upper bound of batch index + 1 */
+  int32_t num_levels;      /* <= 8, in the iteration order of the reference's drop_info dict */
+  int32_t level_id[8];     /* dict keys */
+  int32_t level_lo[8];     /* drop_range[0] */
+  int32_t level_hi[8];     /* drop_range[1] */
+  int32_t level_max_tokens[8];
+} sstb200_window_cfg;
+
+typedef struct {
+  int64_t* batch_win_inds; /* opt [n]   == get_window_coors()[0] */
+  int64_t* coors_in_win;   /* opt [n,3] == get_window_coors()[1]  (z,y,x) */
+  int64_t* drop_level;     /* opt [n]   dict key of the window's level */
+  int64_t* flat2win_inds;  /* opt [n]   rank_in_level * max_tokens + inner */
+  int32_t* pos_code;       /* opt [n]   x | y<<8 | z<<16 of coors_in_win */
+  int32_t* tok_win;        /* [n]   compact window index (rank of the window id among non-empty windows) */
+  int32_t* tok_inner;      /* [n]   stable rank of the token inside its window */
+  int32_t* win_offsets;    /* [n+1] CSR offsets into tok_perm, R+1 entries valid */
+  int32_t* tok_perm;       /* [n]   token indices grouped by window, stable order inside */
+  int32_t* win_level;      /* [n]   level slot (0..num_levels-1) per window, R valid */
+  int32_t* win_rank;       /* [n]   rank of the window among the windows of its level */
+  int32_t* counters;       /* [17]  R, windows per level slot [8], tokens per level slot [8] */
+} sstb200_window_shift;
+
+/* status_host (opt, int32[18]): if non-NULL the call synchronises and returns
+ * [0] = bit0: token outside the window grid, bit1: window count not covered by any drop_range;
+ * [1..17] = copy of counters. */
+int sstb200_window_plan(sstb200_ctx* ctx, const int64_t* coors, int n, const int32_t* n_dev,
+                        const sstb200_window_cfg* cfg, int do_shift, const int64_t* token_level,
+                        const sstb200_window_shift* out, int32_t* status_host);
+int sstb200_window_plan_i32(sstb200_ctx* ctx, const int32_t* coors, int n, const int32_t* n_dev,
+                            const sstb200_window_cfg* cfg, int do_shift, const sstb200_window_shift* out);
+
+/* A1+A2+A3  one Sparse-Regional-Attention encoder layer (EncoderLayer.forward,
+ * mmdet3d/models/sst/sst_basic_block_v2.py:77-126 with WindowAttention :41-75, nn.MultiheadAttention or
+ * CosineMultiheadAttention models/sst/cosine_msa.py:449-536), eval mode (dropout = identity).
+ * All weight pointers are device pointers in the reference's nn.Module layouts (row-major [out,in]). */
+typedef struct {
+  int32_t d_model, nhead, dim_ff;
+  int32_t act;       /* 1 relu, 2 gelu(erf) */
+  int32_t post_norm; /* layer_cfg['post_norm'] (default 1) */
+  float norm_eps;    /* LayerNorm 1e-5 / BatchNorm 1e-5 */
+  const float *in_proj_w, *in_proj_b;   /* [3d,d], [3d] */
+  const float *out_proj_w, *out_proj_b; /* [d,d], [d] */
+  const float *lin1_w, *lin1_b;         /* [ff,d], [ff] */
+  const float *lin2_w, *lin2_b;         /* [d,ff], [d] */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+  const float *norm1_mean, *norm1_var, *norm2_mean, *norm2_var; /* non-NULL: layer_cfg['use_bn'] (eval BN) */
+  const float* tau; /* non-NULL: cosine attention; tau_n = 1 or nhead */
+  int32_t tau_n;
+  float tau_min;
+  /* optional bf16 copies of the four weight matrices (tensor-core path); NULL -> fp32 path only */
+  const void *in_proj_w_bf16, *out_proj_w_bf16, *lin1_w_bf16, *lin2_w_bf16;
+} sstb200_sra_layer;
+
+/* window CSR of one shift (produced by sstb200_window_plan) + positional-embedding table
+ * (SSTInputLayerV2.get_pos_embed, sst_input_layer_v2.py:238-305: pos[t, axis*L + j] =
+ * table[axis][coord_in_win(axis)][j], zero beyond ndim*L). */
+typedef struct {
+  const int32_t* win_offsets; /* [R+1] */
+  const int32_t* tok_perm;    /* [n] */
+  const int32_t* tok_win;     /* [n] */
+  const int32_t* pos_code;    /* [n] */
+  const int32_t* num_windows_dev; /* counters[0] */
+  const float* pos_table;     /* [pos_ndim][pos_maxw][pos_L] fp32 */
+  int32_t pos_L, pos_maxw, pos_ndim;
+  int32_t max_window_tokens;  /* upper bound on tokens per window (e.g. 144) */
+} sstb200_sra_plan;
+
+#define SSTB200_PREC_FP32 0 /* fp32 FFMA everywhere */
+#define SSTB200_PREC_BF16 1 /* bf16 tensor-core GEMMs, fp32 accumulate / softmax / LayerNorm / residual */
+
+/* x, y: [n, d_model] fp32 in flat voxel order (y may alias x only if precision == FP32 is not used).
+ * n may be device-resident (n_dev).  */
+int sstb200_sra_layer_forward(sstb200_ctx* ctx, const sstb200_sra_layer* layer, const sstb200_sra_plan* plan,
+                              const float* x, float* y, int n, const int32_t* n_dev, int precision);
+
+/* nn.Linear forward: out[M,N] = act(A[M,K] . W[N,K]^T + bias), fp32 (act: 0 none, 1 relu, 2 gelu-erf).
+ * Used for SSTv2.linear0 (models/backbones/sst_v2.py:60-61,127-128) and as a building block. */
+int sstb200_linear(sstb200_ctx* ctx, const float* A, const float* W, const float* bias, float* out,
+                   int M, int N, int K, int act);
+
+/* V4 DynamicVFE.forward / V6 DynamicScatterVFE.forward, eval-mode BatchNorm, <= 2 VFE layers
+ * (mmdet3d/models/voxel_encoders/voxel_encoder.py:229-298 and :551-612; layers utils.py:107-144).
+ * points [P,in_channels] fp32, coors [P,4] (b,z,y,x).  Output rows are the non-empty voxels sorted by
+ * (b,z,y,x); capacity P.  drop_first_voxel_per_sample = 1 reproduces DynamicVFE's DynamicScatter behaviour
+ * (scatter_points_cuda.cu:207-210 through the per-sample loop scatter_points.py:85-99); DynamicScatterVFE
+ * (torch.unique based) keeps every voxel. */
+typedef struct {
+  int32_t in_channels;       /* raw point dims F (before decoration) */
+  int32_t num_layers;        /* 1 or 2 */
+  int32_t feat_channels[2];
+  int32_t with_cluster_center, with_voxel_center, with_distance;
+  int32_t mode_max;          /* 1: max pooling, 0: average */
+  int32_t drop_first_voxel_per_sample;
+  int32_t batch_size;
+  int32_t grid_zyx[3];       /* canvas dims (voxel_encoder.py:199-204) */
+  float voxel_size[3];       /* vx, vy, vz */
+  float center_offset[3];    /* v/2 + range_min (voxel_encoder.py:160-162) */
+  float rel_dist_scaler;     /* DynamicScatterVFE only, else 1 */
+  float bn_eps;
+  const float* weight[2];    /* vfe_layers.i.linear.weight  [C_i, in_i] */
+  const float* bn_weight[2]; /* vfe_layers.i.norm.{weight,bias,running_mean,running_var} */
+  const float* bn_bias[2];
+  const float* bn_mean[2];
+  const float* bn_var[2];
+} sstb200_vfe_cfg;
+
+int sstb200_dynamic_vfe_forward(sstb200_ctx* ctx, const sstb200_vfe_cfg* cfg, const float* points,
+                                const int32_t* coors, int num_points, float* voxel_feats, int32_t* voxel_coors,
+                                int32_t* num_voxels_dev, int32_t* num_voxels_host);
+int sstb200_dynamic_scatter_vfe_forward(sstb200_ctx* ctx, const sstb200_vfe_cfg* cfg, const float* points,
+                                        const int64_t* coors, int num_points, float* voxel_feats,
+                                        int64_t* voxel_coors, int64_t* unq_inv, int32_t* num_voxels_dev,
+                                        int32_t* num_voxels_host);
+
+/* V1 (batched, sync-free form used by the frame engine): voxelise a batch of frames stored back to back.
+ * points [capacity,F]; frame_offsets_dev: device int32 [num_frames+1] (row ranges of the frames, last entry =
+ * number of valid rows).  coors4 [capacity,4] int32 = (b,z,y,x) like DynamicVoxelNet.voxelize
+ * (mmdet3d/models/detectors/dynamic_voxelnet.py:49-71); rows beyond the last offset get (-1,-1,-1,-1) and are
+ * ignored by every later stage. */
+int sstb200_voxelize_frames(sstb200_ctx* ctx, const float* points, int capacity, int num_features,
+                            const int32_t* frame_offsets_dev, int num_frames, const float voxel_size[3],
+                            const float coors_range[6], int32_t* coors4);
+
+/* CUDA-graph helpers for callers that chain several entry points per frame (the reference has no
+ * counterpart: it launches ~10^3 ATen kernels per frame with >= 8 host syncs).
+ * begin: start capturing the context's stream; end: stop, instantiate, return an opaque handle and the number
+ * of kernel / memset+memcpy nodes; launch: replay on the context's stream. */
+int sstb200_graph_begin(sstb200_ctx* ctx);
+int sstb200_graph_end(sstb200_ctx* ctx, void** graph_exec_out, int32_t* num_kernel_nodes, int32_t* num_other_nodes);
+int sstb200_graph_launch(sstb200_ctx* ctx, void* graph_exec);
+int sstb200_graph_destroy(sstb200_ctx* ctx, void* graph_exec);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,13 @@
+"""sst_b200 - B200-native (sm_100a) implementation of the SST / FSD data-parallel hot path behind the reference's
+own module / op names (tusen-ai/SST).  The arithmetic lives in libsstb200.so (csrc/*.cu, C ABI in
+include/sstb200.h); this package is the host-side mirror of the reference interface.  There is no CPU or
+PyTorch fallback: using an op without the built library or without a CUDA device raises."""
+from . import registry
+from .registry import BACKBONES, MIDDLE_ENCODERS, MODELS, VOXEL_ENCODERS, build_backbone, build_middle_encoder, build_voxel_encoder  # noqa: F401
+from . import norm  # noqa: F401
+from . import ops  # noqa: F401
+from . import sst_modules, voxel_modules  # noqa: F401
+from .sst_modules import SSTInputLayerV2, SSTv2, PseudoMiddleEncoderForSpconvFSD  # noqa: F401
+from .voxel_modules import DynamicVFE, DynamicScatterVFE  # noqa: F401
+
+__version__ = "0.1.0"

@@ -42,6 +42,24 @@ class SSTB200Error(RuntimeError):
     pass
 
 
+class _Signatures(dict):
+    """name -> (restype, argtypes).  Assigning after the library is loaded binds the prototype immediately, so
+    modules imported late (engine, sir, ...) can never call through an un-prototyped (pointer-truncating) symbol."""
+
+    def __setitem__(self, name, sig):
+        super().__setitem__(name, sig)
+        if _lib is not None:
+            _bind(_lib, name, sig)
+
+
+def _bind(L, name, sig):
+    fn = getattr(L, name)  # AttributeError if the symbol is missing -> loud
+    fn.restype, fn.argtypes = sig
+
+
+SIGNATURES = _Signatures(SIGNATURES)
+
+
 def lib():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
@@ -54,10 +72,8 @@ def lib():
                     f"{LIB_PATH} not found - build it with `python -m sst_b200.build` "
                     "(there is no CPU or PyTorch fallback for this path)")
             L = C.CDLL(LIB_PATH)
-            for name, (res, args) in SIGNATURES.items():
-                fn = getattr(L, name)  # AttributeError if the symbol is missing -> loud
-                fn.restype = res
-                fn.argtypes = args
+            for name, sig in SIGNATURES.items():
+                _bind(L, name, sig)
             _lib = L
     return _lib
 

@@ -1,0 +1,16 @@
+// internal declarations shared by the SRA translation units
+#pragma once
+#include "common.cuh"
+
+void sstb_gemm_rows(cudaStream_t st, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr,
+                    float* out, int ldo, int M_cap, const int32_t* M_dev, int N, int K, int act, const float* pos_tab,
+                    const int32_t* pos_code, int posL, int pos_maxw, int pos_ndim, int pos_ncols);
+void sstb_add_norm(cudaStream_t st, const float* a, const float* b, const float* gamma, const float* beta,
+                   const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d);
+int sstb_win_attn_fp32(sstb200_ctx* c, const float* qkv, int d, int nhead, int n_cap, const int32_t* n_dev,
+                       const int32_t* win_offsets, const int32_t* tok_perm, const int32_t* tok_win, const float* tau,
+                       int tau_n, float tau_min, float* out);
+int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
+                        int n_cap, const int32_t* n_dev);
+int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
+                        int n_cap, const int32_t* n_dev);

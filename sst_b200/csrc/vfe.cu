@@ -1,0 +1,431 @@
+// Fused dynamic voxel feature encoder (V4 DynamicVFE, V6 DynamicScatterVFE), eval-mode BatchNorm.
+//
+// Reference (mmdet3d/models/voxel_encoders/voxel_encoder.py:229-298 / :551-612): three DynamicScatter /
+// scatter_v2 calls (each re-running unique on the same coors), a dense int64 canvas to map voxels back to
+// points, [P,64] and [P,128] point-feature tensors and P*C float atomics.  Here: one bitmap-rank index, one
+// CSR, then one warp per voxel computes the decorated point features, both VFE layers and the max-pool in
+// registers - the per-point feature tensors are never materialised.
+#include <stdarg.h>
+#include "index.cuh"
+
+struct VfeDev {
+  int F, D0, C0, C1, nlayers;
+  int with_cluster, with_center, with_distance, mode_max;
+  float vx, vy, vz, x_off, y_off, z_off;
+  float rel_dist_scaler;
+  const float* W0;  // [C0, D0]
+  const float* W1;  // [C1, 2*C0]
+  const float *s0, *t0, *s1, *t1;  // folded BN: y = x*s + t
+};
+
+// fold eval BatchNorm into scale/shift
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, int C, float* __restrict__ s, float* __restrict__ t) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // F.batch_norm: (x - mean) / sqrt(var + eps) * w + b
+  float inv = 1.0f / sqrtf(var[c] + eps);
+  float sc = w[c] * inv;
+  s[c] = sc;
+  t[c] = b[c] - mean[c] * sc;
+}
+
+// rank -> output row with the reference's "first sorted row of every sample is removed" rule
+// (scatter_points_cuda.cu:207-210 applied per sample by scatter_points.py:85-99).
+struct SampleQuirk {
+  const uint32_t* word_prefix;
+  size_t words_per_sample;
+  int batch;
+  int enabled;
+};
+__device__ __forceinline__ long long quirk_row(const SampleQuirk& q, long long rank, int b) {
+  if (!q.enabled) return rank;
+  long long first_b = q.word_prefix[(size_t)b * q.words_per_sample];
+  if (rank == first_b) return -1;
+  int shift = 0;
+  for (int i = 0; i <= b; i++) {
+    long long f0 = q.word_prefix[(size_t)i * q.words_per_sample], f1 = q.word_prefix[(size_t)(i + 1) * q.words_per_sample];
+    shift += (f1 > f0);
+  }
+  return rank - shift;
+}
+
+template <typename TC>
+__global__ void vfe_mark_kernel(const TC* __restrict__ coors, int P, int B, int Z, int Y, int X, size_t cells_pad,
+                                long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  long long b = (long long)coors[(size_t)i * 4], z = (long long)coors[(size_t)i * 4 + 1], y = (long long)coors[(size_t)i * 4 + 2],
+            x = (long long)coors[(size_t)i * 4 + 3];
+  if (b < 0 || b >= B || z < 0 || z >= Z || y < 0 || y >= Y || x < 0 || x >= X) {
+    keys[i] = -1;
+    flags[0] = 1;
+    return;
+  }
+  long long key = b * (long long)cells_pad + (z * Y + y) * X + x;
+  keys[i] = key;
+  atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+}
+
+template <typename TM>
+__global__ void vfe_map_kernel(const long long* __restrict__ keys, int P, const uint32_t* __restrict__ bitmap,
+                               const uint32_t* __restrict__ word_prefix, size_t cells_pad, SampleQuirk q,
+                               TM* __restrict__ map, int32_t* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  long long key = keys[i];
+  long long row = -1;
+  if (key >= 0) {
+    size_t w = (size_t)(key >> 5);
+    long long rank = (long long)word_prefix[w] + __popc(bitmap[w] & ((1u << (key & 31)) - 1u));
+    row = quirk_row(q, rank, (int)(key / (long long)cells_pad));
+  }
+  map[i] = (TM)row;
+  if (row >= 0) atomicAdd(&count[row], 1);
+}
+
+template <typename TO>
+__global__ void vfe_emit_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, size_t nwords,
+                                size_t cells_pad, int Y, int X, SampleQuirk q, TO* __restrict__ out_coors,
+                                const uint32_t* __restrict__ total, int32_t* __restrict__ num_out) {
+  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w == 0) {
+    long long t = *total;
+    if (q.enabled) {
+      int ne = 0;
+      for (int i = 0; i < q.batch; i++)
+        ne += q.word_prefix[(size_t)(i + 1) * q.words_per_sample] > q.word_prefix[(size_t)i * q.words_per_sample];
+      t -= ne;
+    }
+    *num_out = (int32_t)t;
+  }
+  for (; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+    uint32_t bits = bitmap[w];
+    if (!bits) continue;
+    long long rank = word_prefix[w];
+    int b = (int)((w * 32) / cells_pad);
+    while (bits) {
+      int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      long long row = quirk_row(q, rank, b);
+      if (row >= 0) {
+        long long local = (long long)(w * 32 + bit) - (long long)b * (long long)cells_pad;
+        long long x = local % X, y = (local / X) % Y, z = local / ((long long)X * Y);
+        out_coors[row * 4 + 0] = (TO)b;
+        out_coors[row * 4 + 1] = (TO)z;
+        out_coors[row * 4 + 2] = (TO)y;
+        out_coors[row * 4 + 3] = (TO)x;
+      }
+      rank++;
+    }
+  }
+}
+
+// ---- the fused per-voxel kernels ---------------------------------------------------------------------
+#define VFE_MAXD 16
+
+// decorated features of point p (all lanes get the same values)
+template <typename TC>
+__device__ __forceinline__ void decorate(const VfeDev& v, const float* __restrict__ pts, const TC* __restrict__ coors, int p,
+                                         float mx, float my, float mz, float* f) {
+  int ln = lane_id();
+  float raw = (ln < v.F) ? pts[(size_t)p * v.F + ln] : 0.f;
+  int k = 0;
+  for (; k < v.F; k++) f[k] = __shfl_sync(0xffffffffu, raw, k);
+  float x = f[0], y = f[1], z = f[2];
+  if (v.with_cluster) {
+    f[k++] = (x - mx) / v.rel_dist_scaler;
+    f[k++] = (y - my) / v.rel_dist_scaler;
+    f[k++] = (z - mz) / v.rel_dist_scaler;
+  }
+  if (v.with_center) {
+    // voxel_encoder.py:264-272: x - (coor_x * vx + x_offset)
+    float cx = (float)coors[(size_t)p * 4 + 3], cy = (float)coors[(size_t)p * 4 + 2], cz = (float)coors[(size_t)p * 4 + 1];
+    f[k++] = x - __fadd_rn(__fmul_rn(cx, v.vx), v.x_off);  // two roundings like torch's mul, add
+    f[k++] = y - __fadd_rn(__fmul_rn(cy, v.vy), v.y_off);
+    f[k++] = z - __fadd_rn(__fmul_rn(cz, v.vz), v.z_off);
+  }
+  if (v.with_distance) f[k++] = sqrtf(x * x + y * y + z * z);
+}
+
+// dynamic smem layout: W0t [D0][C0] | s0 t0 [2*C0] | W1at [C0][C1] | W1bt [C0][C1] | s1 t1 [2*C1]
+template <typename TC, int NC0 /*C0/32*/, int NC1 /*C1/32*/>
+__global__ void __launch_bounds__(256) vfe_fused_kernel(VfeDev v, const float* __restrict__ pts, const TC* __restrict__ coors,
+                                                        const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
+                                                        const int32_t* __restrict__ nvox_dev, float* __restrict__ vmean /*[M,3] scratch*/,
+                                                        float* __restrict__ vf0 /*[M,C0] scratch*/, float* __restrict__ out /*[M,Cout]*/,
+                                                        int phase) {
+  extern __shared__ float sm[];
+  const int C0 = NC0 * 32, C1 = NC1 * 32, D0 = v.D0;
+  float* W0t = sm;
+  float* s0 = W0t + D0 * C0;
+  float* t0 = s0 + C0;
+  float* W1at = t0 + C0;
+  float* W1bt = W1at + (size_t)C0 * C1;
+  float* s1 = W1bt + (size_t)C0 * C1;
+  float* t1 = s1 + C1;
+  for (int i = threadIdx.x; i < D0 * C0; i += blockDim.x) W0t[i] = v.W0[(i % C0) * D0 + (i / C0)];
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+    s0[i] = v.s0[i];
+    t0[i] = v.t0[i];
+  }
+  if (phase == 1 && NC1 > 0) {
+    for (int i = threadIdx.x; i < C0 * C1; i += blockDim.x) {
+      int k = i / C1, c = i % C1;
+      W1at[i] = v.W1[(size_t)c * 2 * C0 + k];
+      W1bt[i] = v.W1[(size_t)c * 2 * C0 + C0 + k];
+    }
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) {
+      s1[i] = v.s1[i];
+      t1[i] = v.t1[i];
+    }
+  }
+  __syncthreads();
+  int M = *nvox_dev;
+  int ln = lane_id();
+  int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int vox = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vox < M; vox += warps) {
+    uint32_t b = offsets[vox], e = offsets[vox + 1];
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (v.with_cluster) {
+      if (phase == 0) {
+        double sx = 0, sy = 0, sz = 0;
+        for (uint32_t k = b + ln; k < e; k += 32) {
+          int p = order[k];
+          sx += pts[(size_t)p * v.F];
+          sy += pts[(size_t)p * v.F + 1];
+          sz += pts[(size_t)p * v.F + 2];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+          sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        }
+        float cnt = (float)(e - b);
+        mx = (float)sx / cnt;
+        my = (float)sy / cnt;
+        mz = (float)sz / cnt;
+        if (ln == 0) {
+          vmean[(size_t)vox * 3] = mx;
+          vmean[(size_t)vox * 3 + 1] = my;
+          vmean[(size_t)vox * 3 + 2] = mz;
+        }
+      } else {
+        mx = vmean[(size_t)vox * 3];
+        my = vmean[(size_t)vox * 3 + 1];
+        mz = vmean[(size_t)vox * 3 + 2];
+      }
+    }
+    float f[VFE_MAXD];
+    if (phase == 0) {
+      float best[NC0], sum[NC0];
+#pragma unroll
+      for (int j = 0; j < NC0; j++) {
+        best[j] = -INFINITY;
+        sum[j] = 0.f;
+      }
+      for (uint32_t k = b; k < e; k++) {
+        int p = order[k];
+        decorate<TC>(v, pts, coors, p, mx, my, mz, f);
+#pragma unroll
+        for (int j = 0; j < NC0; j++) {
+          int c = ln + 32 * j;
+          float a = 0.f;
+          for (int d = 0; d < D0; d++) a = fmaf(W0t[d * C0 + c], f[d], a);
+          float y = fmaxf(fmaf(a, s0[c], t0[c]), 0.f);
+          best[j] = fmaxf(best[j], y);
+          sum[j] += y;
+        }
+      }
+      float* dst = (NC1 > 0) ? vf0 : out;
+#pragma unroll
+      for (int j = 0; j < NC0; j++) dst[(size_t)vox * C0 + ln + 32 * j] = v.mode_max ? best[j] : sum[j] / (float)(e - b);
+    } else if (NC1 > 0) {
+      // voxel term: W1[:, C0:] . vf0[vox]
+      float bterm[NC1 > 0 ? NC1 : 1];
+#pragma unroll
+      for (int j = 0; j < NC1; j++) bterm[j] = 0.f;
+      for (int k = 0; k < C0; k++) {
+        float g = vf0[(size_t)vox * C0 + k];
+#pragma unroll
+        for (int j = 0; j < NC1; j++) bterm[j] = fmaf(W1bt[(size_t)k * C1 + ln + 32 * j], g, bterm[j]);
+      }
+      float best[NC1 > 0 ? NC1 : 1], sum[NC1 > 0 ? NC1 : 1];
+#pragma unroll
+      for (int j = 0; j < NC1; j++) {
+        best[j] = -INFINITY;
+        sum[j] = 0.f;
+      }
+      for (uint32_t k = b; k < e; k++) {
+        int p = order[k];
+        decorate<TC>(v, pts, coors, p, mx, my, mz, f);
+        float y0[NC0];
+#pragma unroll
+        for (int j = 0; j < NC0; j++) {
+          int c = ln + 32 * j;
+          float a = 0.f;
+          for (int d = 0; d < D0; d++) a = fmaf(W0t[d * C0 + c], f[d], a);
+          y0[j] = fmaxf(fmaf(a, s0[c], t0[c]), 0.f);
+        }
+        float acc[NC1 > 0 ? NC1 : 1];
+#pragma unroll
+        for (int j = 0; j < NC1; j++) acc[j] = bterm[j];
+#pragma unroll
+        for (int jj = 0; jj < NC0; jj++) {
+#pragma unroll 8
+          for (int l2 = 0; l2 < 32; l2++) {
+            float yk = __shfl_sync(0xffffffffu, y0[jj], l2);
+            const float* wr = W1at + (size_t)(jj * 32 + l2) * C1 + ln;
+#pragma unroll
+            for (int j = 0; j < NC1; j++) acc[j] = fmaf(wr[32 * j], yk, acc[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NC1; j++) {
+          int c = ln + 32 * j;
+          float y = fmaxf(fmaf(acc[j], s1[c], t1[c]), 0.f);
+          best[j] = fmaxf(best[j], y);
+          sum[j] += y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NC1; j++) out[(size_t)vox * C1 + ln + 32 * j] = v.mode_max ? best[j] : sum[j] / (float)(e - b);
+    }
+  }
+}
+
+template <typename TC, int NC0, int NC1>
+static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const TC* coors, const Csr& r, const int32_t* num_dev,
+                      float* vmean, float* vf0, float* out) {
+  int C0 = NC0 * 32, C1 = NC1 * 32;
+  size_t smem = ((size_t)v.D0 * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
+  size_t smem_max = ((size_t)VFE_MAXD * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
+  auto kern = vfe_fused_kernel<TC, NC0, NC1>;
+  static bool attr_set = false;  // not a stream op, but keep it out of CUDA-graph capture after warm-up
+  if (!attr_set) {
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    attr_set = true;
+  }
+  int grid = c->num_sms * 2;
+  kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
+  if (NC1 > 0) kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 1);
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
+template <typename TC>
+static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const float* pts, const TC* coors, int P,
+                            float* out_feats, TC* out_coors, TC* inverse, int32_t* num_dev, int32_t* num_host) {
+  CHECK_ARG(c, c && cfg && P >= 0 && num_dev);
+  if (P == 0) {
+    CUDA_TRY(c, cudaMemsetAsync(num_dev, 0, 4, c->stream));
+    if (num_host) *num_host = 0;
+    return SSTB_OK;
+  }
+  CHECK_ARG(c, pts && coors && out_feats && out_coors);
+  CHECK_ARG(c, cfg->num_layers >= 1 && cfg->num_layers <= 2 && cfg->in_channels >= 3 && cfg->batch_size >= 1);
+  int F = cfg->in_channels;
+  int D0 = F + 3 * (cfg->with_cluster_center != 0) + 3 * (cfg->with_voxel_center != 0) + (cfg->with_distance != 0);
+  int C0 = cfg->feat_channels[0], C1 = cfg->num_layers > 1 ? cfg->feat_channels[1] : 0;
+  if (D0 > VFE_MAXD || F > 32) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE input dim %d > %d", D0, VFE_MAXD);
+  CHECK_ARG(c, cfg->weight[0] && cfg->bn_weight[0] && cfg->bn_bias[0] && cfg->bn_mean[0] && cfg->bn_var[0]);
+  if (C1) CHECK_ARG(c, cfg->weight[1] && cfg->bn_weight[1] && cfg->bn_bias[1] && cfg->bn_mean[1] && cfg->bn_var[1]);
+  int Z = cfg->grid_zyx[0], Y = cfg->grid_zyx[1], X = cfg->grid_zyx[2], B = cfg->batch_size;
+  CHECK_ARG(c, Z > 0 && Y > 0 && X > 0);
+  size_t cells = (size_t)Z * Y * X;
+  size_t cells_pad = (cells + 31) / 32 * 32;
+  long long T = (long long)cells_pad * B;
+  if (T > ((long long)1 << 34)) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "voxel grid too large for bitmap rank (%lld cells)", T);
+  arena_reset(c);
+  int rc = arena_reserve(c, key_index_bytes(P, T) + csr_bytes(P, P) + al256((size_t)P * 4) * 3 + al256((size_t)P * 3 * 4) +
+                                al256((size_t)P * C0 * 4) + al256((size_t)(C0 + C1) * 8) + 8192);
+  if (rc) return rc;
+  KeyIndex k;
+  rc = key_index_alloc(c, k, P, T);
+  if (rc) return rc;
+  int32_t* count = arena_alloc<int32_t>(c, (size_t)P + 2);
+  int32_t* map32 = inverse ? nullptr : arena_alloc<int32_t>(c, P);
+  float* vmean = arena_alloc<float>(c, (size_t)P * 3);
+  float* vf0 = arena_alloc<float>(c, (size_t)P * C0);
+  float* fold = arena_alloc<float>(c, 2 * (size_t)(C0 + C1) + 8);
+  if (!count || !vmean || !vf0 || !fold) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe: arena");
+  CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)P + 2) * 4, c->stream));
+  int nb = (P + 255) / 256;
+  vfe_mark_kernel<TC><<<nb, 256, 0, c->stream>>>(coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
+  key_index_scan(c, k);
+  SampleQuirk q{k.word_prefix, cells_pad / 32, B, cfg->drop_first_voxel_per_sample != 0};
+  int eg = (int)((k.nwords + 255) / 256);
+  if (eg > c->num_sms * 16) eg = c->num_sms * 16;
+  vfe_emit_kernel<TC><<<eg, 256, 0, c->stream>>>(k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
+  Csr r;
+  if (inverse) {
+    vfe_map_kernel<TC><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, inverse, count);
+    rc = csr_build<TC>(c, r, inverse, P, count, P, num_dev);
+  } else {
+    vfe_map_kernel<int32_t><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, map32, count);
+    rc = csr_build<int32_t>(c, r, map32, P, count, P, num_dev);
+  }
+  if (rc) return rc;
+  VfeDev v;
+  v.F = F;
+  v.D0 = D0;
+  v.C0 = C0;
+  v.C1 = C1;
+  v.nlayers = cfg->num_layers;
+  v.with_cluster = cfg->with_cluster_center != 0;
+  v.with_center = cfg->with_voxel_center != 0;
+  v.with_distance = cfg->with_distance != 0;
+  v.mode_max = cfg->mode_max != 0;
+  v.vx = cfg->voxel_size[0];
+  v.vy = cfg->voxel_size[1];
+  v.vz = cfg->voxel_size[2];
+  v.x_off = cfg->center_offset[0];
+  v.y_off = cfg->center_offset[1];
+  v.z_off = cfg->center_offset[2];
+  v.rel_dist_scaler = cfg->rel_dist_scaler;
+  v.W0 = cfg->weight[0];
+  v.W1 = cfg->weight[1];
+  v.s0 = fold;
+  v.t0 = fold + C0;
+  v.s1 = fold + 2 * C0;
+  v.t1 = fold + 2 * C0 + C1;
+  fold_bn_kernel<<<(C0 + 127) / 128, 128, 0, c->stream>>>(cfg->bn_weight[0], cfg->bn_bias[0], cfg->bn_mean[0], cfg->bn_var[0],
+                                                           cfg->bn_eps, C0, fold, fold + C0);
+  if (C1)
+    fold_bn_kernel<<<(C1 + 127) / 128, 128, 0, c->stream>>>(cfg->bn_weight[1], cfg->bn_bias[1], cfg->bn_mean[1], cfg->bn_var[1],
+                                                             cfg->bn_eps, C1, fold + 2 * C0, fold + 2 * C0 + C1);
+  LAUNCH_CHECK(c);
+#define VFE_CASE(a, b)                                                                        \
+  if (C0 == a * 32 && C1 == b * 32) {                                                         \
+    rc = launch_vfe<TC, a, b>(c, v, pts, coors, r, num_dev, vmean, vf0, out_feats);           \
+    goto done;                                                                                \
+  }
+  VFE_CASE(2, 4)
+  VFE_CASE(2, 2)
+  VFE_CASE(1, 2)
+  VFE_CASE(2, 0)
+  VFE_CASE(4, 4)
+  VFE_CASE(4, 0)
+  VFE_CASE(1, 0)
+  VFE_CASE(1, 1)
+  VFE_CASE(2, 8)
+  return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE channel combination (%d,%d) not instantiated", C0, C1);
+done:
+  if (rc) return rc;
+  if (num_host) return read_back_i32(c, num_dev, num_host);
+  return SSTB_OK;
+}
+
+extern "C" int sstb200_dynamic_vfe_forward(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const float* points, const int32_t* coors,
+                                           int P, float* voxel_feats, int32_t* voxel_coors, int32_t* num_dev, int32_t* num_host) {
+  return vfe_forward_impl<int32_t>(c, cfg, points, coors, P, voxel_feats, voxel_coors, nullptr, num_dev, num_host);
+}
+
+extern "C" int sstb200_dynamic_scatter_vfe_forward(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const float* points,
+                                                   const int64_t* coors, int P, float* voxel_feats, int64_t* voxel_coors,
+                                                   int64_t* unq_inv, int32_t* num_dev, int32_t* num_host) {
+  CHECK_ARG(c, unq_inv);
+  return vfe_forward_impl<long long>(c, cfg, points, (const long long*)coors, P, voxel_feats, (long long*)voxel_coors,
+                                     (long long*)unq_inv, num_dev, num_host);
+}

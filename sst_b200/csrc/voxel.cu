@@ -49,6 +49,44 @@ extern "C" int sstb200_dynamic_voxelize(sstb200_ctx* c, const float* points, int
   return SSTB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// V1 batched / sync-free
+// ------------------------------------------------------------------------------------------------
+__global__ void voxelize_frames_kernel(const float* __restrict__ points, int cap, int F, const int32_t* __restrict__ offs, int B,
+                                       float vx, float vy, float vz, float x0, float y0, float z0, int gx, int gy, int gz,
+                                       int32_t* __restrict__ coors4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  int4 o = make_int4(-1, -1, -1, -1);
+  if (i < offs[B]) {
+    int b = 0;
+    while (b + 1 < B && i >= offs[b + 1]) b++;
+    const float* p = points + (size_t)i * F;
+    int cx = (int)floorf(__fdiv_rn(p[0] - x0, vx));
+    int cy = (int)floorf(__fdiv_rn(p[1] - y0, vy));
+    int cz = (int)floorf(__fdiv_rn(p[2] - z0, vz));
+    cx = cx < 0 ? 0 : (cx >= gx ? gx - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= gy ? gy - 1 : cy);
+    cz = cz < 0 ? 0 : (cz >= gz ? gz - 1 : cz);
+    o = make_int4(b, cz, cy, cx);
+  }
+  *(int4*)&coors4[(size_t)i * 4] = o;
+}
+
+extern "C" int sstb200_voxelize_frames(sstb200_ctx* c, const float* points, int cap, int F, const int32_t* offs, int B,
+                                       const float vs[3], const float r[6], int32_t* coors4) {
+  CHECK_ARG(c, c && cap >= 0 && F >= 3 && B >= 1 && offs && vs && r);
+  if (cap == 0) return SSTB_OK;
+  CHECK_ARG(c, points && coors4);
+  int g[3];
+  sstb_grid_size(vs, r, g);
+  voxelize_frames_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(points, cap, F, offs, B, vs[0], vs[1], vs[2], r[0], r[1], r[2],
+                                                                    g[0], g[1], g[2], coors4);
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // V2 dynamic_point_to_voxel_forward
 // ------------------------------------------------------------------------------------------------
@@ -309,3 +347,45 @@ extern "C" int sstb200_set_stream(sstb200_ctx* c, void* s) {
 }
 extern "C" const char* sstb200_last_error(sstb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" int sstb200_num_sms(sstb200_ctx* c) { return c ? c->num_sms : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// CUDA graph helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int sstb200_graph_begin(sstb200_ctx* c) {
+  CHECK_ARG(c, c);
+  CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  return SSTB_OK;
+}
+extern "C" int sstb200_graph_end(sstb200_ctx* c, void** exec_out, int32_t* nk, int32_t* no) {
+  CHECK_ARG(c, c && exec_out);
+  cudaGraph_t g = nullptr;
+  CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
+  size_t n = 0;
+  CUDA_TRY(c, cudaGraphGetNodes(g, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) CUDA_TRY(c, cudaGraphGetNodes(g, nodes.data(), &n));
+  int kn = 0, on = 0;
+  for (size_t i = 0; i < n; i++) {
+    cudaGraphNodeType t;
+    CUDA_TRY(c, cudaGraphNodeGetType(nodes[i], &t));
+    if (t == cudaGraphNodeTypeKernel) kn++;
+    else on++;
+  }
+  if (nk) *nk = kn;
+  if (no) *no = on;
+  cudaGraphExec_t ex = nullptr;
+  CUDA_TRY(c, cudaGraphInstantiate(&ex, g, 0));
+  CUDA_TRY(c, cudaGraphDestroy(g));
+  *exec_out = (void*)ex;
+  return SSTB_OK;
+}
+extern "C" int sstb200_graph_launch(sstb200_ctx* c, void* ex) {
+  CHECK_ARG(c, c && ex);
+  CUDA_TRY(c, cudaGraphLaunch((cudaGraphExec_t)ex, c->stream));
+  return SSTB_OK;
+}
+extern "C" int sstb200_graph_destroy(sstb200_ctx* c, void* ex) {
+  CHECK_ARG(c, c);
+  if (ex) CUDA_TRY(c, cudaGraphExecDestroy((cudaGraphExec_t)ex));
+  return SSTB_OK;
+}

@@ -1,0 +1,142 @@
+"""Sync-free frame engine for the SST hot path (BASELINE config 2):
+
+    points --voxelize--> DynamicVFE --> SSTInputLayerV2 (2 window plans) --> SSTv2 (num_blocks x 2 SRA layers)
+
+It drives the same libsstb200 entry points as the registered modules, but with device-resident row counts
+(`n_dev`) and capacity-sized buffers, so the whole frame is one CUDA graph: no host sync, no allocation, one
+launch per frame.  Mirrors DynamicVoxelNet.extract_feat (mmdet3d/models/detectors/dynamic_voxelnet.py:38-47)
+up to and including the backbone's sparse output.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .sst_modules import PRECISIONS, _SraPlan, SSTInputLayerV2, SSTv2
+from .voxel_modules import DynamicVFE
+
+L.SIGNATURES["sstb200_graph_begin"] = (C.c_int, [L.vp])
+L.SIGNATURES["sstb200_graph_end"] = (C.c_int, [L.vp, C.POINTER(C.c_void_p), L.P_i32, L.P_i32])
+L.SIGNATURES["sstb200_graph_launch"] = (C.c_int, [L.vp, L.vp])
+L.SIGNATURES["sstb200_graph_destroy"] = (C.c_int, [L.vp, L.vp])
+L.SIGNATURES["sstb200_voxelize_frames"] = (C.c_int, [L.vp, L.vp, C.c_int, C.c_int, L.vp, C.c_int, L.P_f32, L.P_f32, L.vp])
+
+
+class SSTEngine:
+    def __init__(self, voxel_size, point_cloud_range, voxel_encoder: DynamicVFE, middle_encoder: SSTInputLayerV2,
+                 backbone: SSTv2, max_points, batch_size=1, precision="fp32", device="cuda:0", use_graph=True):
+        self.dev = torch.device(device)
+        self.vs = [float(v) for v in voxel_size]
+        self.rng = [float(v) for v in point_cloud_range]
+        self.vfe, self.il, self.bb = voxel_encoder.eval(), middle_encoder.eval(), backbone.eval()
+        self.cap, self.B = int(max_points), int(batch_size)
+        self.precision = precision
+        self.F = self.vfe.raw_in_channels
+        self.d = backbone.d_model[0]
+        assert all(d == self.d for d in backbone.d_model), "engine assumes a constant d_model"
+        assert not hasattr(backbone, "linear0"), "linear0 not wired into the engine"
+        self.il.set_drop_info()
+        if self.il._may_drop():
+            raise NotImplementedError("the sync-free engine covers drop_info settings that cannot drop voxels "
+                                      "(eval configs); use the modules for training-time dropping")
+        dev, cap = self.dev, self.cap
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        self.points = torch.zeros((cap, self.F), **f32)
+        self.offsets = torch.zeros((self.B + 1,), **i32)
+        self.coors4 = torch.empty((cap, 4), **i32)
+        self.vf = torch.empty((cap, self.vfe.feat_channels[-1]), **f32)
+        self.vc = torch.empty((cap, 4), **i32)
+        self.num = torch.zeros((1,), **i32)
+        self.x = [torch.empty((cap, self.d), **f32) for _ in range(2)]
+        self.plans = []
+        for _ in range(2):
+            p = {k: torch.empty((cap + 1,) if k == "win_offsets" else (cap,), **i32)
+                 for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank")}
+            p["counters"] = torch.zeros((17,), **i32)
+            self.plans.append(p)
+        self.wcfg, _ = ops._window_cfg(self.il.sparse_shape, self.il.window_shape, self.il.drop_info, self.B)
+        tab, ndim, maxw, Lp = self.il._pos(self.d, dev)
+        self.pos = (tab, ndim, maxw, Lp)
+        self._shift_structs = [ops._WindowShift(None, None, None, None, p["pos_code"].data_ptr(), p["tok_win"].data_ptr(),
+                                                p["tok_inner"].data_ptr(), p["win_offsets"].data_ptr(),
+                                                p["tok_perm"].data_ptr(), p["win_level"].data_ptr(),
+                                                p["win_rank"].data_ptr(), p["counters"].data_ptr()) for p in self.plans]
+        self._plan_structs = [_SraPlan(p["win_offsets"].data_ptr(), p["tok_perm"].data_ptr(), p["tok_win"].data_ptr(),
+                                       p["pos_code"].data_ptr(), p["counters"].data_ptr(), tab.data_ptr(), Lp, maxw, ndim,
+                                       0) for p in self.plans]
+        self.vfe_cfg = self.vfe._cfg(self.B)
+        prec = PRECISIONS[precision]
+        self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]
+        self._vs_arr, self._rng_arr = L.arr(C.c_float, self.vs), L.arr(C.c_float, self.rng)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self.launches_per_frame = None
+        with torch.cuda.stream(self.stream):
+            self._enqueue()           # warm-up: grows the arena, sets kernel attributes
+            self._enqueue()
+        self.stream.synchronize()
+        if use_graph:
+            with torch.cuda.stream(self.stream):
+                lib, c = L.lib(), L.ctx(self.dev)
+                L.check(c, lib.sstb200_graph_begin(c))
+                try:
+                    self._enqueue()
+                finally:
+                    ex, nk, no = C.c_void_p(), C.c_int32(0), C.c_int32(0)
+                    L.check(c, lib.sstb200_graph_end(c, C.byref(ex), C.byref(nk), C.byref(no)))
+                self.graph = ex
+                self.launches_per_frame = nk.value   # kernel nodes of OUR library in one frame
+                self.other_nodes_per_frame = no.value
+            self.stream.synchronize()
+
+    # everything below is stream-ordered and sync-free
+    def _enqueue(self):
+        lib, c = L.lib(), L.ctx(self.dev)
+        prec = PRECISIONS[self.precision]
+        cap = self.cap
+        L.check(c, lib.sstb200_voxelize_frames(c, self.points.data_ptr(), cap, self.F, self.offsets.data_ptr(), self.B,
+                                               self._vs_arr, self._rng_arr, self.coors4.data_ptr()))
+        L.check(c, lib.sstb200_dynamic_vfe_forward(c, C.byref(self.vfe_cfg), self.points.data_ptr(), self.coors4.data_ptr(),
+                                                   cap, self.vf.data_ptr(), self.vc.data_ptr(), self.num.data_ptr(), None))
+        for s in range(2):
+            L.check(c, lib.sstb200_window_plan_i32(c, self.vc.data_ptr(), cap, self.num.data_ptr(), C.byref(self.wcfg), s,
+                                                   C.byref(self._shift_structs[s])))
+        src = self.vf
+        for li, (ls, shift) in enumerate(self._layers):
+            dst = self.x[(li + 1) % 2]
+            L.check(c, lib.sstb200_sra_layer_forward(c, C.byref(ls), C.byref(self._plan_structs[shift]), src.data_ptr(),
+                                                     dst.data_ptr(), cap, self.num.data_ptr(), prec))
+            src = dst
+        self._last = src
+
+    def load_frames_device(self, points_dev, offsets_dev):
+        """points_dev [P,F] fp32 (frames back to back) and offsets_dev int32 [B+1], both already on the device.
+        Stream-ordered D2D copy into the engine's input buffer (no sync)."""
+        n = points_dev.shape[0]
+        assert n <= self.cap and offsets_dev.numel() == self.B + 1
+        with torch.cuda.stream(self.stream):
+            self.points[:n].copy_(points_dev, non_blocking=True)
+            self.offsets.copy_(offsets_dev, non_blocking=True)
+
+    def run(self):
+        """Enqueue one forward over the resident frames (graph replay).  Returns (feats_buf, coors_buf, num_dev)."""
+        with torch.cuda.stream(self.stream):
+            if self.graph is not None:
+                c = L.ctx(self.dev)
+                L.check(c, L.lib().sstb200_graph_launch(c, self.graph))
+            else:
+                self._enqueue()
+        return self._last, self.vc, self.num
+
+    def forward_host(self, pinned_points, offsets_pinned, out_feats_pinned, out_coors_pinned):
+        """End-to-end call on HOST buffers: H2D(points) -> forward -> D2H(num) -> D2H(feats[:M], coors[:M])."""
+        n = pinned_points.shape[0]
+        with torch.cuda.stream(self.stream):
+            self.points[:n].copy_(pinned_points, non_blocking=True)
+            self.offsets.copy_(offsets_pinned, non_blocking=True)
+            feats, coors, num = self.run()
+            M = int(num.item())  # one small sync: the row count is data dependent
+            out_feats_pinned[:M].copy_(feats[:M], non_blocking=True)
+            out_coors_pinned[:M].copy_(coors[:M], non_blocking=True)
+        return M

@@ -1,0 +1,51 @@
+"""Factory for the BASELINE.json configurations (config dicts = the reference's own, e.g.
+configs/sst_refactor/sst_waymoD5_1x_3class_8heads_v2.py:8-72), shared by bench.py, smoke() and the tests."""
+import torch
+
+from .registry import build_backbone, build_middle_encoder, build_voxel_encoder
+from . import sst_modules, voxel_modules  # noqa: F401  (registers the types)
+
+VOXEL_SIZE = (0.32, 0.32, 6)
+WINDOW_SHAPE = (12, 12, 1)
+PC_RANGE = [-74.88, -74.88, -2, 74.88, 74.88, 4]
+DROP_TRAIN = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+              2: {'max_tokens': 100, 'drop_range': (60, 100000)}}
+DROP_TEST = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+             2: {'max_tokens': 100, 'drop_range': (60, 100)}, 3: {'max_tokens': 144, 'drop_range': (100, 100000)}}
+
+
+def sst_cfg(d_model=128, nhead=8, dim_ff=256, num_blocks=6, in_channels=3):
+    return dict(
+        voxel_encoder=dict(type='DynamicVFE', in_channels=in_channels, feat_channels=[64, d_model], with_distance=False,
+                           voxel_size=VOXEL_SIZE, with_cluster_center=True, with_voxel_center=True,
+                           point_cloud_range=PC_RANGE, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)),
+        middle_encoder=dict(type='SSTInputLayerV2', window_shape=WINDOW_SHAPE, sparse_shape=(468, 468, 1),
+                            shuffle_voxels=False, debug=True, drop_info=(DROP_TRAIN, DROP_TEST), pos_temperature=10000,
+                            normalize_pos=False, mute=True),
+        backbone=dict(type='SSTv2', d_model=[d_model] * num_blocks, nhead=[nhead] * num_blocks, num_blocks=num_blocks,
+                      dim_feedforward=[dim_ff] * num_blocks, output_shape=[468, 468], num_attached_conv=0, to_bev=False,
+                      debug=True),
+    )
+
+
+def build_sst(cfg=None, seed=0, randomize_norm=True):
+    """Random-init modules (torch.manual_seed(seed) + the modules' own init, xavier for SSTv2).  BN running stats and
+    affine norm parameters are perturbed so that every term of the arithmetic is exercised."""
+    cfg = cfg or sst_cfg()
+    torch.manual_seed(seed)
+    vfe = build_voxel_encoder(cfg['voxel_encoder']).eval()
+    il = build_middle_encoder(cfg['middle_encoder']).eval()
+    bb = build_backbone(cfg['backbone']).eval()
+    if randomize_norm:
+        g = torch.Generator().manual_seed(seed + 1)
+        with torch.no_grad():
+            for m in (vfe, bb):
+                for n_, p in m.named_parameters():
+                    if p.dim() == 1:
+                        p.copy_(torch.randn(p.shape, generator=g) * 0.1 + (1.0 if 'norm' in n_ and 'weight' in n_ else 0.0))
+                for n_, b in m.named_buffers():
+                    if 'running_mean' in n_:
+                        b.copy_(torch.randn(b.shape, generator=g) * 0.3)
+                    if 'running_var' in n_:
+                        b.copy_(torch.rand(b.shape, generator=g) + 0.5)
+    return vfe, il, bb

@@ -309,3 +309,256 @@ class IngroupIndicesFunction(Function):
 
 
 get_inner_win_inds = IngroupIndicesFunction.apply
+
+
+# ----------------------------------------------------------------------------------------------
+# B1/B3/B4 fused window plan (one shift)
+# ----------------------------------------------------------------------------------------------
+class _WindowCfg(C.Structure):
+    _fields_ = [("sparse_shape", C.c_int32 * 3), ("window_shape", C.c_int32 * 3), ("batch_size", C.c_int32),
+                ("num_levels", C.c_int32), ("level_id", C.c_int32 * 8), ("level_lo", C.c_int32 * 8),
+                ("level_hi", C.c_int32 * 8), ("level_max_tokens", C.c_int32 * 8)]
+
+
+class _WindowShift(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("batch_win_inds", "coors_in_win", "drop_level", "flat2win_inds", "pos_code",
+                                          "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank",
+                                          "counters")]
+
+
+L.SIGNATURES["sstb200_window_plan"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.POINTER(_WindowCfg), C.c_int, L.vp,
+                                                 C.POINTER(_WindowShift), L.P_i32])
+L.SIGNATURES["sstb200_window_plan_i32"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.POINTER(_WindowCfg), C.c_int,
+                                                     C.POINTER(_WindowShift)])
+
+
+def _window_shape3(window_shape, sparse_shape):
+    if len(window_shape) == 2:
+        return (int(window_shape[0]), int(window_shape[1]), int(sparse_shape[-1]))
+    return tuple(int(v) for v in window_shape)
+
+
+def _window_cfg(sparse_shape, window_shape, drop_info, batch_size):
+    cfg = _WindowCfg()
+    w3 = _window_shape3(window_shape, sparse_shape)
+    for i in range(3):
+        cfg.sparse_shape[i] = int(sparse_shape[i])
+        cfg.window_shape[i] = w3[i]
+    cfg.batch_size = int(batch_size)
+    keys = list(drop_info.keys())
+    assert 1 <= len(keys) <= 8, "at most 8 drop levels supported"
+    cfg.num_levels = len(keys)
+    for s, k in enumerate(keys):
+        lo, hi = drop_info[k]["drop_range"]
+        cfg.level_id[s] = int(k)
+        cfg.level_lo[s] = int(min(lo, 2 ** 31 - 1))
+        cfg.level_hi[s] = int(min(hi, 2 ** 31 - 1))
+        cfg.level_max_tokens[s] = int(drop_info[k]["max_tokens"])
+    return cfg, keys
+
+
+class WindowPlan:
+    """Device-resident result of sstb200_window_plan for one shift."""
+    __slots__ = ("n", "batch_win_inds", "coors_in_win", "drop_level", "flat2win_inds", "pos_code", "tok_win",
+                 "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "counters", "level_keys",
+                 "num_windows", "level_windows", "level_tokens", "status")
+
+
+def window_plan(coors, sparse_shape, window_shape, drop_info, do_shift, batch_size, token_level=None, sync=True):
+    """coors [n,4] int64 (b,z,y,x) on CUDA.  Returns a WindowPlan (reference index tensors + window CSR)."""
+    _need_cuda(coors)
+    assert coors.dtype == torch.int64 and coors.dim() == 2 and coors.shape[1] == 4
+    coors = coors.contiguous()
+    n, dev = coors.shape[0], coors.device
+    cfg, keys = _window_cfg(sparse_shape, window_shape, drop_info, batch_size)
+    p = WindowPlan()
+    p.n, p.level_keys = n, keys
+    i64 = dict(dtype=torch.int64, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    p.batch_win_inds = torch.empty((n,), **i64)
+    p.coors_in_win = torch.empty((n, 3), **i64)
+    p.drop_level = torch.empty((n,), **i64)
+    p.flat2win_inds = torch.empty((n,), **i64)
+    p.pos_code = torch.empty((n,), **i32)
+    p.tok_win = torch.empty((n,), **i32)
+    p.tok_inner = torch.empty((n,), **i32)
+    p.win_offsets = torch.empty((n + 1,), **i32)
+    p.tok_perm = torch.empty((n,), **i32)
+    p.win_level = torch.empty((n,), **i32)
+    p.win_rank = torch.empty((n,), **i32)
+    p.counters = torch.empty((17,), **i32)
+    out = _WindowShift(*[getattr(p, k).data_ptr() for k, _ in _WindowShift._fields_])
+    status = (C.c_int32 * 18)()
+    if token_level is not None:
+        assert token_level.dtype == torch.int64 and token_level.is_cuda and token_level.is_contiguous()
+    c = L.ctx(dev)
+    L.check(c, L.lib().sstb200_window_plan(c, coors.data_ptr(), n, None, C.byref(cfg), int(bool(do_shift)),
+                                           L.ptr(token_level), C.byref(out), status if sync else None))
+    if sync:
+        p.status = status[0]
+        if status[0] & 1:
+            raise L.SSTB200Error("window_plan: voxel coordinate outside batch_size/sparse_shape window grid")
+        if status[0] & 2:
+            raise AssertionError("a window's token count is not covered by any drop_range (reference asserts too)")
+        p.num_windows = status[1]
+        p.level_windows = list(status[2:2 + len(keys)])
+        p.level_tokens = list(status[10:10 + len(keys)])
+    return p
+
+
+@torch.no_grad()
+def get_window_coors(coors, sparse_shape, window_shape, do_shift):
+    """ops/sst/sst_ops.py:266-314."""
+    assert sparse_shape[2] < sparse_shape[0], "Usually holds... in case of wrong order"
+    n = coors.shape[0]
+    if n == 0:
+        return coors.new_empty((0,)), coors.new_empty((0, 3))
+    B = int(coors[:, 0].max()) + 1
+    p = window_plan(coors.long(), sparse_shape, window_shape, {0: dict(max_tokens=1, drop_range=(0, 2 ** 31 - 1))},
+                    do_shift, B)
+    return p.batch_win_inds, p.coors_in_win
+
+
+@torch.no_grad()
+def make_continuous_inds(inds):
+    """ops/sst/sst_ops.py:316-331."""
+    if inds.numel() == 0:
+        return inds.clone()
+    return unique_rows(inds.long().view(-1, 1))[1].to(inds.dtype)
+
+
+@torch.no_grad()
+def get_flat2win_inds(batch_win_inds, voxel_drop_lvl, drop_info, debug=True):
+    """ops/sst/sst_ops.py:27-64 (compat path; the fused path is window_plan)."""
+    d = {}
+    for dl in drop_info:
+        dl_mask = voxel_drop_lvl == dl
+        if not dl_mask.any():
+            continue
+        conti = make_continuous_inds(batch_win_inds[dl_mask])
+        inner = get_inner_win_inds(conti)
+        d[dl] = (conti * drop_info[dl]["max_tokens"] + inner, torch.where(dl_mask))
+    return d
+
+
+def get_flat2win_inds_v2(batch_win_inds, voxel_drop_lvl, drop_info, debug=True):
+    d = get_flat2win_inds(batch_win_inds, voxel_drop_lvl, drop_info, debug)
+    d["voxel_drop_level"] = voxel_drop_lvl
+    d["batching_info"] = drop_info
+    return d
+
+
+def flat2window(feat, voxel_drop_lvl, flat2win_inds_dict, drop_info, padding=0):
+    """ops/sst/sst_ops.py:67-104.  Reference-layout (padded [R,T,C]) materialisation: API parity only - the
+    attention kernels of this build consume the ragged CSR and never call this."""
+    out = {}
+    for dl in drop_info:
+        dl_mask = voxel_drop_lvl == dl
+        if not dl_mask.any():
+            continue
+        this_inds = flat2win_inds_dict[dl][0]
+        T = drop_info[dl]["max_tokens"]
+        R = int((this_inds // T).max()) + 1
+        buf = torch.full((R * T, feat.shape[-1]), padding, dtype=feat.dtype, device=feat.device)
+        buf[this_inds] = feat[dl_mask]
+        out[dl] = buf.reshape(R, T, feat.shape[-1])
+    return out
+
+
+def window2flat(feat_3d_dict, inds_dict):
+    """ops/sst/sst_ops.py:106-132."""
+    n = sum(inds_dict[dl][0].shape[0] for dl in inds_dict)
+    first = feat_3d_dict[next(iter(feat_3d_dict))]
+    out = torch.zeros((n, first.shape[-1]), device=first.device, dtype=first.dtype)
+    for dl in feat_3d_dict:
+        inds, flat_pos = inds_dict[dl]
+        out[flat_pos] = feat_3d_dict[dl].reshape(-1, first.shape[-1])[inds]
+    return out
+
+
+def window2flat_v2(feat_3d_dict, inds_dict):
+    return window2flat(feat_3d_dict, {k: inds_dict[k] for k in inds_dict if not isinstance(k, str)})
+
+
+def flat2window_v2(feat, inds_dict, padding=0):
+    assert "voxel_drop_level" in inds_dict, "voxel_drop_level should be in inds_dict in v2 function"
+    inds_v1 = {k: inds_dict[k] for k in inds_dict if not isinstance(k, str)}
+    return flat2window(feat, inds_dict["voxel_drop_level"], inds_v1, inds_dict["batching_info"], padding=padding)
+
+
+# ----------------------------------------------------------------------------------------------
+# S3 small builders (host logic only)
+# ----------------------------------------------------------------------------------------------
+def get_activation(activation):
+    """ops/sst/sst_ops.py:363-371."""
+    if activation == "relu":
+        return torch.nn.functional.relu
+    if activation == "gelu":
+        return torch.nn.functional.gelu
+    if activation == "glu":
+        return torch.nn.functional.glu
+    raise RuntimeError(f"activation should be relu/gelu, not {activation}.")
+
+
+def get_activation_layer(act, dim=None):
+    """ops/sst/sst_ops.py:373-392."""
+    act = act.lower()
+    table = {"relu": lambda: nn.ReLU(inplace=True), "gelu": nn.GELU, "leakyrelu": lambda: nn.LeakyReLU(inplace=True),
+             "prelu": lambda: nn.PReLU(num_parameters=dim), "swish": lambda: nn.SiLU(inplace=True),
+             "silu": lambda: nn.SiLU(inplace=True), "glu": nn.GLU, "elu": lambda: nn.ELU(inplace=True)}
+    if act not in table:
+        raise NotImplementedError
+    return table[act]()
+
+
+def build_norm_layer(cfg, num_features):
+    """mmcv.cnn.build_norm_layer for the norm types the path uses; returns (name, layer)."""
+    from .norm import NaiveSyncBatchNorm1d, NaiveSyncBatchNorm2d
+    cfg = dict(cfg)
+    t = cfg.pop("type")
+    cfg.pop("requires_grad", None)
+    if t == "LN":
+        return "ln", nn.LayerNorm(num_features, **cfg)
+    if t in ("BN1d", "BN"):
+        return "bn", nn.BatchNorm1d(num_features, **cfg)
+    if t == "naiveSyncBN1d":
+        return "bn", NaiveSyncBatchNorm1d(num_features, **cfg)
+    if t == "BN2d":
+        return "bn", nn.BatchNorm2d(num_features, **cfg)
+    if t == "naiveSyncBN2d":
+        return "bn", NaiveSyncBatchNorm2d(num_features, **cfg)
+    raise NotImplementedError(f"norm type {t}")
+
+
+def build_mlp(in_channel, hidden_dims, norm_cfg, is_head=False, act="relu", bias=False, dropout=0):
+    """ops/sst/sst_ops.py:334-361 (parameter container: `mlp.{i}.0.weight`, `mlp.{i}.1.{weight,bias}`)."""
+    layers = []
+    last = in_channel
+    if isinstance(hidden_dims, int):
+        hidden_dims = [hidden_dims]
+    for i, ch in enumerate(hidden_dims):
+        if i == len(hidden_dims) - 1 and is_head:
+            layers.append(nn.Linear(last, ch, bias=True))
+        else:
+            sq = [nn.Linear(last, ch, bias=bias), build_norm_layer(norm_cfg, ch)[1], get_activation_layer(act, ch)]
+            if dropout > 0:
+                sq.append(nn.Dropout(dropout))
+            layers.append(nn.Sequential(*sq))
+        last = ch
+    return nn.Sequential(*layers)
+
+
+L.SIGNATURES["sstb200_linear"] = (C.c_int, [L.vp, L.vp, L.vp, L.vp, L.vp, C.c_int, C.c_int, C.c_int, C.c_int])
+
+
+def linear(x, weight, bias=None, act=None):
+    """nn.Linear forward (fp32) through libsstb200; act in (None, 'relu', 'gelu')."""
+    _need_cuda(x, weight)
+    x = x.float().contiguous()
+    w = weight.detach().float().contiguous()
+    b = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+    c = L.ctx(x.device)
+    L.check(c, L.lib().sstb200_linear(c, x.data_ptr(), w.data_ptr(), L.ptr(b), out.data_ptr(), x.shape[0], w.shape[0],
+                                      w.shape[1], {None: 0, "relu": 1, "gelu": 2}[act]))
+    return out
