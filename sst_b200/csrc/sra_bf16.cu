@@ -100,7 +100,7 @@ struct GemmArgs {
 constexpr int TILE_M = 128;
 
 template <int K, int NT, int PRO, int EPI>
-__global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned operand tiles (SWIZZLE_128B atoms)
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
   uint8_t* sW = sA + (size_t)TILE_M * K * 2;    // K/64 chunks x NT rows x 128 B
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float red[2][TILE_M][2];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int M = g.M_dev ? *g.M_dev : g.M_cap;
@@ -125,47 +126,96 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
-  // ---- stage W tile: rows n0..n0+NT of W[., K] ------------------------------------------------------------
+  // ---- stage W tile (rows n0..n0+NT of W[., K]) and A tile: 16-byte chunks, 8 loads in flight per thread -------------
   constexpr int CH = K / 8;  // 16-byte chunks per row
-  for (int idx = tid; idx < NT * CH; idx += 128) {
-    int r = idx / CH, j = idx % CH;
-    int4 v = *reinterpret_cast<const int4*>(g.W + (size_t)(n0 + r) * K + j * 8);
-    int c = j >> 3, jj = j & 7;
-    *reinterpret_cast<int4*>(sW + (size_t)c * NT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
-  }
-  // ---- stage A tile ------------------------------------------------------------------------------------------
-  const bool add_pos = (PRO == PRO_F32) && g.pos_tab != nullptr && (int)blockIdx.y < g.pos_ntiles;
-  for (int idx = tid; idx < TILE_M * CH; idx += 128) {
-    int r = idx / CH, j = idx % CH;
-    int gr = row0 + r;
-    int4 v = make_int4(0, 0, 0, 0);
-    if (gr < M) {
-      if (PRO == PRO_BF16) {
-        v = *reinterpret_cast<const int4*>((const __nv_bfloat16*)g.A + (size_t)gr * g.lda + j * 8);
-      } else {
-        const float* ap = (const float*)g.A + (size_t)gr * g.lda + j * 8;
-        float4 f0 = *reinterpret_cast<const float4*>(ap), f1 = *reinterpret_cast<const float4*>(ap + 4);
-        float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-        if (add_pos) {
-          int code = g.pos_code[gr];
+  constexpr int NTH = 256, UNR = 8;
+  {
+    const __nv_bfloat16* wsrc = g.W + (size_t)n0 * K;
+    for (int i0 = tid; i0 < NT * CH; i0 += NTH * UNR) {
+      int4 v[UNR];
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            int k = j * 8 + e;
-            int axis = k / g.posL;
-            if (axis < g.pos_ndim) {
-              int cv = (code >> (8 * axis)) & 255;
-              f[e] += g.pos_tab[((size_t)axis * g.pos_maxw + cv) * g.posL + (k - axis * g.posL)];
-            }
-          }
+      for (int u = 0; u < UNR; u++) {
+        int idx = i0 + u * NTH;
+        if (idx < NT * CH) v[u] = __ldg(reinterpret_cast<const int4*>(wsrc) + idx);  // rows are K*2 bytes = CH chunks: contiguous
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        int idx = i0 + u * NTH;
+        if (idx < NT * CH) {
+          int r = idx / CH, j = idx % CH;
+          int c = j >> 3, jj = j & 7;
+          *reinterpret_cast<int4*>(sW + (size_t)c * NT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
         }
-        v.x = (int)pack_bf16(f[0], f[1]);
-        v.y = (int)pack_bf16(f[2], f[3]);
-        v.z = (int)pack_bf16(f[4], f[5]);
-        v.w = (int)pack_bf16(f[6], f[7]);
       }
     }
-    int c = j >> 3, jj = j & 7;
-    *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
+  }
+  const bool add_pos = (PRO == PRO_F32) && g.pos_tab != nullptr && (int)blockIdx.y < g.pos_ntiles;
+  if (PRO == PRO_BF16) {
+    for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UNR) {
+      int4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        int idx = i0 + u * NTH;
+        int r = idx / CH, j = idx % CH;
+        v[u] = make_int4(0, 0, 0, 0);
+        if (idx < TILE_M * CH && row0 + r < M)
+          v[u] = *reinterpret_cast<const int4*>((const __nv_bfloat16*)g.A + (size_t)(row0 + r) * g.lda + j * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        int idx = i0 + u * NTH;
+        if (idx < TILE_M * CH) {
+          int r = idx / CH, j = idx % CH;
+          int c = j >> 3, jj = j & 7;
+          *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+        }
+      }
+    }
+  } else {
+    constexpr int UF = 4;
+    for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UF) {
+      float4 f0[UF], f1[UF];
+      int code[UF];
+#pragma unroll
+      for (int u = 0; u < UF; u++) {
+        int idx = i0 + u * NTH;
+        int r = idx / CH, j = idx % CH;
+        f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        code[u] = 0;
+        if (idx < TILE_M * CH && row0 + r < M) {
+          const float* ap = (const float*)g.A + (size_t)(row0 + r) * g.lda + j * 8;
+          f0[u] = *reinterpret_cast<const float4*>(ap);
+          f1[u] = *reinterpret_cast<const float4*>(ap + 4);
+          if (add_pos) code[u] = g.pos_code[row0 + r];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UF; u++) {
+        int idx = i0 + u * NTH;
+        if (idx < TILE_M * CH) {
+          int r = idx / CH, j = idx % CH;
+          float f[8] = {f0[u].x, f0[u].y, f0[u].z, f0[u].w, f1[u].x, f1[u].y, f1[u].z, f1[u].w};
+          if (add_pos && row0 + r < M) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              int k = j * 8 + e;
+              int axis = k / g.posL;
+              if (axis < g.pos_ndim) {
+                int cv = (code[u] >> (8 * axis)) & 255;
+                f[e] += __ldg(&g.pos_tab[((size_t)axis * g.pos_maxw + cv) * g.posL + (k - axis * g.posL)]);
+              }
+            }
+          }
+          int4 v;
+          v.x = (int)pack_bf16(f[0], f[1]);
+          v.y = (int)pack_bf16(f[2], f[3]);
+          v.z = (int)pack_bf16(f[4], f[5]);
+          v.w = (int)pack_bf16(f[6], f[7]);
+          int c = j >> 3, jj = j & 7;
+          *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
+        }
+      }
+    }
   }
   // generic-proxy smem writes -> visible to the tensor core (async proxy); TMEM address visible to all
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -194,12 +244,16 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
   // ---- epilogue: thread t owns output row row0+t == TMEM lane t -------------------------------------------------------
-  const int grow = row0 + tid;
+  const int half = warp >> 2;                  // warps 0-3: columns [0,NT/2), warps 4-7: [NT/2,NT)
+  const int lrow = (warp & 3) * 32 + (tid & 31);  // TMEM lane == row inside the tile
+  const int grow = row0 + lrow;
   const bool live = grow < M;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr int CB = NT / 2;
+  const int cbeg = half * CB;
   if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
       float v[32];
       tmem_ld32(tlane + c0, v);
       if (live) {
@@ -221,7 +275,7 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
   } else {  // EPI_RES_LN : NT == row width
     float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
       float v[32];
       tmem_ld32(tlane + c0, v);
       if (live) {
@@ -236,11 +290,16 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(GemmArgs g) {
         }
       }
     }
+    red[half][lrow][0] = sum;
+    red[half][lrow][1] = sq;
+    __syncthreads();
+    sum = red[0][lrow][0] + red[1][lrow][0];
+    sq = red[0][lrow][1] + red[1][lrow][1];
     const float mean = sum * (1.0f / NT);
     const float var = fmaxf(sq * (1.0f / NT) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + g.eps);
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
       float v[32];
       tmem_ld32(tlane + c0, v);
       if (live) {
@@ -286,7 +345,7 @@ int launch_umma(sstb200_ctx* c, const GemmArgs& g, int n_tiles_y) {
     attr_set = true;
   }
   dim3 grid((g.M_cap + TILE_M - 1) / TILE_M, n_tiles_y);
-  kern<<<grid, 128, smem, c->stream>>>(g);
+  kern<<<grid, 256, smem, c->stream>>>(g);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }
@@ -331,8 +390,11 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   rc = launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3);
   if (rc) return rc;
   // 2. ragged window attention (fp32 math on bf16 q/k/v)
-  rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
-                                                   L->tau, L->tau_n, L->tau_min, att);
+  if (!L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT && P->num_windows_dev)
+    rc = sstb_win_attn_mma(c, qkv, L->nhead, P->num_windows_dev, P->win_offsets, P->tok_perm, att);
+  else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
+    rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
+                                                     L->tau, L->tau_n, L->tau_min, att);
   if (rc) return rc;
   // 3. out-projection + residual + LayerNorm1
   memset(&g, 0, sizeof(g));

@@ -64,7 +64,7 @@ class SSTEngine:
                                                 p["win_rank"].data_ptr(), p["counters"].data_ptr()) for p in self.plans]
         self._plan_structs = [_SraPlan(p["win_offsets"].data_ptr(), p["tok_perm"].data_ptr(), p["tok_win"].data_ptr(),
                                        p["pos_code"].data_ptr(), p["counters"].data_ptr(), tab.data_ptr(), Lp, maxw, ndim,
-                                       0) for p in self.plans]
+                                       max(v["max_tokens"] for v in self.il.drop_info.values())) for p in self.plans]
         self.vfe_cfg = self.vfe._cfg(self.B)
         prec = PRECISIONS[precision]
         self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]

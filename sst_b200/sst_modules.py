@@ -188,7 +188,8 @@ class SSTInputLayerV2(nn.Module):
             info[f"batch_win_inds_shift{i}"] = p.batch_win_inds
             info[f"coors_in_win_shift{i}"] = p.coors_in_win
             info[f"voxel_drop_level_shift{i}"] = p.drop_level
-            info[f"sra_plan_shift{i}"] = dict(plan=p, pos_table=tab, pos_ndim=ndim, pos_maxw=maxw, pos_L=Lp)
+            info[f"sra_plan_shift{i}"] = dict(plan=p, pos_table=tab, pos_ndim=ndim, pos_maxw=maxw, pos_L=Lp,
+                                              max_tokens=max(v["max_tokens"] for v in self.drop_info.values()))
             f2w = _LazyDict(lambda p=p: self._flat2win_dict(p))
             info[f"flat2win_inds_shift{i}"] = f2w
             info[f"pos_dict_shift{i}"] = _LazyDict(
@@ -258,7 +259,7 @@ def make_sra_plan(sp):
     p = sp["plan"]
     return _SraPlan(p.win_offsets.data_ptr(), p.tok_perm.data_ptr(), p.tok_win.data_ptr(), p.pos_code.data_ptr(),
                     p.counters.data_ptr(), sp["pos_table"].data_ptr(), sp["pos_L"], sp["pos_maxw"], sp["pos_ndim"],
-                    int(getattr(p, "max_tokens", 0) or 0))
+                    int(sp.get("max_tokens", 0) or 0))
 
 
 class WindowAttention(nn.Module):
