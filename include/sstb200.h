@@ -235,6 +235,36 @@ int sstb200_graph_end(sstb200_ctx* ctx, void** graph_exec_out, int32_t* num_kern
 int sstb200_graph_launch(sstb200_ctx* ctx, void* graph_exec);
 int sstb200_graph_destroy(sstb200_ctx* ctx, void* graph_exec);
 
+/* S1-S3  SIRLayer.forward (mmdet3d/models/voxel_encoders/voxel_encoder.py:696-764; build_mlp ops/sst/sst_ops.py:334-361;
+ * DynamicVFELayerV2 voxel_encoders/utils.py:147-189), LayerNorm norm, mode='max', with_rel_mlp=True.
+ * in_feats [N,in_channels] = cat(points, feats) as SIR.forward builds it (models/backbones/sir.py:77), f_cluster [N,3]
+ * (un-scaled; divided by rel_dist_scaler inside), group index inv [N] int64 in [0,G) (torch.unique inverse).
+ * out_point [N, C_last]; out_group [G, C0+C1] = concatenated per-layer group max (voxel_encoder.py:751). */
+typedef struct {
+  int32_t in_channels;
+  int32_t rel_in;          /* rel_mlp_in_channel (3) */
+  int32_t num_rel;         /* number of rel-MLP layers (hidden dims + in_channels) */
+  int32_t rel_dims[4];
+  int32_t num_vfe;         /* 1 or 2 */
+  int32_t feat_channels[2];
+  int32_t act;             /* 1 relu, 2 gelu */
+  int32_t mode_max;
+  int32_t with_shortcut;
+  float norm_eps;
+  float xyz_normalizer[3];
+  float rel_dist_scaler;
+  const float* rel_w[4];    /* rel_mlp.i.0.weight [dims[i], in_i] */
+  const float* rel_ln_w[4]; /* rel_mlp.i.1.weight */
+  const float* rel_ln_b[4];
+  const float* vfe_w[2];    /* vfe_layers.i.linear.weight  [C_i, in_i] (in_1 = 2*C0) */
+  const float* vfe_ln_w[2];
+  const float* vfe_ln_b[2];
+} sstb200_sir_layer;
+
+int sstb200_sir_layer_forward(sstb200_ctx* ctx, const sstb200_sir_layer* layer, const float* in_feats,
+                              const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
+                              float* out_point, float* out_group);
+
 #ifdef __cplusplus
 }
 #endif

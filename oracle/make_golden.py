@@ -1,0 +1,152 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.npz by running the UNMODIFIED reference Python
+(/root/reference, through oracle/ref_shim.py) on small seeded inputs.  Run in the build container only:
+
+    python -m oracle.make_golden
+
+Each fixture stores inputs, the reference module's state_dict and the reference outputs, so that
+tests/test_oracle_golden.py can pin oracle/sst_oracle.py against them anywhere (the GPU box has no
+/root/reference).  DynamicScatter inside DynamicVFE uses the restatement (the reference has no CPU
+dynamic_point_to_voxel, voxelization.h:96-108); that op is pinned separately (restated reference test +
+reference CUDA build in oracle/_ref on GPU boxes).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim, sst_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+VS = (0.32, 0.32, 6)
+RNG = [-74.88, -74.88, -2, 74.88, 74.88, 4]
+DROP_TRAIN = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+              2: {'max_tokens': 100, 'drop_range': (60, 100000)}}
+DROP_TEST = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+             2: {'max_tokens': 100, 'drop_range': (60, 100)}, 3: {'max_tokens': 144, 'drop_range': (100, 100000)}}
+
+
+def _rand_norm(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.2 + (1.0 if "norm" in n_ and "weight" in n_ else 0.0))
+            if n_.endswith("tau"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.5 + 0.05)
+        for n_, b in m.named_buffers():
+            if "running_mean" in n_:
+                b.copy_(torch.randn(b.shape, generator=g) * 0.3)
+            if "running_var" in n_:
+                b.copy_(torch.rand(b.shape, generator=g) + 0.5)
+
+
+def _sd(m, prefix):
+    return {prefix + k: v.detach().numpy() for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+
+
+def sst_fixture(R):
+    torch.manual_seed(0)
+    pts = torch.cat([O.synth_frame(5, 2500), O.synth_frame(6, 1500)])
+    pts[:, :2] *= 0.2  # dense enough to populate every drop level incl. > 100 tokens
+    c3 = O.dynamic_voxelize(pts, VS, RNG)
+    coors = torch.cat([torch.nn.functional.pad(c3[:2500], (1, 0), value=0), torch.nn.functional.pad(c3[2500:], (1, 0), value=1)])
+    vfe = R.DynamicVFE(in_channels=3, feat_channels=[16, 32], with_cluster_center=True, with_voxel_center=True, voxel_size=VS,
+                       point_cloud_range=RNG, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)).eval()
+    _rand_norm(vfe, 1)
+    out = {"points": pts.numpy(), "coors": coors.numpy()}
+    with torch.no_grad():
+        vf, vc = vfe(pts, coors)
+        out.update(vfe_feats=vf.numpy(), vfe_coors=vc.numpy(), **_sd(vfe, "vfe."))
+        for tag, drop, train in (("eval", (DROP_TRAIN, DROP_TEST), False), ("train", (DROP_TRAIN, DROP_TEST), True)):
+            il = R.SSTInputLayerV2(drop, (12, 12, 1), (468, 468, 1), shuffle_voxels=False, debug=True)
+            il.train(train)
+            info = il(vf, vc, 2)
+            for i in range(2):
+                out[f"{tag}.batch_win_inds_shift{i}"] = info[f"batch_win_inds_shift{i}"].numpy()
+                out[f"{tag}.coors_in_win_shift{i}"] = info[f"coors_in_win_shift{i}"].numpy()
+                out[f"{tag}.drop_level_shift{i}"] = info[f"voxel_drop_level_shift{i}"].numpy()
+                for dl, v in info[f"flat2win_inds_shift{i}"].items():
+                    if isinstance(dl, str):
+                        continue
+                    # the reference's inner order is implementation defined (sst_ops.py:203): the shim uses the
+                    # canonical stable order, so these are comparable element-wise
+                    out[f"{tag}.f2w{i}.{dl}.inds"] = v[0].numpy()
+                    out[f"{tag}.f2w{i}.{dl}.pos"] = v[1][0].numpy()
+                    out[f"{tag}.pos{i}.{dl}"] = info[f"pos_dict_shift{i}"][dl].numpy()
+                    out[f"{tag}.mask{i}.{dl}"] = info[f"key_mask_shift{i}"][dl].numpy()
+            out[f"{tag}.keep"] = info["voxel_keep_inds"].numpy()
+            if tag == "eval":
+                for name, lc in (("plain", {}), ("cosine", dict(cosine=True, tau_min=0.01)), ("prebn", dict(post_norm=False, use_bn=True))):
+                    torch.manual_seed(3)
+                    bb = R.SSTv2(d_model=[32] * 2, nhead=[4] * 2, num_blocks=2, dim_feedforward=[64] * 2, output_shape=[468, 468],
+                                 num_attached_conv=0, to_bev=False, layer_cfg=lc).eval()
+                    _rand_norm(bb, 4)
+                    y = bb(info)[0]["voxel_feats"]
+                    out[f"sst.{name}.out"] = y.numpy()
+                    out.update(_sd(bb, f"sst.{name}.w."))
+    np.savez_compressed(os.path.join(OUT, "sst_small.npz"), **out)
+    print("sst_small", len(out), "arrays", vf.shape)
+
+
+def sir_fixture(R):
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(11)
+    N, G = 3000, 23
+    points = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1)
+    feats = torch.randn(N, 27, generator=g)
+    gid = torch.randint(0, G, (N,), generator=g)
+    coors = torch.stack([gid % 3, gid % 2, gid], 1)
+    fcl = torch.randn(N, 3, generator=g) * 2
+    sir = R.SIR(num_blocks=3, in_channels=[32, 37, 37], feat_channels=[[32, 32]] * 3, rel_mlp_hidden_dims=[[16, 32] for _ in range(3)],
+                norm_cfg=dict(type='LN', eps=1e-3), mode='max', xyz_normalizer=[20, 20, 4], act='gelu', unique_once=True).eval()
+    _rand_norm(sir, 2)
+    with torch.no_grad():
+        a, b, c = sir(points, feats, coors, fcl)
+    out = dict(points=points.numpy(), feats=feats.numpy(), coors=coors.numpy(), f_cluster=fcl.numpy(), out_point=a.numpy(),
+               out_group=b.numpy(), out_coors=c.numpy(), **_sd(sir, "w."))
+    np.savez_compressed(os.path.join(OUT, "sir_small.npz"), **out)
+    print("sir_small", a.shape, b.shape)
+
+
+def dsvfe_fixture(R):
+    torch.manual_seed(0)
+    vs, rng = (0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4]
+    pts = torch.cat([O.synth_frame(3, 3000), torch.rand(3000, 2)], 1)
+    co = torch.nn.functional.pad(O.dynamic_voxelize(pts, vs, rng), (1, 0), value=0).long()
+    co[1500:, 0] = 1
+    m = R.DynamicScatterVFE(in_channels=5, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True, voxel_size=vs,
+                            point_cloud_range=rng, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), unique_once=True,
+                            rel_dist_scaler=10.0).eval()
+    _rand_norm(m, 7)
+    with torch.no_grad():
+        f, c, inv = m(pts, co, return_inv=True)
+    np.savez_compressed(os.path.join(OUT, "dsvfe_small.npz"), points=pts.numpy(), coors=co.numpy(), feats=f.numpy(),
+                        vcoors=c.numpy(), inv=inv.numpy(), **_sd(m, "w."))
+    print("dsvfe_small", f.shape)
+
+
+def scatter_fixture():
+    """Seeded restatement of tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:56-84: expected values are the
+    brute-force per-voxel loop the reference test itself uses as ground truth."""
+    g = torch.Generator().manual_seed(0)
+    feats = torch.rand(20000, 3, generator=g) * 100 - 50
+    coors = torch.randint(-1, 20, (20000, 3), generator=g, dtype=torch.int32)
+    ref_coors = coors.unique(dim=0, sorted=True)
+    ref_coors = ref_coors[ref_coors.min(dim=-1).values >= 0]
+    mean = torch.stack([feats[coors.eq(rc).all(dim=-1)].mean(dim=0) for rc in ref_coors])
+    mx = torch.stack([feats[coors.eq(rc).all(dim=-1)].max(dim=0).values for rc in ref_coors])
+    np.savez_compressed(os.path.join(OUT, "dynamic_scatter.npz"), feats=feats.numpy(), coors=coors.numpy(),
+                        ref_coors=ref_coors.numpy(), ref_mean=mean.numpy(), ref_max=mx.numpy())
+    print("dynamic_scatter", ref_coors.shape)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    R = ref_shim.load()
+    sst_fixture(R)
+    sir_fixture(R)
+    dsvfe_fixture(R)
+    scatter_fixture()

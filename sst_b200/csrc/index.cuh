@@ -282,3 +282,16 @@ static __global__ void __launch_bounds__(256) stable_rank_kernel(const uint32_t*
   }
 }
 
+
+static __global__ void count_index_kernel(const long long* __restrict__ idx, int n, int nseg, int32_t* __restrict__ count,
+                                   int32_t* __restrict__ err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long v = idx[i];
+  if (v < 0 || v >= nseg) {
+    *err = 1;
+    return;
+  }
+  atomicAdd(&count[v], 1);
+}
+

@@ -32,7 +32,8 @@ template <int ACT /*0 none,1 relu,2 gelu*/>
 __global__ void __launch_bounds__(256) gemm_rows_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                         const float* __restrict__ bias, const float* __restrict__ res, int ldr,
                                                         float* __restrict__ out, int ldo, int M, const int32_t* __restrict__ M_dev,
-                                                        int N, int K, PosTab pos, int pos_ncols) {
+                                                        int N, int K, PosTab pos, int pos_ncols, int ldw,
+                                                        const long long* __restrict__ res_index) {
   __shared__ float As[GBK][GBM + 4];
   __shared__ float Bs[GBK][GBN + 4];
   if (M_dev) M = *M_dev;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(const float* __restrict_
       int e = tid + i * 256;
       int n = e / GBK, k = e % GBK;
       int gn = col0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < N && gk < K) ? W[(size_t)gn * K + gk] : 0.f;
+      Bs[k][n] = (gn < N && gk < K) ? W[(size_t)gn * ldw + gk] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -93,24 +94,30 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(const float* __restrict_
       float v = acc[i][j] + (bias ? bias[gn] : 0.f);
       if (ACT == 1) v = fmaxf(v, 0.f);
       if (ACT == 2) v = gelu_erf(v);
-      if (res) v += res[(size_t)gr * ldr + gn];
+      if (res) v += res[(size_t)(res_index ? res_index[gr] : (long long)gr) * ldr + gn];
       out[(size_t)gr * ldo + gn] = v;
     }
   }
 }
 
-void sstb_gemm_rows(cudaStream_t st, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr,
-                    float* out, int ldo, int M_cap, const int32_t* M_dev, int N, int K, int act, const float* pos_tab,
-                    const int32_t* pos_code, int posL, int pos_maxw, int pos_ndim, int pos_ncols) {
+void sstb_gemm_rows_ex(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, const float* res,
+                       int ldr, const long long* res_index, float* out, int ldo, int M_cap, const int32_t* M_dev, int N, int K,
+                       int act, const float* pos_tab, const int32_t* pos_code, int posL, int pos_maxw, int pos_ndim, int pos_ncols) {
   if (M_cap <= 0) return;
   dim3 grid((M_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
   PosTab p{pos_tab, pos_code, posL, pos_maxw, pos_ndim};
   if (act == 0)
-    gemm_rows_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols);
+    gemm_rows_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
   else if (act == 1)
-    gemm_rows_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols);
+    gemm_rows_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
   else
-    gemm_rows_kernel<2><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols);
+    gemm_rows_kernel<2><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
+}
+void sstb_gemm_rows(cudaStream_t st, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr,
+                    float* out, int ldo, int M_cap, const int32_t* M_dev, int N, int K, int act, const float* pos_tab,
+                    const int32_t* pos_code, int posL, int pos_maxw, int pos_ndim, int pos_ncols) {
+  sstb_gemm_rows_ex(st, A, lda, W, K, bias, res, ldr, nullptr, out, ldo, M_cap, M_dev, N, K, act, pos_tab, pos_code, posL, pos_maxw,
+                    pos_ndim, pos_ncols);
 }
 
 int sstb_win_attn_fp32(sstb200_ctx* c, const float* qkv, int d, int nhead, int n_cap, const int32_t* n_dev,
@@ -125,7 +132,8 @@ int sstb_win_attn_fp32(sstb200_ctx* c, const float* qkv, int d, int nhead, int n
 __global__ void __launch_bounds__(256) add_norm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ bn_mean, const float* __restrict__ bn_var,
-                                                       float eps, float* __restrict__ out, int n, const int32_t* __restrict__ n_dev, int d) {
+                                                       float eps, float* __restrict__ out, int n, const int32_t* __restrict__ n_dev, int d,
+                                                       int act) {
   if (n_dev) n = *n_dev;
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
@@ -155,14 +163,23 @@ __global__ void __launch_bounds__(256) add_norm_kernel(const float* __restrict__
   }
   float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
   cnt = 0;
-  for (int c = ln; c < d; c += 32, cnt++) out[(size_t)row * d + c] = (v[cnt] - mean) * rstd * gamma[c] + beta[c];
+  for (int c = ln; c < d; c += 32, cnt++) {
+    float o = (v[cnt] - mean) * rstd * gamma[c] + beta[c];
+    if (act == 1) o = fmaxf(o, 0.f);
+    if (act == 2) o = gelu_erf(o);
+    out[(size_t)row * d + c] = o;
+  }
 }
 
-void sstb_add_norm(cudaStream_t st, const float* a, const float* b, const float* gamma, const float* beta,
-                   const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d) {
+void sstb_add_norm_act(cudaStream_t st, const float* a, const float* b, const float* gamma, const float* beta,
+                       const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d, int act) {
   if (n_cap <= 0) return;
   unsigned grid = (unsigned)(((size_t)n_cap * 32 + 255) / 256);
-  add_norm_kernel<<<grid, 256, 0, st>>>(a, b, gamma, beta, bn_mean, bn_var, eps, out, n_cap, n_dev, d);
+  add_norm_kernel<<<grid, 256, 0, st>>>(a, b, gamma, beta, bn_mean, bn_var, eps, out, n_cap, n_dev, d, act);
+}
+void sstb_add_norm(cudaStream_t st, const float* a, const float* b, const float* gamma, const float* beta,
+                   const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d) {
+  sstb_add_norm_act(st, a, b, gamma, beta, bn_mean, bn_var, eps, out, n_cap, n_dev, d, 0);
 }
 
 // ------------------------------------------------------------------------------------------------

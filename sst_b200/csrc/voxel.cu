@@ -248,18 +248,6 @@ extern "C" int sstb200_unique_rows_i64(sstb200_ctx* c, const int64_t* coors, int
 // ------------------------------------------------------------------------------------------------
 // V5b segment reduce by a given index
 // ------------------------------------------------------------------------------------------------
-__global__ void count_index_kernel(const long long* __restrict__ idx, int n, int nseg, int32_t* __restrict__ count,
-                                   int32_t* __restrict__ err) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  long long v = idx[i];
-  if (v < 0 || v >= nseg) {
-    *err = 1;
-    return;
-  }
-  atomicAdd(&count[v], 1);
-}
-
 extern "C" int sstb200_segment_reduce(sstb200_ctx* c, const float* src, const int64_t* index, int P, int C, int nseg,
                                       int reduce_type, float* out, int64_t* argmax) {
   CHECK_ARG(c, c && P >= 0 && C >= 1 && nseg >= 0 && reduce_type >= 0 && reduce_type <= 2);

@@ -1,0 +1,126 @@
+"""CPU: pins oracle/sst_oracle.py against golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py, run in the build container) and against the reference's own DynamicScatter test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sst_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+VS = (0.32, 0.32, 6)
+RNG = [-74.88, -74.88, -2, 74.88, 74.88, 4]
+DROP_TRAIN = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+              2: {'max_tokens': 100, 'drop_range': (60, 100000)}}
+DROP_TEST = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+             2: {'max_tokens': 100, 'drop_range': (60, 100)}, 3: {'max_tokens': 144, 'drop_range': (100, 100000)}}
+
+
+def _load(name):
+    z = np.load(os.path.join(G, name))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _w(z, prefix):
+    return {k[len(prefix):]: v for k, v in z.items() if k.startswith(prefix)}
+
+
+def test_dynamic_scatter_reference_test_restated():
+    """tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:56-84 (seeded): sorted coors with negatives
+    removed equal exactly; mean / max feats allclose(atol=1e-2, rtol=1e-5) to the brute-force loop."""
+    z = _load("dynamic_scatter.npz")
+    for red, ref in (("mean", z["ref_mean"]), ("max", z["ref_max"])):
+        f, c, m, n = O.dynamic_point_to_voxel_forward(z["feats"], z["coors"], red)
+        assert torch.equal(c, z["ref_coors"])
+        assert torch.allclose(f, ref, atol=1e-2, rtol=1e-5)
+        assert int(n.sum()) == int((z["coors"].min(dim=-1).values >= 0).sum())
+    # empty input keeps shapes (:22-36)
+    f, c, m, n = O.dynamic_point_to_voxel_forward(torch.rand(0, 3), torch.zeros((0, 3), dtype=torch.int32), "mean")
+    assert f.shape == (0, 3) and c.shape == (0, 3)
+
+
+def test_dynamic_scatter_backward_matches_autograd():
+    g = torch.Generator().manual_seed(1)
+    feats = torch.rand(500, 4, generator=g, dtype=torch.float64)
+    coors = torch.randint(-1, 6, (500, 3), generator=g, dtype=torch.int32)
+    for red in ("sum", "mean", "max"):
+        f, c, m, n = O.dynamic_point_to_voxel_forward(feats, coors, red)
+        gr = torch.rand(f.shape, generator=g, dtype=torch.float64)
+        got = O.dynamic_point_to_voxel_backward(gr, feats, f, m, n, red)
+        x = feats.clone().requires_grad_(True)
+        valid = m >= 0
+        idx = m[valid].long()[:, None].expand(-1, 4)
+        if red == "max":
+            y = torch.full(f.shape, -1e30, dtype=torch.float64).scatter_reduce(0, idx, x[valid], "amax")
+        else:
+            y = torch.zeros(f.shape, dtype=torch.float64).scatter_reduce(0, idx, x[valid], red, include_self=False)
+        (y * gr).sum().backward()
+        assert torch.allclose(got, x.grad, atol=1e-12)  # random doubles: no ties, so amax grad == lowest-index rule
+
+
+def test_vfe_and_input_layer_golden():
+    z = _load("sst_small.npz")
+    vf, vc = O.dynamic_vfe_forward(z["points"], z["coors"], _w(z, "vfe."), VS, RNG, 2)
+    assert torch.equal(vc, z["vfe_coors"])
+    torch.testing.assert_close(vf, z["vfe_feats"], rtol=1e-5, atol=1e-5)
+    dropped = False
+    for tag, drop in (("eval", DROP_TEST), ("train", DROP_TRAIN)):
+        info = O.input_layer_v2(z["vfe_feats"], z["vfe_coors"], drop, (12, 12, 1), (468, 468, 1))
+        assert torch.equal(info["voxel_keep_inds"], z[f"{tag}.keep"])
+        dropped |= info["voxel_keep_inds"].numel() < z["vfe_coors"].shape[0]
+        for i in range(2):
+            assert torch.equal(info[f"batch_win_inds_shift{i}"], z[f"{tag}.batch_win_inds_shift{i}"])
+            assert torch.equal(info[f"coors_in_win_shift{i}"], z[f"{tag}.coors_in_win_shift{i}"])
+            assert torch.equal(info[f"voxel_drop_level_shift{i}"], z[f"{tag}.drop_level_shift{i}"])
+            levels = [k for k in info[f"flat2win_inds_shift{i}"] if not isinstance(k, str)]
+            assert sorted(levels) == sorted(int(k.split(".")[2]) for k in z if k.startswith(f"{tag}.f2w{i}.") and k.endswith(".inds"))
+            for dl in levels:
+                inds, pos = info[f"flat2win_inds_shift{i}"][dl]
+                assert torch.equal(inds, z[f"{tag}.f2w{i}.{dl}.inds"]) and torch.equal(pos[0], z[f"{tag}.f2w{i}.{dl}.pos"])
+                assert torch.equal(info[f"pos_dict_shift{i}"][dl], z[f"{tag}.pos{i}.{dl}"])
+                assert torch.equal(info[f"key_mask_shift{i}"][dl], z[f"{tag}.mask{i}.{dl}"])
+    assert dropped, "the training fixture is meant to exercise voxel dropping"
+
+
+@pytest.mark.parametrize("name,lc", [("plain", {}), ("cosine", dict(cosine=True, tau_min=0.01)),
+                                     ("prebn", dict(post_norm=False, use_bn=True))])
+def test_sstv2_golden(name, lc):
+    z = _load("sst_small.npz")
+    info = O.input_layer_v2(z["vfe_feats"], z["vfe_coors"], DROP_TEST, (12, 12, 1), (468, 468, 1))
+    out = O.sstv2_forward(info, _w(z, f"sst.{name}.w."), [4, 4], 2, "gelu", lc)
+    torch.testing.assert_close(out, z[f"sst.{name}.out"], rtol=1e-4, atol=1e-5)
+
+
+def test_sir_golden():
+    z = _load("sir_small.npz")
+    a, b, c = O.sir_forward(z["points"], z["feats"], z["coors"], z["f_cluster"], _w(z, "w."), 3, 3, 2, [20, 20, 4])
+    assert torch.equal(c, z["out_coors"])
+    torch.testing.assert_close(a, z["out_point"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(b, z["out_group"], rtol=1e-4, atol=1e-5)
+
+
+def test_dynamic_scatter_vfe_golden():
+    z = _load("dsvfe_small.npz")
+    f, c, inv = O.dynamic_scatter_vfe_forward(z["points"], z["coors"], _w(z, "w."), (0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4], 2,
+                                              rel_dist_scaler=10.0)
+    assert torch.equal(c, z["vcoors"]) and torch.equal(inv, z["inv"])
+    torch.testing.assert_close(f, z["feats"], rtol=1e-5, atol=1e-5)
+
+
+def test_voxelize_float32_grid():
+    """grid = ceil((max-min)/vs) must be evaluated in float32 like the C++ (voxelization_cpu.cpp:151-158)."""
+    assert O.grid_size(VS, RNG) == [468, 468, 1]
+    p = torch.tensor([[74.87, -74.88, 3.99], [80.0, -90.0, 10.0], [-74.88, 0.0, -2.0]])
+    c = O.dynamic_voxelize(p, VS, RNG)
+    assert c.tolist() == [[0, 0, 467], [0, 0, 467], [0, 234, 0]]
+
+
+def test_ingroup_and_window_helpers():
+    g = torch.tensor([3, 1, 3, 3, 0, 1])
+    assert O.ingroup_indices(g).tolist() == [0, 0, 1, 2, 0, 1]
+    assert O.make_continuous_inds(torch.tensor([7, 3, 7, 100])).tolist() == [1, 0, 1, 2]
+    co = torch.tensor([[0, 0, 5, 13], [1, 0, 467, 467]])
+    w, ciw = O.get_window_coors(co, (468, 468, 1), (12, 12, 1), False)
+    # no shift: shift = window size (sst_ops.py:283-286) -> x=13+12=25 -> win 2 rem 1; y=5+12=17 -> win 1 rem 5
+    assert w.tolist() == [2 * 80 + 1 * 2 + 0, 3200 + 39 * 80 + 39 * 2] and ciw.tolist() == [[0, 5, 1], [0, 11, 11]]

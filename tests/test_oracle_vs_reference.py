@@ -1,0 +1,61 @@
+"""CPU, build container only: runs the reference's own Python (unmodified, through oracle/ref_shim.py) beside the
+oracle on seeded inputs.  Skipped where /root/reference does not exist (e.g. the GPU box)."""
+import pytest
+import torch
+
+from oracle import ref_shim, sst_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+VS = (0.32, 0.32, 6)
+RNG = [-74.88, -74.88, -2, 74.88, 74.88, 4]
+DROP_TEST = {0: {'max_tokens': 30, 'drop_range': (0, 30)}, 1: {'max_tokens': 60, 'drop_range': (30, 60)},
+             2: {'max_tokens': 100, 'drop_range': (60, 100)}, 3: {'max_tokens': 144, 'drop_range': (100, 100000)}}
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_shim.load()
+
+
+def test_config1_path(R):
+    """BASELINE config 1: 20k points, DynamicScatter + 1 SRA block d=64 h=4 on CPU (reference plumbing)."""
+    torch.manual_seed(0)
+    pts = O.synth_frame(1000, 20000)
+    coors = torch.nn.functional.pad(O.dynamic_voxelize(pts, VS, RNG), (1, 0), value=0)
+    vfe = R.DynamicVFE(in_channels=3, feat_channels=[64, 64], with_cluster_center=True, with_voxel_center=True, voxel_size=VS,
+                       point_cloud_range=RNG, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)).eval()
+    il = R.SSTInputLayerV2(DROP_TEST, (12, 12, 1), (468, 468, 1), shuffle_voxels=False, debug=True, mute=True).eval()
+    bb = R.SSTv2(d_model=[64], nhead=[4], num_blocks=1, dim_feedforward=[128], output_shape=[468, 468], num_attached_conv=0,
+                 to_bev=False).eval()
+    with torch.no_grad():
+        vf_r, vc_r = vfe(pts, coors)
+        info_r = il(vf_r, vc_r, 1)
+        out_r = bb(info_r)[0]["voxel_feats"]
+    vf_o, vc_o = O.dynamic_vfe_forward(pts, coors, dict(vfe.state_dict()), VS, RNG, 2)
+    assert torch.equal(vc_o, vc_r)
+    torch.testing.assert_close(vf_o, vf_r, rtol=1e-6, atol=1e-6)
+    info_o = O.input_layer_v2(vf_r, vc_r, DROP_TEST, (12, 12, 1), (468, 468, 1))
+    for i in range(2):
+        for k in (f"batch_win_inds_shift{i}", f"coors_in_win_shift{i}", f"voxel_drop_level_shift{i}"):
+            assert torch.equal(info_r[k], info_o[k])
+    out_o = O.sstv2_forward(info_o, dict(bb.state_dict()), [4], 1)
+    torch.testing.assert_close(out_o, out_r, rtol=1e-5, atol=1e-6)
+
+
+def test_state_dict_keys_match_reference(R):
+    """The registered modules are checkpoint-compatible: same state-dict keys and shapes as the reference's."""
+    from sst_b200 import flagship as fl
+    cfg = fl.sst_cfg(num_blocks=2)
+    vfe, il, bb = fl.build_sst(cfg)
+    r_vfe = R.DynamicVFE(**{k: v for k, v in cfg['voxel_encoder'].items() if k != 'type'})
+    r_bb = R.SSTv2(**{k: v for k, v in cfg['backbone'].items() if k != 'type'})
+    for ours, ref in ((vfe, r_vfe), (bb, r_bb)):
+        a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        assert a == b
+    from sst_b200.sst_modules import SSTv2
+    lc = dict(cosine=True, non_shared_tau=True, use_bn=True)
+    o = SSTv2(d_model=[32], nhead=[4], num_blocks=1, dim_feedforward=[64], num_attached_conv=0, to_bev=False, layer_cfg=lc)
+    r = R.SSTv2(d_model=[32], nhead=[4], num_blocks=1, dim_feedforward=[64], num_attached_conv=0, to_bev=False, layer_cfg=lc)
+    assert {k: tuple(v.shape) for k, v in o.state_dict().items()} == {k: tuple(v.shape) for k, v in r.state_dict().items()}
