@@ -32,6 +32,8 @@ typedef struct sstb200_ctx sstb200_ctx;
 #define SSTB200_REDUCE_SUM 0
 #define SSTB200_REDUCE_MEAN 1
 #define SSTB200_REDUCE_MAX 2
+#define SSTB200_PREC_FP32 0 /* fp32 FFMA everywhere */
+#define SSTB200_PREC_BF16 1 /* bf16 tensor-core GEMMs, fp32 accumulate / softmax / LayerNorm / residual */
 
 int sstb200_version(void);
 sstb200_ctx* sstb200_create(int device);
@@ -123,6 +125,7 @@ typedef struct {
   int32_t* win_level;      /* [n]   level slot (0..num_levels-1) per window, R valid */
   int32_t* win_rank;       /* [n]   rank of the window among the windows of its level */
   int32_t* counters;       /* [17]  R, windows per level slot [8], tokens per level slot [8] */
+  int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
 } sstb200_window_shift;
 
 /* status_host (opt, int32[18]): if non-NULL the call synchronises and returns
@@ -168,10 +171,9 @@ typedef struct {
   const float* pos_table;     /* [pos_ndim][pos_maxw][pos_L] fp32 */
   int32_t pos_L, pos_maxw, pos_ndim;
   int32_t max_window_tokens;  /* upper bound on tokens per window (e.g. 144) */
+  const int32_t* tok_slot;    /* [n] inverse of tok_perm (needed by the bf16 path) */
 } sstb200_sra_plan;
 
-#define SSTB200_PREC_FP32 0 /* fp32 FFMA everywhere */
-#define SSTB200_PREC_BF16 1 /* bf16 tensor-core GEMMs, fp32 accumulate / softmax / LayerNorm / residual */
 
 /* x, y: [n, d_model] fp32 in flat voxel order (y may alias x only if precision == FP32 is not used).
  * n may be device-resident (n_dev).  */
@@ -202,6 +204,7 @@ typedef struct {
   float center_offset[3];    /* v/2 + range_min (voxel_encoder.py:160-162) */
   float rel_dist_scaler;     /* DynamicScatterVFE only, else 1 */
   float bn_eps;
+  int32_t precision;         /* SSTB200_PREC_FP32: FFMA everywhere; SSTB200_PREC_BF16: layer 1 on tcgen05 (bf16 operands) */
   const float* weight[2];    /* vfe_layers.i.linear.weight  [C_i, in_i] */
   const float* bn_weight[2]; /* vfe_layers.i.norm.{weight,bias,running_mean,running_var} */
   const float* bn_bias[2];

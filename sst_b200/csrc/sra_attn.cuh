@@ -126,6 +126,8 @@ int sstb_win_attn(sstb200_ctx* c, const TI* qkv, int d, int nhead, int n_cap, co
 //   softmax            fp32, quad shuffles for the row max / sum
 //   O = P V_h          P re-used from the S accumulators as A fragments (no smem round trip), V via ldmatrix.trans
 // Windows hold <= 144 tokens on this path (12x12 pillars), i.e. <= 18 key tiles.
+// q/k/v and the output are in SLOT order (row s = token tok_perm[s]; the QKV GEMM's epilogue scatters into it), so a
+// window is a contiguous block of rows: K/V staging is a straight coalesced copy with no index indirection.
 // ------------------------------------------------------------------------------------------------
 #define ATT_MAXT 144
 #define ATT_LD 136  // bf16 elements per staged row (128 + 8 pad -> conflict-free fragment loads)
@@ -142,14 +144,12 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int nhead,
                                                            const int32_t* __restrict__ nwin_dev,
-                                                           const int32_t* __restrict__ win_offsets,
-                                                           const int32_t* __restrict__ tok_perm, float scale,
+                                                           const int32_t* __restrict__ win_offsets, float scale,
                                                            __nv_bfloat16* __restrict__ out) {
   constexpr int D = 128, DH = 16, KT = ATT_MAXT / 8;
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
   __nv_bfloat16* sV = sK + ATT_MAXT * ATT_LD;
-  __shared__ int sTok[ATT_MAXT];
   const int R = *nwin_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 2, t4 = lane & 3;
@@ -158,14 +158,11 @@ static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfl
     const int n = min(win_offsets[w + 1] - kb, ATT_MAXT);
     const int npad = (n + 15) & ~15;
     __syncthreads();  // previous window fully consumed
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) sTok[i] = i < n ? tok_perm[kb + i] : -1;
-    __syncthreads();
     // stage K and V rows (16-byte chunks; 16 chunks per row each)
     for (int idx = threadIdx.x; idx < npad * 32; idx += blockDim.x) {
       int r = idx >> 5, c = idx & 31;
-      int tok = sTok[r];
       int4 v = make_int4(0, 0, 0, 0);
-      if (tok >= 0) v = *reinterpret_cast<const int4*>(qkv + (size_t)tok * 3 * D + D + c * 8);
+      if (r < n) v = *reinterpret_cast<const int4*>(qkv + (size_t)(kb + r) * 3 * D + D + c * 8);
       __nv_bfloat16* dst = (c < 16 ? sK : sV) + r * ATT_LD + (c & 15) * 8;
       *reinterpret_cast<int4*>(dst) = v;
     }
@@ -176,7 +173,7 @@ static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfl
       const int qt = item / nhead, h = item % nhead;
       // Q fragment
       const int r0 = qt * 16 + g4, r1 = r0 + 8;
-      const int tok0 = r0 < n ? sTok[r0] : -1, tok1 = r1 < n ? sTok[r1] : -1;
+      const int tok0 = r0 < n ? kb + r0 : -1, tok1 = r1 < n ? kb + r1 : -1;
       uint32_t qa[4] = {0, 0, 0, 0};
       if (tok0 >= 0) {
         const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok0 * 3 * D + h * DH);
@@ -262,14 +259,14 @@ static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfl
 }
 
 static inline int sstb_win_attn_mma(sstb200_ctx* c, const __nv_bfloat16* qkv, int nhead, const int32_t* nwin_dev,
-                                    const int32_t* win_offsets, const int32_t* tok_perm, __nv_bfloat16* out) {
+                                    const int32_t* win_offsets, __nv_bfloat16* out) {
   size_t smem = (size_t)2 * ATT_MAXT * ATT_LD * sizeof(__nv_bfloat16);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(c, cudaFuncSetAttribute(win_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  win_attn_mma_kernel<<<c->num_sms * 2, 256, smem, c->stream>>>(qkv, nhead, nwin_dev, win_offsets, tok_perm, 0.25f, out);
+  win_attn_mma_kernel<<<c->num_sms * 2, 256, smem, c->stream>>>(qkv, nhead, nwin_dev, win_offsets, 0.25f, out);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }

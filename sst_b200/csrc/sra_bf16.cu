@@ -12,73 +12,15 @@
 #include <stdarg.h>
 #include "sra.cuh"
 #include "sra_attn.cuh"
+#include "umma.cuh"
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B (64 bf16), 8-row atoms of 1024 B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);   // start address >> 4
-  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: 8-row group pitch = 1024 B
-  d |= (uint64_t)1 << 46;                   // descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                   // layout type SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, dense
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar_saddr) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar_saddr) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t saddr, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(saddr),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 enum { PRO_BF16 = 0, PRO_F32 = 1 };
 enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_RES_LN = 2 };
 
 struct GemmArgs {
-  const void* A;        // [M, lda] bf16 or fp32
+  const void* A;        // [M, lda] bf16 or fp32; tile rows are consecutive rows of A
   int lda;
   const __nv_bfloat16* W;  // [N_total, K] bf16
   const float* bias;    // [N_total]
@@ -87,8 +29,10 @@ struct GemmArgs {
   // prologue
   const float* pos_tab;
   const int32_t* pos_code;
-  int posL, pos_maxw, pos_ndim, pos_ntiles;  // add pos for blockIdx.y < pos_ntiles
+  int posL, pos_maxw, pos_ndim, pos_ntiles;  // add pos for n-tile < pos_ntiles
+  int ny;                                    // number of n tiles
   // epilogue
+  const int32_t* out_row_map;  // nullable: output / residual row of tile row i is out_row_map[i] (scatter), else i
   __nv_bfloat16* out_bf16;  // [M, ldo]
   int ldo;
   const float* res;     // [M, NT] fp32 residual (EPI_RES_LN)
@@ -99,253 +43,312 @@ struct GemmArgs {
 
 constexpr int TILE_M = 128;
 
+// Persistent over (row tile, n tile) items.  Per item: stage W and A (16-byte chunks, 8 loads in flight per thread) in
+// the K-major SWIZZLE_128B layout -> one thread issues the MMAs -> commit/mbarrier -> epilogue.  The epilogue goes through
+// shared memory (the operand buffers are free once the MMA has completed) so that every global access is a coalesced row
+// segment: thread-per-row TMEM reads meet warp-per-row global traffic in an XOR-swizzled staging tile.
 template <int K, int NT, int PRO, int EPI>
 __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-B aligned operand tiles (SWIZZLE_128B atoms)
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                           // K/64 chunks x 128 rows x 128 B
   uint8_t* sW = sA + (size_t)TILE_M * K * 2;    // K/64 chunks x NT rows x 128 B
+  uint8_t* sE = base;                           // epilogue staging (aliases the operands)
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[2][TILE_M][2];
+  __shared__ int sRow[TILE_M];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int M = g.M_dev ? *g.M_dev : g.M_cap;
-  const int row0 = blockIdx.x * TILE_M;
-  if (row0 >= M) return;  // uniform per CTA: nothing allocated yet
-  const int n0 = blockIdx.y * NT;
+  const int n_items = ((M + TILE_M - 1) / TILE_M) * g.ny;
+  if ((int)blockIdx.x >= n_items) return;  // uniform per CTA: nothing allocated yet
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)NT)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
+  if (warp == 0) tmem_alloc(&tmem_slot, NT);
   if (tid == 0) {
     mbar_init(smem_u32(&mbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-
-  // ---- stage W tile (rows n0..n0+NT of W[., K]) and A tile: 16-byte chunks, 8 loads in flight per thread -------------
-  constexpr int CH = K / 8;  // 16-byte chunks per row
+  constexpr int CH = K / 8;  // 16-byte chunks per operand row
   constexpr int NTH = 256, UNR = 8;
-  {
-    const __nv_bfloat16* wsrc = g.W + (size_t)n0 * K;
-    for (int i0 = tid; i0 < NT * CH; i0 += NTH * UNR) {
-      int4 v[UNR];
+  uint32_t parity = 0;
+  uint32_t tmem = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int ytile = item % g.ny;
+    const int row0 = (item / g.ny) * TILE_M;
+    const int n0 = ytile * NT;
+    if (tid < TILE_M) {
+      int gr = row0 + tid;
+      sRow[tid] = gr < M ? (g.out_row_map ? g.out_row_map[gr] : gr) : -1;
+    }
+    // ---- stage W tile (rows n0..n0+NT of W[., K]) ----------------------------------------------------------------
+    {
+      const __nv_bfloat16* wsrc = g.W + (size_t)n0 * K;
+      for (int i0 = tid; i0 < NT * CH; i0 += NTH * UNR) {
+        int4 v[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        int idx = i0 + u * NTH;
-        if (idx < NT * CH) v[u] = __ldg(reinterpret_cast<const int4*>(wsrc) + idx);  // rows are K*2 bytes = CH chunks: contiguous
-      }
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
+          if (idx < NT * CH) v[u] = __ldg(reinterpret_cast<const int4*>(wsrc) + idx);
+        }
 #pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        int idx = i0 + u * NTH;
-        if (idx < NT * CH) {
-          int r = idx / CH, j = idx % CH;
-          int c = j >> 3, jj = j & 7;
-          *reinterpret_cast<int4*>(sW + (size_t)c * NT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
+          if (idx < NT * CH) {
+            int r = idx / CH, j = idx % CH;
+            int c = j >> 3, jj = j & 7;
+            *reinterpret_cast<int4*>(sW + (size_t)c * NT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+          }
         }
       }
     }
-  }
-  const bool add_pos = (PRO == PRO_F32) && g.pos_tab != nullptr && (int)blockIdx.y < g.pos_ntiles;
-  if (PRO == PRO_BF16) {
-    for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UNR) {
-      int4 v[UNR];
+    // ---- stage A tile -------------------------------------------------------------------------------------------------
+    const bool add_pos = (PRO == PRO_F32) && g.pos_tab != nullptr && ytile < g.pos_ntiles;
+    if (PRO == PRO_BF16) {
+      for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UNR) {
+        int4 v[UNR];
 #pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        int idx = i0 + u * NTH;
-        int r = idx / CH, j = idx % CH;
-        v[u] = make_int4(0, 0, 0, 0);
-        if (idx < TILE_M * CH && row0 + r < M)
-          v[u] = *reinterpret_cast<const int4*>((const __nv_bfloat16*)g.A + (size_t)(row0 + r) * g.lda + j * 8);
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        int idx = i0 + u * NTH;
-        if (idx < TILE_M * CH) {
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
           int r = idx / CH, j = idx % CH;
-          int c = j >> 3, jj = j & 7;
-          *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+          v[u] = make_int4(0, 0, 0, 0);
+          if (idx < TILE_M * CH && row0 + r < M)
+            v[u] = *reinterpret_cast<const int4*>((const __nv_bfloat16*)g.A + (size_t)(row0 + r) * g.lda + j * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
+          if (idx < TILE_M * CH) {
+            int r = idx / CH, j = idx % CH;
+            int c = j >> 3, jj = j & 7;
+            *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v[u];
+          }
         }
       }
-    }
-  } else {
-    constexpr int UF = 4;
-    for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UF) {
-      float4 f0[UF], f1[UF];
-      int code[UF];
+    } else {
+      constexpr int UF = 4;
+      for (int i0 = tid; i0 < TILE_M * CH; i0 += NTH * UF) {
+        float4 f0[UF], f1[UF];
+        int code[UF];
 #pragma unroll
-      for (int u = 0; u < UF; u++) {
-        int idx = i0 + u * NTH;
-        int r = idx / CH, j = idx % CH;
-        f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        code[u] = 0;
-        if (idx < TILE_M * CH && row0 + r < M) {
-          const float* ap = (const float*)g.A + (size_t)(row0 + r) * g.lda + j * 8;
-          f0[u] = *reinterpret_cast<const float4*>(ap);
-          f1[u] = *reinterpret_cast<const float4*>(ap + 4);
-          if (add_pos) code[u] = g.pos_code[row0 + r];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UF; u++) {
-        int idx = i0 + u * NTH;
-        if (idx < TILE_M * CH) {
+        for (int u = 0; u < UF; u++) {
+          int idx = i0 + u * NTH;
           int r = idx / CH, j = idx % CH;
-          float f[8] = {f0[u].x, f0[u].y, f0[u].z, f0[u].w, f1[u].x, f1[u].y, f1[u].z, f1[u].w};
-          if (add_pos && row0 + r < M) {
+          f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          code[u] = 0;
+          if (idx < TILE_M * CH && row0 + r < M) {
+            const float* ap = (const float*)g.A + (size_t)(row0 + r) * g.lda + j * 8;
+            f0[u] = *reinterpret_cast<const float4*>(ap);
+            f1[u] = *reinterpret_cast<const float4*>(ap + 4);
+            if (add_pos) code[u] = g.pos_code[row0 + r];
+          }
+        }
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-              int k = j * 8 + e;
-              int axis = k / g.posL;
-              if (axis < g.pos_ndim) {
-                int cv = (code[u] >> (8 * axis)) & 255;
-                f[e] += __ldg(&g.pos_tab[((size_t)axis * g.pos_maxw + cv) * g.posL + (k - axis * g.posL)]);
+        for (int u = 0; u < UF; u++) {
+          int idx = i0 + u * NTH;
+          if (idx < TILE_M * CH) {
+            int r = idx / CH, j = idx % CH;
+            float f[8] = {f0[u].x, f0[u].y, f0[u].z, f0[u].w, f1[u].x, f1[u].y, f1[u].z, f1[u].w};
+            if (add_pos && row0 + r < M) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                int k = j * 8 + e;
+                int axis = k / g.posL;
+                if (axis < g.pos_ndim) {
+                  int cv = (code[u] >> (8 * axis)) & 255;
+                  f[e] += __ldg(&g.pos_tab[((size_t)axis * g.pos_maxw + cv) * g.posL + (k - axis * g.posL)]);
+                }
               }
             }
+            int4 v;
+            v.x = (int)pack_bf16(f[0], f[1]);
+            v.y = (int)pack_bf16(f[2], f[3]);
+            v.z = (int)pack_bf16(f[4], f[5]);
+            v.w = (int)pack_bf16(f[6], f[7]);
+            int c = j >> 3, jj = j & 7;
+            *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
           }
-          int4 v;
-          v.x = (int)pack_bf16(f[0], f[1]);
-          v.y = (int)pack_bf16(f[2], f[3]);
-          v.z = (int)pack_bf16(f[4], f[5]);
-          v.w = (int)pack_bf16(f[6], f[7]);
-          int c = j >> 3, jj = j & 7;
-          *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
         }
       }
     }
-  }
-  // generic-proxy smem writes -> visible to the tensor core (async proxy); TMEM address visible to all
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = tmem_slot;
+    // generic-proxy smem writes -> visible to the tensor core (async proxy); TMEM address visible to all
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem = tmem_slot;
 
-  // ---- MMA issue: one thread ----------------------------------------------------------------------------------------
-  if (tid == 0) {
-    const uint32_t idesc = umma_idesc(TILE_M, NT);
-    const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
+    // ---- MMA issue: one thread ------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      const uint32_t idesc = umma_idesc(TILE_M, NT);
+      const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
 #pragma unroll
-    for (int c = 0; c < K / 64; c++) {
+      for (int c = 0; c < K / 64; c++) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        uint64_t ad = umma_desc_sw128(a0 + c * TILE_M * 128 + s * 32);
-        uint64_t bd = umma_desc_sw128(w0 + c * NT * 128 + s * 32);
-        umma_bf16(tmem, ad, bd, idesc, (c | s) ? 1u : 0u);
+        for (int s = 0; s < 4; s++) {
+          uint64_t ad = umma_desc_sw128(a0 + c * TILE_M * 128 + s * 32);
+          uint64_t bd = umma_desc_sw128(w0 + c * NT * 128 + s * 32);
+          umma_bf16(tmem, ad, bd, idesc, (c | s) ? 1u : 0u);
+        }
       }
+      umma_commit(smem_u32(&mbar));  // implicit tcgen05.fence::before_thread_sync
     }
-    umma_commit(smem_u32(&mbar));  // implicit tcgen05.fence::before_thread_sync
-  }
-  __syncwarp();
-  mbar_wait(smem_u32(&mbar), 0);
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    __syncwarp();
+    mbar_wait(smem_u32(&mbar), parity);
+    parity ^= 1u;
+    tc_fence_after();
 
-  // ---- epilogue: thread t owns output row row0+t == TMEM lane t -------------------------------------------------------
-  const int half = warp >> 2;                  // warps 0-3: columns [0,NT/2), warps 4-7: [NT/2,NT)
-  const int lrow = (warp & 3) * 32 + (tid & 31);  // TMEM lane == row inside the tile
-  const int grow = row0 + lrow;
-  const bool live = grow < M;
-  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr int CB = NT / 2;
-  const int cbeg = half * CB;
-  if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    // ---- epilogue ----------------------------------------------------------------------------------------------------------
+    const int half = warp >> 2;                      // warps 0-3: columns [0,NT/2), warps 4-7: [NT/2,NT)
+    const int lrow = (warp & 3) * 32 + (tid & 31);   // TMEM lane == row inside the tile
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int CB = NT / 2;
+    const int cbeg = half * CB;
+    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+      // thread-per-row: bias (+GELU), pack, into the bf16 staging tile [128][NT] (16-byte chunks XOR-swizzled by row)
+      constexpr int ECH = NT / 8;
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
-      float v[32];
-      tmem_ld32(tlane + c0, v);
-      if (live) {
+      for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
+        float v[32];
+        tmem_ld32(tlane + c0, v);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float a = v[i] + g.bias[n0 + c0 + i], b = v[i + 1] + g.bias[n0 + c0 + i + 1];
+          float a = v[i] + __ldg(&g.bias[n0 + c0 + i]), b = v[i + 1] + __ldg(&g.bias[n0 + c0 + i + 1]);
           if (EPI == EPI_BF16_GELU) {
             a = gelu_erf(a);
             b = gelu_erf(b);
           }
           pk[i >> 1] = pack_bf16(a, b);
         }
-        int4* dst = reinterpret_cast<int4*>(g.out_bf16 + (size_t)grow * g.ldo + n0 + c0);
 #pragma unroll
-        for (int q = 0; q < 4; q++) dst[q] = make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
-      }
-    }
-  } else {  // EPI_RES_LN : NT == row width
-    float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
-      float v[32];
-      tmem_ld32(tlane + c0, v);
-      if (live) {
-        const float4* rp = reinterpret_cast<const float4*>(g.res + (size_t)grow * NT + c0);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          float4 r4 = rp[q];
-          float t0 = v[4 * q] + g.bias[c0 + 4 * q] + r4.x, t1 = v[4 * q + 1] + g.bias[c0 + 4 * q + 1] + r4.y;
-          float t2 = v[4 * q + 2] + g.bias[c0 + 4 * q + 2] + r4.z, t3 = v[4 * q + 3] + g.bias[c0 + 4 * q + 3] + r4.w;
-          sum += (t0 + t1) + (t2 + t3);
-          sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+        for (int q = 0; q < 4; q++) {
+          int ch = (c0 >> 3) + q;
+          *reinterpret_cast<int4*>(sE + (size_t)lrow * NT * 2 + ((ch ^ (lrow & (ECH - 1))) << 4)) =
+              make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
         }
       }
-    }
-    red[half][lrow][0] = sum;
-    red[half][lrow][1] = sq;
-    __syncthreads();
-    sum = red[0][lrow][0] + red[1][lrow][0];
-    sq = red[0][lrow][1] + red[1][lrow][1];
-    const float mean = sum * (1.0f / NT);
-    const float var = fmaxf(sq * (1.0f / NT) - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + g.eps);
+      tc_fence_before();
+      __syncthreads();
+      for (int idx = tid; idx < TILE_M * ECH; idx += NTH) {
+        int r = idx / ECH, ch = idx % ECH;
+        int gr = sRow[r];
+        if (gr >= 0)
+          *reinterpret_cast<int4*>(g.out_bf16 + (size_t)gr * g.ldo + n0 + ch * 8) =
+              *reinterpret_cast<const int4*>(sE + (size_t)r * NT * 2 + ((ch ^ (r & (ECH - 1))) << 4));
+      }
+    } else {  // EPI_RES_LN : NT == row width, fp32 staging tile [128][NT] (16-byte chunks XOR-swizzled by row)
+      constexpr int ECH = NT / 4;  // float4 chunks per row
+      static_assert(ECH == 32, "LayerNorm epilogue is written for 128-wide rows");
+      // 1. residual tile, coalesced
+      for (int i0 = tid; i0 < TILE_M * ECH; i0 += NTH * UNR) {
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
+          int r = idx / ECH, ch = idx % ECH;
+          int gr = sRow[r];
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gr >= 0) v[u] = *reinterpret_cast<const float4*>(g.res + (size_t)gr * NT + ch * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          int idx = i0 + u * NTH;
+          int r = idx / ECH, ch = idx % ECH;
+          *reinterpret_cast<float4*>(sE + (size_t)r * NT * 4 + ((ch ^ (r & 31)) << 4)) = v[u];
+        }
+      }
+      __syncthreads();
+      // 2. thread-per-row: t = acc + bias + residual (kept in the staging tile), row statistics
+      float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
-      float v[32];
-      tmem_ld32(tlane + c0, v);
-      if (live) {
-        const float4* rp = reinterpret_cast<const float4*>(g.res + (size_t)grow * NT + c0);
-        float4* op = reinterpret_cast<float4*>(g.out_f32 + (size_t)grow * NT + c0);
-        uint32_t pk[16];
+      for (int c0 = cbeg; c0 < cbeg + CB; c0 += 32) {
+        float v[32];
+        tmem_ld32(tlane + c0, v);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          float4 r4 = rp[q];
-          float o[4];
-          float t[4] = {v[4 * q] + r4.x, v[4 * q + 1] + r4.y, v[4 * q + 2] + r4.z, v[4 * q + 3] + r4.w};
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            int cc = c0 + 4 * q + e;
-            o[e] = (t[e] + g.bias[cc] - mean) * rstd * g.gamma[cc] + g.beta[cc];
+          int ch = (c0 >> 2) + q;
+          float4* sp = reinterpret_cast<float4*>(sE + (size_t)lrow * NT * 4 + ((ch ^ (lrow & 31)) << 4));
+          float4 r4 = *sp;
+          float4 t;
+          t.x = v[4 * q] + __ldg(&g.bias[c0 + 4 * q]) + r4.x;
+          t.y = v[4 * q + 1] + __ldg(&g.bias[c0 + 4 * q + 1]) + r4.y;
+          t.z = v[4 * q + 2] + __ldg(&g.bias[c0 + 4 * q + 2]) + r4.z;
+          t.w = v[4 * q + 3] + __ldg(&g.bias[c0 + 4 * q + 3]) + r4.w;
+          *sp = t;
+          sum += (t.x + t.y) + (t.z + t.w);
+          sq += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+        }
+      }
+      red[half][lrow][0] = sum;
+      red[half][lrow][1] = sq;
+      tc_fence_before();
+      __syncthreads();
+      sum = red[0][lrow][0] + red[1][lrow][0];
+      sq = red[0][lrow][1] + red[1][lrow][1];
+      const float mean = sum * (1.0f / NT);
+      const float var = fmaxf(sq * (1.0f / NT) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + g.eps);
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + CB; c0 += 4) {
+        int ch = c0 >> 2;
+        float4* sp = reinterpret_cast<float4*>(sE + (size_t)lrow * NT * 4 + ((ch ^ (lrow & 31)) << 4));
+        float4 t = *sp;
+        t.x = (t.x - mean) * rstd * __ldg(&g.gamma[c0]) + __ldg(&g.beta[c0]);
+        t.y = (t.y - mean) * rstd * __ldg(&g.gamma[c0 + 1]) + __ldg(&g.beta[c0 + 1]);
+        t.z = (t.z - mean) * rstd * __ldg(&g.gamma[c0 + 2]) + __ldg(&g.beta[c0 + 2]);
+        t.w = (t.w - mean) * rstd * __ldg(&g.gamma[c0 + 3]) + __ldg(&g.beta[c0 + 3]);
+        *sp = t;
+      }
+      __syncthreads();
+      // 3. coalesced stores: fp32 rows (+ bf16 copy for the next GEMM's A operand)
+      for (int idx = tid; idx < TILE_M * ECH; idx += NTH) {
+        int r = idx / ECH, ch = idx % ECH;
+        int gr = sRow[r];
+        if (gr >= 0)
+          *reinterpret_cast<float4*>(g.out_f32 + (size_t)gr * NT + ch * 4) =
+              *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + ((ch ^ (r & 31)) << 4));
+      }
+      if (g.out_bf16) {
+        for (int idx = tid; idx < TILE_M * (NT / 8); idx += NTH) {
+          int r = idx / (NT / 8), c8 = idx % (NT / 8);
+          int gr = sRow[r];
+          if (gr >= 0) {
+            float4 a = *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + (((2 * c8) ^ (r & 31)) << 4));
+            float4 b = *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + (((2 * c8 + 1) ^ (r & 31)) << 4));
+            *reinterpret_cast<int4*>(g.out_bf16 + (size_t)gr * g.ldo + c8 * 8) =
+                make_int4((int)pack_bf16(a.x, a.y), (int)pack_bf16(a.z, a.w), (int)pack_bf16(b.x, b.y), (int)pack_bf16(b.z, b.w));
           }
-          op[q] = make_float4(o[0], o[1], o[2], o[3]);
-          pk[2 * q] = pack_bf16(o[0], o[1]);
-          pk[2 * q + 1] = pack_bf16(o[2], o[3]);
-        }
-        if (g.out_bf16) {
-          int4* dst = reinterpret_cast<int4*>(g.out_bf16 + (size_t)grow * g.ldo + c0);
-#pragma unroll
-          for (int q = 0; q < 4; q++) dst[q] = make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
         }
       }
     }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
-  }
+    // TMEM fully read and the staging tile stored before the next item overwrites operands / accumulators
+    tc_fence_before();
+    __syncthreads();
+  }  // item loop
+  if (warp == 0) tmem_dealloc(tmem, NT);
 }
 
 template <int K, int NT, int PRO, int EPI>
 int launch_umma(sstb200_ctx* c, const GemmArgs& g, int n_tiles_y) {
-  size_t smem = (size_t)TILE_M * K * 2 + (size_t)NT * K * 2 + 1024;
+  size_t ops = (size_t)TILE_M * K * 2 + (size_t)NT * K * 2;
+  size_t stage = (EPI == EPI_RES_LN) ? (size_t)TILE_M * NT * 4 : (size_t)TILE_M * NT * 2;
+  size_t smem = (ops > stage ? ops : stage) + 1024;
   auto kern = umma_gemm_kernel<K, NT, PRO, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid((g.M_cap + TILE_M - 1) / TILE_M, n_tiles_y);
-  kern<<<grid, 256, smem, c->stream>>>(g);
+  GemmArgs ga = g;
+  ga.ny = n_tiles_y;
+  int items_cap = ((g.M_cap + TILE_M - 1) / TILE_M) * n_tiles_y;
+  int per_sm = (int)((220 * 1024) / (smem + 6144));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 512 / NT) per_sm = 512 / NT;   // TMEM columns
+  int grid = c->num_sms * per_sm;
+  if (grid > items_cap) grid = items_cap;
+  kern<<<grid, 256, smem, c->stream>>>(ga);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }
@@ -370,6 +373,9 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   float* x1 = arena_alloc<float>(c, (size_t)n_cap * d);
   if (!qkv || !att || !x1b || !hid || !x1) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra bf16 layer: arena too small");
   int rc;
+  // tensor-core attention path: plain scaled-dot-product, 8 heads x 16, windows <= 144 tokens
+  const bool slot_order = !L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
+                          P->num_windows_dev && P->tok_slot;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M_cap = n_cap;
@@ -387,11 +393,12 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.pos_ntiles = 2;
   g.out_bf16 = qkv;
   g.ldo = 3 * d;
+  g.out_row_map = slot_order ? P->tok_slot : nullptr;  // rows land in window (slot) order for the tensor-core attention
   rc = launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3);
   if (rc) return rc;
   // 2. ragged window attention (fp32 math on bf16 q/k/v)
-  if (!L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT && P->num_windows_dev)
-    rc = sstb_win_attn_mma(c, qkv, L->nhead, P->num_windows_dev, P->win_offsets, P->tok_perm, att);
+  if (slot_order)
+    rc = sstb_win_attn_mma(c, qkv, L->nhead, P->num_windows_dev, P->win_offsets, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
@@ -411,6 +418,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.out_f32 = x1;
   g.out_bf16 = x1b;
   g.ldo = d;
+  g.out_row_map = slot_order ? P->tok_perm : nullptr;  // attention output rows are in slot order: scatter back to tokens
   rc = launch_umma<128, 128, PRO_BF16, EPI_RES_LN>(c, g, 1);
   if (rc) return rc;
   // 4. FFN1 + GELU

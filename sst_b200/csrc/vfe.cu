@@ -7,6 +7,7 @@
 // registers - the per-point feature tensors are never materialised.
 #include <stdarg.h>
 #include "index.cuh"
+#include "umma.cuh"
 
 struct VfeDev {
   int F, D0, C0, C1, nlayers;
@@ -295,9 +296,316 @@ __global__ void __launch_bounds__(256) vfe_fused_kernel(VfeDev v, const float* _
   }
 }
 
+
+// =====================================================================================================
+// Tile path (max pooling): points are visited in CSR (voxel-sorted) order in tiles of 128.
+//   vfe_mean_kernel     per-voxel xyz mean (4 lanes per voxel, fp64 accumulate)
+//   vfe_l0_tile_kernel  decorate + layer 0 (FFMA, fp32 exact) + in-tile segmented max -> vf0 [M,C0]
+//   vfe_l1_umma_kernel  A = bf16([y0 || vf0[voxel]]) [128 x 2*C0], B = bf16(W1) -> tcgen05.mma into TMEM,
+//                       epilogue BN+ReLU, post-activation tile to smem, in-tile segmented max -> vf1 [M,C1]
+// Post-ReLU values are >= 0, so the max across tile edges is an integer atomicMax on the float bits
+// (exact, order independent); segments interior to a tile are written with plain stores.
+// =====================================================================================================
+#define VT 128  // points per tile
+
+__global__ void vfe_mean_kernel(const float* __restrict__ pts, int F, const uint32_t* __restrict__ offsets,
+                                const int32_t* __restrict__ order, const int32_t* __restrict__ nvox_dev,
+                                float* __restrict__ vmean) {
+  int M = *nvox_dev;
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, l = threadIdx.x & 3;
+  int ng = (gridDim.x * blockDim.x) >> 2;
+  for (int v = g; v < M; v += ng) {
+    uint32_t b = offsets[v], e = offsets[v + 1];
+    double sx = 0, sy = 0, sz = 0;
+    for (uint32_t k = b + l; k < e; k += 4) {
+      const float* p = pts + (size_t)order[k] * F;
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (l == 0) {
+      float cnt = (float)(e - b);
+      vmean[(size_t)v * 3] = (float)sx / cnt;
+      vmean[(size_t)v * 3 + 1] = (float)sy / cnt;
+      vmean[(size_t)v * 3 + 2] = (float)sz / cnt;
+    }
+  }
+}
+
+// decorated features of the tile's points -> sF[VT][VFE_MAXD]; voxel id per row -> sVox
+template <typename TC, typename TM>
+__device__ __forceinline__ void tile_decorate(const VfeDev& v, const float* __restrict__ pts, const TC* __restrict__ coors,
+                                              const int32_t* __restrict__ order, const TM* __restrict__ map,
+                                              const float* __restrict__ vmean, int k0, int nrow, float (*sF)[VFE_MAXD], int* sVox) {
+  for (int r = threadIdx.x; r < VT; r += blockDim.x) {
+    if (r < nrow) {
+      int p = order[k0 + r];
+      int vox = (int)map[p];
+      sVox[r] = vox;
+      const float* pp = pts + (size_t)p * v.F;
+      float x = pp[0], y = pp[1], z = pp[2];
+      int k = 0;
+      for (; k < v.F; k++) sF[r][k] = pp[k];
+      if (v.with_cluster) {
+        sF[r][k++] = (x - vmean[(size_t)vox * 3]) / v.rel_dist_scaler;
+        sF[r][k++] = (y - vmean[(size_t)vox * 3 + 1]) / v.rel_dist_scaler;
+        sF[r][k++] = (z - vmean[(size_t)vox * 3 + 2]) / v.rel_dist_scaler;
+      }
+      if (v.with_center) {
+        float cx = (float)coors[(size_t)p * 4 + 3], cy = (float)coors[(size_t)p * 4 + 2], cz = (float)coors[(size_t)p * 4 + 1];
+        sF[r][k++] = x - __fadd_rn(__fmul_rn(cx, v.vx), v.x_off);
+        sF[r][k++] = y - __fadd_rn(__fmul_rn(cy, v.vy), v.y_off);
+        sF[r][k++] = z - __fadd_rn(__fmul_rn(cz, v.vz), v.z_off);
+      }
+      if (v.with_distance) sF[r][k++] = sqrtf(x * x + y * y + z * z);
+    } else {
+      sVox[r] = -1;
+    }
+  }
+}
+
+// column-wise segmented max over the tile's rows (rows sorted by voxel); tile [VT][ld] fp32 in smem
+__device__ __forceinline__ void tile_segmax(const float* tile, int ld, const int* sVox, int nrow, int C, float* __restrict__ out) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int seg = sVox[0];
+    bool first = true;  // segment may continue from the previous tile
+    float m = 0.f;      // post-ReLU values are >= 0
+    for (int r = 0; r < nrow; r++) {
+      int sg = sVox[r];
+      if (sg != seg) {
+        if (first) atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));
+        else out[(size_t)seg * C + c] = m;
+        first = false;
+        seg = sg;
+        m = 0.f;
+      }
+      m = fmaxf(m, tile[r * ld + c]);
+    }
+    atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));  // may continue into the next tile
+  }
+}
+
+template <typename TC, typename TM, int C0>
+__global__ void __launch_bounds__(256) vfe_l0_tile_kernel(VfeDev v, const float* __restrict__ pts, const TC* __restrict__ coors,
+                                                          const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
+                                                          const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
+                                                          const float* __restrict__ vmean, float* __restrict__ vf0) {
+  __shared__ float sF[VT][VFE_MAXD];
+  __shared__ int sVox[VT];
+  __shared__ float sW[VFE_MAXD][C0];  // W0 transposed
+  __shared__ float sS[C0], sT[C0];
+  extern __shared__ float sY[];  // [VT][C0+1]
+  const int D0 = v.D0;
+  for (int i = threadIdx.x; i < D0 * C0; i += blockDim.x) sW[i / C0][i % C0] = v.W0[(i % C0) * D0 + (i / C0)];
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+    sS[i] = v.s0[i];
+    sT[i] = v.t0[i];
+  }
+  const int M = *nvox_dev;
+  const int nvalid = M > 0 ? (int)offsets[M] : 0;
+  for (int k0 = blockIdx.x * VT; k0 < nvalid; k0 += gridDim.x * VT) {
+    int nrow = min(VT, nvalid - k0);
+    __syncthreads();
+    tile_decorate<TC, TM>(v, pts, coors, order, map, vmean, k0, nrow, sF, sVox);
+    __syncthreads();
+    for (int i = threadIdx.x; i < VT * C0; i += blockDim.x) {
+      int r = i / C0, c = i % C0;
+      float y = 0.f;
+      if (r < nrow) {
+        float a = 0.f;
+        for (int d = 0; d < D0; d++) a = fmaf(sW[d][c], sF[r][d], a);
+        y = fmaxf(fmaf(a, sS[c], sT[c]), 0.f);
+      }
+      sY[r * (C0 + 1) + c] = y;
+    }
+    __syncthreads();
+    tile_segmax(sY, C0 + 1, sVox, nrow, C0, vf0);
+  }
+}
+
+// layer 1 on tensor cores.  K = 2*C0 (== 128 for C0 = 64), N = C1 (128).
+template <typename TC, typename TM, int C0, int C1>
+__global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float* __restrict__ pts, const TC* __restrict__ coors,
+                                                          const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
+                                                          const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
+                                                          const float* __restrict__ vmean, const float* __restrict__ vf0,
+                                                          float* __restrict__ vf1) {
+  constexpr int K = 2 * C0;
+  static_assert(K % 64 == 0 && C1 % 16 == 0 && C1 <= 256, "shape");
+  extern __shared__ uint8_t l1_smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)l1_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                       // K/64 chunks x 128 rows x 128 B
+  uint8_t* sB = sA + (size_t)VT * K * 2;    // K/64 chunks x C1 rows x 128 B
+  float* sTile = reinterpret_cast<float*>(base);  // re-used after the MMA: [VT][C1+1] fp32
+  __shared__ float sF[VT][VFE_MAXD];
+  __shared__ int sVox[VT];
+  __shared__ float sW0[VFE_MAXD][C0];
+  __shared__ float sS0[C0], sT0[C0], sS1[C1], sT1[C1];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int D0 = v.D0;
+  const int M = *nvox_dev;
+  const int nvalid = M > 0 ? (int)offsets[M] : 0;
+  if ((int)blockIdx.x * VT >= nvalid) return;
+  for (int i = tid; i < D0 * C0; i += blockDim.x) sW0[i / C0][i % C0] = v.W0[(i % C0) * D0 + (i / C0)];
+  for (int i = tid; i < C0; i += blockDim.x) {
+    sS0[i] = v.s0[i];
+    sT0[i] = v.t0[i];
+  }
+  for (int i = tid; i < C1; i += blockDim.x) {
+    sS1[i] = v.s1[i];
+    sT1[i] = v.t1[i];
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, C1 < 32 ? 32 : C1);
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t parity = 0;
+  for (int k0 = blockIdx.x * VT; k0 < nvalid; k0 += gridDim.x * VT) {
+    const int nrow = min(VT, nvalid - k0);
+    __syncthreads();  // previous tile's smem (sTile aliases sA/sB) fully consumed
+    tile_decorate<TC, TM>(v, pts, coors, order, map, vmean, k0, nrow, sF, sVox);
+    // B operand: W1 [C1, K] fp32 -> bf16, K-major SWIZZLE_128B
+    for (int idx = tid; idx < C1 * (K / 8); idx += blockDim.x) {
+      int r = idx / (K / 8), j = idx % (K / 8);
+      const float* wp = v.W1 + (size_t)r * K + j * 8;
+      float4 f0 = *reinterpret_cast<const float4*>(wp), f1 = *reinterpret_cast<const float4*>(wp + 4);
+      int4 q;
+      q.x = (int)pack_bf16(f0.x, f0.y);
+      q.y = (int)pack_bf16(f0.z, f0.w);
+      q.z = (int)pack_bf16(f1.x, f1.y);
+      q.w = (int)pack_bf16(f1.z, f1.w);
+      int c = j >> 3, jj = j & 7;
+      *reinterpret_cast<int4*>(sB + (size_t)c * C1 * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+    }
+    __syncthreads();
+    // A operand: row r = [ y0(point) (C0) || vf0[voxel] (C0) ] in bf16
+    for (int idx = tid; idx < VT * (K / 8); idx += blockDim.x) {
+      int r = idx / (K / 8), j = idx % (K / 8);
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) f[e] = 0.f;
+      if (r < nrow) {
+        if (j < C0 / 8) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            int c = j * 8 + e;
+            float a = 0.f;
+            for (int d = 0; d < D0; d++) a = fmaf(sW0[d][c], sF[r][d], a);
+            f[e] = fmaxf(fmaf(a, sS0[c], sT0[c]), 0.f);
+          }
+        } else {
+          const float* gp = vf0 + (size_t)sVox[r] * C0 + (j - C0 / 8) * 8;
+          float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+          f[0] = g0.x; f[1] = g0.y; f[2] = g0.z; f[3] = g0.w; f[4] = g1.x; f[5] = g1.y; f[6] = g1.z; f[7] = g1.w;
+        }
+      }
+      int4 q;
+      q.x = (int)pack_bf16(f[0], f[1]);
+      q.y = (int)pack_bf16(f[2], f[3]);
+      q.z = (int)pack_bf16(f[4], f[5]);
+      q.w = (int)pack_bf16(f[6], f[7]);
+      int c = j >> 3, jj = j & 7;
+      *reinterpret_cast<int4*>(sA + (size_t)c * VT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+      const uint32_t idesc = umma_idesc(128, C1);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+      for (int c = 0; c < K / 64; c++)
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          umma_bf16(tmem, umma_desc_sw128(a0 + c * VT * 128 + s * 32), umma_desc_sw128(b0 + c * C1 * 128 + s * 32), idesc,
+                    (c | s) ? 1u : 0u);
+      umma_commit(smem_u32(&mbar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&mbar), parity);
+    parity ^= 1u;
+    tc_fence_after();
+    // epilogue: BN + ReLU, tile to smem (operand buffers are free now: the MMA has completed)
+    const int half = warp >> 2;
+    const int lrow = (warp & 3) * 32 + (tid & 31);
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int CB = C1 / 2;
+#pragma unroll 1
+    for (int c0 = half * CB; c0 < half * CB + CB; c0 += 32) {
+      float acc[32];
+      tmem_ld32(tlane + c0, acc);
+#pragma unroll
+      for (int i = 0; i < 32; i++) sTile[lrow * (C1 + 1) + c0 + i] = fmaxf(fmaf(acc[i], sS1[c0 + i], sT1[c0 + i]), 0.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tile_segmax(sTile, C1 + 1, sVox, nrow, C1, vf1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot, C1 < 32 ? 32 : C1);
+}
+
+
+// rows of `out` that may be reached by atomicMax from two tiles (first / last voxel of every tile) start at 0
+template <typename TM>
+__global__ void vfe_zero_edges_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
+                                      const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev, int C, float* __restrict__ out) {
+  const int M = *nvox_dev;
+  const int nvalid = M > 0 ? (int)offsets[M] : 0;
+  for (int t = blockIdx.x; t * VT < nvalid; t += gridDim.x) {
+    int k0 = t * VT, k1 = min(k0 + VT, nvalid) - 1;
+    int v0 = (int)map[order[k0]], v1 = (int)map[order[k1]];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      out[(size_t)v0 * C + c] = 0.f;
+      out[(size_t)v1 * C + c] = 0.f;
+    }
+  }
+}
+
+template <typename TC, typename TM, int C0, int C1>
+static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, const TC* coors, const Csr& r, const TM* map,
+                            const int32_t* num_dev, float* vmean, float* vf0, float* out, bool umma_l1, bool* l1_done) {
+  cudaStream_t st = c->stream;
+  int grid = c->num_sms * 3;
+  vfe_mean_kernel<<<c->num_sms * 8, 256, 0, st>>>(pts, v.F, r.offsets, r.order, num_dev, vmean);
+  float* dst0 = (C1 > 0) ? vf0 : out;
+  vfe_zero_edges_kernel<TM><<<c->num_sms * 2, 64, 0, st>>>(r.offsets, r.order, map, num_dev, C0, dst0);
+  size_t smem0 = (size_t)VT * (C0 + 1) * 4;
+  vfe_l0_tile_kernel<TC, TM, C0><<<grid, 256, smem0, st>>>(v, pts, coors, r.offsets, r.order, map, num_dev, vmean, dst0);
+  *l1_done = false;
+  if (C1 > 0 && umma_l1) {
+    constexpr int C1s = C1 > 0 ? C1 : 32;
+    size_t ops = (size_t)VT * 2 * C0 * 2 + (size_t)C1s * 2 * C0 * 2, tile = (size_t)VT * (C1s + 1) * 4;
+    size_t smem1 = (ops > tile ? ops : tile) + 1024;
+    auto kern = vfe_l1_umma_kernel<TC, TM, C0, C1s>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      attr_set = true;
+    }
+    vfe_zero_edges_kernel<TM><<<c->num_sms * 2, 64, 0, st>>>(r.offsets, r.order, map, num_dev, C1s, out);
+    kern<<<grid, 256, smem1, st>>>(v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out);
+    *l1_done = true;
+  }
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
 template <typename TC, int NC0, int NC1>
 static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const TC* coors, const Csr& r, const int32_t* num_dev,
-                      float* vmean, float* vf0, float* out) {
+                      float* vmean, float* vf0, float* out, bool skip_phase0 = false) {
   int C0 = NC0 * 32, C1 = NC1 * 32;
   size_t smem = ((size_t)v.D0 * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
   size_t smem_max = ((size_t)VFE_MAXD * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
@@ -308,7 +616,7 @@ static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const T
     attr_set = true;
   }
   int grid = c->num_sms * 2;
-  kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
+  if (!skip_phase0) kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
   if (NC1 > 0) kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 1);
   LAUNCH_CHECK(c);
   return SSTB_OK;
@@ -396,21 +704,40 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
     fold_bn_kernel<<<(C1 + 127) / 128, 128, 0, c->stream>>>(cfg->bn_weight[1], cfg->bn_bias[1], cfg->bn_mean[1], cfg->bn_var[1],
                                                              cfg->bn_eps, C1, fold + 2 * C0, fold + 2 * C0 + C1);
   LAUNCH_CHECK(c);
-#define VFE_CASE(a, b)                                                                        \
-  if (C0 == a * 32 && C1 == b * 32) {                                                         \
-    rc = launch_vfe<TC, a, b>(c, v, pts, coors, r, num_dev, vmean, vf0, out_feats);           \
-    goto done;                                                                                \
+  {
+    // tile path (max pooling, the configurations on the hot path): layer 0 FFMA tiles; layer 1 on tcgen05 when bf16
+    bool l1_done = false, tiled = false;
+    const bool umma = cfg->precision == SSTB200_PREC_BF16;
+#define VFE_TILE(a, b)                                                                                                          \
+  if (!tiled && v.mode_max && C0 == a && C1 == b) {                                                                             \
+    if (inverse) rc = launch_vfe_tiles<TC, TC, a, b>(c, v, pts, coors, r, inverse, num_dev, vmean, vf0, out_feats, umma, &l1_done); \
+    else rc = launch_vfe_tiles<TC, int32_t, a, b>(c, v, pts, coors, r, map32, num_dev, vmean, vf0, out_feats, umma, &l1_done);    \
+    if (rc) return rc;                                                                                                          \
+    tiled = true;                                                                                                               \
   }
-  VFE_CASE(2, 4)
-  VFE_CASE(2, 2)
-  VFE_CASE(1, 2)
-  VFE_CASE(2, 0)
-  VFE_CASE(4, 4)
-  VFE_CASE(4, 0)
-  VFE_CASE(1, 0)
-  VFE_CASE(1, 1)
-  VFE_CASE(2, 8)
-  return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE channel combination (%d,%d) not instantiated", C0, C1);
+    VFE_TILE(64, 128)
+    VFE_TILE(64, 64)
+    VFE_TILE(64, 0)
+    VFE_TILE(32, 64)
+#undef VFE_TILE
+#define VFE_CASE(a, b)                                                                                     \
+  if (C0 == a * 32 && C1 == b * 32) {                                                                      \
+    if (!(tiled && (l1_done || C1 == 0)))                                                                  \
+      rc = launch_vfe<TC, a, b>(c, v, pts, coors, r, num_dev, vmean, vf0, out_feats, /*skip_phase0=*/tiled); \
+    goto done;                                                                                             \
+  }
+    VFE_CASE(2, 4)
+    VFE_CASE(2, 2)
+    VFE_CASE(1, 2)
+    VFE_CASE(2, 0)
+    VFE_CASE(4, 4)
+    VFE_CASE(4, 0)
+    VFE_CASE(1, 0)
+    VFE_CASE(1, 1)
+    VFE_CASE(2, 8)
+#undef VFE_CASE
+    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE channel combination (%d,%d) not instantiated", C0, C1);
+  }
 done:
   if (rc) return rc;
   if (num_host) return read_back_i32(c, num_dev, num_host);

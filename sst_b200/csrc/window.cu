@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(1024) win_level_kernel(const uint32_t* __restr
 __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, const int32_t* __restrict__ tok_win,
                                   const int32_t* __restrict__ tok_inner, const int32_t* __restrict__ win_level,
                                   const int32_t* __restrict__ win_rank, LevelCfg lv, long long* __restrict__ drop_level,
-                                  long long* __restrict__ flat2win) {
+                                  long long* __restrict__ flat2win, const uint32_t* __restrict__ offsets,
+                                  int32_t* __restrict__ tok_slot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -166,8 +167,10 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
   if (w < 0) {
     if (drop_level) drop_level[i] = -1;
     if (flat2win) flat2win[i] = -1;
+    if (tok_slot) tok_slot[i] = -1;
     return;
   }
+  if (tok_slot) tok_slot[i] = (int32_t)offsets[w] + tok_inner[i];
   int slot = win_level[w];
   if (drop_level) drop_level[i] = lv.id[slot];
   if (flat2win) flat2win[i] = (long long)win_rank[w] * lv.maxtok[slot] + tok_inner[i];
@@ -227,7 +230,7 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   win_level_kernel<<<1, 1024, 0, c->stream>>>(r.offsets, o->tok_perm, nwin, lv, (const long long*)token_level, o->win_level,
                                               o->win_rank, o->counters, k.flags);
   tok_finish_kernel<<<nb, 256, 0, c->stream>>>(n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
-                                               (long long*)o->drop_level, (long long*)o->flat2win_inds);
+                                               (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
   // offsets -> caller buffer (int32 [n+1]); only R+1 entries are meaningful
   CUDA_TRY(c, cudaMemcpyAsync(o->win_offsets, r.offsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
   LAUNCH_CHECK(c);

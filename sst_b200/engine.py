@@ -52,7 +52,7 @@ class SSTEngine:
         self.plans = []
         for _ in range(2):
             p = {k: torch.empty((cap + 1,) if k == "win_offsets" else (cap,), **i32)
-                 for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank")}
+                 for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "tok_slot")}
             p["counters"] = torch.zeros((17,), **i32)
             self.plans.append(p)
         self.wcfg, _ = ops._window_cfg(self.il.sparse_shape, self.il.window_shape, self.il.drop_info, self.B)
@@ -61,11 +61,14 @@ class SSTEngine:
         self._shift_structs = [ops._WindowShift(None, None, None, None, p["pos_code"].data_ptr(), p["tok_win"].data_ptr(),
                                                 p["tok_inner"].data_ptr(), p["win_offsets"].data_ptr(),
                                                 p["tok_perm"].data_ptr(), p["win_level"].data_ptr(),
-                                                p["win_rank"].data_ptr(), p["counters"].data_ptr()) for p in self.plans]
+                                                p["win_rank"].data_ptr(), p["counters"].data_ptr(), p["tok_slot"].data_ptr())
+                               for p in self.plans]
         self._plan_structs = [_SraPlan(p["win_offsets"].data_ptr(), p["tok_perm"].data_ptr(), p["tok_win"].data_ptr(),
                                        p["pos_code"].data_ptr(), p["counters"].data_ptr(), tab.data_ptr(), Lp, maxw, ndim,
-                                       max(v["max_tokens"] for v in self.il.drop_info.values())) for p in self.plans]
+                                       max(v["max_tokens"] for v in self.il.drop_info.values()), p["tok_slot"].data_ptr())
+                              for p in self.plans]
         self.vfe_cfg = self.vfe._cfg(self.B)
+        self.vfe_cfg.precision = PRECISIONS[precision]
         prec = PRECISIONS[precision]
         self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]
         self._vs_arr, self._rng_arr = L.arr(C.c_float, self.vs), L.arr(C.c_float, self.rng)

@@ -45,7 +45,7 @@ class _VfeCfg(C.Structure):
                 ("with_cluster_center", C.c_int32), ("with_voxel_center", C.c_int32), ("with_distance", C.c_int32),
                 ("mode_max", C.c_int32), ("drop_first_voxel_per_sample", C.c_int32), ("batch_size", C.c_int32),
                 ("grid_zyx", C.c_int32 * 3), ("voxel_size", C.c_float * 3), ("center_offset", C.c_float * 3),
-                ("rel_dist_scaler", C.c_float), ("bn_eps", C.c_float), ("weight", C.c_void_p * 2),
+                ("rel_dist_scaler", C.c_float), ("bn_eps", C.c_float), ("precision", C.c_int32), ("weight", C.c_void_p * 2),
                 ("bn_weight", C.c_void_p * 2), ("bn_bias", C.c_void_p * 2), ("bn_mean", C.c_void_p * 2),
                 ("bn_var", C.c_void_p * 2)]
 
@@ -103,6 +103,8 @@ class DynamicVFE(nn.Module):
         r = self.point_cloud_range
         return (round((r[5] - r[2]) / self.vz), round((r[4] - r[1]) / self.vy), round((r[3] - r[0]) / self.vx))
 
+    precision = "fp32"  # 'bf16': second VFE layer on tensor cores (bf16 operands, fp32 accumulate)
+
     def _cfg(self, batch_size):
         if self._with_distance:
             raise NotImplementedError("with_distance: the reference's channel count is inconsistent (+3 vs 1)")
@@ -127,6 +129,7 @@ class DynamicVFE(nn.Module):
         cfg.center_offset[0], cfg.center_offset[1], cfg.center_offset[2] = self.x_offset, self.y_offset, self.z_offset
         cfg.rel_dist_scaler = float(self.rel_dist_scaler)
         cfg.bn_eps = float(self.norm_eps)
+        cfg.precision = {"fp32": 0, "bf16": 1}[self.precision]
         for i, l in enumerate(self.vfe_layers):
             if not isinstance(l.norm, nn.modules.batchnorm._BatchNorm):
                 raise NotImplementedError("fused VFE expects BatchNorm layers")
