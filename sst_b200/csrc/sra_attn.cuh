@@ -3,6 +3,7 @@
 // token order; the window CSR gives the key set, so no padding, no mask, no per-level batches.
 //   cosine mode (models/sst/cosine_msa.py:123-185): q,k L2-normalised, logits / clamp(tau, tau_min).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 template <typename T, int N>
@@ -137,6 +138,15 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -267,6 +277,148 @@ static inline int sstb_win_attn_mma(sstb200_ctx* c, const __nv_bfloat16* qkv, in
     attr_set = true;
   }
   win_attn_mma_kernel<<<c->num_sms * 2, 256, smem, c->stream>>>(qkv, nhead, nwin_dev, win_offsets, 0.25f, out);
+  CUDA_TRY(c, cudaGetLastError());
+  return SSTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// v3: warp-autonomous ragged attention.  One warp owns one (window, head): K_h and V_h^T of the whole window live in
+// REGISTERS as mma B-fragments (<= 72 registers for 144 keys), loaded once straight from the slot-ordered q/k/v rows,
+// then the warp sweeps the window's 16-query tiles.  No shared memory, no block-level barrier, no index indirection:
+// per-SM residency is bounded by registers only, which is what this latency-bound kernel needs.
+// Softmax is two-pass over S (QK^T is recomputed in pass 2 - tensor-core work is free here, registers are not).
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) win_attn_warp_kernel(const __half* __restrict__ qkv,
+                                                                   const int32_t* __restrict__ nwin_dev,
+                                                                   const int32_t* __restrict__ win_offsets, float scale,
+                                                                   __nv_bfloat16* __restrict__ out) {
+  constexpr int D = 128, DH = 16, NH = 8, KT = ATT_MAXT / 8;
+  const int R = *nwin_dev;
+  const int lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < R * NH; u += warps_total) {
+    const int w = u / NH, h = u % NH;
+    const int kb = win_offsets[w];
+    const int n = min(win_offsets[w + 1] - kb, ATT_MAXT);
+    const int nkt = (n + 7) >> 3;
+    const __half* base = qkv + (size_t)kb * 3 * D + h * DH;
+    // K fragments: B[k = dim][n = key]  -> lane holds K[key = 8j+g4][dims 2*t4, 2*t4+1] and [+8, +9]
+    uint32_t kf[KT][2];
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+      kf[j][0] = kf[j][1] = 0u;
+      int key = 8 * j + g4;
+      if (j < nkt && key < n) {
+        const uint32_t* kp = reinterpret_cast<const uint32_t*>(base + (size_t)key * 3 * D + D);
+        kf[j][0] = kp[t4];
+        kf[j][1] = kp[t4 + 4];
+      }
+    }
+    // V^T fragments: B[k = key][n = dim] -> lane holds {V[2*t4][g4], V[2*t4+1][g4]}, keys +8, dims +8
+    uint32_t vf[KT / 2][4];
+#pragma unroll
+    for (int kc = 0; kc < KT / 2; kc++) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) vf[kc][q] = 0u;
+      if (kc * 16 < n) {
+        const unsigned short* vp = reinterpret_cast<const unsigned short*>(base + 2 * D);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int k0 = kc * 16 + 2 * t4 + (q & 1) * 8, dim = g4 + (q >> 1) * 8;
+          unsigned lo = k0 < n ? vp[(size_t)k0 * 3 * D + dim] : 0;
+          unsigned hi = k0 + 1 < n ? vp[(size_t)(k0 + 1) * 3 * D + dim] : 0;
+          vf[kc][q] = lo | (hi << 16);
+        }
+      }
+    }
+    const int ntile = (n + 15) >> 4;
+    for (int qt = 0; qt < ntile; qt++) {
+      const int r0 = qt * 16 + g4, r1 = r0 + 8;
+      uint32_t qa[4] = {0u, 0u, 0u, 0u};
+      if (r0 < n) {
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 3 * D);
+        qa[0] = qp[t4];
+        qa[2] = qp[t4 + 4];
+      }
+      if (r1 < n) {
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 3 * D);
+        qa[1] = qp[t4];
+        qa[3] = qp[t4 + 4];
+      }
+      // pass 1: row maxima
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KT; j++) {
+        if (j < nkt) {
+          float s[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16_16816(s, qa, kf[j][0], kf[j][1]);
+          const int c0 = j * 8 + 2 * t4;
+          if (c0 < n) {
+            m0 = fmaxf(m0, s[0]);
+            m1 = fmaxf(m1, s[2]);
+          }
+          if (c0 + 1 < n) {
+            m0 = fmaxf(m0, s[1]);
+            m1 = fmaxf(m1, s[3]);
+          }
+        }
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      const float ms0 = m0 * scale, ms1 = m1 * scale;  // scale > 0: max commutes with the scaling
+      // pass 2: P = exp(scale*S - max), O += P V
+      float l0 = 0.f, l1 = 0.f;
+      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int kc = 0; kc < KT / 2; kc++) {
+        if (kc * 16 < n) {
+          float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16_16816(sa, qa, kf[2 * kc][0], kf[2 * kc][1]);
+          mma_f16_16816(sb, qa, kf[2 * kc + 1][0], kf[2 * kc + 1][1]);
+          const int c0 = kc * 16 + 2 * t4;
+          float p[8];
+          p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
+          p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
+          p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
+          p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
+          p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
+          p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
+          p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
+          p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
+          l0 += (p[0] + p[1]) + (p[4] + p[5]);
+          l1 += (p[2] + p[3]) + (p[6] + p[7]);
+          uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
+          mma_f16_16816(o[0], pa, vf[kc][0], vf[kc][1]);
+          mma_f16_16816(o[1], pa, vf[kc][2], vf[kc][3]);
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      if (r0 < n) {
+        const float i0 = 1.0f / l0;
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r0) * D + h * DH);
+        op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
+        op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
+      }
+      if (r1 < n) {
+        const float i1 = 1.0f / l1;
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r1) * D + h * DH);
+        op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
+        op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
+      }
+    }
+  }
+}
+
+static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const int32_t* nwin_dev, const int32_t* win_offsets,
+                                     __nv_bfloat16* out) {
+  // 128 threads (4 warps) per CTA; ~120 registers -> 4 CTAs (16 warps) per SM
+  win_attn_warp_kernel<<<c->num_sms * 4, 128, 0, c->stream>>>(qkv, nwin_dev, win_offsets, 0.25f, out);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }

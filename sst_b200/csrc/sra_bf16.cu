@@ -10,14 +10,33 @@
 // plain bf16 rows; both write the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect.
 // fp32 stays the type of the residual stream, softmax, LayerNorm and all accumulation.
 #include <stdarg.h>
+#include <cuda_fp16.h>
 #include "sra.cuh"
 #include "sra_attn.cuh"
 #include "umma.cuh"
 
 namespace {
 
+// exact-form GELU (x * Phi(x)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): ~12 instructions instead of
+// erff's ~30, same accuracy class as fp32 erff for an output that is rounded to bf16 anyway.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 enum { PRO_BF16 = 0, PRO_F32 = 1 };
-enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_RES_LN = 2 };
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_RES_LN = 2, EPI_F16 = 3 };
 
 struct GemmArgs {
   const void* A;        // [M, lda] bf16 or fp32; tile rows are consecutive rows of A
@@ -150,14 +169,14 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
             int r = idx / CH, j = idx % CH;
             float f[8] = {f0[u].x, f0[u].y, f0[u].z, f0[u].w, f1[u].x, f1[u].y, f1[u].z, f1[u].w};
             if (add_pos && row0 + r < M) {
-#pragma unroll
-              for (int e = 0; e < 8; e++) {
-                int k = j * 8 + e;
-                int axis = k / g.posL;
-                if (axis < g.pos_ndim) {
-                  int cv = (code[u] >> (8 * axis)) & 255;
-                  f[e] += __ldg(&g.pos_tab[((size_t)axis * g.pos_maxw + cv) * g.posL + (k - axis * g.posL)]);
-                }
+              const int k0 = j * 8;
+              const int axis = k0 / g.posL;  // posL % 8 == 0 (checked on the host): the chunk lies inside one axis
+              if (axis < g.pos_ndim) {
+                const int cv = (code[u] >> (8 * axis)) & 255;
+                const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)axis * g.pos_maxw + cv) * g.posL + (k0 - axis * g.posL));
+                float4 p0 = __ldg(tp), p1 = __ldg(tp + 1);
+                f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w;
+                f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
               }
             }
             int4 v;
@@ -204,7 +223,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     constexpr int CB = NT / 2;
     const int cbeg = half * CB;
-    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+    if (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_F16) {
       // thread-per-row: bias (+GELU), pack, into the bf16 staging tile [128][NT] (16-byte chunks XOR-swizzled by row)
       constexpr int ECH = NT / 8;
 #pragma unroll 1
@@ -212,14 +231,19 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
         float v[32];
         tmem_ld32(tlane + c0, v);
         uint32_t pk[16];
+        const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a = v[i] + __ldg(&g.bias[n0 + c0 + i]), b = v[i + 1] + __ldg(&g.bias[n0 + c0 + i + 1]);
+        for (int i = 0; i < 32; i += 4) {
+          float4 b4 = __ldg(bp + (i >> 2));
+          float a0 = v[i] + b4.x, a1 = v[i + 1] + b4.y, a2 = v[i + 2] + b4.z, a3 = v[i + 3] + b4.w;
           if (EPI == EPI_BF16_GELU) {
-            a = gelu_erf(a);
-            b = gelu_erf(b);
+            a0 = gelu_fast(a0);
+            a1 = gelu_fast(a1);
+            a2 = gelu_fast(a2);
+            a3 = gelu_fast(a3);
           }
-          pk[i >> 1] = pack_bf16(a, b);
+          pk[i >> 1] = (EPI == EPI_F16) ? pack_f16(a0, a1) : pack_bf16(a0, a1);
+          pk[(i >> 1) + 1] = (EPI == EPI_F16) ? pack_f16(a2, a3) : pack_bf16(a2, a3);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -270,11 +294,11 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
           int ch = (c0 >> 2) + q;
           float4* sp = reinterpret_cast<float4*>(sE + (size_t)lrow * NT * 4 + ((ch ^ (lrow & 31)) << 4));
           float4 r4 = *sp;
-          float4 t;
-          t.x = v[4 * q] + __ldg(&g.bias[c0 + 4 * q]) + r4.x;
-          t.y = v[4 * q + 1] + __ldg(&g.bias[c0 + 4 * q + 1]) + r4.y;
-          t.z = v[4 * q + 2] + __ldg(&g.bias[c0 + 4 * q + 2]) + r4.z;
-          t.w = v[4 * q + 3] + __ldg(&g.bias[c0 + 4 * q + 3]) + r4.w;
+          float4 t, b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c0) + q);
+          t.x = v[4 * q] + b4.x + r4.x;
+          t.y = v[4 * q + 1] + b4.y + r4.y;
+          t.z = v[4 * q + 2] + b4.z + r4.z;
+          t.w = v[4 * q + 3] + b4.w + r4.w;
           *sp = t;
           sum += (t.x + t.y) + (t.z + t.w);
           sq += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
@@ -294,10 +318,11 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
         int ch = c0 >> 2;
         float4* sp = reinterpret_cast<float4*>(sE + (size_t)lrow * NT * 4 + ((ch ^ (lrow & 31)) << 4));
         float4 t = *sp;
-        t.x = (t.x - mean) * rstd * __ldg(&g.gamma[c0]) + __ldg(&g.beta[c0]);
-        t.y = (t.y - mean) * rstd * __ldg(&g.gamma[c0 + 1]) + __ldg(&g.beta[c0 + 1]);
-        t.z = (t.z - mean) * rstd * __ldg(&g.gamma[c0 + 2]) + __ldg(&g.beta[c0 + 2]);
-        t.w = (t.w - mean) * rstd * __ldg(&g.gamma[c0 + 3]) + __ldg(&g.beta[c0 + 3]);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g.gamma + c0)), b4 = __ldg(reinterpret_cast<const float4*>(g.beta + c0));
+        t.x = (t.x - mean) * rstd * g4.x + b4.x;
+        t.y = (t.y - mean) * rstd * g4.y + b4.y;
+        t.z = (t.z - mean) * rstd * g4.z + b4.z;
+        t.w = (t.w - mean) * rstd * g4.w + b4.w;
         *sp = t;
       }
       __syncthreads();
@@ -364,8 +389,8 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
                      "bf16 tensor-core path is built for d_model=128, dim_ff=256, post-norm LayerNorm, gelu (got d=%d ff=%d)", d, ff);
   if (!L->in_proj_w_bf16 || !L->out_proj_w_bf16 || !L->lin1_w_bf16 || !L->lin2_w_bf16)
     return sstb_fail(c, SSTB_ERR_ARG, "bf16 path needs the *_w_bf16 weight copies");
-  if (P->pos_table && P->pos_L % 8 != 0 && P->pos_L * P->pos_ndim != d)  // (no alignment requirement; sanity only)
-    return sstb_fail(c, SSTB_ERR_ARG, "bad positional table");
+  if (P->pos_table && P->pos_L % 8 != 0)
+    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "bf16 path needs the per-axis positional length (%d) to be a multiple of 8", P->pos_L);
   __nv_bfloat16* qkv = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * 3 * d);
   __nv_bfloat16* att = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
   __nv_bfloat16* x1b = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
@@ -394,11 +419,13 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.out_bf16 = qkv;
   g.ldo = 3 * d;
   g.out_row_map = slot_order ? P->tok_slot : nullptr;  // rows land in window (slot) order for the tensor-core attention
-  rc = launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3);
+  // q/k/v for the tensor-core attention are written as fp16 (softmax logits need the mantissa: with bf16 q,k the logit
+  // error dominates the layer's error budget); the SIMT fallback reads bf16.
+  rc = slot_order ? launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3) : launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3);
   if (rc) return rc;
   // 2. ragged window attention (fp32 math on bf16 q/k/v)
   if (slot_order)
-    rc = sstb_win_attn_mma(c, qkv, L->nhead, P->num_windows_dev, P->win_offsets, att);
+    rc = sstb_win_attn_warp(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);

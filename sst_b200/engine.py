@@ -133,13 +133,29 @@ class SSTEngine:
         return self._last, self.vc, self.num
 
     def forward_host(self, pinned_points, offsets_pinned, out_feats_pinned, out_coors_pinned):
-        """End-to-end call on HOST buffers: H2D(points) -> forward -> D2H(num) -> D2H(feats[:M], coors[:M])."""
+        """End-to-end call on HOST buffers: H2D(points) -> forward -> D2H(num) -> D2H(feats[:M], coors[:M]).
+        Returns M; the output copies are stream-ordered (synchronise the engine stream before reading them)."""
+        self.submit_host(pinned_points, offsets_pinned)
+        return self.collect_host(out_feats_pinned, out_coors_pinned)
+
+    def submit_host(self, pinned_points, offsets_pinned):
+        """Asynchronous half of forward_host: enqueue H2D + forward + D2H of the row count; returns immediately, so
+        several engines (streams) can be kept in flight by one host thread."""
         n = pinned_points.shape[0]
+        if not hasattr(self, "_num_pinned"):
+            self._num_pinned = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self._done = torch.cuda.Event()
         with torch.cuda.stream(self.stream):
             self.points[:n].copy_(pinned_points, non_blocking=True)
             self.offsets.copy_(offsets_pinned, non_blocking=True)
-            feats, coors, num = self.run()
-            M = int(num.item())  # one small sync: the row count is data dependent
-            out_feats_pinned[:M].copy_(feats[:M], non_blocking=True)
-            out_coors_pinned[:M].copy_(coors[:M], non_blocking=True)
+            self.run()
+            self._num_pinned.copy_(self.num, non_blocking=True)
+            self._done.record(self.stream)
+
+    def collect_host(self, out_feats_pinned, out_coors_pinned):
+        self._done.synchronize()            # the row count is data dependent: one small wait per frame
+        M = int(self._num_pinned[0])
+        with torch.cuda.stream(self.stream):
+            out_feats_pinned[:M].copy_(self._last[:M], non_blocking=True)
+            out_coors_pinned[:M].copy_(self.vc[:M], non_blocking=True)
         return M
