@@ -4,8 +4,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sstb200.h"
@@ -84,6 +86,61 @@ inline T* arena_alloc(sstb200_ctx* c, size_t n) {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Every kernel of the library starts with pdl_wait() (griddepcontrol.wait: block until the producer grid has completed
+// and its writes are visible) followed by pdl_launch() (griddepcontrol.launch_dependents: allow the next kernel of the
+// stream / graph to be scheduled while this one still runs).  Launches carry the programmatic-stream-serialization
+// attribute, so inside the per-frame CUDA graph consecutive kernels are linked by programmatic edges and the launch
+// latency of kernel N+1 overlaps the execution of kernel N.  SSTB200_PDL=0 disables the attribute (plain launches).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline int sstb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSTB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+// All kernels of the library ask for the same shared-memory carveout (max shared): consecutive kernels with different
+// carveouts force the SMs to drain and re-partition L1/shared between launches, which costs more than any L1 hit here.
+inline int sstb_uniform_carveout() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSTB200_CARVEOUT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static void* seen[32];  // per kernel signature & TU; the attribute is sticky per function -> set once, before any capture
+  static int nseen = 0;
+  if (sstb_uniform_carveout()) {
+    bool found = false;
+    for (int i = 0; i < nseen; i++) found |= (seen[i] == (void*)kern);
+    if (!found) {
+      cudaFuncSetAttribute((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (nseen < 32) seen[nseen++] = (void*)kern;
+    }
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = sstb_pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ---- device helpers ------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -159,6 +216,8 @@ template <typename Load>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_phaseA(Load load, size_t n_host, const int32_t* n_dev,
                                                             uint32_t* block_sums, uint32_t* block_prefix,
                                                             uint32_t* ticket, uint32_t* total_out) {
+  pdl_wait();
+  pdl_launch();
   __shared__ uint32_t sh[9];
   __shared__ bool is_last;
   size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
@@ -203,6 +262,8 @@ template <typename Load>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_phaseB(Load load, size_t n_host, const int32_t* n_dev,
                                                             const uint32_t* block_prefix, uint32_t* out,
                                                             bool write_total_at_n) {
+  pdl_wait();
+  pdl_launch();
   __shared__ uint32_t sh[9];
   size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
   size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
@@ -239,6 +300,6 @@ static inline void launch_exclusive_scan(cudaStream_t st, Load load, size_t n_ca
                                          ScanTemps t, uint32_t* out, uint32_t* total_out, bool write_total_at_n) {
   unsigned nblk = (unsigned)((n_cap + 1 + SCAN_TILE - 1) / SCAN_TILE);
   if (nblk == 0) nblk = 1;
-  scan_phaseA<Load><<<nblk, SCAN_THREADS, 0, st>>>(load, n_cap, n_dev, t.block_sums, t.block_prefix, t.ticket, total_out);
-  scan_phaseB<Load><<<nblk, SCAN_THREADS, 0, st>>>(load, n_cap, n_dev, t.block_prefix, out, write_total_at_n);
+  launch_pdl(scan_phaseA<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)(0), st, load, n_cap, n_dev, t.block_sums, t.block_prefix, t.ticket, total_out);
+  launch_pdl(scan_phaseB<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)(0), st, load, n_cap, n_dev, t.block_prefix, out, write_total_at_n);
 }

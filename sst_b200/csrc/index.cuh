@@ -55,6 +55,8 @@ template <typename TI>
 __global__ void mark_rows_kernel(const TI* __restrict__ rows, int n, Extents e, bool negative_is_invalid,
                                  long long* __restrict__ keys, uint32_t* __restrict__ bitmap,
                                  int32_t* __restrict__ flags, const int32_t* __restrict__ n_dev = nullptr) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -82,6 +84,8 @@ template <typename TO>
 __global__ void emit_rows_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
                                  size_t nwords, Extents e, int shift_if_no_invalid, const int32_t* __restrict__ flags,
                                  TO* __restrict__ out_rows, const uint32_t* __restrict__ total, int32_t* __restrict__ num_out) {
+  pdl_wait();
+  pdl_launch();
   int shift = (shift_if_no_invalid && flags[0] == 0) ? 1 : 0;
   size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0) {
@@ -117,6 +121,8 @@ __global__ void map_count_kernel(const long long* __restrict__ keys, int n, cons
                                  const uint32_t* __restrict__ word_prefix, int shift_if_no_invalid,
                                  const int32_t* __restrict__ flags, TM* __restrict__ map, int32_t* __restrict__ count,
                                  const int32_t* __restrict__ n_dev = nullptr) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -136,6 +142,8 @@ template <typename TM>
 __global__ void csr_fill_kernel(const TM* __restrict__ map, int n, const uint32_t* __restrict__ offsets,
                                 int32_t* __restrict__ cursor, int32_t* __restrict__ order,
                                 const int32_t* __restrict__ n_dev = nullptr) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -153,6 +161,8 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
                                                              const int32_t* __restrict__ nseg_dev, int mode,
                                                              float empty_value, float* __restrict__ out,
                                                              long long* __restrict__ argmax, int n_rows) {
+  pdl_wait();
+  pdl_launch();
   int nseg = nseg_dev ? *nseg_dev : nseg_host;
   int groups_per_block = blockDim.x / GROUP;
   int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
@@ -190,11 +200,11 @@ static void launch_segment_reduce(sstb200_ctx* c, const float* src, int C, const
                                   float empty_value, float* out, long long* argmax, int n_rows) {
   int grid = c->num_sms * 8;
   if (C >= 32)
-    segment_reduce_kernel<32><<<grid, 256, 0, c->stream>>>(src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
+    launch_pdl(segment_reduce_kernel<32>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
   else if (C > 4)
-    segment_reduce_kernel<8><<<grid, 256, 0, c->stream>>>(src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
+    launch_pdl(segment_reduce_kernel<8>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
   else
-    segment_reduce_kernel<4><<<grid, 256, 0, c->stream>>>(src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
+    launch_pdl(segment_reduce_kernel<4>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
 }
 
 // CSR over a map -> (offsets[nseg+1], order[n]) ; count must already hold per-segment counts.
@@ -225,7 +235,7 @@ static int csr_build(sstb200_ctx* c, Csr& r, const TM* map, int n, const int32_t
   CUDA_TRY(c, cudaMemsetAsync(r.st.ticket, 0, 64 * 4, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(r.cursor, 0, (nseg_cap + 2) * 4, c->stream));
   launch_exclusive_scan(c->stream, LoadU32{(const uint32_t*)count}, nseg_cap, nseg_dev, r.st, r.offsets, r.total, true);
-  if (n > 0) csr_fill_kernel<TM><<<(n + 255) / 256, 256, 0, c->stream>>>(map, n, r.offsets, r.cursor, r.order, n_dev);
+  if (n > 0) launch_pdl(csr_fill_kernel<TM>, dim3((n + 255) / 256), dim3(256), (size_t)(0), c->stream, map, n, r.offsets, r.cursor, r.order, n_dev);
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }
@@ -265,6 +275,8 @@ static int make_extents(sstb200_ctx* c, Extents& e, int ndim, const long long* l
 static __global__ void __launch_bounds__(256) stable_rank_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                                           const int32_t* __restrict__ nseg_dev, int32_t* __restrict__ sorted_order,
                                                           long long* __restrict__ rank_out_i64, int32_t* __restrict__ rank_out_i32) {
+  pdl_wait();
+  pdl_launch();
   int nseg = *nseg_dev;
   int warps = (gridDim.x * blockDim.x) >> 5;
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -285,6 +297,8 @@ static __global__ void __launch_bounds__(256) stable_rank_kernel(const uint32_t*
 
 static __global__ void count_index_kernel(const long long* __restrict__ idx, int n, int nseg, int32_t* __restrict__ count,
                                    int32_t* __restrict__ err) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long v = idx[i];

@@ -28,6 +28,8 @@ __device__ __forceinline__ float act_fn(float x, int act) { return act == 2 ? ge
 __global__ void __launch_bounds__(256) sir_rel_gate_kernel(RelDev r, const float* __restrict__ feats /*[N,cin]*/,
                                                            const float* __restrict__ f_cluster /*[N,3]*/, int N,
                                                            float* __restrict__ x0 /*[N,cin]*/) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sw[];  // transposed weights: layer l stored [in_l][out_l]
   float* wl[4];
   {
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256) sir_rel_gate_kernel(RelDev r, const float
 
 // ---- sorted segmented max: rows visited in CSR order, one thread per channel -----------------------------
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -116,6 +120,8 @@ __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
 __global__ void __launch_bounds__(128) segmax_sorted_kernel(const float* __restrict__ src, int C, const int32_t* __restrict__ order,
                                                             const long long* __restrict__ seg_of_row, int N,
                                                             uint32_t* __restrict__ out_ord /*[G, C] order-preserving uint*/) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_row[SEG_ROWS];
   __shared__ int s_seg[SEG_ROWS];
   int k0 = blockIdx.x * SEG_ROWS;
@@ -142,6 +148,8 @@ __global__ void __launch_bounds__(128) segmax_sorted_kernel(const float* __restr
   }
 }
 __global__ void segmax_finalize_kernel(const uint32_t* __restrict__ ord, int G, int C, float* __restrict__ out, int ldo, int col0) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)G * C) return;
   int g = (int)(i / C), c = (int)(i % C);
@@ -151,6 +159,8 @@ __global__ void segmax_finalize_kernel(const uint32_t* __restrict__ ord, int G, 
 
 // with_shortcut (voxel_encoder.py:753-759): point_feats += features[:, 3:] when the shapes agree
 __global__ void shortcut_kernel(float* __restrict__ out, const float* __restrict__ in_feats, int N, int C, int cin) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * C) return;
   int p = (int)(i / C), ch = (int)(i % C);
@@ -185,7 +195,7 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
   float* gterm = arena_alloc<float>(c, (size_t)G * Cmax);
   if (!count || !x0 || !t || !p0 || !gord || !gterm) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)G + 2) * 4, st));
-  count_index_kernel<<<(N + 255) / 256, 256, 0, st>>>((const long long*)inv, N, G, count, count + G + 1);
+  launch_pdl(count_index_kernel, dim3((N + 255) / 256), dim3(256), (size_t)(0), st, (const long long*)inv, N, G, count, count + G + 1);
   Csr r;
   rc = csr_build<long long>(c, r, (const long long*)inv, N, count, G, nullptr);
   if (rc) return rc;
@@ -220,7 +230,7 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
       CUDA_TRY(c, cudaFuncSetAttribute(sir_rel_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_smem = 200 * 1024;
     }
-    sir_rel_gate_kernel<<<c->num_sms * 4, 256, smem, st>>>(rd, in_feats, f_cluster, N, x0);
+    launch_pdl(sir_rel_gate_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(smem), st, rd, in_feats, f_cluster, N, x0);
     xin = x0;
   } else {
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIRLayer without rel-MLP is not built");
@@ -232,9 +242,9 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
   sstb_add_norm_act(st, t, nullptr, L->vfe_ln_w[0], L->vfe_ln_b[0], nullptr, nullptr, L->norm_eps, p0out, N, nullptr, C0, L->act);
   const int Cg = C0 + C1;
   size_t gn = (size_t)G * C0;
-  fill_u32_kernel<<<(unsigned)((gn + 255) / 256), 256, 0, st>>>(gord, gn, 0u);
-  segmax_sorted_kernel<<<(N + SEG_ROWS - 1) / SEG_ROWS, 128, 0, st>>>(p0out, C0, r.order, (const long long*)inv, N, gord);
-  segmax_finalize_kernel<<<(unsigned)((gn + 255) / 256), 256, 0, st>>>(gord, G, C0, out_group, Cg, 0);
+  launch_pdl(fill_u32_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, gn, 0u);
+  launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, p0out, C0, r.order, (const long long*)inv, N, gord);
+  launch_pdl(segmax_finalize_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, G, C0, out_group, Cg, 0);
   if (C1) {
     CHECK_ARG(c, L->vfe_w[1] && L->vfe_ln_w[1] && L->vfe_ln_b[1]);
     // 3. layer 1 on [p0 || g0[group]]:  W1a p0 + (W1b g0)[group]
@@ -244,14 +254,14 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
                       nullptr, 0, 0, 0, 0);
     sstb_add_norm_act(st, t, nullptr, L->vfe_ln_w[1], L->vfe_ln_b[1], nullptr, nullptr, L->norm_eps, out_point, N, nullptr, C1, L->act);
     gn = (size_t)G * C1;
-    fill_u32_kernel<<<(unsigned)((gn + 255) / 256), 256, 0, st>>>(gord, gn, 0u);
-    segmax_sorted_kernel<<<(N + SEG_ROWS - 1) / SEG_ROWS, 128, 0, st>>>(out_point, C1, r.order, (const long long*)inv, N, gord);
-    segmax_finalize_kernel<<<(unsigned)((gn + 255) / 256), 256, 0, st>>>(gord, G, C1, out_group, Cg, C0);
+    launch_pdl(fill_u32_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, gn, 0u);
+    launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, out_point, C1, r.order, (const long long*)inv, N, gord);
+    launch_pdl(segmax_finalize_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, G, C1, out_group, Cg, C0);
   }
   {
     int Cl = C1 ? C1 : C0;
     if (L->with_shortcut && cin - 3 == Cl)
-      shortcut_kernel<<<(unsigned)(((size_t)N * Cl + 255) / 256), 256, 0, st>>>(out_point, in_feats, N, Cl, cin);
+      launch_pdl(shortcut_kernel, dim3((unsigned)(((size_t)N * Cl + 255) / 256)), dim3(256), (size_t)(0), st, out_point, in_feats, N, Cl, cin);
   }
   LAUNCH_CHECK(c);
   return SSTB_OK;

@@ -19,3 +19,6 @@ int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
                         int n_cap, const int32_t* n_dev);
 int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
                         int n_cap, const int32_t* n_dev);
+
+int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const int32_t* row_map, const float* x,
+                        float* y, int n_cap, const int32_t* n_dev);

@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256) win_attn_kernel(const TI* __restrict__ qk
                                                        const int32_t* __restrict__ tok_win, float scale,
                                                        const float* __restrict__ tau, int tau_n, float tau_min,
                                                        TO* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   if (n_dev) n = *n_dev;
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int slot = (int)(g / nhead), h = (int)(g % nhead);
@@ -109,7 +111,7 @@ int sstb_win_attn(sstb200_ctx* c, const TI* qkv, int d, int nhead, int n_cap, co
   float scale = 1.0f / sqrtf((float)dh);
   if (grid == 0) return SSTB_OK;
 #define LAUNCH_ATT(DH)                                                                                                  \
-  win_attn_kernel<TI, TO, DH><<<grid, 256, 0, c->stream>>>(qkv, d, nhead, n_cap, n_dev, win_offsets, tok_perm, tok_win, \
+  launch_pdl(win_attn_kernel<TI, TO, DH>, dim3(grid), dim3(256), (size_t)(0), c->stream, qkv, d, nhead, n_cap, n_dev, win_offsets, tok_perm, tok_win, \
                                                            scale, tau, tau_n, tau_min, out)
   if (dh == 16) LAUNCH_ATT(16);
   else if (dh == 8) LAUNCH_ATT(8);
@@ -156,6 +158,8 @@ static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfl
                                                            const int32_t* __restrict__ nwin_dev,
                                                            const int32_t* __restrict__ win_offsets, float scale,
                                                            __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   constexpr int D = 128, DH = 16, KT = ATT_MAXT / 8;
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
@@ -276,7 +280,7 @@ static inline int sstb_win_attn_mma(sstb200_ctx* c, const __nv_bfloat16* qkv, in
     CUDA_TRY(c, cudaFuncSetAttribute(win_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  win_attn_mma_kernel<<<c->num_sms * 2, 256, smem, c->stream>>>(qkv, nhead, nwin_dev, win_offsets, 0.25f, out);
+  launch_pdl(win_attn_mma_kernel, dim3(c->num_sms * 2), dim3(256), (size_t)(smem), c->stream, qkv, nhead, nwin_dev, win_offsets, 0.25f, out);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }
@@ -288,11 +292,125 @@ static inline int sstb_win_attn_mma(sstb200_ctx* c, const __nv_bfloat16* qkv, in
 // per-SM residency is bounded by registers only, which is what this latency-bound kernel needs.
 // Softmax is two-pass over S (QK^T is recomputed in pass 2 - tensor-core work is free here, registers are not).
 // ------------------------------------------------------------------------------------------------
+// one (window, head) unit with at most KT*8 keys; everything indexed by KT is fully unrolled, so small windows run a
+// short instruction stream (the K/V fragment prologue is ~6x shorter for KT=4 than for KT=18)
+template <int KT>
+__device__ __forceinline__ void attn_unit(const __half* __restrict__ base, int kb, int n, int h, float scale,
+                                          __nv_bfloat16* __restrict__ out, int g4, int t4) {
+  constexpr int D = 128, DH = 16;
+  const int nkt = (n + 7) >> 3;
+  uint32_t kf[KT][2];
+#pragma unroll
+  for (int j = 0; j < KT; j++) {
+    kf[j][0] = kf[j][1] = 0u;
+    int key = 8 * j + g4;
+    if (key < n) {
+      const uint32_t* kp = reinterpret_cast<const uint32_t*>(base + (size_t)key * 3 * D + D);
+      kf[j][0] = kp[t4];
+      kf[j][1] = kp[t4 + 4];
+    }
+  }
+  uint32_t vf[(KT + 1) / 2][4];
+#pragma unroll
+  for (int kc = 0; kc < (KT + 1) / 2; kc++) {
+    const unsigned short* vp = reinterpret_cast<const unsigned short*>(base + 2 * D);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int k0 = kc * 16 + 2 * t4 + (q & 1) * 8, dim = g4 + (q >> 1) * 8;
+      unsigned lo = k0 < n ? vp[(size_t)k0 * 3 * D + dim] : 0;
+      unsigned hi = k0 + 1 < n ? vp[(size_t)(k0 + 1) * 3 * D + dim] : 0;
+      vf[kc][q] = lo | (hi << 16);
+    }
+  }
+  const int ntile = (n + 15) >> 4;
+  for (int qt = 0; qt < ntile; qt++) {
+    const int r0 = qt * 16 + g4, r1 = r0 + 8;
+    uint32_t qa[4] = {0u, 0u, 0u, 0u};
+    if (r0 < n) {
+      const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 3 * D);
+      qa[0] = qp[t4];
+      qa[2] = qp[t4 + 4];
+    }
+    if (r1 < n) {
+      const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 3 * D);
+      qa[1] = qp[t4];
+      qa[3] = qp[t4 + 4];
+    }
+    // pass 1: row maxima
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+      if (j < nkt) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16_16816(s, qa, kf[j][0], kf[j][1]);
+        const int c0 = j * 8 + 2 * t4;
+        if (c0 < n) {
+          m0 = fmaxf(m0, s[0]);
+          m1 = fmaxf(m1, s[2]);
+        }
+        if (c0 + 1 < n) {
+          m0 = fmaxf(m0, s[1]);
+          m1 = fmaxf(m1, s[3]);
+        }
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float ms0 = m0 * scale, ms1 = m1 * scale;  // scale > 0: max commutes with the scaling
+    // pass 2: P = exp(scale*S - max), O += P V
+    float l0 = 0.f, l1 = 0.f;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kc = 0; kc < (KT + 1) / 2; kc++) {
+      if (kc * 16 < n) {
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16_16816(sa, qa, kf[2 * kc][0], kf[2 * kc][1]);
+        if (2 * kc + 1 < KT) mma_f16_16816(sb, qa, kf[(2 * kc + 1 < KT) ? 2 * kc + 1 : 0][0], kf[(2 * kc + 1 < KT) ? 2 * kc + 1 : 0][1]);
+        const int c0 = kc * 16 + 2 * t4;
+        float p[8];
+        p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
+        p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
+        p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
+        p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
+        p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
+        p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
+        p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
+        p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
+        l0 += (p[0] + p[1]) + (p[4] + p[5]);
+        l1 += (p[2] + p[3]) + (p[6] + p[7]);
+        uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
+        mma_f16_16816(o[0], pa, vf[kc][0], vf[kc][1]);
+        mma_f16_16816(o[1], pa, vf[kc][2], vf[kc][3]);
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (r0 < n) {
+      const float i0 = 1.0f / l0;
+      uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r0) * D + h * DH);
+      op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
+      op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
+    }
+    if (r1 < n) {
+      const float i1 = 1.0f / l1;
+      uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r1) * D + h * DH);
+      op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
+      op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
+    }
+  }
+}
+
 static __global__ void __launch_bounds__(128) win_attn_warp_kernel(const __half* __restrict__ qkv,
                                                                    const int32_t* __restrict__ nwin_dev,
                                                                    const int32_t* __restrict__ win_offsets, float scale,
                                                                    __nv_bfloat16* __restrict__ out) {
-  constexpr int D = 128, DH = 16, NH = 8, KT = ATT_MAXT / 8;
+  pdl_wait();
+  pdl_launch();
+  constexpr int D = 128, DH = 16, NH = 8;
   const int R = *nwin_dev;
   const int lane = threadIdx.x & 31;
   const int g4 = lane >> 2, t4 = lane & 3;
@@ -301,124 +419,17 @@ static __global__ void __launch_bounds__(128) win_attn_warp_kernel(const __half*
     const int w = u / NH, h = u % NH;
     const int kb = win_offsets[w];
     const int n = min(win_offsets[w + 1] - kb, ATT_MAXT);
-    const int nkt = (n + 7) >> 3;
     const __half* base = qkv + (size_t)kb * 3 * D + h * DH;
-    // K fragments: B[k = dim][n = key]  -> lane holds K[key = 8j+g4][dims 2*t4, 2*t4+1] and [+8, +9]
-    uint32_t kf[KT][2];
-#pragma unroll
-    for (int j = 0; j < KT; j++) {
-      kf[j][0] = kf[j][1] = 0u;
-      int key = 8 * j + g4;
-      if (j < nkt && key < n) {
-        const uint32_t* kp = reinterpret_cast<const uint32_t*>(base + (size_t)key * 3 * D + D);
-        kf[j][0] = kp[t4];
-        kf[j][1] = kp[t4 + 4];
-      }
-    }
-    // V^T fragments: B[k = key][n = dim] -> lane holds {V[2*t4][g4], V[2*t4+1][g4]}, keys +8, dims +8
-    uint32_t vf[KT / 2][4];
-#pragma unroll
-    for (int kc = 0; kc < KT / 2; kc++) {
-#pragma unroll
-      for (int q = 0; q < 4; q++) vf[kc][q] = 0u;
-      if (kc * 16 < n) {
-        const unsigned short* vp = reinterpret_cast<const unsigned short*>(base + 2 * D);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          int k0 = kc * 16 + 2 * t4 + (q & 1) * 8, dim = g4 + (q >> 1) * 8;
-          unsigned lo = k0 < n ? vp[(size_t)k0 * 3 * D + dim] : 0;
-          unsigned hi = k0 + 1 < n ? vp[(size_t)(k0 + 1) * 3 * D + dim] : 0;
-          vf[kc][q] = lo | (hi << 16);
-        }
-      }
-    }
-    const int ntile = (n + 15) >> 4;
-    for (int qt = 0; qt < ntile; qt++) {
-      const int r0 = qt * 16 + g4, r1 = r0 + 8;
-      uint32_t qa[4] = {0u, 0u, 0u, 0u};
-      if (r0 < n) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 3 * D);
-        qa[0] = qp[t4];
-        qa[2] = qp[t4 + 4];
-      }
-      if (r1 < n) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 3 * D);
-        qa[1] = qp[t4];
-        qa[3] = qp[t4 + 4];
-      }
-      // pass 1: row maxima
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < KT; j++) {
-        if (j < nkt) {
-          float s[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_f16_16816(s, qa, kf[j][0], kf[j][1]);
-          const int c0 = j * 8 + 2 * t4;
-          if (c0 < n) {
-            m0 = fmaxf(m0, s[0]);
-            m1 = fmaxf(m1, s[2]);
-          }
-          if (c0 + 1 < n) {
-            m0 = fmaxf(m0, s[1]);
-            m1 = fmaxf(m1, s[3]);
-          }
-        }
-      }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      const float ms0 = m0 * scale, ms1 = m1 * scale;  // scale > 0: max commutes with the scaling
-      // pass 2: P = exp(scale*S - max), O += P V
-      float l0 = 0.f, l1 = 0.f;
-      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int kc = 0; kc < KT / 2; kc++) {
-        if (kc * 16 < n) {
-          float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_f16_16816(sa, qa, kf[2 * kc][0], kf[2 * kc][1]);
-          mma_f16_16816(sb, qa, kf[2 * kc + 1][0], kf[2 * kc + 1][1]);
-          const int c0 = kc * 16 + 2 * t4;
-          float p[8];
-          p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
-          p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
-          p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
-          p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
-          p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
-          p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
-          p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
-          p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
-          l0 += (p[0] + p[1]) + (p[4] + p[5]);
-          l1 += (p[2] + p[3]) + (p[6] + p[7]);
-          uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
-          mma_f16_16816(o[0], pa, vf[kc][0], vf[kc][1]);
-          mma_f16_16816(o[1], pa, vf[kc][2], vf[kc][3]);
-        }
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      if (r0 < n) {
-        const float i0 = 1.0f / l0;
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r0) * D + h * DH);
-        op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
-        op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
-      }
-      if (r1 < n) {
-        const float i1 = 1.0f / l1;
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r1) * D + h * DH);
-        op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
-        op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
-      }
-    }
+    if (n <= 32) attn_unit<4>(base, kb, n, h, scale, out, g4, t4);
+    else if (n <= 64) attn_unit<8>(base, kb, n, h, scale, out, g4, t4);
+    else attn_unit<ATT_MAXT / 8>(base, kb, n, h, scale, out, g4, t4);
   }
 }
 
 static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const int32_t* nwin_dev, const int32_t* win_offsets,
                                      __nv_bfloat16* out) {
   // 128 threads (4 warps) per CTA; ~120 registers -> 4 CTAs (16 warps) per SM
-  win_attn_warp_kernel<<<c->num_sms * 4, 128, 0, c->stream>>>(qkv, nwin_dev, win_offsets, 0.25f, out);
+  launch_pdl(win_attn_warp_kernel, dim3(c->num_sms * 4), dim3(128), (size_t)(0), c->stream, qkv, nwin_dev, win_offsets, 0.25f, out);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }

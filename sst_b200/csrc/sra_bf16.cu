@@ -68,6 +68,8 @@ constexpr int TILE_M = 128;
 // segment: thread-per-row TMEM reads meet warp-per-row global traffic in an XOR-swizzled staging tile.
 template <int K, int NT, int PRO, int EPI>
 __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                           // K/64 chunks x 128 rows x 128 B
@@ -373,7 +375,7 @@ int launch_umma(sstb200_ctx* c, const GemmArgs& g, int n_tiles_y) {
   if (per_sm > 512 / NT) per_sm = 512 / NT;   // TMEM columns
   int grid = c->num_sms * per_sm;
   if (grid > items_cap) grid = items_cap;
-  kern<<<grid, 256, smem, c->stream>>>(ga);
+  launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem), c->stream, ga);
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }
@@ -430,7 +432,16 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
   if (rc) return rc;
-  // 3. out-projection + residual + LayerNorm1
+  // 3-5 fused: out-projection + LN1 + FFN1 + GELU + FFN2 + LN2 in one persistent tcgen05 kernel (csrc/sra_chain.cu)
+  {
+    static int use_chain = -1;
+    if (use_chain < 0) {
+      const char* e = getenv("SSTB200_CHAIN");
+      use_chain = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_chain) return sstb_sra_chain_bf16(c, L, att, slot_order ? P->tok_perm : nullptr, x, y, n_cap, n_dev);
+  }
+  // 3. out-projection + residual + LayerNorm1 (unfused reference path, SSTB200_CHAIN=0)
   memset(&g, 0, sizeof(g));
   g.M_cap = n_cap;
   g.M_dev = n_dev;

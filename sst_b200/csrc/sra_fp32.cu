@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(const float* __restrict_
                                                         float* __restrict__ out, int ldo, int M, const int32_t* __restrict__ M_dev,
                                                         int N, int K, PosTab pos, int pos_ncols, int ldw,
                                                         const long long* __restrict__ res_index) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float As[GBK][GBM + 4];
   __shared__ float Bs[GBK][GBN + 4];
   if (M_dev) M = *M_dev;
@@ -107,11 +109,11 @@ void sstb_gemm_rows_ex(cudaStream_t st, const float* A, int lda, const float* W,
   dim3 grid((M_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
   PosTab p{pos_tab, pos_code, posL, pos_maxw, pos_ndim};
   if (act == 0)
-    gemm_rows_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
+    launch_pdl(gemm_rows_kernel<0>, dim3(grid), dim3(256), (size_t)(0), st, A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
   else if (act == 1)
-    gemm_rows_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
+    launch_pdl(gemm_rows_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
   else
-    gemm_rows_kernel<2><<<grid, 256, 0, st>>>(A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
+    launch_pdl(gemm_rows_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, A, lda, W, bias, res, ldr, out, ldo, M_cap, M_dev, N, K, p, pos_ncols, ldw, res_index);
 }
 void sstb_gemm_rows(cudaStream_t st, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr,
                     float* out, int ldo, int M_cap, const int32_t* M_dev, int N, int K, int act, const float* pos_tab,
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(256) add_norm_kernel(const float* __restrict__
                                                        const float* __restrict__ bn_mean, const float* __restrict__ bn_var,
                                                        float eps, float* __restrict__ out, int n, const int32_t* __restrict__ n_dev, int d,
                                                        int act) {
+  pdl_wait();
+  pdl_launch();
   if (n_dev) n = *n_dev;
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
@@ -175,7 +179,7 @@ void sstb_add_norm_act(cudaStream_t st, const float* a, const float* b, const fl
                        const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d, int act) {
   if (n_cap <= 0) return;
   unsigned grid = (unsigned)(((size_t)n_cap * 32 + 255) / 256);
-  add_norm_kernel<<<grid, 256, 0, st>>>(a, b, gamma, beta, bn_mean, bn_var, eps, out, n_cap, n_dev, d, act);
+  launch_pdl(add_norm_kernel, dim3(grid), dim3(256), (size_t)(0), st, a, b, gamma, beta, bn_mean, bn_var, eps, out, n_cap, n_dev, d, act);
 }
 void sstb_add_norm(cudaStream_t st, const float* a, const float* b, const float* gamma, const float* beta,
                    const float* bn_mean, const float* bn_var, float eps, float* out, int n_cap, const int32_t* n_dev, int d) {

@@ -22,6 +22,8 @@ struct VfeDev {
 // fold eval BatchNorm into scale/shift
 __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, int C, float* __restrict__ s, float* __restrict__ t) {
+  pdl_wait();
+  pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   // F.batch_norm: (x - mean) / sqrt(var + eps) * w + b
@@ -54,6 +56,8 @@ __device__ __forceinline__ long long quirk_row(const SampleQuirk& q, long long r
 template <typename TC>
 __global__ void vfe_mark_kernel(const TC* __restrict__ coors, int P, int B, int Z, int Y, int X, size_t cells_pad,
                                 long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   long long b = (long long)coors[(size_t)i * 4], z = (long long)coors[(size_t)i * 4 + 1], y = (long long)coors[(size_t)i * 4 + 2],
@@ -72,6 +76,8 @@ template <typename TM>
 __global__ void vfe_map_kernel(const long long* __restrict__ keys, int P, const uint32_t* __restrict__ bitmap,
                                const uint32_t* __restrict__ word_prefix, size_t cells_pad, SampleQuirk q,
                                TM* __restrict__ map, int32_t* __restrict__ count) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   long long key = keys[i];
@@ -89,6 +95,8 @@ template <typename TO>
 __global__ void vfe_emit_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, size_t nwords,
                                 size_t cells_pad, int Y, int X, SampleQuirk q, TO* __restrict__ out_coors,
                                 const uint32_t* __restrict__ total, int32_t* __restrict__ num_out) {
+  pdl_wait();
+  pdl_launch();
   size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0) {
     long long t = *total;
@@ -156,6 +164,8 @@ __global__ void __launch_bounds__(256) vfe_fused_kernel(VfeDev v, const float* _
                                                         const int32_t* __restrict__ nvox_dev, float* __restrict__ vmean /*[M,3] scratch*/,
                                                         float* __restrict__ vf0 /*[M,C0] scratch*/, float* __restrict__ out /*[M,Cout]*/,
                                                         int phase) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int C0 = NC0 * 32, C1 = NC1 * 32, D0 = v.D0;
   float* W0t = sm;
@@ -311,6 +321,8 @@ __global__ void __launch_bounds__(256) vfe_fused_kernel(VfeDev v, const float* _
 __global__ void vfe_mean_kernel(const float* __restrict__ pts, int F, const uint32_t* __restrict__ offsets,
                                 const int32_t* __restrict__ order, const int32_t* __restrict__ nvox_dev,
                                 float* __restrict__ vmean) {
+  pdl_wait();
+  pdl_launch();
   int M = *nvox_dev;
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, l = threadIdx.x & 3;
   int ng = (gridDim.x * blockDim.x) >> 2;
@@ -396,6 +408,8 @@ __global__ void __launch_bounds__(256) vfe_l0_tile_kernel(VfeDev v, const float*
                                                           const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                                           const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
                                                           const float* __restrict__ vmean, float* __restrict__ vf0) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float sF[VT][VFE_MAXD];
   __shared__ int sVox[VT];
   __shared__ float sW[VFE_MAXD][C0];  // W0 transposed
@@ -436,6 +450,8 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
                                                           const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
                                                           const float* __restrict__ vmean, const float* __restrict__ vf0,
                                                           float* __restrict__ vf1) {
+  pdl_wait();
+  pdl_launch();
   constexpr int K = 2 * C0;
   static_assert(K % 64 == 0 && C1 % 16 == 0 && C1 <= 256, "shape");
   extern __shared__ uint8_t l1_smem_raw[];
@@ -562,6 +578,8 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
 template <typename TM>
 __global__ void vfe_zero_edges_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                       const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev, int C, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   const int M = *nvox_dev;
   const int nvalid = M > 0 ? (int)offsets[M] : 0;
   for (int t = blockIdx.x; t * VT < nvalid; t += gridDim.x) {
@@ -579,11 +597,11 @@ static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, c
                             const int32_t* num_dev, float* vmean, float* vf0, float* out, bool umma_l1, bool* l1_done) {
   cudaStream_t st = c->stream;
   int grid = c->num_sms * 3;
-  vfe_mean_kernel<<<c->num_sms * 8, 256, 0, st>>>(pts, v.F, r.offsets, r.order, num_dev, vmean);
+  launch_pdl(vfe_mean_kernel, dim3(c->num_sms * 8), dim3(256), (size_t)(0), st, pts, v.F, r.offsets, r.order, num_dev, vmean);
   float* dst0 = (C1 > 0) ? vf0 : out;
-  vfe_zero_edges_kernel<TM><<<c->num_sms * 2, 64, 0, st>>>(r.offsets, r.order, map, num_dev, C0, dst0);
+  launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 2), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C0, dst0);
   size_t smem0 = (size_t)VT * (C0 + 1) * 4;
-  vfe_l0_tile_kernel<TC, TM, C0><<<grid, 256, smem0, st>>>(v, pts, coors, r.offsets, r.order, map, num_dev, vmean, dst0);
+  launch_pdl(vfe_l0_tile_kernel<TC, TM, C0>, dim3(grid), dim3(256), (size_t)(smem0), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, dst0);
   *l1_done = false;
   if (C1 > 0 && umma_l1) {
     constexpr int C1s = C1 > 0 ? C1 : 32;
@@ -595,8 +613,8 @@ static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, c
       CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       attr_set = true;
     }
-    vfe_zero_edges_kernel<TM><<<c->num_sms * 2, 64, 0, st>>>(r.offsets, r.order, map, num_dev, C1s, out);
-    kern<<<grid, 256, smem1, st>>>(v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out);
+    launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 2), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C1s, out);
+    launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem1), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out);
     *l1_done = true;
   }
   LAUNCH_CHECK(c);
@@ -616,8 +634,8 @@ static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const T
     attr_set = true;
   }
   int grid = c->num_sms * 2;
-  if (!skip_phase0) kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
-  if (NC1 > 0) kern<<<grid, 256, smem, c->stream>>>(v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 1);
+  if (!skip_phase0) launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem), c->stream, v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
+  if (NC1 > 0) launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem), c->stream, v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 1);
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }
@@ -660,18 +678,18 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   if (!count || !vmean || !vf0 || !fold) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)P + 2) * 4, c->stream));
   int nb = (P + 255) / 256;
-  vfe_mark_kernel<TC><<<nb, 256, 0, c->stream>>>(coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
+  launch_pdl(vfe_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
   key_index_scan(c, k);
   SampleQuirk q{k.word_prefix, cells_pad / 32, B, cfg->drop_first_voxel_per_sample != 0};
   int eg = (int)((k.nwords + 255) / 256);
   if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  vfe_emit_kernel<TC><<<eg, 256, 0, c->stream>>>(k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
+  launch_pdl(vfe_emit_kernel<TC>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
   Csr r;
   if (inverse) {
-    vfe_map_kernel<TC><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, inverse, count);
+    launch_pdl(vfe_map_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, inverse, count);
     rc = csr_build<TC>(c, r, inverse, P, count, P, num_dev);
   } else {
-    vfe_map_kernel<int32_t><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, map32, count);
+    launch_pdl(vfe_map_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, map32, count);
     rc = csr_build<int32_t>(c, r, map32, P, count, P, num_dev);
   }
   if (rc) return rc;
@@ -698,10 +716,10 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   v.t0 = fold + C0;
   v.s1 = fold + 2 * C0;
   v.t1 = fold + 2 * C0 + C1;
-  fold_bn_kernel<<<(C0 + 127) / 128, 128, 0, c->stream>>>(cfg->bn_weight[0], cfg->bn_bias[0], cfg->bn_mean[0], cfg->bn_var[0],
+  launch_pdl(fold_bn_kernel, dim3((C0 + 127) / 128), dim3(128), (size_t)(0), c->stream, cfg->bn_weight[0], cfg->bn_bias[0], cfg->bn_mean[0], cfg->bn_var[0],
                                                            cfg->bn_eps, C0, fold, fold + C0);
   if (C1)
-    fold_bn_kernel<<<(C1 + 127) / 128, 128, 0, c->stream>>>(cfg->bn_weight[1], cfg->bn_bias[1], cfg->bn_mean[1], cfg->bn_var[1],
+    launch_pdl(fold_bn_kernel, dim3((C1 + 127) / 128), dim3(128), (size_t)(0), c->stream, cfg->bn_weight[1], cfg->bn_bias[1], cfg->bn_mean[1], cfg->bn_var[1],
                                                              cfg->bn_eps, C1, fold + 2 * C0, fold + 2 * C0 + C1);
   LAUNCH_CHECK(c);
   {

@@ -17,6 +17,8 @@
 // ------------------------------------------------------------------------------------------------
 __global__ void dynamic_voxelize_kernel(const float* __restrict__ points, int P, int F, float vx, float vy, float vz,
                                         float x0, float y0, float z0, int gx, int gy, int gz, int32_t* __restrict__ coors) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const float* p = points + (size_t)i * F;
@@ -43,7 +45,7 @@ extern "C" int sstb200_dynamic_voxelize(sstb200_ctx* c, const float* points, int
   if (P == 0) return SSTB_OK;
   int g[3];
   sstb_grid_size(vs, r, g);
-  dynamic_voxelize_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(points, P, F, vs[0], vs[1], vs[2], r[0], r[1], r[2],
+  launch_pdl(dynamic_voxelize_kernel, dim3((P + 255) / 256), dim3(256), (size_t)(0), c->stream, points, P, F, vs[0], vs[1], vs[2], r[0], r[1], r[2],
                                                                    g[0], g[1], g[2], coors);
   LAUNCH_CHECK(c);
   return SSTB_OK;
@@ -56,6 +58,8 @@ extern "C" int sstb200_dynamic_voxelize(sstb200_ctx* c, const float* points, int
 __global__ void voxelize_frames_kernel(const float* __restrict__ points, int cap, int F, const int32_t* __restrict__ offs, int B,
                                        float vx, float vy, float vz, float x0, float y0, float z0, int gx, int gy, int gz,
                                        int32_t* __restrict__ coors4) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   int4 o = make_int4(-1, -1, -1, -1);
@@ -81,7 +85,7 @@ extern "C" int sstb200_voxelize_frames(sstb200_ctx* c, const float* points, int 
   CHECK_ARG(c, points && coors4);
   int g[3];
   sstb_grid_size(vs, r, g);
-  voxelize_frames_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(points, cap, F, offs, B, vs[0], vs[1], vs[2], r[0], r[1], r[2],
+  launch_pdl(voxelize_frames_kernel, dim3((cap + 255) / 256), dim3(256), (size_t)(0), c->stream, points, cap, F, offs, B, vs[0], vs[1], vs[2], r[0], r[1], r[2],
                                                                     g[0], g[1], g[2], coors4);
   LAUNCH_CHECK(c);
   return SSTB_OK;
@@ -118,12 +122,12 @@ extern "C" int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* c, const floa
   if (rc) return rc;
   CUDA_TRY(c, cudaMemsetAsync(reduce_count, 0, (size_t)P * 4, c->stream));
   int nb = (P + 255) / 256;
-  mark_rows_kernel<int32_t><<<nb, 256, 0, c->stream>>>(coors, P, e, true, k.keys, k.bitmap, k.flags);
+  launch_pdl(mark_rows_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, e, true, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
   int eg = (int)((k.nwords + 255) / 256);
   if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  emit_rows_kernel<int32_t><<<eg, 256, 0, c->stream>>>(k.bitmap, k.word_prefix, k.nwords, e, 1, k.flags, out_coors, k.total, num_dev);
-  map_count_kernel<int32_t><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, 1, k.flags, coors_map, reduce_count);
+  launch_pdl(emit_rows_kernel<int32_t>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, e, 1, k.flags, out_coors, k.total, num_dev);
+  launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 1, k.flags, coors_map, reduce_count, nullptr);
   LAUNCH_CHECK(c);
   Csr r;
   rc = csr_build<int32_t>(c, r, coors_map, P, reduce_count, P, num_dev);
@@ -140,6 +144,8 @@ extern "C" int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* c, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void dp2v_bwd_add_kernel(float* __restrict__ g, const float* __restrict__ gr, const int32_t* __restrict__ map,
                                     const int32_t* __restrict__ cnt, int P, int C, int mean) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)P * C) return;
   int p = (int)(i / C), ch = (int)(i % C);
@@ -154,6 +160,8 @@ __global__ void dp2v_bwd_add_kernel(float* __restrict__ g, const float* __restri
 // max: gradient goes to the LOWEST point index attaining the max (scatter_points_cuda.cu:150-152)
 __global__ void dp2v_bwd_argmin_kernel(const float* __restrict__ feats, const float* __restrict__ red,
                                        const int32_t* __restrict__ map, int P, int C, int32_t* __restrict__ from) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)P * C) return;
   int p = (int)(i / C), ch = (int)(i % C);
@@ -163,6 +171,8 @@ __global__ void dp2v_bwd_argmin_kernel(const float* __restrict__ feats, const fl
 }
 __global__ void dp2v_bwd_scatter_kernel(float* __restrict__ g, const float* __restrict__ gr,
                                         const int32_t* __restrict__ from, int M, int C, int P) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)M * C) return;
   int ch = (int)(i % C);
@@ -170,6 +180,8 @@ __global__ void dp2v_bwd_scatter_kernel(float* __restrict__ g, const float* __re
   if (p < P) g[(size_t)p * C + ch] = gr[i];
 }
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+  pdl_wait();
+  pdl_launch();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -189,7 +201,7 @@ extern "C" int sstb200_dynamic_point_to_voxel_backward(sstb200_ctx* c, float* gr
   CHECK_ARG(c, grad_reduced && feats && reduced && coors_map && reduce_count);
   unsigned nb = (unsigned)((n + 255) / 256);
   if (reduce_type != SSTB200_REDUCE_MAX) {
-    dp2v_bwd_add_kernel<<<nb, 256, 0, c->stream>>>(grad_feats, grad_reduced, coors_map, reduce_count, P, C,
+    launch_pdl(dp2v_bwd_add_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, grad_feats, grad_reduced, coors_map, reduce_count, P, C,
                                                    reduce_type == SSTB200_REDUCE_MEAN);
   } else {
     arena_reset(c);
@@ -198,10 +210,10 @@ extern "C" int sstb200_dynamic_point_to_voxel_backward(sstb200_ctx* c, float* gr
     int32_t* from = arena_alloc<int32_t>(c, (size_t)M * C);
     size_t m = (size_t)M * C;
     unsigned mb = (unsigned)((m + 255) / 256);
-    fill_i32_kernel<<<mb, 256, 0, c->stream>>>(from, m, P);
+    launch_pdl(fill_i32_kernel, dim3(mb), dim3(256), (size_t)(0), c->stream, from, m, P);
     CUDA_TRY(c, cudaMemsetAsync(grad_feats, 0, n * 4, c->stream));
-    dp2v_bwd_argmin_kernel<<<nb, 256, 0, c->stream>>>(feats, reduced, coors_map, P, C, from);
-    dp2v_bwd_scatter_kernel<<<mb, 256, 0, c->stream>>>(grad_feats, grad_reduced, from, M, C, P);
+    launch_pdl(dp2v_bwd_argmin_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, feats, reduced, coors_map, P, C, from);
+    launch_pdl(dp2v_bwd_scatter_kernel, dim3(mb), dim3(256), (size_t)(0), c->stream, grad_feats, grad_reduced, from, M, C, P);
   }
   LAUNCH_CHECK(c);
   return SSTB_OK;
@@ -232,14 +244,14 @@ extern "C" int sstb200_unique_rows_i64(sstb200_ctx* c, const int64_t* coors, int
   if (rc) return rc;
   if (counts) CUDA_TRY(c, cudaMemsetAsync(counts, 0, (size_t)P * 4, c->stream));
   int nb = (P + 255) / 256;
-  mark_rows_kernel<long long><<<nb, 256, 0, c->stream>>>((const long long*)coors, P, e, false, k.keys, k.bitmap, k.flags);
+  launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)coors, P, e, false, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
   int eg = (int)((k.nwords + 255) / 256);
   if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  emit_rows_kernel<long long><<<eg, 256, 0, c->stream>>>(k.bitmap, k.word_prefix, k.nwords, e, 0, k.flags,
+  launch_pdl(emit_rows_kernel<long long>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, e, 0, k.flags,
                                                          (long long*)new_coors, k.total, num_dev);
-  map_count_kernel<long long><<<nb, 256, 0, c->stream>>>(k.keys, P, k.bitmap, k.word_prefix, 0, k.flags,
-                                                         (long long*)inverse, counts);
+  launch_pdl(map_count_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 0, k.flags,
+                                                         (long long*)inverse, counts, nullptr);
   LAUNCH_CHECK(c);
   if (num_host) return read_back_i32(c, num_dev, num_host);
   return SSTB_OK;
@@ -258,7 +270,7 @@ extern "C" int sstb200_segment_reduce(sstb200_ctx* c, const float* src, const in
   if (rc) return rc;
   int32_t* count = arena_alloc<int32_t>(c, (size_t)nseg + 2);
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)nseg + 2) * 4, c->stream));
-  if (P > 0) count_index_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>((const long long*)index, P, nseg, count, count + nseg + 1);
+  if (P > 0) launch_pdl(count_index_kernel, dim3((P + 255) / 256), dim3(256), (size_t)(0), c->stream, (const long long*)index, P, nseg, count, count + nseg + 1);
   Csr r;
   rc = csr_build<long long>(c, r, (const long long*)index, P, count, nseg, nullptr);
   if (rc) return rc;
@@ -290,14 +302,14 @@ extern "C" int sstb200_ingroup_indices(sstb200_ctx* c, const int64_t* group, int
   int32_t* ng = (int32_t*)(k.st.ticket + 8);
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)N + 2) * 4, c->stream));
   int nb = (N + 255) / 256;
-  mark_rows_kernel<long long><<<nb, 256, 0, c->stream>>>((const long long*)group, N, e, false, k.keys, k.bitmap, k.flags);
+  launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)group, N, e, false, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
-  map_count_kernel<int32_t><<<nb, 256, 0, c->stream>>>(k.keys, N, k.bitmap, k.word_prefix, 0, k.flags, cid, count);
+  launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, N, k.bitmap, k.word_prefix, 0, k.flags, cid, count, nullptr);
   CUDA_TRY(c, cudaMemcpyAsync(ng, k.total, 4, cudaMemcpyDeviceToDevice, c->stream));
   Csr r;
   rc = csr_build<int32_t>(c, r, cid, N, count, N, ng);
   if (rc) return rc;
-  stable_rank_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(r.offsets, r.order, ng, nullptr, (long long*)out, nullptr);
+  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, ng, nullptr, (long long*)out, nullptr);
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }

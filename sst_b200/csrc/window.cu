@@ -44,6 +44,8 @@ __global__ void win_mark_kernel(const TC* __restrict__ coors, int n, const int32
                                 long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags,
                                 long long* __restrict__ batch_win_inds, long long* __restrict__ coors_in_win,
                                 int32_t* __restrict__ pos_code) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -83,6 +85,8 @@ __global__ void __launch_bounds__(1024) win_level_kernel(const uint32_t* __restr
                                                          const long long* __restrict__ token_level,
                                                          int32_t* __restrict__ win_level, int32_t* __restrict__ win_rank,
                                                          int32_t* __restrict__ counters /*[1+8+8]*/, int32_t* __restrict__ flags) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int sh[8][1024 + 1];
   int R = *nwin_dev;
   int per = (R + blockDim.x - 1) / blockDim.x;
@@ -160,6 +164,8 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
                                   const int32_t* __restrict__ win_rank, LevelCfg lv, long long* __restrict__ drop_level,
                                   long long* __restrict__ flat2win, const uint32_t* __restrict__ offsets,
                                   int32_t* __restrict__ tok_slot) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = *n_dev;
   if (i >= n) return;
@@ -177,6 +183,8 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
 }
 
 __global__ void zero_counters_kernel(int32_t* c) {
+  pdl_wait();
+  pdl_launch();
   if (threadIdx.x < 17) c[threadIdx.x] = 0;
 }
 
@@ -197,7 +205,7 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
     lv.hi[l] = l < lv.n ? cfg->level_hi[l] : 0;
     lv.maxtok[l] = l < lv.n ? cfg->level_max_tokens[l] : 0;
   }
-  zero_counters_kernel<<<1, 32, 0, c->stream>>>(o->counters);
+  launch_pdl(zero_counters_kernel, dim3(1), dim3(32), (size_t)(0), c->stream, o->counters);
   if (n == 0) {
     LAUNCH_CHECK(c);
     return SSTB_OK;
@@ -216,20 +224,20 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   if (!count) return sstb_fail(c, SSTB_ERR_WORKSPACE, "window plan: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, (nwcap + 2) * 4, c->stream));
   int nb = (n + 255) / 256;
-  win_mark_kernel<TC><<<nb, 256, 0, c->stream>>>(coors, n, n_dev, g, k.keys, k.bitmap, k.flags, (long long*)o->batch_win_inds,
+  launch_pdl(win_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, n, n_dev, g, k.keys, k.bitmap, k.flags, (long long*)o->batch_win_inds,
                                                  (long long*)o->coors_in_win, o->pos_code);
   key_index_scan(c, k);
-  map_count_kernel<int32_t><<<nb, 256, 0, c->stream>>>(k.keys, n, k.bitmap, k.word_prefix, 0, k.flags, o->tok_win, count, n_dev);
+  launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, n, k.bitmap, k.word_prefix, 0, k.flags, o->tok_win, count, n_dev);
   int32_t* nwin = (int32_t*)(k.st.ticket + 8);
   CUDA_TRY(c, cudaMemcpyAsync(nwin, k.total, 4, cudaMemcpyDeviceToDevice, c->stream));
   Csr r;
   r.offsets = nullptr;
   rc = csr_build<int32_t>(c, r, o->tok_win, n, count, nwcap, nwin, n_dev);
   if (rc) return rc;
-  stable_rank_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(r.offsets, r.order, nwin, o->tok_perm, nullptr, o->tok_inner);
-  win_level_kernel<<<1, 1024, 0, c->stream>>>(r.offsets, o->tok_perm, nwin, lv, (const long long*)token_level, o->win_level,
+  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, nwin, o->tok_perm, nullptr, o->tok_inner);
+  launch_pdl(win_level_kernel, dim3(1), dim3(1024), (size_t)(0), c->stream, r.offsets, o->tok_perm, nwin, lv, (const long long*)token_level, o->win_level,
                                               o->win_rank, o->counters, k.flags);
-  tok_finish_kernel<<<nb, 256, 0, c->stream>>>(n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
+  launch_pdl(tok_finish_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
                                                (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
   // offsets -> caller buffer (int32 [n+1]); only R+1 entries are meaningful
   CUDA_TRY(c, cudaMemcpyAsync(o->win_offsets, r.offsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
