@@ -124,13 +124,14 @@ typedef struct {
   int32_t* tok_perm;       /* [n]   token indices grouped by window, stable order inside */
   int32_t* win_level;      /* [n]   level slot (0..num_levels-1) per window, R valid */
   int32_t* win_rank;       /* [n]   rank of the window among the windows of its level */
-  int32_t* counters;       /* [17]  R, windows per level slot [8], tokens per level slot [8] */
+  int32_t* counters;       /* [18]  R, windows per level slot [8], tokens per level slot [8], number of window batches */
   int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
+  int32_t* win_batch;      /* opt [n+1] window-index boundaries of batches of consecutive windows holding <= 144 tokens */
 } sstb200_window_shift;
 
 /* status_host (opt, int32[18]): if non-NULL the call synchronises and returns
  * [0] = bit0: token outside the window grid, bit1: window count not covered by any drop_range;
- * [1..17] = copy of counters. */
+ * [1..17] = copy of counters[0..16]. */
 int sstb200_window_plan(sstb200_ctx* ctx, const int64_t* coors, int n, const int32_t* n_dev,
                         const sstb200_window_cfg* cfg, int do_shift, const int64_t* token_level,
                         const sstb200_window_shift* out, int32_t* status_host);
@@ -172,6 +173,7 @@ typedef struct {
   int32_t pos_L, pos_maxw, pos_ndim;
   int32_t max_window_tokens;  /* upper bound on tokens per window (e.g. 144) */
   const int32_t* tok_slot;    /* [n] inverse of tok_perm (needed by the bf16 path) */
+  const int32_t* win_batch;   /* opt [.] window batches (see sstb200_window_shift); counters[17] = number of batches */
 } sstb200_sra_plan;
 
 

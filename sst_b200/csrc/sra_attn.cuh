@@ -433,3 +433,196 @@ static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const in
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// v4: batched ragged attention.  One CTA stages a *batch* of consecutive whole windows (<= 144 tokens, built by
+// win_batch_kernel) - K and V rows of the batch are one contiguous block in slot order, copied with cp.async - and its 8
+// warps sweep the batch's (16-query tile, head) items out of shared memory: K fragments by 32-bit LDS (conflict-free
+// 272-byte pitch), V^T fragments by ldmatrix.trans, two-pass softmax with QK^T recomputed (no S array in registers).
+// Compared with one-window-per-CTA this amortises the staging round trip and the barrier over ~5 windows, and compared
+// with the register-resident warp kernel every inner-loop operand comes from shared memory instead of L2.
+// ------------------------------------------------------------------------------------------------
+#define ATT_BT 144
+
+// NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which halves
+// the critical path of batches that hold one big window and raises the number of resident warps per SM.
+template <int NHL>
+static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half* __restrict__ qkv,
+                                                                    const int32_t* __restrict__ counters,
+                                                                    const int32_t* __restrict__ win_offsets,
+                                                                    const int32_t* __restrict__ win_batch, float scale,
+                                                                    __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int D = 128, DH = 16, LD = NHL * 16 + 8, HSPLIT = 8 / NHL, PPR = NHL * 2;  // PPR: 16-byte pieces per row per matrix
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __half* sK = reinterpret_cast<__half*>(att_smem);
+  __half* sV = sK + (ATT_BT + 16) * LD;
+  __shared__ int sTileRow[ATT_BT];   // first local row of q-tile k
+  __shared__ int sTileKb[ATT_BT];    // local key range of its window
+  __shared__ int sTileKe[ATT_BT];
+  __shared__ int sNumTiles;
+  const int nbatch = counters[17];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  for (int unit = blockIdx.x; unit < nbatch * HSPLIT; unit += gridDim.x) {
+    const int b = unit / HSPLIT, hs = unit % HSPLIT;
+    const int wb = win_batch[b], we = win_batch[b + 1];
+    const int s0 = win_offsets[wb], s1 = win_offsets[we];
+    const int nrow = min(s1 - s0, ATT_BT);
+    const int npad = (nrow + 15) & ~15;
+    __syncthreads();  // previous batch fully consumed
+    // stage K | V rows (contiguous in slot order): 32 x 16-byte pieces per row
+    {
+      const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV);
+      const int nfill = min(npad + 16, ATT_BT + 16);  // key chunks may run up to 15 rows past the batch: keep them finite (0)
+      for (int idx = threadIdx.x; idx < nfill * 2 * PPR; idx += blockDim.x) {
+        int r = idx / (2 * PPR), c = idx % (2 * PPR);
+        const bool isv = c >= PPR;
+        const int pc = isv ? c - PPR : c;
+        uint32_t dst = (isv ? v0 : k0) + (uint32_t)(r * LD + pc * 8) * 2;
+        if (r < nrow) {
+          const __half* src = qkv + (size_t)(s0 + r) * 3 * D + (isv ? 2 * D : D) + hs * NHL * DH + pc * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+        } else {
+          *reinterpret_cast<int4*>((isv ? sV : sK) + r * LD + pc * 8) = make_int4(0, 0, 0, 0);
+        }
+      }
+    }
+    // q-tile table (warp 0): windows of the batch -> tiles
+    if (warp == 0) {
+      int cnt = 0;
+      for (int w0 = wb; w0 < we; w0 += 32) {
+        int w = w0 + lane;
+        int kb = 0, n = 0;
+        if (w < we) {
+          kb = win_offsets[w] - s0;
+          n = win_offsets[w + 1] - s0 - kb;
+          if (kb + n > ATT_BT) n = max(ATT_BT - kb, 0);
+        }
+        int nt = (n + 15) >> 4;
+        int x = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        int base = cnt + x - nt;
+        for (int k = 0; k < nt; k++) {
+          if (base + k < ATT_BT) {
+            sTileRow[base + k] = kb + 16 * k;
+            sTileKb[base + k] = kb;
+            sTileKe[base + k] = kb + n;
+          }
+        }
+        cnt += __shfl_sync(0xffffffffu, x, 31);
+      }
+      if (lane == 0) sNumTiles = min(cnt, ATT_BT);
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    const int nitems = sNumTiles * NHL;
+    for (int item = warp; item < nitems; item += 8) {
+      const int tk = item / NHL, hl = item % NHL, h = hs * NHL + hl;
+      const int row = sTileRow[tk], kb = sTileKb[tk], ke = sTileKe[tk];
+      const int n = ke - kb;
+      const int r0 = row + g4, r1 = r0 + 8;
+      uint32_t qa[4] = {0u, 0u, 0u, 0u};
+      if (r0 < ke) {
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)(s0 + r0) * 3 * D + h * DH);
+        qa[0] = qp[t4];
+        qa[2] = qp[t4 + 4];
+      }
+      if (r1 < ke) {
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)(s0 + r1) * 3 * D + h * DH);
+        qa[1] = qp[t4];
+        qa[3] = qp[t4 + 4];
+      }
+      const int nkt = (n + 7) >> 3;
+      const __half* kbase = sK + (size_t)kb * LD + hl * DH;
+      // pass 1: row maxima
+      float m0 = -INFINITY, m1 = -INFINITY;
+      for (int j = 0; j < nkt; j++) {
+        const uint32_t* kp = reinterpret_cast<const uint32_t*>(kbase + (j * 8 + g4) * LD);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16_16816(s, qa, kp[t4], kp[t4 + 4]);
+        const int c0 = j * 8 + 2 * t4;
+        if (c0 < n) {
+          m0 = fmaxf(m0, s[0]);
+          m1 = fmaxf(m1, s[2]);
+        }
+        if (c0 + 1 < n) {
+          m0 = fmaxf(m0, s[1]);
+          m1 = fmaxf(m1, s[3]);
+        }
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      const float ms0 = m0 * scale, ms1 = m1 * scale;
+      // pass 2
+      float l0 = 0.f, l1 = 0.f;
+      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const int nkc = (n + 15) >> 4;
+      for (int kc = 0; kc < nkc; kc++) {
+        const uint32_t* kp0 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + g4) * LD);
+        const uint32_t* kp1 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + 8 + g4) * LD);
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16_16816(sa, qa, kp0[t4], kp0[t4 + 4]);
+        mma_f16_16816(sb, qa, kp1[t4], kp1[t4 + 4]);   // rows beyond the window are other windows' keys or zero padding: masked below
+        const int c0 = kc * 16 + 2 * t4;
+        float p[8];
+        p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
+        p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
+        p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
+        p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
+        p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
+        p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
+        p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
+        p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
+        l0 += (p[0] + p[1]) + (p[4] + p[5]);
+        l1 += (p[2] + p[3]) + (p[6] + p[7]);
+        uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
+        const __half* vrow = sV + (size_t)(kb + kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + hl * DH + (lane >> 4) * 8;
+        uint32_t vb[4];
+        uint32_t saddr = (uint32_t)__cvta_generic_to_shared(vrow);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
+                     : "r"(saddr));
+        mma_f16_16816(o[0], pa, vb[0], vb[1]);
+        mma_f16_16816(o[1], pa, vb[2], vb[3]);
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      if (r0 < ke) {
+        const float i0 = 1.0f / l0;
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r0) * D + h * DH);
+        op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
+        op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
+      }
+      if (r1 < ke) {
+        const float i1 = 1.0f / l1;
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r1) * D + h * DH);
+        op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
+        op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
+      }
+    }
+  }
+}
+
+static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
+                                      const int32_t* win_batch, __nv_bfloat16* out) {
+  constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
+  size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(c, cudaFuncSetAttribute(win_attn_batch_kernel<NHL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(c->num_sms * 6), dim3(256), smem, c->stream, qkv, counters, win_offsets,
+                         win_batch, 0.25f, out));
+  return SSTB_OK;
+}

@@ -400,6 +400,11 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   float* x1 = arena_alloc<float>(c, (size_t)n_cap * d);
   if (!qkv || !att || !x1b || !hid || !x1) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra bf16 layer: arena too small");
   int rc;
+  static int dbg_skip = -1;  // SSTB200_DEBUG_SKIP bitmask (timing experiments only): 1 QKV, 2 attention, 4 chain
+  if (dbg_skip < 0) {
+    const char* e = getenv("SSTB200_DEBUG_SKIP");
+    dbg_skip = e ? atoi(e) : 0;
+  }
   // tensor-core attention path: plain scaled-dot-product, 8 heads x 16, windows <= 144 tokens
   const bool slot_order = !L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
                           P->num_windows_dev && P->tok_slot;
@@ -423,10 +428,14 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.out_row_map = slot_order ? P->tok_slot : nullptr;  // rows land in window (slot) order for the tensor-core attention
   // q/k/v for the tensor-core attention are written as fp16 (softmax logits need the mantissa: with bf16 q,k the logit
   // error dominates the layer's error budget); the SIMT fallback reads bf16.
-  rc = slot_order ? launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3) : launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3);
+  rc = (dbg_skip & 1) ? 0 : (slot_order ? launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3) : launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3));
   if (rc) return rc;
   // 2. ragged window attention (fp32 math on bf16 q/k/v)
-  if (slot_order)
+  if (dbg_skip & 2)
+    rc = 0;
+  else if (slot_order && P->win_batch)
+    rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, P->win_batch, att);
+  else if (slot_order)
     rc = sstb_win_attn_warp(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
@@ -439,6 +448,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
       const char* e = getenv("SSTB200_CHAIN");
       use_chain = (e && e[0] == '0') ? 0 : 1;
     }
+    if (dbg_skip & 4) return SSTB_OK;
     if (use_chain) return sstb_sra_chain_bf16(c, L, att, slot_order ? P->tok_perm : nullptr, x, y, n_cap, n_dev);
   }
   // 3. out-projection + residual + LayerNorm1 (unfused reference path, SSTB200_CHAIN=0)

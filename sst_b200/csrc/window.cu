@@ -182,10 +182,50 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
   if (flat2win) flat2win[i] = (long long)win_rank[w] * lv.maxtok[slot] + tok_inner[i];
 }
 
+// Greedy packing of consecutive windows into batches of <= bt tokens (one CTA of the batched attention kernel stages one
+// batch).  Sequential by nature; R is ~10^3 per frame and the offsets sit in shared memory, so one thread does it.
+__global__ void __launch_bounds__(1024) win_batch_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ nwin_dev,
+                                                         int bt, int32_t* __restrict__ batch_win /*[R+1]*/, int32_t* __restrict__ counters) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ uint32_t s_off[];
+  const int R = *nwin_dev;
+  const int cap = 12000;
+  const bool in_smem = R + 1 <= cap;
+  if (in_smem)
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp-cooperative greedy: one ballot finds the end of the current batch among the next 32 windows
+    const uint32_t* off = in_smem ? s_off : offsets;
+    const int lane = threadIdx.x;
+    int nb = 0, start = 0;
+    if (lane == 0) batch_win[0] = 0;
+    while (start < R) {
+      int w = start + 1 + lane;  // candidate end (exclusive) of the batch: windows [start, w)
+      bool over = (w > R) || ((int)(off[min(w, R)] - off[start]) > bt);
+      unsigned m = __ballot_sync(0xffffffffu, over);
+      int end;
+      if (m == 0) {            // all 32 candidates fit: the batch spans at least 32 windows, keep extending
+        int e = start + 32;
+        while (e < R && (int)(off[e + 1] - off[start]) <= bt) e++;
+        end = e;
+      } else {
+        end = start + __ffs(m) - 1;   // first candidate that does not fit -> batch = [start, end)
+        if (end == start) end = start + 1;  // a single window always forms a batch
+      }
+      nb++;
+      if (lane == 0) batch_win[nb] = end;
+      start = end;
+    }
+    if (lane == 0) counters[17] = nb;
+  }
+}
+
 __global__ void zero_counters_kernel(int32_t* c) {
   pdl_wait();
   pdl_launch();
-  if (threadIdx.x < 17) c[threadIdx.x] = 0;
+  if (threadIdx.x < 18) c[threadIdx.x] = 0;
 }
 
 template <typename TC>
@@ -239,6 +279,9 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
                                               o->win_rank, o->counters, k.flags);
   launch_pdl(tok_finish_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
                                                (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
+  if (o->win_batch)
+    launch_pdl(win_batch_kernel, dim3(1), dim3(1024), (size_t)(12000 * 4), c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin, 144,
+               o->win_batch, o->counters);
   // offsets -> caller buffer (int32 [n+1]); only R+1 entries are meaningful
   CUDA_TRY(c, cudaMemcpyAsync(o->win_offsets, r.offsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
   LAUNCH_CHECK(c);

@@ -51,9 +51,10 @@ class SSTEngine:
         self.x = [torch.empty((cap, self.d), **f32) for _ in range(2)]
         self.plans = []
         for _ in range(2):
-            p = {k: torch.empty((cap + 1,) if k == "win_offsets" else (cap,), **i32)
-                 for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "tok_slot")}
-            p["counters"] = torch.zeros((17,), **i32)
+            p = {k: torch.empty((cap + 1,) if k in ("win_offsets", "win_batch") else (cap,), **i32)
+                 for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "tok_slot",
+                           "win_batch")}
+            p["counters"] = torch.zeros((18,), **i32)
             self.plans.append(p)
         self.wcfg, _ = ops._window_cfg(self.il.sparse_shape, self.il.window_shape, self.il.drop_info, self.B)
         tab, ndim, maxw, Lp = self.il._pos(self.d, dev)
@@ -61,11 +62,13 @@ class SSTEngine:
         self._shift_structs = [ops._WindowShift(None, None, None, None, p["pos_code"].data_ptr(), p["tok_win"].data_ptr(),
                                                 p["tok_inner"].data_ptr(), p["win_offsets"].data_ptr(),
                                                 p["tok_perm"].data_ptr(), p["win_level"].data_ptr(),
-                                                p["win_rank"].data_ptr(), p["counters"].data_ptr(), p["tok_slot"].data_ptr())
+                                                p["win_rank"].data_ptr(), p["counters"].data_ptr(), p["tok_slot"].data_ptr(),
+                                                p["win_batch"].data_ptr())
                                for p in self.plans]
         self._plan_structs = [_SraPlan(p["win_offsets"].data_ptr(), p["tok_perm"].data_ptr(), p["tok_win"].data_ptr(),
                                        p["pos_code"].data_ptr(), p["counters"].data_ptr(), tab.data_ptr(), Lp, maxw, ndim,
-                                       max(v["max_tokens"] for v in self.il.drop_info.values()), p["tok_slot"].data_ptr())
+                                       max(v["max_tokens"] for v in self.il.drop_info.values()), p["tok_slot"].data_ptr(),
+                                       p["win_batch"].data_ptr())
                               for p in self.plans]
         self.vfe_cfg = self.vfe._cfg(self.B)
         self.vfe_cfg.precision = PRECISIONS[precision]

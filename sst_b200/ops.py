@@ -323,7 +323,7 @@ class _WindowCfg(C.Structure):
 class _WindowShift(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("batch_win_inds", "coors_in_win", "drop_level", "flat2win_inds", "pos_code",
                                           "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank",
-                                          "counters", "tok_slot")]
+                                          "counters", "tok_slot", "win_batch")]
 
 
 L.SIGNATURES["sstb200_window_plan"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.POINTER(_WindowCfg), C.c_int, L.vp,
@@ -360,7 +360,7 @@ def _window_cfg(sparse_shape, window_shape, drop_info, batch_size):
 class WindowPlan:
     """Device-resident result of sstb200_window_plan for one shift."""
     __slots__ = ("n", "batch_win_inds", "coors_in_win", "drop_level", "flat2win_inds", "pos_code", "tok_win",
-                 "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "counters", "tok_slot", "level_keys",
+                 "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "counters", "tok_slot", "win_batch", "level_keys",
                  "num_windows", "level_windows", "level_tokens", "status")
 
 
@@ -386,8 +386,9 @@ def window_plan(coors, sparse_shape, window_shape, drop_info, do_shift, batch_si
     p.tok_perm = torch.empty((n,), **i32)
     p.win_level = torch.empty((n,), **i32)
     p.win_rank = torch.empty((n,), **i32)
-    p.counters = torch.empty((17,), **i32)
+    p.counters = torch.empty((18,), **i32)
     p.tok_slot = torch.empty((n,), **i32)
+    p.win_batch = torch.empty((n + 1,), **i32)
     out = _WindowShift(*[getattr(p, k).data_ptr() for k, _ in _WindowShift._fields_])
     status = (C.c_int32 * 18)()
     if token_level is not None:

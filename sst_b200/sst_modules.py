@@ -246,7 +246,7 @@ class _SraPlan(C.Structure):
     _fields_ = ([(k, C.c_void_p) for k in ("win_offsets", "tok_perm", "tok_win", "pos_code", "num_windows_dev",
                                            "pos_table")] +
                 [("pos_L", C.c_int32), ("pos_maxw", C.c_int32), ("pos_ndim", C.c_int32),
-                 ("max_window_tokens", C.c_int32), ("tok_slot", C.c_void_p)])
+                 ("max_window_tokens", C.c_int32), ("tok_slot", C.c_void_p), ("win_batch", C.c_void_p)])
 
 
 L.SIGNATURES["sstb200_sra_layer_forward"] = (C.c_int, [L.vp, C.POINTER(_SraLayer), C.POINTER(_SraPlan), L.vp, L.vp,
@@ -259,7 +259,7 @@ def make_sra_plan(sp):
     p = sp["plan"]
     return _SraPlan(p.win_offsets.data_ptr(), p.tok_perm.data_ptr(), p.tok_win.data_ptr(), p.pos_code.data_ptr(),
                     p.counters.data_ptr(), sp["pos_table"].data_ptr(), sp["pos_L"], sp["pos_maxw"], sp["pos_ndim"],
-                    int(sp.get("max_tokens", 0) or 0), p.tok_slot.data_ptr())
+                    int(sp.get("max_tokens", 0) or 0), p.tok_slot.data_ptr(), p.win_batch.data_ptr())
 
 
 class WindowAttention(nn.Module):
