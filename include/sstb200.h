@@ -126,7 +126,7 @@ typedef struct {
   int32_t* win_rank;       /* [n]   rank of the window among the windows of its level */
   int32_t* counters;       /* [18]  R, windows per level slot [8], tokens per level slot [8], number of window batches */
   int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
-  int32_t* win_batch;      /* opt [n+1] window-index boundaries of batches of consecutive windows holding <= 144 tokens */
+  int32_t* win_batch;      /* opt [n+1] batch b = windows [win_batch[b], win_batch[b+1]) whose first slot lies in [112b, 112b+112) */
 } sstb200_window_shift;
 
 /* status_host (opt, int32[18]): if non-NULL the call synchronises and returns

@@ -287,6 +287,64 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_phaseB(Load load, size_t n_
   }
 }
 
+// Single-block variant (one launch) for small inputs: 1024 threads x 8 items per round with a running carry.
+template <typename Load>
+__global__ void __launch_bounds__(1024) scan_single_block(Load load, size_t n_host, const int32_t* n_dev, uint32_t* out,
+                                                          uint32_t* total_out, bool write_total_at_n) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (size_t base0 = 0; base0 < n || base0 == 0; base0 += 8192) {
+    size_t base = base0 + (size_t)threadIdx.x * 8;
+    uint32_t v[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      v[i] = (base + i < n) ? load(base + i) : 0;
+      s += v[i];
+    }
+    uint32_t x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t t = wsum[lane], t0 = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      wsum[lane] = t - t0;  // exclusive warp offsets
+    }
+    __syncthreads();
+    uint32_t ex = carry_s + wsum[w] + x - s;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      size_t k = base + i;
+      if (k < n) out[k] = ex;
+      else if (k == n && write_total_at_n) out[k] = ex;
+      ex += v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = ex;  // ex of the last thread after its 8 items == carry + tile total
+    __syncthreads();
+    if (n == 0) break;
+  }
+  if (threadIdx.x == 0) {
+    *total_out = carry_s;
+    // when n is a multiple of 8192 the element at index n was not visited: write the total there
+    if (write_total_at_n && n > 0 && (n % 8192) == 0) out[n] = carry_s;
+  }
+}
+
 struct ScanTemps {
   uint32_t* block_sums;
   uint32_t* block_prefix;
@@ -298,6 +356,10 @@ static inline size_t scan_num_blocks(size_t n_cap) { return (n_cap + 1 + SCAN_TI
 template <typename Load>
 static inline void launch_exclusive_scan(cudaStream_t st, Load load, size_t n_cap, const int32_t* n_dev,
                                          ScanTemps t, uint32_t* out, uint32_t* total_out, bool write_total_at_n) {
+  if (n_cap <= ((size_t)1 << 18)) {  // one launch instead of two; the block only walks the actual (device) length
+    launch_pdl(scan_single_block<Load>, dim3(1), dim3(1024), (size_t)0, st, load, n_cap, n_dev, out, total_out, write_total_at_n);
+    return;
+  }
   unsigned nblk = (unsigned)((n_cap + 1 + SCAN_TILE - 1) / SCAN_TILE);
   if (nblk == 0) nblk = 1;
   launch_pdl(scan_phaseA<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)(0), st, load, n_cap, n_dev, t.block_sums, t.block_prefix, t.ticket, total_out);

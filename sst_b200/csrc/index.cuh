@@ -274,7 +274,8 @@ static int make_extents(sstb200_ctx* c, Extents& e, int ndim, const long long* l
 // (<= a few hundred tokens); cost O(n^2/32) per warp.
 static __global__ void __launch_bounds__(256) stable_rank_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                                           const int32_t* __restrict__ nseg_dev, int32_t* __restrict__ sorted_order,
-                                                          long long* __restrict__ rank_out_i64, int32_t* __restrict__ rank_out_i32) {
+                                                          long long* __restrict__ rank_out_i64, int32_t* __restrict__ rank_out_i32,
+                                                          int32_t* __restrict__ slot_out) {
   pdl_wait();
   pdl_launch();
   int nseg = *nseg_dev;
@@ -290,6 +291,7 @@ static __global__ void __launch_bounds__(256) stable_rank_kernel(const uint32_t*
       if (sorted_order) sorted_order[b + r] = me;
       if (rank_out_i64) rank_out_i64[me] = r;
       if (rank_out_i32) rank_out_i32[me] = r;
+      if (slot_out) slot_out[me] = (int32_t)(b + r);
     }
   }
 }

@@ -442,7 +442,8 @@ static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const in
 // Compared with one-window-per-CTA this amortises the staging round trip and the barrier over ~5 windows, and compared
 // with the register-resident warp kernel every inner-loop operand comes from shared memory instead of L2.
 // ------------------------------------------------------------------------------------------------
-#define ATT_BT 144
+#define ATT_CHUNK 112
+#define ATT_BT 256   // >= ATT_CHUNK - 1 + 144 rows per batch
 
 // NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which halves
 // the critical path of batches that hold one big window and raises the number of resident warps per SM.
@@ -462,12 +463,15 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
   __shared__ int sTileKb[ATT_BT];    // local key range of its window
   __shared__ int sTileKe[ATT_BT];
   __shared__ int sNumTiles;
+  // batch b = the windows whose first slot lies in [b*ATT_CHUNK, (b+1)*ATT_CHUNK) (win_batch_kernel, csrc/window.cu); it holds
+  // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows
   const int nbatch = counters[17];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 2, t4 = lane & 3;
   for (int unit = blockIdx.x; unit < nbatch * HSPLIT; unit += gridDim.x) {
     const int b = unit / HSPLIT, hs = unit % HSPLIT;
     const int wb = win_batch[b], we = win_batch[b + 1];
+    if (wb == we) continue;  // a big window covers this chunk entirely (uniform per CTA)
     const int s0 = win_offsets[wb], s1 = win_offsets[we];
     const int nrow = min(s1 - s0, ATT_BT);
     const int npad = (nrow + 15) & ~15;

@@ -456,9 +456,9 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
   static_assert(K % 64 == 0 && C1 % 16 == 0 && C1 <= 256, "shape");
   extern __shared__ uint8_t l1_smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)l1_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = base;                       // K/64 chunks x 128 rows x 128 B
-  uint8_t* sB = sA + (size_t)VT * K * 2;    // K/64 chunks x C1 rows x 128 B
-  float* sTile = reinterpret_cast<float*>(base);  // re-used after the MMA: [VT][C1+1] fp32
+  uint8_t* sB = base;                       // K/64 chunks x C1 rows x 128 B - staged ONCE per CTA (persistent over tiles)
+  uint8_t* sA = sB + (size_t)C1 * K * 2;    // K/64 chunks x 128 rows x 128 B
+  float* sTile = reinterpret_cast<float*>(sA);  // the A operand region is re-used after the MMA: [VT][C1+1] fp32
   __shared__ float sF[VT][VFE_MAXD];
   __shared__ int sVox[VT];
   __shared__ float sW0[VFE_MAXD][C0];
@@ -484,44 +484,53 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
     mbar_init(smem_u32(&mbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  // B operand: W1 [C1, K] fp32 -> bf16, K-major SWIZZLE_128B, once per CTA (4 pieces in flight per thread)
+  for (int i0 = tid; i0 < C1 * (K / 8); i0 += blockDim.x * 4) {
+    float4 f0[4], f1[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int idx = i0 + u * blockDim.x;
+      if (idx < C1 * (K / 8)) {
+        const float* wp = v.W1 + (size_t)(idx / (K / 8)) * K + (idx % (K / 8)) * 8;
+        f0[u] = __ldg(reinterpret_cast<const float4*>(wp));
+        f1[u] = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int idx = i0 + u * blockDim.x;
+      if (idx < C1 * (K / 8)) {
+        int r = idx / (K / 8), j = idx % (K / 8);
+        int4 q;
+        q.x = (int)pack_bf16(f0[u].x, f0[u].y);
+        q.y = (int)pack_bf16(f0[u].z, f0[u].w);
+        q.z = (int)pack_bf16(f1[u].x, f1[u].y);
+        q.w = (int)pack_bf16(f1[u].z, f1[u].w);
+        int c = j >> 3, jj = j & 7;
+        *reinterpret_cast<int4*>(sB + (size_t)c * C1 * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+      }
+    }
+  }
   uint32_t parity = 0;
   for (int k0 = blockIdx.x * VT; k0 < nvalid; k0 += gridDim.x * VT) {
     const int nrow = min(VT, nvalid - k0);
-    __syncthreads();  // previous tile's smem (sTile aliases sA/sB) fully consumed
+    __syncthreads();  // previous tile's smem (sTile aliases sA) fully consumed
     tile_decorate<TC, TM>(v, pts, coors, order, map, vmean, k0, nrow, sF, sVox);
-    // B operand: W1 [C1, K] fp32 -> bf16, K-major SWIZZLE_128B
-    for (int idx = tid; idx < C1 * (K / 8); idx += blockDim.x) {
-      int r = idx / (K / 8), j = idx % (K / 8);
-      const float* wp = v.W1 + (size_t)r * K + j * 8;
-      float4 f0 = *reinterpret_cast<const float4*>(wp), f1 = *reinterpret_cast<const float4*>(wp + 4);
-      int4 q;
-      q.x = (int)pack_bf16(f0.x, f0.y);
-      q.y = (int)pack_bf16(f0.z, f0.w);
-      q.z = (int)pack_bf16(f1.x, f1.y);
-      q.w = (int)pack_bf16(f1.z, f1.w);
-      int c = j >> 3, jj = j & 7;
-      *reinterpret_cast<int4*>(sB + (size_t)c * C1 * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
-    }
     __syncthreads();
-    // A operand: row r = [ y0(point) (C0) || vf0[voxel] (C0) ] in bf16
-    for (int idx = tid; idx < VT * (K / 8); idx += blockDim.x) {
-      int r = idx / (K / 8), j = idx % (K / 8);
+    // A operand: row r = [ y0(point) (C0) || vf0[voxel] (C0) ] in bf16.  Two uniform loops (no divergence inside a warp):
+    // (1) layer-0 features recomputed from the decorated point (FFMA), (2) the voxel's layer-0 max, gathered 4 rows in flight
+    for (int idx = tid; idx < VT * (C0 / 8); idx += blockDim.x) {
+      int r = idx / (C0 / 8), j = idx % (C0 / 8);
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; e++) f[e] = 0.f;
       if (r < nrow) {
-        if (j < C0 / 8) {
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            int c = j * 8 + e;
-            float a = 0.f;
-            for (int d = 0; d < D0; d++) a = fmaf(sW0[d][c], sF[r][d], a);
-            f[e] = fmaxf(fmaf(a, sS0[c], sT0[c]), 0.f);
-          }
-        } else {
-          const float* gp = vf0 + (size_t)sVox[r] * C0 + (j - C0 / 8) * 8;
-          float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
-          f[0] = g0.x; f[1] = g0.y; f[2] = g0.z; f[3] = g0.w; f[4] = g1.x; f[5] = g1.y; f[6] = g1.z; f[7] = g1.w;
+        for (int e = 0; e < 8; e++) {
+          int c = j * 8 + e;
+          float a = 0.f;
+          for (int d = 0; d < D0; d++) a = fmaf(sW0[d][c], sF[r][d], a);
+          f[e] = fmaxf(fmaf(a, sS0[c], sT0[c]), 0.f);
         }
       }
       int4 q;
@@ -531,6 +540,34 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
       q.w = (int)pack_bf16(f[6], f[7]);
       int c = j >> 3, jj = j & 7;
       *reinterpret_cast<int4*>(sA + (size_t)c * VT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+    }
+    for (int i0 = tid; i0 < VT * (C0 / 8); i0 += blockDim.x * 4) {
+      float4 g0[4], g1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int idx = i0 + u * blockDim.x;
+        int r = idx / (C0 / 8), j = idx % (C0 / 8);
+        g0[u] = g1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < VT * (C0 / 8) && r < nrow) {
+          const float* gp = vf0 + (size_t)sVox[r] * C0 + j * 8;
+          g0[u] = *reinterpret_cast<const float4*>(gp);
+          g1[u] = *reinterpret_cast<const float4*>(gp + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int idx = i0 + u * blockDim.x;
+        if (idx < VT * (C0 / 8)) {
+          int r = idx / (C0 / 8), j = idx % (C0 / 8) + C0 / 8;
+          int4 q;
+          q.x = (int)pack_bf16(g0[u].x, g0[u].y);
+          q.y = (int)pack_bf16(g0[u].z, g0[u].w);
+          q.z = (int)pack_bf16(g1[u].x, g1[u].y);
+          q.w = (int)pack_bf16(g1[u].z, g1[u].w);
+          int c = j >> 3, jj = j & 7;
+          *reinterpret_cast<int4*>(sA + (size_t)c * VT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+        }
+      }
     }
     fence_async_smem();
     tc_fence_before();
@@ -605,8 +642,8 @@ static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, c
   *l1_done = false;
   if (C1 > 0 && umma_l1) {
     constexpr int C1s = C1 > 0 ? C1 : 32;
-    size_t ops = (size_t)VT * 2 * C0 * 2 + (size_t)C1s * 2 * C0 * 2, tile = (size_t)VT * (C1s + 1) * 4;
-    size_t smem1 = (ops > tile ? ops : tile) + 1024;
+    size_t opA = (size_t)VT * 2 * C0 * 2, opB = (size_t)C1s * 2 * C0 * 2, tile = (size_t)VT * (C1s + 1) * 4;
+    size_t smem1 = opB + (opA > tile ? opA : tile) + 1024;
     auto kern = vfe_l1_umma_kernel<TC, TM, C0, C1s>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -309,7 +309,7 @@ extern "C" int sstb200_ingroup_indices(sstb200_ctx* c, const int64_t* group, int
   Csr r;
   rc = csr_build<int32_t>(c, r, cid, N, count, N, ng);
   if (rc) return rc;
-  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, ng, nullptr, (long long*)out, nullptr);
+  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, ng, nullptr, (long long*)out, nullptr, nullptr);
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }

@@ -182,43 +182,29 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
   if (flat2win) flat2win[i] = (long long)win_rank[w] * lv.maxtok[slot] + tok_inner[i];
 }
 
-// Greedy packing of consecutive windows into batches of <= bt tokens (one CTA of the batched attention kernel stages one
-// batch).  Sequential by nature; R is ~10^3 per frame and the offsets sit in shared memory, so one thread does it.
-__global__ void __launch_bounds__(1024) win_batch_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ nwin_dev,
-                                                         int bt, int32_t* __restrict__ batch_win /*[R+1]*/, int32_t* __restrict__ counters) {
+// Window batches for the batched attention kernel: batch b = the windows whose first slot lies in [b*chunk, (b+1)*chunk).
+// batch_win[b] = lower_bound(offsets[0..R), b*chunk) - one binary search per thread; counters[17] = number of batches.
+// A batch holds at most chunk - 1 + max_window_tokens rows.
+__global__ void win_batch_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ nwin_dev, int chunk,
+                                 int32_t* __restrict__ batch_win, int32_t* __restrict__ counters) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ uint32_t s_off[];
   const int R = *nwin_dev;
-  const int cap = 12000;
-  const bool in_smem = R + 1 <= cap;
-  if (in_smem)
-    for (int i = threadIdx.x; i <= R; i += blockDim.x) s_off[i] = offsets[i];
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    // warp-cooperative greedy: one ballot finds the end of the current batch among the next 32 windows
-    const uint32_t* off = in_smem ? s_off : offsets;
-    const int lane = threadIdx.x;
-    int nb = 0, start = 0;
-    if (lane == 0) batch_win[0] = 0;
-    while (start < R) {
-      int w = start + 1 + lane;  // candidate end (exclusive) of the batch: windows [start, w)
-      bool over = (w > R) || ((int)(off[min(w, R)] - off[start]) > bt);
-      unsigned m = __ballot_sync(0xffffffffu, over);
-      int end;
-      if (m == 0) {            // all 32 candidates fit: the batch spans at least 32 windows, keep extending
-        int e = start + 32;
-        while (e < R && (int)(off[e + 1] - off[start]) <= bt) e++;
-        end = e;
-      } else {
-        end = start + __ffs(m) - 1;   // first candidate that does not fit -> batch = [start, end)
-        if (end == start) end = start + 1;  // a single window always forms a batch
-      }
-      nb++;
-      if (lane == 0) batch_win[nb] = end;
-      start = end;
+  const int ntok = (int)offsets[R];
+  const int nb = (ntok + chunk - 1) / chunk;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x) {
+    const uint32_t t0 = (uint32_t)b * (uint32_t)chunk;
+    int lo = 0, hi = R;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (offsets[mid] < t0) lo = mid + 1;
+      else hi = mid;
     }
-    if (lane == 0) counters[17] = nb;
+    batch_win[b] = lo;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[17] = nb;
+    counters[0] = R;
   }
 }
 
@@ -274,14 +260,20 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   r.offsets = nullptr;
   rc = csr_build<int32_t>(c, r, o->tok_win, n, count, nwcap, nwin, n_dev);
   if (rc) return rc;
-  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, nwin, o->tok_perm, nullptr, o->tok_inner);
-  launch_pdl(win_level_kernel, dim3(1), dim3(1024), (size_t)(0), c->stream, r.offsets, o->tok_perm, nwin, lv, (const long long*)token_level, o->win_level,
-                                              o->win_rank, o->counters, k.flags);
-  launch_pdl(tok_finish_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
-                                               (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
+  // the reference-layout outputs (drop level, flat2win index, per-level window rank) are only produced on request; the
+  // fused kernels need the CSR, the stable in-window rank and the slot of every token - all written by stable_rank_kernel
+  const bool want_levels = o->drop_level || o->flat2win_inds || token_level || err_host;
+  launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, nwin, o->tok_perm, nullptr, o->tok_inner,
+             want_levels ? nullptr : o->tok_slot);
+  if (want_levels) {
+    launch_pdl(win_level_kernel, dim3(1), dim3(1024), (size_t)(0), c->stream, r.offsets, o->tok_perm, nwin, lv, (const long long*)token_level,
+               o->win_level, o->win_rank, o->counters, k.flags);
+    launch_pdl(tok_finish_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
+               (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
+  }
   if (o->win_batch)
-    launch_pdl(win_batch_kernel, dim3(1), dim3(1024), (size_t)(12000 * 4), c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin, 144,
-               o->win_batch, o->counters);
+    launch_pdl(win_batch_kernel, dim3((n / 112 + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
+               112, o->win_batch, o->counters);
   // offsets -> caller buffer (int32 [n+1]); only R+1 entries are meaningful
   CUDA_TRY(c, cudaMemcpyAsync(o->win_offsets, r.offsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
   LAUNCH_CHECK(c);
