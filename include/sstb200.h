@@ -270,6 +270,15 @@ int sstb200_sir_layer_forward(sstb200_ctx* ctx, const sstb200_sir_layer* layer, 
                               const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
                               float* out_point, float* out_group);
 
+/* A4  the whole encoder stack (SSTv2.forward's block loop, mmdet3d/models/backbones/sst_v2.py:129-133 with
+ * BasicShiftBlockV2.forward, models/sst/sst_basic_block_v2.py:144-169): layer l uses the windows of shift l % 2.
+ * x [n,d] input (not modified), y [n,d] output, tmp [n,d] scratch; all fp32, distinct buffers.  With precision BF16 and the
+ * SST-6 shape (d=128, h=8, ff=256, post-norm LayerNorm, GELU) this runs 2 launches per layer: ragged window attention and a
+ * fused tcgen05 kernel (out-proj + LN1 + FFN + LN2 + the next layer's QKV); otherwise it loops sstb200_sra_layer_forward. */
+int sstb200_sra_stack_forward(sstb200_ctx* ctx, const sstb200_sra_layer* layers, int num_layers,
+                              const sstb200_sra_plan* plan_shift0, const sstb200_sra_plan* plan_shift1, const float* x,
+                              float* y, float* tmp, int n, const int32_t* n_dev, int precision);
+
 #ifdef __cplusplus
 }
 #endif

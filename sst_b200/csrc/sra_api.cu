@@ -29,3 +29,28 @@ extern "C" int sstb200_linear(sstb200_ctx* c, const float* A, const float* W, co
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }
+
+extern "C" int sstb200_sra_stack_forward(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plan_shift0,
+                                         const sstb200_sra_plan* plan_shift1, const float* x, float* y, float* tmp, int n,
+                                         const int32_t* n_dev, int precision) {
+  CHECK_ARG(c, c && layers && num_layers >= 0 && plan_shift0 && plan_shift1 && n >= 0);
+  if (n == 0 || num_layers == 0) return SSTB_OK;
+  CHECK_ARG(c, x && y && tmp && x != y && tmp != y && tmp != x);
+  sstb200_sra_plan plans[2] = {*plan_shift0, *plan_shift1};
+  if (precision == SSTB200_PREC_BF16) {
+    arena_reset(c);
+    int rc = arena_reserve(c, (size_t)n * 128 * 8 + (1 << 20));
+    if (rc) return rc;
+    rc = sstb_sra_stack_bf16(c, layers, num_layers, plans, x, y, tmp, n, n_dev);
+    if (rc != SSTB_ERR_UNSUPPORTED) return rc;
+  }
+  // generic path: layer by layer, ping-pong between tmp and y so that the last layer lands in y
+  const float* src = x;
+  for (int l = 0; l < num_layers; l++) {
+    float* dst = ((num_layers - 1 - l) & 1) ? tmp : y;
+    int rc = sstb200_sra_layer_forward(c, &layers[l], &plans[l & 1], src, dst, n, n_dev, precision);
+    if (rc) return rc;
+    src = dst;
+  }
+  return SSTB_OK;
+}

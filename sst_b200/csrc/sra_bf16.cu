@@ -497,3 +497,62 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   rc = launch_umma<256, 128, PRO_BF16, EPI_RES_LN>(c, g, 1);
   return rc;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// whole encoder stack, bf16 tensor-core path: QKV(0) -> [attention(l) -> chain(l) (+ QKV(l+1) fused)] x L
+// 2 launches per layer; q/k/v, attention output and the residual stream never take a detour.
+// ------------------------------------------------------------------------------------------------
+static bool layer_supported_tc(const sstb200_sra_layer* L, const sstb200_sra_plan* P) {
+  return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && !L->norm1_mean && L->act == 2 && !L->tau && L->nhead == 8 &&
+         L->in_proj_w_bf16 && L->out_proj_w_bf16 && L->lin1_w_bf16 && L->lin2_w_bf16 && P->max_window_tokens > 0 &&
+         P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->tok_slot && P->win_batch && P->pos_table && P->pos_L % 32 == 0;
+}
+
+int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans, const float* x,
+                        float* y, float* scratch, int n_cap, const int32_t* n_dev) {
+  (void)scratch;
+  for (int l = 0; l < num_layers; l++)
+    if (!layer_supported_tc(&layers[l], &plans[l & 1])) return SSTB_ERR_UNSUPPORTED;  // caller falls back to per-layer calls
+  const int d = 128;
+  __half* qkv = arena_alloc<__half>(c, (size_t)n_cap * 3 * d);
+  __nv_bfloat16* att = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
+  if (!qkv || !att) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
+  // QKV of layer 0 (stand-alone GEMM, fp32 x + pos -> fp16 rows in slot order of shift 0)
+  {
+    const sstb200_sra_layer* L = &layers[0];
+    const sstb200_sra_plan* P = &plans[0];
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M_cap = n_cap;
+    g.M_dev = n_dev;
+    g.A = x;
+    g.lda = d;
+    g.W = (const __nv_bfloat16*)L->in_proj_w_bf16;
+    g.bias = L->in_proj_b;
+    g.pos_tab = P->pos_table;
+    g.pos_code = P->pos_code;
+    g.posL = P->pos_L;
+    g.pos_maxw = P->pos_maxw;
+    g.pos_ndim = P->pos_ndim;
+    g.pos_ntiles = 2;
+    g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(qkv);
+    g.ldo = 3 * d;
+    g.out_row_map = P->tok_slot;
+    int rc = launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3);
+    if (rc) return rc;
+  }
+  const float* xin = x;
+  for (int l = 0; l < num_layers; l++) {
+    const sstb200_sra_plan* P = &plans[l & 1];
+    int rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, att);
+    if (rc) return rc;
+    const bool has_next = l + 1 < num_layers;
+    // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
+    rc = sstb_sra_chain_bf16(c, &layers[l], att, P->tok_perm, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
+                             has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
+    if (rc) return rc;
+    xin = y;
+  }
+  return SSTB_OK;
+}

@@ -13,6 +13,7 @@
 // Replaces three launches (out-proj+LN1, FFN1+GELU, FFN2+LN2) and the x1 / x1_bf16 / hidden round trips of the
 // unfused path (csrc/sra_bf16.cu).
 #include <stdarg.h>
+#include <cuda_fp16.h>
 #include "sra.cuh"
 #include "umma.cuh"
 
@@ -34,6 +35,14 @@ struct ChainArgs {
   float eps;
   int M_cap;
   const int32_t* M_dev;
+  // optional fused tail: q/k/v of the NEXT encoder layer (which runs on the other shift's windows)
+  const __nv_bfloat16* Wqkv;     // next layer in_proj_weight [384,128] bf16, or nullptr
+  const float* bqkv;             // [384]
+  const int32_t* next_slot;      // [tokens] slot of the token in the next layer's window order
+  const int32_t* next_pos_code;  // [tokens]
+  const float* pos_tab;          // [ndim][maxw][L]
+  int posL, pos_maxw, pos_ndim;
+  __half* qkv_out;               // [M, 384] fp16, rows in the next layer's slot order
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
     stage_chunk(sH + 16384, g.att + (size_t)row0 * D, D, 64, TM, tid, M - row0);
     stage_chunk(sWr + 0 * SLOT, g.Wo, D, 0, 128, tid);
     stage_chunk(sWr + 0 * SLOT + 16384, g.Wo, D, 64, 128, tid);
-    if (tile == (int)blockIdx.x) {
+    if (tile == (int)blockIdx.x || g.Wqkv) {   // with the fused QKV tail the slots are recycled for Wq/Wk/Wv: restage
       stage_chunk(sWr + 1 * SLOT, g.W1, D, 0, 128, tid);                 // slot1: W1 rows 0..127
       stage_chunk(sWr + 1 * SLOT + 16384, g.W1, D, 64, 128, tid);
       stage_chunk(sWr + 2 * SLOT, g.W1 + 128 * D, D, 0, 128, tid);       // slot2: W1 rows 128..255
@@ -249,6 +258,12 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
     parity ^= 1u;
     tc_fence_after();
 
+    if (g.Wqkv) {  // W1 is dead: prefetch the next layer's Wq / Wk into slots 1 / 2 (lands during GELU, GEMM3, LN2)
+      stage_chunk(sWr + 1 * SLOT, g.Wqkv, D, 0, 128, tid);
+      stage_chunk(sWr + 1 * SLOT + 16384, g.Wqkv, D, 64, 128, tid);
+      stage_chunk(sWr + 2 * SLOT, g.Wqkv + 128 * D, D, 0, 128, tid);
+      stage_chunk(sWr + 2 * SLOT + 16384, g.Wqkv + 128 * D, D, 64, 128, tid);
+    }
     // ---- epilogue 2: hidden = GELU(acc2 + b1) -> bf16 operand layout [128 x 256] in sH (4 K-chunks) -----------------------
 #pragma unroll 1
     for (int cc = 0; cc < 2; cc++) {
@@ -331,6 +346,10 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
         o.w = (t[4 * q + 3] - mean) * rstd * g4.w + e4.w;
         int ch = (c0 >> 2) + q;
         *reinterpret_cast<float4*>(sH + (size_t)lrow * 512 + ((ch ^ (lrow & 31)) << 4)) = o;  // hidden is dead (GEMM3 retired)
+        t[4 * q] = o.x;
+        t[4 * q + 1] = o.y;
+        t[4 * q + 2] = o.z;
+        t[4 * q + 3] = o.w;
       }
     }
     __syncthreads();
@@ -341,6 +360,99 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
         *reinterpret_cast<float4*>(g.y + (size_t)gr * D + ch * 4) =
             *reinterpret_cast<const float4*>(sH + (size_t)r * 512 + ((ch ^ (r & 31)) << 4));
     }
+    if (g.Wqkv) {
+      // ---- fused tail: q,k = (y + pos_next) . Wq^T / Wk^T, v = y . Wv^T for the next layer, scattered into its slot order ----
+      stage_chunk(sWr + 3 * SLOT, g.Wqkv + 256 * D, D, 0, 128, tid);        // Wv -> slot 3 (W2[:, 0:128] is dead)
+      stage_chunk(sWr + 3 * SLOT + 16384, g.Wqkv + 256 * D, D, 64, 128, tid);
+      __syncthreads();  // y staging tile fully stored -> sH becomes the two A operands
+      {
+        const int tok = sRow[lrow];
+        float pe[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) pe[i] = 0.f;
+        const int axis = c0 / g.posL;  // posL % 32 == 0 (checked on the host): the 32-column span lies inside one axis
+        if (tok >= 0 && axis < g.pos_ndim) {
+          const int cv = (g.next_pos_code[tok] >> (8 * axis)) & 255;
+          const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)axis * g.pos_maxw + cv) * g.posL + (c0 - axis * g.posL));
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            float4 p4 = __ldg(tp + q);
+            pe[4 * q] = p4.x;
+            pe[4 * q + 1] = p4.y;
+            pe[4 * q + 2] = p4.z;
+            pe[4 * q + 3] = p4.w;
+          }
+        }
+        const int kc = c0 >> 6, j0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float* sy = &t[q * 8];
+          const float* sp = &pe[q * 8];
+          const uint32_t off = kc * 16384 + lrow * 128 + (((j0 + q) ^ (lrow & 7)) << 4);
+          *reinterpret_cast<int4*>(sH + off) = make_int4((int)pack_bf16(sy[0] + sp[0], sy[1] + sp[1]), (int)pack_bf16(sy[2] + sp[2], sy[3] + sp[3]),
+                                                         (int)pack_bf16(sy[4] + sp[4], sy[5] + sp[5]), (int)pack_bf16(sy[6] + sp[6], sy[7] + sp[7]));
+          *reinterpret_cast<int4*>(sH + SLOT + off) = make_int4((int)pack_bf16(sy[0], sy[1]), (int)pack_bf16(sy[2], sy[3]),
+                                                                (int)pack_bf16(sy[4], sy[5]), (int)pack_bf16(sy[6], sy[7]));
+        }
+      }
+      cp_async_wait_all();
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) {
+        const uint32_t ap = smem_u32(sH), ax = smem_u32(sH + SLOT);
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) {
+          const uint32_t a0 = nt < 2 ? ap : ax, b0 = smem_u32(sWr + (1 + nt) * SLOT);
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int s2 = 0; s2 < 4; s2++)
+              umma_bf16(tmem + nt * 128, umma_desc_sw128(a0 + c * 16384 + s2 * 32), umma_desc_sw128(b0 + c * 16384 + s2 * 32), idesc,
+                        (c | s2) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&mbar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&mbar), parity);
+      parity ^= 1u;
+      tc_fence_after();
+      // epilogue 4: + bias -> fp16 -> staging tiles (q -> sH[0:32K], k -> sH[32K:64K], v -> ring slot 0) -> rows in next-slot order
+#pragma unroll 1
+      for (int nt = 0; nt < 3; nt++) {
+        float v[32];
+        tmem_ld32(tlane + nt * 128 + c0, v);
+        const float4* bp = reinterpret_cast<const float4*>(g.bqkv + nt * 128 + c0);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b4 = __ldg(bp + (i >> 2));
+          __half2 h0 = __floats2half2_rn(v[i] + b4.x, v[i + 1] + b4.y), h1 = __floats2half2_rn(v[i + 2] + b4.z, v[i + 3] + b4.w);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        uint8_t* st = nt < 2 ? sH + nt * SLOT : sWr;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int ch = (c0 >> 3) + q;  // 16-byte chunk (8 halfs) of the 128-wide row, XOR-swizzled by row
+          *reinterpret_cast<int4*>(st + (size_t)lrow * 256 + ((ch ^ (lrow & 15)) << 4)) =
+              make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      for (int idx = tid; idx < TM * 48; idx += NTHR) {
+        int r = idx / 48, cc = idx % 48;
+        int nt = cc >> 4, ch = cc & 15;
+        int tok = sRow[r];
+        if (tok >= 0) {
+          const uint8_t* st = nt < 2 ? sH + nt * SLOT : sWr;
+          *reinterpret_cast<int4*>(g.qkv_out + (size_t)g.next_slot[tok] * 384 + nt * 128 + ch * 8) =
+              *reinterpret_cast<const int4*>(st + (size_t)r * 256 + ((ch ^ (r & 15)) << 4));
+        }
+      }
+    }
     tc_fence_before();
     __syncthreads();  // staging tile / TMEM fully consumed before the next tile re-stages
   }
@@ -350,8 +462,23 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
 }  // namespace
 
 int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const int32_t* row_map, const float* x,
-                        float* y, int n_cap, const int32_t* n_dev) {
+                        float* y, int n_cap, const int32_t* n_dev, const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan,
+                        void* next_qkv) {
   ChainArgs g;
+  memset(&g, 0, sizeof(g));
+  if (next && next_plan && next_qkv) {
+    if (next_plan->pos_L % 32 != 0 || !next_plan->tok_slot || !next_plan->pos_code)
+      return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs pos_L %% 32 == 0 and the next plan's tok_slot / pos_code");
+    g.Wqkv = (const __nv_bfloat16*)next->in_proj_w_bf16;
+    g.bqkv = next->in_proj_b;
+    g.next_slot = next_plan->tok_slot;
+    g.next_pos_code = next_plan->pos_code;
+    g.pos_tab = next_plan->pos_table;
+    g.posL = next_plan->pos_L;
+    g.pos_maxw = next_plan->pos_maxw;
+    g.pos_ndim = next_plan->pos_ndim;
+    g.qkv_out = (__half*)next_qkv;
+  }
   g.att = att;
   g.row_map = row_map;
   g.x = x;

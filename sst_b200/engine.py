@@ -74,6 +74,8 @@ class SSTEngine:
         self.vfe_cfg.precision = PRECISIONS[precision]
         prec = PRECISIONS[precision]
         self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]
+        from .sst_modules import _SraLayer
+        self._layer_array = (_SraLayer * max(len(self._layers), 1))(*[ls for ls, _ in self._layers])
         self._vs_arr, self._rng_arr = L.arr(C.c_float, self.vs), L.arr(C.c_float, self.rng)
         self.stream = torch.cuda.Stream(device=dev)
         self.graph = None
@@ -108,13 +110,13 @@ class SSTEngine:
         for s in range(2):
             L.check(c, lib.sstb200_window_plan_i32(c, self.vc.data_ptr(), cap, self.num.data_ptr(), C.byref(self.wcfg), s,
                                                    C.byref(self._shift_structs[s])))
-        src = self.vf
-        for li, (ls, shift) in enumerate(self._layers):
-            dst = self.x[(li + 1) % 2]
-            L.check(c, lib.sstb200_sra_layer_forward(c, C.byref(ls), C.byref(self._plan_structs[shift]), src.data_ptr(),
-                                                     dst.data_ptr(), cap, self.num.data_ptr(), prec))
-            src = dst
-        self._last = src
+        if self._layers:
+            L.check(c, lib.sstb200_sra_stack_forward(c, self._layer_array, len(self._layers), C.byref(self._plan_structs[0]),
+                                                     C.byref(self._plan_structs[1]), self.vf.data_ptr(), self.x[0].data_ptr(),
+                                                     self.x[1].data_ptr(), cap, self.num.data_ptr(), prec))
+            self._last = self.x[0]
+        else:
+            self._last = self.vf
 
     def load_frames_device(self, points_dev, offsets_dev):
         """points_dev [P,F] fp32 (frames back to back) and offsets_dev int32 [B+1], both already on the device.

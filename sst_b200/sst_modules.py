@@ -252,6 +252,9 @@ class _SraPlan(C.Structure):
 L.SIGNATURES["sstb200_sra_layer_forward"] = (C.c_int, [L.vp, C.POINTER(_SraLayer), C.POINTER(_SraPlan), L.vp, L.vp,
                                                        C.c_int, L.vp, C.c_int])
 
+L.SIGNATURES["sstb200_sra_stack_forward"] = (C.c_int, [L.vp, C.POINTER(_SraLayer), C.c_int, C.POINTER(_SraPlan),
+                                                       C.POINTER(_SraPlan), L.vp, L.vp, L.vp, C.c_int, L.vp, C.c_int])
+
 PRECISIONS = {"fp32": 0, "bf16": 1}
 
 
