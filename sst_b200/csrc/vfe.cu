@@ -376,41 +376,51 @@ __device__ __forceinline__ void tile_decorate(const VfeDev& v, const float* __re
         sF[r][k++] = z - __fadd_rn(__fmul_rn(cz, v.vz), v.z_off);
       }
       if (v.with_distance) sF[r][k++] = sqrtf(x * x + y * y + z * z);
+      for (; k < VFE_MAXD; k++) sF[r][k] = 0.f;
     } else {
       sVox[r] = -1;
     }
   }
 }
 
-// column-wise segmented max over the tile's rows (rows sorted by voxel); tile [VT][ld] fp32 in smem
+// column-wise segmented max over the tile's rows (rows sorted by voxel); tile [VT][ld] fp32 in smem.  blockDim.x / C row
+// groups work in parallel, each on VT / groups consecutive rows; a segment fully inside a group's rows is written with a
+// plain store, the first / last segment of a group may continue in a neighbouring group or tile -> integer atomicMax on the
+// float bits (values are >= 0 after ReLU; the rows concerned are zeroed beforehand by vfe_zero_edges_kernel).
+#define VSUB 32  // finest row-group granularity used by the kernels below
 __device__ __forceinline__ void tile_segmax(const float* tile, int ld, const int* sVox, int nrow, int C, float* __restrict__ out) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int seg = sVox[0];
-    bool first = true;  // segment may continue from the previous tile
-    float m = 0.f;      // post-ReLU values are >= 0
-    for (int r = 0; r < nrow; r++) {
-      int sg = sVox[r];
-      if (sg != seg) {
-        if (first) atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));
-        else out[(size_t)seg * C + c] = m;
-        first = false;
-        seg = sg;
-        m = 0.f;
-      }
-      m = fmaxf(m, tile[r * ld + c]);
+  const int groups = blockDim.x / C;
+  const int rows_per = VT / groups;
+  const int c = threadIdx.x % C, grp = threadIdx.x / C;
+  if (grp >= groups) return;
+  const int r0 = grp * rows_per, r1 = min(r0 + rows_per, nrow);
+  if (r0 >= r1) return;
+  int seg = sVox[r0];
+  bool first = true;  // the segment may have started in the previous group / tile
+  float m = 0.f;      // post-ReLU values are >= 0
+  for (int r = r0; r < r1; r++) {
+    int sg = sVox[r];
+    if (sg != seg) {
+      if (first) atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));
+      else out[(size_t)seg * C + c] = m;
+      first = false;
+      seg = sg;
+      m = 0.f;
     }
-    atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));  // may continue into the next tile
+    m = fmaxf(m, tile[r * ld + c]);
   }
+  atomicMax((int*)&out[(size_t)seg * C + c], __float_as_int(m));  // may continue into the next group / tile
 }
 
 template <typename TC, typename TM, int C0>
 __global__ void __launch_bounds__(256) vfe_l0_tile_kernel(VfeDev v, const float* __restrict__ pts, const TC* __restrict__ coors,
                                                           const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                                           const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
-                                                          const float* __restrict__ vmean, float* __restrict__ vf0) {
+                                                          const float* __restrict__ vmean, float* __restrict__ vf0,
+                                                          __nv_bfloat16* __restrict__ y0buf /*[P, C0] in CSR order, or null*/) {
   pdl_wait();
   pdl_launch();
-  __shared__ float sF[VT][VFE_MAXD];
+  __shared__ __align__(16) float sF[VT][VFE_MAXD];
   __shared__ int sVox[VT];
   __shared__ float sW[VFE_MAXD][C0];  // W0 transposed
   __shared__ float sS[C0], sT[C0];
@@ -428,15 +438,31 @@ __global__ void __launch_bounds__(256) vfe_l0_tile_kernel(VfeDev v, const float*
     __syncthreads();
     tile_decorate<TC, TM>(v, pts, coors, order, map, vmean, k0, nrow, sF, sVox);
     __syncthreads();
-    for (int i = threadIdx.x; i < VT * C0; i += blockDim.x) {
-      int r = i / C0, c = i % C0;
-      float y = 0.f;
-      if (r < nrow) {
-        float a = 0.f;
-        for (int d = 0; d < D0; d++) a = fmaf(sW[d][c], sF[r][d], a);
-        y = fmaxf(fmaf(a, sS[c], sT[c]), 0.f);
+    {
+      // thread = (channel c, row group): the channel's weights live in registers, the decorated point is read as float4
+      const int c = threadIdx.x % C0, grp = threadIdx.x / C0, ngrp = blockDim.x / C0;
+      float wreg[VFE_MAXD];
+#pragma unroll
+      for (int d = 0; d < VFE_MAXD; d++) wreg[d] = d < D0 ? sW[d][c] : 0.f;
+      const float sc = sS[c], sh = sT[c];
+      for (int r = grp; r < VT; r += ngrp) {
+        float y = 0.f;
+        if (r < nrow) {
+          const float4* fp = reinterpret_cast<const float4*>(sF[r]);
+          float a = 0.f;
+#pragma unroll
+          for (int q = 0; q < VFE_MAXD / 4; q++) {
+            float4 f4 = fp[q];  // broadcast: all lanes of the warp read the same row
+            a = fmaf(wreg[4 * q], f4.x, a);
+            a = fmaf(wreg[4 * q + 1], f4.y, a);
+            a = fmaf(wreg[4 * q + 2], f4.z, a);
+            a = fmaf(wreg[4 * q + 3], f4.w, a);
+          }
+          y = fmaxf(fmaf(a, sc, sh), 0.f);
+          if (y0buf) y0buf[(size_t)(k0 + r) * C0 + c] = __float2bfloat16(y);
+        }
+        sY[r * (C0 + 1) + c] = y;
       }
-      sY[r * (C0 + 1) + c] = y;
     }
     __syncthreads();
     tile_segmax(sY, C0 + 1, sVox, nrow, C0, vf0);
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
                                                           const uint32_t* __restrict__ offsets, const int32_t* __restrict__ order,
                                                           const TM* __restrict__ map, const int32_t* __restrict__ nvox_dev,
                                                           const float* __restrict__ vmean, const float* __restrict__ vf0,
-                                                          float* __restrict__ vf1) {
+                                                          float* __restrict__ vf1, const __nv_bfloat16* __restrict__ y0buf) {
   pdl_wait();
   pdl_launch();
   constexpr int K = 2 * C0;
@@ -515,31 +541,19 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
   for (int k0 = blockIdx.x * VT; k0 < nvalid; k0 += gridDim.x * VT) {
     const int nrow = min(VT, nvalid - k0);
     __syncthreads();  // previous tile's smem (sTile aliases sA) fully consumed
-    tile_decorate<TC, TM>(v, pts, coors, order, map, vmean, k0, nrow, sF, sVox);
+    for (int r = tid; r < VT; r += blockDim.x) sVox[r] = r < nrow ? (int)map[order[k0 + r]] : -1;
     __syncthreads();
-    // A operand: row r = [ y0(point) (C0) || vf0[voxel] (C0) ] in bf16.  Two uniform loops (no divergence inside a warp):
-    // (1) layer-0 features recomputed from the decorated point (FFMA), (2) the voxel's layer-0 max, gathered 4 rows in flight
+    // A operand: row r = [ y0(point) (C0) || vf0[voxel] (C0) ] in bf16.  (1) y0 was written (bf16, CSR order) by the layer-0
+    // kernel: plain cp.async into the swizzled operand; (2) the voxel's layer-0 max is gathered 4 rows in flight
     for (int idx = tid; idx < VT * (C0 / 8); idx += blockDim.x) {
       int r = idx / (C0 / 8), j = idx % (C0 / 8);
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; e++) f[e] = 0.f;
-      if (r < nrow) {
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          int c = j * 8 + e;
-          float a = 0.f;
-          for (int d = 0; d < D0; d++) a = fmaf(sW0[d][c], sF[r][d], a);
-          f[e] = fmaxf(fmaf(a, sS0[c], sT0[c]), 0.f);
-        }
-      }
-      int4 q;
-      q.x = (int)pack_bf16(f[0], f[1]);
-      q.y = (int)pack_bf16(f[2], f[3]);
-      q.z = (int)pack_bf16(f[4], f[5]);
-      q.w = (int)pack_bf16(f[6], f[7]);
       int c = j >> 3, jj = j & 7;
-      *reinterpret_cast<int4*>(sA + (size_t)c * VT * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = q;
+      uint8_t* dst = sA + (size_t)c * VT * 128 + r * 128 + ((jj ^ (r & 7)) << 4);
+      if (r < nrow) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(y0buf + (size_t)(k0 + r) * C0 + j * 8) : "memory");
+      } else {
+        *reinterpret_cast<int4*>(dst) = make_int4(0, 0, 0, 0);
+      }
     }
     for (int i0 = tid; i0 < VT * (C0 / 8); i0 += blockDim.x * 4) {
       float4 g0[4], g1[4];
@@ -569,6 +583,7 @@ __global__ void __launch_bounds__(256) vfe_l1_umma_kernel(VfeDev v, const float*
         }
       }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -619,8 +634,8 @@ __global__ void vfe_zero_edges_kernel(const uint32_t* __restrict__ offsets, cons
   pdl_launch();
   const int M = *nvox_dev;
   const int nvalid = M > 0 ? (int)offsets[M] : 0;
-  for (int t = blockIdx.x; t * VT < nvalid; t += gridDim.x) {
-    int k0 = t * VT, k1 = min(k0 + VT, nvalid) - 1;
+  for (int t = blockIdx.x; t * VSUB < nvalid; t += gridDim.x) {
+    int k0 = t * VSUB, k1 = min(k0 + VSUB, nvalid) - 1;
     int v0 = (int)map[order[k0]], v1 = (int)map[order[k1]];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       out[(size_t)v0 * C + c] = 0.f;
@@ -631,14 +646,16 @@ __global__ void vfe_zero_edges_kernel(const uint32_t* __restrict__ offsets, cons
 
 template <typename TC, typename TM, int C0, int C1>
 static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, const TC* coors, const Csr& r, const TM* map,
-                            const int32_t* num_dev, float* vmean, float* vf0, float* out, bool umma_l1, bool* l1_done) {
+                            const int32_t* num_dev, float* vmean, float* vf0, float* out, bool umma_l1, bool* l1_done,
+                            __nv_bfloat16* y0buf) {
   cudaStream_t st = c->stream;
   int grid = c->num_sms * 3;
   launch_pdl(vfe_mean_kernel, dim3(c->num_sms * 8), dim3(256), (size_t)(0), st, pts, v.F, r.offsets, r.order, num_dev, vmean);
   float* dst0 = (C1 > 0) ? vf0 : out;
-  launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 2), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C0, dst0);
+  launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 8), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C0, dst0);
   size_t smem0 = (size_t)VT * (C0 + 1) * 4;
-  launch_pdl(vfe_l0_tile_kernel<TC, TM, C0>, dim3(grid), dim3(256), (size_t)(smem0), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, dst0);
+  launch_pdl(vfe_l0_tile_kernel<TC, TM, C0>, dim3(grid), dim3(256), (size_t)(smem0), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, dst0,
+             (C1 > 0 && umma_l1) ? y0buf : (__nv_bfloat16*)nullptr);
   *l1_done = false;
   if (C1 > 0 && umma_l1) {
     constexpr int C1s = C1 > 0 ? C1 : 32;
@@ -650,8 +667,9 @@ static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, c
       CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       attr_set = true;
     }
-    launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 2), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C1s, out);
-    launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem1), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out);
+    launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 8), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C1s, out);
+    launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem1), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out,
+               (const __nv_bfloat16*)y0buf);
     *l1_done = true;
   }
   LAUNCH_CHECK(c);
@@ -702,7 +720,7 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   if (T > ((long long)1 << 34)) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "voxel grid too large for bitmap rank (%lld cells)", T);
   arena_reset(c);
   int rc = arena_reserve(c, key_index_bytes(P, T) + csr_bytes(P, P) + al256((size_t)P * 4) * 3 + al256((size_t)P * 3 * 4) +
-                                al256((size_t)P * C0 * 4) + al256((size_t)(C0 + C1) * 8) + 8192);
+                                al256((size_t)P * C0 * 4) + al256((size_t)P * C0 * 2 + 128) + al256((size_t)(C0 + C1) * 8) + 8192);
   if (rc) return rc;
   KeyIndex k;
   rc = key_index_alloc(c, k, P, T);
@@ -712,7 +730,8 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   float* vmean = arena_alloc<float>(c, (size_t)P * 3);
   float* vf0 = arena_alloc<float>(c, (size_t)P * C0);
   float* fold = arena_alloc<float>(c, 2 * (size_t)(C0 + C1) + 8);
-  if (!count || !vmean || !vf0 || !fold) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe: arena");
+  __nv_bfloat16* y0buf = arena_alloc<__nv_bfloat16>(c, (size_t)P * C0 + 64);  // layer-0 point features (bf16, CSR order) for the tcgen05 layer 1
+  if (!count || !vmean || !vf0 || !fold || !y0buf) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)P + 2) * 4, c->stream));
   int nb = (P + 255) / 256;
   launch_pdl(vfe_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
@@ -765,8 +784,8 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
     const bool umma = cfg->precision == SSTB200_PREC_BF16;
 #define VFE_TILE(a, b)                                                                                                          \
   if (!tiled && v.mode_max && C0 == a && C1 == b) {                                                                             \
-    if (inverse) rc = launch_vfe_tiles<TC, TC, a, b>(c, v, pts, coors, r, inverse, num_dev, vmean, vf0, out_feats, umma, &l1_done); \
-    else rc = launch_vfe_tiles<TC, int32_t, a, b>(c, v, pts, coors, r, map32, num_dev, vmean, vf0, out_feats, umma, &l1_done);    \
+    if (inverse) rc = launch_vfe_tiles<TC, TC, a, b>(c, v, pts, coors, r, inverse, num_dev, vmean, vf0, out_feats, umma, &l1_done, y0buf); \
+    else rc = launch_vfe_tiles<TC, int32_t, a, b>(c, v, pts, coors, r, map32, num_dev, vmean, vf0, out_feats, umma, &l1_done, y0buf);    \
     if (rc) return rc;                                                                                                          \
     tiled = true;                                                                                                               \
   }
