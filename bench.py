@@ -27,6 +27,11 @@ P_POINTS = 150000
 METRIC = "lidar_frames_per_sec_sst6_fwd_150k"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the two kernels
+# of one bf16 SRA layer (profiles/r01_ncu_full_attn_chain_raw.csv): attention 30.2+104.2 KB, chain 87.0+167.9 KB.
+NCU_LAYER_DRAM_BYTES = int((30.208 + 104.192 + 87.040 + 167.936) * 1e3)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -334,7 +339,10 @@ def main():
         ach = flops / (layer_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": f"SRA encoder layer ({precision} path, all launches of one layer)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel runs inside a 12-layer step)",
+                "traffic": NCU_LAYER_DRAM_BYTES if precision == "bf16" else None,
+                "traffic_source": "profiles/r01_ncu_full_attn_chain_raw.csv (ncu --set full, dram read+write of the "
+                                  "layer's two kernels; activations stay L2-resident between launches)",
+                "peak_source": pk["src"] + " bf16 sustained (kernel runs inside a 12-layer step)",
                 "flops_per_launch": flops, "ms_per_launch": layer_ms, "M": Mv, "sum_n2": sum_n2,
                 "layer_share_of_step": 12 * layer_ms / latency_ms}
 
