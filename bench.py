@@ -189,7 +189,6 @@ def main():
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
 
-    from oracle import sst_oracle as O   # only for the synthetic frame generator + the cpu_baseline leg
     from sst_b200 import build, flagship as fl
     build.build()
     from sst_b200.engine import SSTEngine
@@ -208,7 +207,7 @@ def main():
     # inputs larger than L2: NF distinct resident sweeps (1.8 MB each, > 126 MB in total) are cycled, so no timed step
     # finds its input in L2; weights (3 MB) are legitimately L2-resident in steady state.
     NF = 80
-    base_frames = [O.synth_frame(1000 + rank * 8 + i, P_POINTS) for i in range(8)]
+    base_frames = [fl.synth_frame(1000 + rank * 8 + i, P_POINTS) for i in range(8)]
     frames_h = base_frames
     g = torch.Generator().manual_seed(7 + rank)
     frames_d = []

@@ -55,7 +55,8 @@ int sstb200_dynamic_voxelize(sstb200_ctx* ctx, const float* points, int num_poin
  *     coordinates per column (the reference needs none because it sorts; this build ranks through a
  *     bitmap over the bounding grid).  Outputs (capacity P rows): reduced [.,C], out_coors [.,3],
  *     coors_map [P] (-1 = dropped), reduce_count [.].  num_voxels_dev: device int32.
- *     If num_voxels_host != NULL the call synchronises the stream and stores the count there.
+ *     If num_voxels_host != NULL the call synchronises the stream and stores the count there; it then also fails
+ *     (SSTB200 error, no silent result) if a row with non-negative coordinates lay outside coor_lo/hi.
  *     Reproduces the reference's unconditional removal of the first sorted row (:207-210). */
 int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* ctx, const float* feats, const int32_t* coors,
                                            int num_points, int num_feats, int reduce_type,

@@ -167,8 +167,10 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ---- generic exclusive scan over uint32 values ----------------------------------------------
-// Two launches: (A) per-block totals, last-arriving block scans the totals; (B) per-block scan +
-// block prefix.  `Load` maps element index -> uint32 value.  Block = 256 threads x 8 items.
+// ONE launch, any length: single-pass chained scan with decoupled look-back.  Tiles of 256 threads x 8 items are
+// claimed through an atomic ticket (so a tile only ever waits for tiles that are already running), publish
+// (status, value) as one 64-bit word and look back 32 predecessors at a time.  `Load` maps element index -> uint32.
+// ScanTemps must be zero before the launch (scan_temps_alloc memsets it; one scan per allocation).
 #define SCAN_ITEMS 8
 #define SCAN_THREADS 256
 #define SCAN_TILE (SCAN_ITEMS * SCAN_THREADS)
@@ -176,10 +178,24 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 struct LoadU32 {
   const uint32_t* p;
   __device__ __forceinline__ uint32_t operator()(size_t i) const { return p[i]; }
+  __device__ __forceinline__ void load8(size_t base, size_t n, uint32_t* v) const {
+    if (base + 8 <= n && (((uintptr_t)p) & 15) == 0) {
+      uint4 a = *reinterpret_cast<const uint4*>(p + base), b = *reinterpret_cast<const uint4*>(p + base + 4);
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (base + i < n) ? p[base + i] : 0u;
+    }
+  }
 };
 struct LoadPopc {
   const uint32_t* p;
   __device__ __forceinline__ uint32_t operator()(size_t i) const { return __popc(p[i]); }
+  __device__ __forceinline__ void load8(size_t base, size_t n, uint32_t* v) const {
+    LoadU32{p}.load8(base, n, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __popc(v[i]);
+  }
 };
 
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* total, uint32_t* sh /*[9]*/) {
@@ -211,157 +227,77 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   return res;
 }
 
+struct ScanTemps {
+  uint32_t* ticket;            // [64] words: [0] tile ticket; [1..] free for the owner (totals, flags, counters)
+  unsigned long long* state;   // [tiles] (status << 32 | value); status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix
+};
+static inline size_t scan_num_blocks(size_t n_cap) { return (n_cap + 1 + SCAN_TILE - 1) / SCAN_TILE; }
+static inline size_t scan_temps_bytes(size_t n_cap) { return al256(64 * 4 + (scan_num_blocks(n_cap) + 1) * 8); }
+
 // n may be read from device memory (n_dev != nullptr) so that data-dependent sizes never sync.
 template <typename Load>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_phaseA(Load load, size_t n_host, const int32_t* n_dev,
-                                                            uint32_t* block_sums, uint32_t* block_prefix,
-                                                            uint32_t* ticket, uint32_t* total_out) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(Load load, size_t n_host, const int32_t* n_dev, uint32_t* out,
+                                                                     uint32_t* total_out, bool write_total_at_n, ScanTemps t) {
   pdl_wait();
   pdl_launch();
   __shared__ uint32_t sh[9];
-  __shared__ bool is_last;
-  size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
-  size_t nblk_needed = (n + SCAN_TILE - 1) / SCAN_TILE;
-  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-  uint32_t s = 0;
-  if ((size_t)blockIdx.x < nblk_needed) {
+  __shared__ uint32_t tile_s, prefix_s;
+  const size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
+  if (threadIdx.x == 0) tile_s = atomicAdd(t.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  if ((size_t)tile * SCAN_TILE > n) return;  // index n (the total's slot) lives in tile n / SCAN_TILE
+  const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], s = 0;
+  load.load8(base, n, v);
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-      size_t k = base + i;
-      if (k < n) s += load(k);
+  for (int i = 0; i < SCAN_ITEMS; i++) s += v[i];
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan_256(s, &tot, sh);
+  volatile unsigned long long* state = t.state;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint32_t run = 0;
+    if (tile > 0) {
+      if (lane == 0) state[tile] = (1ull << 32) | tot;
+      long long top = (long long)tile - 1;
+      while (true) {
+        long long idx = top - lane;
+        unsigned long long sv = idx >= 0 ? state[idx] : (2ull << 32);
+        while (__any_sync(0xffffffffu, (sv >> 32) == 0)) sv = idx >= 0 ? state[idx] : (2ull << 32);
+        unsigned incl = __ballot_sync(0xffffffffu, (sv >> 32) == 2);
+        int first = incl ? __ffs(incl) - 1 : 31;
+        uint32_t c = lane <= first ? (uint32_t)sv : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        run += c;
+        if (incl) break;
+        top -= 32;
+      }
+    }
+    if (lane == 0) {
+      state[tile] = (2ull << 32) | (unsigned long long)(run + tot);
+      prefix_s = run;
     }
   }
-  uint32_t tot;
-  block_exclusive_scan_256(s, &tot, sh);
-  if (threadIdx.x == 0) {
-    block_sums[blockIdx.x] = tot;
-    __threadfence();
-    uint32_t t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // last block: scan block_sums[0..gridDim.x) with a running carry
-  uint32_t carry = 0;
-  for (uint32_t b0 = 0; b0 < gridDim.x; b0 += SCAN_THREADS) {
-    uint32_t b = b0 + threadIdx.x;
-    uint32_t v = (b < gridDim.x) ? ((volatile uint32_t*)block_sums)[b] : 0;
-    uint32_t t2;
-    uint32_t ex = block_exclusive_scan_256(v, &t2, sh);
-    if (b < gridDim.x) block_prefix[b] = carry + ex;
-    carry += t2;
-  }
-  if (threadIdx.x == 0) {
-    *total_out = carry;
-    *ticket = 0;  // self-reset so the buffer can be reused by the next scan on the stream
-  }
-}
-
-template <typename Load>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_phaseB(Load load, size_t n_host, const int32_t* n_dev,
-                                                            const uint32_t* block_prefix, uint32_t* out,
-                                                            bool write_total_at_n) {
-  pdl_wait();
-  pdl_launch();
-  __shared__ uint32_t sh[9];
-  size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
-  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-  if ((size_t)blockIdx.x * SCAN_TILE > n) return;
-  uint32_t v[SCAN_ITEMS];
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; i++) {
-    size_t k = base + i;
-    v[i] = (k < n) ? load(k) : 0;
-    s += v[i];
-  }
-  uint32_t tot;
-  uint32_t ex = block_exclusive_scan_256(s, &tot, sh) + block_prefix[blockIdx.x];
+  ex += prefix_s;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; i++) {
     size_t k = base + i;
     if (k < n) out[k] = ex;
-    else if (k == n && write_total_at_n) out[k] = ex;
+    else if (k == n) {
+      if (write_total_at_n) out[k] = ex;
+      *total_out = ex;
+    }
     ex += v[i];
   }
 }
 
-// Single-block variant (one launch) for small inputs: 1024 threads x 8 items per round with a running carry.
-template <typename Load>
-__global__ void __launch_bounds__(1024) scan_single_block(Load load, size_t n_host, const int32_t* n_dev, uint32_t* out,
-                                                          uint32_t* total_out, bool write_total_at_n) {
-  pdl_wait();
-  pdl_launch();
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
-  const size_t n = n_dev ? (size_t)max(*n_dev, 0) : n_host;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (size_t base0 = 0; base0 < n || base0 == 0; base0 += 8192) {
-    size_t base = base0 + (size_t)threadIdx.x * 8;
-    uint32_t v[8], s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      v[i] = (base + i < n) ? load(base + i) : 0;
-      s += v[i];
-    }
-    uint32_t x = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t t = wsum[lane], t0 = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
-      }
-      wsum[lane] = t - t0;  // exclusive warp offsets
-    }
-    __syncthreads();
-    uint32_t ex = carry_s + wsum[w] + x - s;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      size_t k = base + i;
-      if (k < n) out[k] = ex;
-      else if (k == n && write_total_at_n) out[k] = ex;
-      ex += v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = ex;  // ex of the last thread after its 8 items == carry + tile total
-    __syncthreads();
-    if (n == 0) break;
-  }
-  if (threadIdx.x == 0) {
-    *total_out = carry_s;
-    // when n is a multiple of 8192 the element at index n was not visited: write the total there
-    if (write_total_at_n && n > 0 && (n % 8192) == 0) out[n] = carry_s;
-  }
-}
-
-struct ScanTemps {
-  uint32_t* block_sums;
-  uint32_t* block_prefix;
-  uint32_t* ticket;  // must be zero before first use (self-resetting afterwards)
-};
-static inline size_t scan_num_blocks(size_t n_cap) { return (n_cap + 1 + SCAN_TILE - 1) / SCAN_TILE + 0; }
-
-// out has n(+1 if write_total_at_n) entries; total_out receives the grand total.
+// out has n(+1 if write_total_at_n) entries; total_out receives the grand total.  `t` must be freshly zeroed.
 template <typename Load>
 static inline void launch_exclusive_scan(cudaStream_t st, Load load, size_t n_cap, const int32_t* n_dev,
                                          ScanTemps t, uint32_t* out, uint32_t* total_out, bool write_total_at_n) {
-  if (n_cap <= ((size_t)1 << 18)) {  // one launch instead of two; the block only walks the actual (device) length
-    launch_pdl(scan_single_block<Load>, dim3(1), dim3(1024), (size_t)0, st, load, n_cap, n_dev, out, total_out, write_total_at_n);
-    return;
-  }
-  unsigned nblk = (unsigned)((n_cap + 1 + SCAN_TILE - 1) / SCAN_TILE);
-  if (nblk == 0) nblk = 1;
-  launch_pdl(scan_phaseA<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)(0), st, load, n_cap, n_dev, t.block_sums, t.block_prefix, t.ticket, total_out);
-  launch_pdl(scan_phaseB<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)(0), st, load, n_cap, n_dev, t.block_prefix, out, write_total_at_n);
+  unsigned nblk = (unsigned)scan_num_blocks(n_cap);
+  launch_pdl(scan_lookback_kernel<Load>, dim3(nblk), dim3(SCAN_THREADS), (size_t)0, st, load, n_cap, n_dev, out, total_out, write_total_at_n, t);
 }

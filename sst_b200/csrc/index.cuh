@@ -23,31 +23,37 @@ struct KeyIndex {
 
 static size_t key_index_bytes(size_t P, long long T) {
   size_t nwords = (size_t)((T + 31) / 32);
-  size_t nblk = scan_num_blocks(nwords) + 2;
-  return al256(P * 8) + al256(nwords * 4) + al256((nwords + 1) * 4) + 4 * al256(nblk * 4) + 1024;
+  return al256(P * 8) + al256(nwords * 4) + al256((nwords + 1) * 4) + scan_temps_bytes(nwords) + 1024;
 }
 
 static int key_index_alloc(sstb200_ctx* c, KeyIndex& k, size_t P, long long T) {
   k.T = T;
   k.nwords = (size_t)((T + 31) / 32);
-  size_t nblk = scan_num_blocks(k.nwords) + 2;
   k.keys = arena_alloc<long long>(c, P ? P : 1);
-  k.bitmap = arena_alloc<uint32_t>(c, k.nwords);
+  // bitmap and scan temporaries are adjacent: ONE memset clears both
+  size_t bm_bytes = al256(k.nwords * 4), st_bytes = scan_temps_bytes(k.nwords);
+  uint8_t* z = arena_alloc<uint8_t>(c, bm_bytes + st_bytes);
   k.word_prefix = arena_alloc<uint32_t>(c, k.nwords + 1);
-  k.st.block_sums = arena_alloc<uint32_t>(c, nblk);
-  k.st.block_prefix = arena_alloc<uint32_t>(c, nblk);
-  k.st.ticket = arena_alloc<uint32_t>(c, 64);
+  if (!k.keys || !z || !k.word_prefix) return sstb_fail(c, SSTB_ERR_WORKSPACE, "key index: arena too small");
+  k.bitmap = (uint32_t*)z;
+  k.st.ticket = (uint32_t*)(z + bm_bytes);
+  k.st.state = (unsigned long long*)(k.st.ticket + 64);
   k.total = k.st.ticket + 1;
   k.flags = (int32_t*)(k.st.ticket + 2);
-  if (!k.keys || !k.bitmap || !k.word_prefix || !k.st.block_sums || !k.st.block_prefix || !k.st.ticket)
-    return sstb_fail(c, SSTB_ERR_WORKSPACE, "key index: arena too small");
-  CUDA_TRY(c, cudaMemsetAsync(k.bitmap, 0, k.nwords * 4, c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(k.st.ticket, 0, 64 * 4, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(z, 0, bm_bytes + st_bytes, c->stream));
   return SSTB_OK;
 }
 
 static void key_index_scan(sstb200_ctx* c, KeyIndex& k) {
   launch_exclusive_scan(c->stream, LoadPopc{k.bitmap}, k.nwords, nullptr, k.st, k.word_prefix, k.total, true);
+}
+
+// Set one bit; most points fall into an already-marked cell, so test (L2 read, never L1: the bitmap is written by atomics
+// of other SMs) before paying for the atomic.
+__device__ __forceinline__ void bitmap_set(uint32_t* __restrict__ bitmap, long long key) {
+  uint32_t* w = bitmap + (key >> 5);
+  uint32_t bit = 1u << (key & 31);
+  if ((__ldcg(w) & bit) == 0) atomicOr(w, bit);
 }
 
 // ---- mark kernels --------------------------------------------------------------------------------
@@ -61,27 +67,29 @@ __global__ void mark_rows_kernel(const TI* __restrict__ rows, int n, Extents e, 
   if (n_dev) n = *n_dev;
   if (i >= n) return;
   long long key = 0;
-  bool bad = false;
+  bool bad = false, neg = false;
 #pragma unroll 4
   for (int d = 0; d < e.ndim; d++) {
     long long v = (long long)rows[(size_t)i * e.ndim + d];
-    if (negative_is_invalid && v < 0) bad = true;
+    if (negative_is_invalid && v < 0) neg = true;
     long long r = v - e.lo[d];
     if (r < 0 || r >= e.ext[d]) bad = true;
     key = key * e.ext[d] + r;
   }
-  if (bad) {
+  if (bad || neg) {
     keys[i] = -1;
     flags[0] = 1;
+    if (!neg) flags[1] = 1;  // a row outside the caller's bounds (not a "negative = invalid" row): the bounds were wrong
     return;
   }
   keys[i] = key;
-  atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+  bitmap_set(bitmap, key);
 }
 
 // ---- emit unique rows (decode keys of set bits) ----------------------------------------------------
-template <typename TO>
-__global__ void emit_rows_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
+// One thread per bitmap word; SMALL = the whole key space fits 31 bits (32-bit divisions instead of 64-bit ones).
+template <typename TO, bool SMALL>
+__global__ void __launch_bounds__(64) emit_rows_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
                                  size_t nwords, Extents e, int shift_if_no_invalid, const int32_t* __restrict__ flags,
                                  TO* __restrict__ out_rows, const uint32_t* __restrict__ total, int32_t* __restrict__ num_out) {
   pdl_wait();
@@ -100,19 +108,40 @@ __global__ void emit_rows_kernel(const uint32_t* __restrict__ bitmap, const uint
       int b = __ffs(bits) - 1;
       bits &= bits - 1;
       if (v >= 0) {
-        long long key = (long long)w * 32 + b;
         TO c[4];
+        if (SMALL) {
+          uint32_t key = (uint32_t)w * 32u + (uint32_t)b;
 #pragma unroll 4
-        for (int d = e.ndim - 1; d >= 0; d--) {
-          long long q = key / e.ext[d];
-          c[d] = (TO)(key - q * e.ext[d] + e.lo[d]);
-          key = q;
+          for (int d = e.ndim - 1; d >= 0; d--) {
+            uint32_t ext = (uint32_t)e.ext[d], q = key / ext;
+            c[d] = (TO)((long long)(key - q * ext) + e.lo[d]);
+            key = q;
+          }
+        } else {
+          long long key = (long long)w * 32 + b;
+#pragma unroll 4
+          for (int d = e.ndim - 1; d >= 0; d--) {
+            long long q = key / e.ext[d];
+            c[d] = (TO)(key - q * e.ext[d] + e.lo[d]);
+            key = q;
+          }
         }
         for (int d = 0; d < e.ndim; d++) out_rows[(size_t)v * e.ndim + d] = c[d];
       }
       v++;
     }
   }
+}
+template <typename TO>
+static void launch_emit_rows(sstb200_ctx* c, const KeyIndex& k, const Extents& e, int shift_if_no_invalid, TO* out_rows,
+                             int32_t* num_out) {
+  size_t eg = (k.nwords + 63) / 64;
+  if (eg > (size_t)c->num_sms * 32) eg = (size_t)c->num_sms * 32;
+  if (eg == 0) eg = 1;
+  if (k.T < ((long long)1 << 31))
+    launch_pdl(emit_rows_kernel<TO, true>, dim3((unsigned)eg), dim3(64), (size_t)(0), c->stream, (const uint32_t*)k.bitmap, (const uint32_t*)k.word_prefix, k.nwords, e, shift_if_no_invalid, (const int32_t*)k.flags, out_rows, (const uint32_t*)k.total, num_out);
+  else
+    launch_pdl(emit_rows_kernel<TO, false>, dim3((unsigned)eg), dim3(64), (size_t)(0), c->stream, (const uint32_t*)k.bitmap, (const uint32_t*)k.word_prefix, k.nwords, e, shift_if_no_invalid, (const int32_t*)k.flags, out_rows, (const uint32_t*)k.total, num_out);
 }
 
 // ---- map + count -------------------------------------------------------------------------------------
@@ -195,10 +224,132 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
   }
 }
 
+// Vector variant (C % 4 == 0, 16-B aligned rows): GROUP lanes own one segment, each lane owns float4 channel groups
+// lane, lane+GROUP, ... (NV4 of them, C = 4*GROUP*NV4 at most), and FOUR points are in flight per lane (independent index and row
+// loads) - a 128-channel row is one 512-B warp transaction.  Same arithmetic as the scalar kernel (max with lowest-index tie
+// break for argmax; sum/mean in fp64, so independent of the CSR order).
+template <int GROUP, int NV4>
+__global__ void __launch_bounds__(256) segment_reduce_v4_kernel(const float* __restrict__ src, int C,
+                                                                const uint32_t* __restrict__ offsets,
+                                                                const int32_t* __restrict__ order, int nseg_host,
+                                                                const int32_t* __restrict__ nseg_dev, int mode,
+                                                                float empty_value, float* __restrict__ out,
+                                                                long long* __restrict__ argmax, int n_rows) {
+  pdl_wait();
+  pdl_launch();
+  const int nseg = nseg_dev ? *nseg_dev : nseg_host;
+  const int groups_per_block = blockDim.x / GROUP;
+  const int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
+  const int C4 = C >> 2;
+  const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+  for (int s = blockIdx.x * groups_per_block + g; s < nseg; s += gridDim.x * groups_per_block) {
+    const uint32_t b = offsets[s], e = offsets[s + 1];
+    if (mode == SSTB200_REDUCE_MAX) {
+      float4 m[NV4];
+      int am[NV4][4];
+#pragma unroll
+      for (int j = 0; j < NV4; j++) {
+        m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        am[j][0] = am[j][1] = am[j][2] = am[j][3] = n_rows;
+      }
+      for (uint32_t k = b; k < e; k += 4) {
+        int p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = (k + u < e) ? order[k + u] : -1;
+        float4 v[4][NV4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int j = 0; j < NV4; j++)
+            if (p[u] >= 0 && l + j * GROUP < C4) v[u][j] = __ldg(&src4[(size_t)p[u] * C4 + l + j * GROUP]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (p[u] < 0) continue;
+#pragma unroll
+          for (int j = 0; j < NV4; j++) {
+            if (l + j * GROUP >= C4) continue;
+            const float x[4] = {v[u][j].x, v[u][j].y, v[u][j].z, v[u][j].w};
+            float* mm = &m[j].x;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (x[q] > mm[q] || (x[q] == mm[q] && p[u] < am[j][q])) {
+                mm[q] = x[q];
+                am[j][q] = p[u];
+              }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV4; j++) {
+        int c4 = l + j * GROUP;
+        if (c4 >= C4) continue;
+        if (b == e) m[j] = make_float4(empty_value, empty_value, empty_value, empty_value);
+        reinterpret_cast<float4*>(out)[(size_t)s * C4 + c4] = m[j];
+        if (argmax) {
+          longlong2* a2 = reinterpret_cast<longlong2*>(argmax + (size_t)s * C + 4 * c4);
+          a2[0] = make_longlong2(am[j][0], am[j][1]);
+          a2[1] = make_longlong2(am[j][2], am[j][3]);
+        }
+      }
+    } else {
+      double acc[NV4][4];
+#pragma unroll
+      for (int j = 0; j < NV4; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+      for (uint32_t k = b; k < e; k += 4) {
+        int p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = (k + u < e) ? order[k + u] : -1;
+        float4 v[4][NV4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int j = 0; j < NV4; j++)
+            v[u][j] = (p[u] >= 0 && l + j * GROUP < C4) ? __ldg(&src4[(size_t)p[u] * C4 + l + j * GROUP])
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int j = 0; j < NV4; j++) {
+            acc[j][0] += (double)v[u][j].x;
+            acc[j][1] += (double)v[u][j].y;
+            acc[j][2] += (double)v[u][j].z;
+            acc[j][3] += (double)v[u][j].w;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < NV4; j++) {
+        int c4 = l + j * GROUP;
+        if (c4 >= C4) continue;
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          r[q] = (float)acc[j][q];
+          if (mode == SSTB200_REDUCE_MEAN && e > b) r[q] = (float)acc[j][q] / (float)(e - b);
+        }
+        reinterpret_cast<float4*>(out)[(size_t)s * C4 + c4] = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+}
+
 static void launch_segment_reduce(sstb200_ctx* c, const float* src, int C, const uint32_t* offsets,
                                   const int32_t* order, int nseg_cap, const int32_t* nseg_dev, int mode,
                                   float empty_value, float* out, long long* argmax, int n_rows) {
   int grid = c->num_sms * 8;
+  const bool vec = (C % 4 == 0) && C <= 256 && (((uintptr_t)src | (uintptr_t)out | (uintptr_t)argmax) & 15) == 0;
+#define SEGV4(G, NV) launch_pdl(segment_reduce_v4_kernel<G, NV>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows)
+  if (vec) {
+    int c4 = C / 4;
+    if (c4 > 32) SEGV4(32, 2);
+    else if (c4 > 16) SEGV4(32, 1);
+    else if (c4 > 8) SEGV4(16, 1);
+    else if (c4 > 4) SEGV4(8, 1);
+    else if (c4 > 2) SEGV4(4, 1);
+    else if (c4 > 1) SEGV4(2, 1);
+    else SEGV4(1, 1);
+    return;
+  }
+#undef SEGV4
   if (C >= 32)
     launch_pdl(segment_reduce_kernel<32>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows);
   else if (C > 4)
@@ -209,31 +360,29 @@ static void launch_segment_reduce(sstb200_ctx* c, const float* src, int C, const
 
 // CSR over a map -> (offsets[nseg+1], order[n]) ; count must already hold per-segment counts.
 struct Csr {
-  uint32_t* offsets;
+  uint32_t* offsets = nullptr;
   int32_t* order;
   int32_t* cursor;
   ScanTemps st;
   uint32_t* total;
 };
 static size_t csr_bytes(size_t n, size_t nseg_cap) {
-  size_t nblk = scan_num_blocks(nseg_cap) + 2;
-  return al256((nseg_cap + 2) * 4) * 2 + al256(n * 4 + 4) + 3 * al256(nblk * 4) + 2048;
+  return al256((nseg_cap + 2) * 4) * 2 + al256(n * 4 + 4) + scan_temps_bytes(nseg_cap) + 2048;
 }
 template <typename TM>
 static int csr_build(sstb200_ctx* c, Csr& r, const TM* map, int n, const int32_t* count, size_t nseg_cap,
                      const int32_t* nseg_dev, const int32_t* n_dev = nullptr) {
-  size_t nblk = scan_num_blocks(nseg_cap) + 2;
-  r.offsets = arena_alloc<uint32_t>(c, nseg_cap + 2);
-  r.cursor = arena_alloc<int32_t>(c, nseg_cap + 2);
+  if (!r.offsets) r.offsets = arena_alloc<uint32_t>(c, nseg_cap + 2);  // preset = caller-owned [nseg_cap + 1]
+  // cursor and scan temporaries are adjacent: ONE memset clears both
+  size_t cur_bytes = al256((nseg_cap + 2) * 4), st_bytes = scan_temps_bytes(nseg_cap);
+  uint8_t* z = arena_alloc<uint8_t>(c, cur_bytes + st_bytes);
   r.order = arena_alloc<int32_t>(c, n + 1);
-  r.st.block_sums = arena_alloc<uint32_t>(c, nblk);
-  r.st.block_prefix = arena_alloc<uint32_t>(c, nblk);
-  r.st.ticket = arena_alloc<uint32_t>(c, 64);
-  if (!r.offsets || !r.cursor || !r.order || !r.st.block_sums || !r.st.block_prefix || !r.st.ticket)
-    return sstb_fail(c, SSTB_ERR_WORKSPACE, "csr: arena too small");
+  if (!r.offsets || !z || !r.order) return sstb_fail(c, SSTB_ERR_WORKSPACE, "csr: arena too small");
+  r.cursor = (int32_t*)z;
+  r.st.ticket = (uint32_t*)(z + cur_bytes);
+  r.st.state = (unsigned long long*)(r.st.ticket + 64);
   r.total = r.st.ticket + 1;
-  CUDA_TRY(c, cudaMemsetAsync(r.st.ticket, 0, 64 * 4, c->stream));
-  CUDA_TRY(c, cudaMemsetAsync(r.cursor, 0, (nseg_cap + 2) * 4, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(z, 0, cur_bytes + st_bytes, c->stream));
   launch_exclusive_scan(c->stream, LoadU32{(const uint32_t*)count}, nseg_cap, nseg_dev, r.st, r.offsets, r.total, true);
   if (n > 0) launch_pdl(csr_fill_kernel<TM>, dim3((n + 255) / 256), dim3(256), (size_t)(0), c->stream, map, n, r.offsets, r.cursor, r.order, n_dev);
   LAUNCH_CHECK(c);

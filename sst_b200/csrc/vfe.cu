@@ -69,7 +69,7 @@ __global__ void vfe_mark_kernel(const TC* __restrict__ coors, int P, int B, int 
   }
   long long key = b * (long long)cells_pad + (z * Y + y) * X + x;
   keys[i] = key;
-  atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+  bitmap_set(bitmap, key);
 }
 
 template <typename TM>
@@ -112,14 +112,23 @@ __global__ void vfe_emit_kernel(const uint32_t* __restrict__ bitmap, const uint3
     uint32_t bits = bitmap[w];
     if (!bits) continue;
     long long rank = word_prefix[w];
-    int b = (int)((w * 32) / cells_pad);
+    int b = (w * 32 < cells_pad) ? 0 : (int)((w * 32) / cells_pad);
     while (bits) {
       int bit = __ffs(bits) - 1;
       bits &= bits - 1;
       long long row = quirk_row(q, rank, b);
       if (row >= 0) {
         long long local = (long long)(w * 32 + bit) - (long long)b * (long long)cells_pad;
-        long long x = local % X, y = (local / X) % Y, z = local / ((long long)X * Y);
+        long long x, y, z;
+        if (cells_pad < ((size_t)1 << 31)) {  // 32-bit divisions (every real canvas)
+          uint32_t lc = (uint32_t)local, q1 = lc / (uint32_t)X;
+          x = lc - q1 * (uint32_t)X;
+          uint32_t q2 = q1 / (uint32_t)Y;
+          y = q1 - q2 * (uint32_t)Y;
+          z = q2;
+        } else {
+          x = local % X, y = (local / X) % Y, z = local / ((long long)X * Y);
+        }
         out_coors[row * 4 + 0] = (TO)b;
         out_coors[row * 4 + 1] = (TO)z;
         out_coors[row * 4 + 2] = (TO)y;
@@ -737,9 +746,9 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   launch_pdl(vfe_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
   key_index_scan(c, k);
   SampleQuirk q{k.word_prefix, cells_pad / 32, B, cfg->drop_first_voxel_per_sample != 0};
-  int eg = (int)((k.nwords + 255) / 256);
-  if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  launch_pdl(vfe_emit_kernel<TC>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
+  int eg = (int)((k.nwords + 63) / 64);
+  if (eg > c->num_sms * 32) eg = c->num_sms * 32;
+  launch_pdl(vfe_emit_kernel<TC>, dim3(eg), dim3(64), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
   Csr r;
   if (inverse) {
     launch_pdl(vfe_map_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, inverse, count);

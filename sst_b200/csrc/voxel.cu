@@ -124,9 +124,7 @@ extern "C" int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* c, const floa
   int nb = (P + 255) / 256;
   launch_pdl(mark_rows_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, e, true, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
-  int eg = (int)((k.nwords + 255) / 256);
-  if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  launch_pdl(emit_rows_kernel<int32_t>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, e, 1, k.flags, out_coors, k.total, num_dev);
+  launch_emit_rows<int32_t>(c, k, e, 1, out_coors, num_dev);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 1, k.flags, coors_map, reduce_count, nullptr);
   LAUNCH_CHECK(c);
   Csr r;
@@ -135,7 +133,13 @@ extern "C" int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* c, const floa
   launch_segment_reduce(c, feats, C, r.offsets, r.order, P, num_dev, reduce_type,
                         reduce_type == SSTB200_REDUCE_MAX ? -INFINITY : 0.f, reduced, nullptr, P);
   LAUNCH_CHECK(c);
-  if (num_host) return read_back_i32(c, num_dev, num_host);
+  if (num_host) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, num_dev, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32 + 1, k.flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *num_host = c->pinned_i32[0];
+    if (c->pinned_i32[1]) return sstb_fail(c, SSTB_ERR_ARG, "dynamic_point_to_voxel_forward: a non-negative row lies outside coor_lo/hi");
+  }
   return SSTB_OK;
 }
 
@@ -246,10 +250,7 @@ extern "C" int sstb200_unique_rows_i64(sstb200_ctx* c, const int64_t* coors, int
   int nb = (P + 255) / 256;
   launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)coors, P, e, false, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
-  int eg = (int)((k.nwords + 255) / 256);
-  if (eg > c->num_sms * 16) eg = c->num_sms * 16;
-  launch_pdl(emit_rows_kernel<long long>, dim3(eg), dim3(256), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, e, 0, k.flags,
-                                                         (long long*)new_coors, k.total, num_dev);
+  launch_emit_rows<long long>(c, k, e, 0, (long long*)new_coors, num_dev);
   launch_pdl(map_count_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 0, k.flags,
                                                          (long long*)inverse, counts, nullptr);
   LAUNCH_CHECK(c);
@@ -299,14 +300,14 @@ extern "C" int sstb200_ingroup_indices(sstb200_ctx* c, const int64_t* group, int
   if (rc) return rc;
   int32_t* cid = arena_alloc<int32_t>(c, N);
   int32_t* count = arena_alloc<int32_t>(c, (size_t)N + 2);
-  int32_t* ng = (int32_t*)(k.st.ticket + 8);
+  const int32_t* ng = (const int32_t*)k.total;  // #distinct groups, written by the bitmap scan
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)N + 2) * 4, c->stream));
   int nb = (N + 255) / 256;
   launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)group, N, e, false, k.keys, k.bitmap, k.flags, nullptr);
   key_index_scan(c, k);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, N, k.bitmap, k.word_prefix, 0, k.flags, cid, count, nullptr);
-  CUDA_TRY(c, cudaMemcpyAsync(ng, k.total, 4, cudaMemcpyDeviceToDevice, c->stream));
   Csr r;
+  r.offsets = nullptr;
   rc = csr_build<int32_t>(c, r, cid, N, count, N, ng);
   if (rc) return rc;
   launch_pdl(stable_rank_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(0), c->stream, r.offsets, r.order, ng, nullptr, (long long*)out, nullptr, nullptr);

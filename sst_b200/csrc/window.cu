@@ -70,7 +70,7 @@ __global__ void win_mark_kernel(const TC* __restrict__ coors, int n, const int32
     return;
   }
   keys[i] = key;
-  atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+  bitmap_set(bitmap, key);
 }
 
 struct LevelCfg {
@@ -254,10 +254,9 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
                                                  (long long*)o->coors_in_win, o->pos_code);
   key_index_scan(c, k);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, n, k.bitmap, k.word_prefix, 0, k.flags, o->tok_win, count, n_dev);
-  int32_t* nwin = (int32_t*)(k.st.ticket + 8);
-  CUDA_TRY(c, cudaMemcpyAsync(nwin, k.total, 4, cudaMemcpyDeviceToDevice, c->stream));
+  const int32_t* nwin = (const int32_t*)k.total;  // #distinct windows, written by the bitmap scan
   Csr r;
-  r.offsets = nullptr;
+  r.offsets = (uint32_t*)o->win_offsets;  // int32 [n+1] caller buffer (only R+1 entries are meaningful): the scan writes it in place
   rc = csr_build<int32_t>(c, r, o->tok_win, n, count, nwcap, nwin, n_dev);
   if (rc) return rc;
   // the reference-layout outputs (drop level, flat2win index, per-level window rank) are only produced on request; the
@@ -274,8 +273,6 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   if (o->win_batch)
     launch_pdl(win_batch_kernel, dim3((n / 112 + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
                112, o->win_batch, o->counters);
-  // offsets -> caller buffer (int32 [n+1]); only R+1 entries are meaningful
-  CUDA_TRY(c, cudaMemcpyAsync(o->win_offsets, r.offsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
   LAUNCH_CHECK(c);
   if (err_host) {
     CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, k.flags, 8, cudaMemcpyDeviceToHost, c->stream));

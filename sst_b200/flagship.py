@@ -1,5 +1,7 @@
 """Factory for the BASELINE.json configurations (config dicts = the reference's own, e.g.
 configs/sst_refactor/sst_waymoD5_1x_3class_8heads_v2.py:8-72), shared by bench.py, smoke() and the tests."""
+import math
+
 import torch
 
 from .registry import build_backbone, build_middle_encoder, build_voxel_encoder
@@ -49,3 +51,15 @@ def build_sst(cfg=None, seed=0, randomize_norm=True):
                     if 'running_var' in n_:
                         b.copy_(torch.rand(b.shape, generator=g) + 0.5)
     return vfe, il, bb
+
+
+def synth_frame(seed, P=150000, extra_dims=0, sigma=0.04):
+    """The seeded "64-beam ring" synthetic sweep of SURVEY.md 8(d): beam ~ U{0..63}; r0 = 2.5*(74/2.5)^(beam/63);
+    r = r0 + sigma*N(0,1); theta ~ U[0,2pi); z ~ U[-2,4); extra dims ~ U[0,1).  CPU tensor [P, 3+extra_dims] fp32."""
+    g = torch.Generator().manual_seed(seed)
+    beam = torch.randint(0, 64, (P,), generator=g).float()
+    r = 2.5 * (74.0 / 2.5) ** (beam / 63.0) + sigma * torch.randn(P, generator=g)
+    th = torch.rand(P, generator=g) * (2 * math.pi)
+    z = torch.rand(P, generator=g) * 6.0 - 2.0
+    cols = [r * torch.cos(th), r * torch.sin(th), z] + [torch.rand(P, generator=g) for _ in range(extra_dims)]
+    return torch.stack(cols, dim=1).contiguous()

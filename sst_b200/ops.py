@@ -11,6 +11,7 @@ and error behaviour; no CPU path - CPU tensors raise.
     build_mlp, get_activation(_layer) ops/sst/sst_ops.py:334-392             (S3)
 """
 import ctypes as C
+import math
 
 import numpy as np
 import torch
@@ -132,9 +133,9 @@ class _dynamic_scatter(Function):
     """ops/voxel/scatter_points.py:9-49."""
 
     @staticmethod
-    def forward(ctx, feats, coors, reduce_type="max"):
+    def forward(ctx, feats, coors, reduce_type="max", coor_bounds=None):
         voxel_feats, voxel_coors, point2voxel_map, voxel_points_count = dynamic_point_to_voxel_forward(
-            feats, coors, reduce_type)
+            feats, coors, reduce_type, coor_bounds)
         ctx.reduce_type = reduce_type
         ctx.save_for_backward(feats, voxel_feats, point2voxel_map, voxel_points_count)
         ctx.mark_non_differentiable(voxel_coors)
@@ -146,7 +147,7 @@ class _dynamic_scatter(Function):
         grad_feats = torch.empty_like(feats)
         dynamic_point_to_voxel_backward(grad_feats, grad_voxel_feats.contiguous(), feats, voxel_feats.contiguous(),
                                         point2voxel_map, voxel_points_count.contiguous(), ctx.reduce_type)
-        return grad_feats, None, None
+        return grad_feats, None, None, None
 
 
 dynamic_scatter = _dynamic_scatter.apply
@@ -160,10 +161,18 @@ class DynamicScatter(nn.Module):
         self.voxel_size = voxel_size
         self.point_cloud_range = point_cloud_range
         self.average_points = average_points
+        # (z, y, x) grid of the voxelisation this layer is paired with (voxelize.py:95-100): the bitmap-rank index is
+        # sized from it, so no reduction + host sync over the coordinates is needed.  Coordinates outside this grid
+        # (impossible when they come from `Voxelization` with the same range) make the call fail loudly.
+        self._bounds = None
+        if voxel_size is not None and point_cloud_range is not None:
+            r, v = point_cloud_range, voxel_size
+            g = [int(math.ceil((r[3 + i] - r[i]) / v[i])) + 1 for i in range(3)]  # ceil-grid of voxelization_cpu.cpp:151-158, +1 slack
+            self._bounds = ([0, 0, 0], [g[2], g[1], g[0]])
 
     def forward_single(self, points, coors):
         reduce = "mean" if self.average_points else "max"
-        return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce)
+        return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce, self._bounds)
 
     def forward(self, points, coors):
         if coors.size(-1) == 3:

@@ -84,3 +84,10 @@ def test_reference_configs_load_and_build_unchanged():
     for t in ("DynamicVFE", "SSTInputLayerV2", "SSTv2", "DynamicScatterVFE", "SIR"):
         assert built.get(t, 0) >= 1, f"no config exercised {t}: {built}"
     assert not built.get("unsupported"), built.get("unsupported")
+
+
+def test_product_synth_frame_equals_oracle_generator():
+    """bench.py draws its sweeps from sst_b200.flagship.synth_frame; the oracle's generator is the checker."""
+    from sst_b200 import flagship as fl
+    for seed, P, extra in ((1000, 5000, 0), (3, 777, 2)):
+        assert torch.equal(fl.synth_frame(seed, P, extra), O.synth_frame(seed, P, extra))

@@ -1,12 +1,11 @@
 """In-graph latency of the frame engine as a function of the number of SRA blocks (slope = true per-layer cost)."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
-from oracle import sst_oracle as O
 from sst_b200 import flagship as fl
 from sst_b200.engine import SSTEngine
 dev = torch.device('cuda:0')
 P = 150000
-pts = O.synth_frame(1000, P).to(dev)
+pts = fl.synth_frame(1000, P).to(dev)
 offs = torch.tensor([0, P], dtype=torch.int32, device=dev)
 prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16'
 for nb in (0, 1, 2, 4, 6):
