@@ -271,6 +271,20 @@ int sstb200_sir_layer_forward(sstb200_ctx* ctx, const sstb200_sir_layer* layer, 
                               const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
                               float* out_point, float* out_group);
 
+/* S1' as above, plus: a cached group CSR (csr_offsets [G+1], csr_order [N] from sstb200_group_csr; both NULL = built inside),
+ * `precision` (SSTB200_PREC_BF16: the rel-MLP's last layer and both VFE layers run as tcgen05 GEMMs with bf16 operands and fp32
+ * accumulation - needs feat_channels [128,128], rel-MLP [16,32,cin], cin <= 192, else SSTB200 "unsupported" error) and a row
+ * pitch for out_point (>= C_last; lets SIR.forward write block i's point features straight into block i+1's [points || feats]
+ * input; bf16 path only, 0 = dense). */
+int sstb200_sir_layer_forward_ex(sstb200_ctx* ctx, const sstb200_sir_layer* layer, const float* in_feats,
+                                 const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
+                                 const int32_t* csr_offsets, const int32_t* csr_order, int precision, float* out_point,
+                                 int out_point_ld, float* out_group);
+
+/* Points grouped by `inv` (values in [0, num_groups)): offsets [num_groups+1] int32, order [num_points] int32 (order inside a
+ * group unspecified).  What SIR.forward (models/backbones/sir.py:67-87, `unique_once`) shares between its blocks. */
+int sstb200_group_csr(sstb200_ctx* ctx, const int64_t* inv, int num_points, int num_groups, int32_t* offsets, int32_t* order);
+
 /* A4  the whole encoder stack (SSTv2.forward's block loop, mmdet3d/models/backbones/sst_v2.py:129-133 with
  * BasicShiftBlockV2.forward, models/sst/sst_basic_block_v2.py:144-169): layer l uses the windows of shift l % 2.
  * x [n,d] input (not modified), y [n,d] output, tmp [n,d] scratch; all fp32, distinct buffers.  With precision BF16 and the

@@ -182,6 +182,59 @@ __global__ void csr_fill_kernel(const TM* __restrict__ map, int n, const uint32_
   order[offsets[v] + pos] = i;
 }
 
+// ---- few-segment variants (e.g. FSD instance groups: 150k points in ~256 groups) ----------------------------------------
+// Direct atomics would serialise on a handful of addresses; here every block first ranks its CSR_SMALL_ITEMS points in
+// shared memory and touches each global counter once.
+#define CSR_SMALL_MAX 4096
+#define CSR_SMALL_ITEMS 4096
+template <typename TM>
+__global__ void __launch_bounds__(1024) count_small_kernel(const TM* __restrict__ map, int n, int nseg, int32_t* __restrict__ count,
+                                                           int32_t* __restrict__ err) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ int sh_cnt[];
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x) sh_cnt[s] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * CSR_SMALL_ITEMS;
+  for (int i = base + threadIdx.x; i < min(base + CSR_SMALL_ITEMS, n); i += blockDim.x) {
+    long long v = (long long)map[i];
+    if (v < 0 || v >= nseg) *err = 1;
+    else atomicAdd(&sh_cnt[v], 1);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x)
+    if (sh_cnt[s]) atomicAdd(&count[s], sh_cnt[s]);
+}
+template <typename TM>
+__global__ void __launch_bounds__(1024) csr_fill_small_kernel(const TM* __restrict__ map, int n, int nseg, const uint32_t* __restrict__ offsets,
+                                                              int32_t* __restrict__ cursor, int32_t* __restrict__ order) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ int sh_cnt[];  // [nseg] counts, then [nseg] bases
+  int* sh_base = sh_cnt + nseg;
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x) sh_cnt[s] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * CSR_SMALL_ITEMS;
+  int rank[CSR_SMALL_ITEMS / 1024];
+#pragma unroll
+  for (int k = 0; k < CSR_SMALL_ITEMS / 1024; k++) {
+    int i = base + k * 1024 + threadIdx.x;
+    rank[k] = -1;
+    if (i < n) {
+      long long v = (long long)map[i];
+      if (v >= 0 && v < nseg) rank[k] = atomicAdd(&sh_cnt[v], 1);
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < nseg; s += blockDim.x) sh_base[s] = sh_cnt[s] ? (int)offsets[s] + atomicAdd(&cursor[s], sh_cnt[s]) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < CSR_SMALL_ITEMS / 1024; k++) {
+    int i = base + k * 1024 + threadIdx.x;
+    if (rank[k] >= 0) order[sh_base[(long long)map[i]] + rank[k]] = i;
+  }
+}
+
 // ---- segmented reduce: GROUP lanes cooperate on one segment, lanes stride the channels --------------------
 template <int GROUP>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __restrict__ src, int C,
@@ -360,8 +413,8 @@ static void launch_segment_reduce(sstb200_ctx* c, const float* src, int C, const
 
 // CSR over a map -> (offsets[nseg+1], order[n]) ; count must already hold per-segment counts.
 struct Csr {
-  uint32_t* offsets = nullptr;
-  int32_t* order;
+  uint32_t* offsets = nullptr;  // preset = caller-owned
+  int32_t* order = nullptr;     // preset = caller-owned
   int32_t* cursor;
   ScanTemps st;
   uint32_t* total;
@@ -371,12 +424,12 @@ static size_t csr_bytes(size_t n, size_t nseg_cap) {
 }
 template <typename TM>
 static int csr_build(sstb200_ctx* c, Csr& r, const TM* map, int n, const int32_t* count, size_t nseg_cap,
-                     const int32_t* nseg_dev, const int32_t* n_dev = nullptr) {
+                     const int32_t* nseg_dev, const int32_t* n_dev = nullptr, int small_nseg = 0) {
   if (!r.offsets) r.offsets = arena_alloc<uint32_t>(c, nseg_cap + 2);  // preset = caller-owned [nseg_cap + 1]
   // cursor and scan temporaries are adjacent: ONE memset clears both
   size_t cur_bytes = al256((nseg_cap + 2) * 4), st_bytes = scan_temps_bytes(nseg_cap);
   uint8_t* z = arena_alloc<uint8_t>(c, cur_bytes + st_bytes);
-  r.order = arena_alloc<int32_t>(c, n + 1);
+  if (!r.order) r.order = arena_alloc<int32_t>(c, n + 1);
   if (!r.offsets || !z || !r.order) return sstb_fail(c, SSTB_ERR_WORKSPACE, "csr: arena too small");
   r.cursor = (int32_t*)z;
   r.st.ticket = (uint32_t*)(z + cur_bytes);
@@ -384,7 +437,11 @@ static int csr_build(sstb200_ctx* c, Csr& r, const TM* map, int n, const int32_t
   r.total = r.st.ticket + 1;
   CUDA_TRY(c, cudaMemsetAsync(z, 0, cur_bytes + st_bytes, c->stream));
   launch_exclusive_scan(c->stream, LoadU32{(const uint32_t*)count}, nseg_cap, nseg_dev, r.st, r.offsets, r.total, true);
-  if (n > 0) launch_pdl(csr_fill_kernel<TM>, dim3((n + 255) / 256), dim3(256), (size_t)(0), c->stream, map, n, r.offsets, r.cursor, r.order, n_dev);
+  if (n > 0 && small_nseg > 0 && small_nseg <= CSR_SMALL_MAX && !n_dev)
+    launch_pdl(csr_fill_small_kernel<TM>, dim3((n + CSR_SMALL_ITEMS - 1) / CSR_SMALL_ITEMS), dim3(1024), (size_t)small_nseg * 8, c->stream, map, n, small_nseg,
+               (const uint32_t*)r.offsets, r.cursor, r.order);
+  else if (n > 0)
+    launch_pdl(csr_fill_kernel<TM>, dim3((n + 255) / 256), dim3(256), (size_t)(0), c->stream, map, n, r.offsets, r.cursor, r.order, n_dev);
   LAUNCH_CHECK(c);
   return SSTB_OK;
 }

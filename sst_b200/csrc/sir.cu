@@ -157,6 +157,11 @@ __global__ void segmax_finalize_kernel(const uint32_t* __restrict__ ord, int G, 
   out[(size_t)g * ldo + col0 + c] = (u == 0u) ? 0.f : ord2f(u);  // empty segment -> 0 like torch_scatter
 }
 
+void sstb_sir_segmax_finalize(cudaStream_t st, const uint32_t* ord, int G, int C, float* out, int ldo, int col0) {
+  size_t gn = (size_t)G * C;
+  launch_pdl(segmax_finalize_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, ord, G, C, out, ldo, col0);
+}
+
 // with_shortcut (voxel_encoder.py:753-759): point_feats += features[:, 3:] when the shapes agree
 __global__ void shortcut_kernel(float* __restrict__ out, const float* __restrict__ in_feats, int N, int C, int cin) {
   pdl_wait();
@@ -167,38 +172,95 @@ __global__ void shortcut_kernel(float* __restrict__ out, const float* __restrict
   out[i] += in_feats[(size_t)p * cin + 3 + ch];
 }
 
-extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster,
-                                         const int64_t* inv, int N, int G, float* out_point, float* out_group) {
+// Group CSR (offsets [G+1] int32, order [N] int32): points grouped by `inv`; shared by every block of a SIR backbone.
+static int group_csr(sstb200_ctx* c, const long long* inv, int N, int G, int32_t* offsets_out, int32_t* order_out) {
+  cudaStream_t st = c->stream;
+  int32_t* count = arena_alloc<int32_t>(c, (size_t)G + 2);
+  if (!count) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
+  CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)G + 2) * 4, st));
+  const bool small = G <= CSR_SMALL_MAX;
+  if (small)
+    launch_pdl(count_small_kernel<long long>, dim3((N + CSR_SMALL_ITEMS - 1) / CSR_SMALL_ITEMS), dim3(1024), (size_t)G * 4, st, inv, N, G, count, count + G + 1);
+  else
+    launch_pdl(count_index_kernel, dim3((N + 255) / 256), dim3(256), (size_t)(0), st, inv, N, G, count, count + G + 1);
+  Csr r;
+  r.offsets = (uint32_t*)offsets_out;
+  r.order = order_out;
+  int rc = csr_build<long long>(c, r, inv, N, count, G, nullptr, nullptr, small ? G : 0);
+  if (rc) return rc;
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
+extern "C" int sstb200_group_csr(sstb200_ctx* c, const int64_t* inv, int N, int G, int32_t* offsets, int32_t* order) {
+  CHECK_ARG(c, c && N >= 0 && G >= 0);
+  if (N == 0 || G == 0) return SSTB_OK;
+  CHECK_ARG(c, inv && offsets && order);
+  arena_reset(c);
+  int rc = arena_reserve(c, csr_bytes(N, G) + al256((size_t)G * 4 + 8) + 65536);
+  if (rc) return rc;
+  return group_csr(c, (const long long*)inv, N, G, offsets, order);
+}
+
+int sstb_sir_layer_bf16(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster, const long long* inv,
+                        const int32_t* order, int N, int G, __nv_bfloat16* p0buf, uint32_t* gord, float* gterm, float* out_point, int ldo,
+                        float* out_group);
+
+extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster,
+                                            const int64_t* inv, int N, int G, const int32_t* csr_offsets, const int32_t* csr_order,
+                                            int precision, float* out_point, int out_point_ld, float* out_group) {
   CHECK_ARG(c, c && L && N >= 0 && G >= 0);
   if (N == 0 || G == 0) return SSTB_OK;
   CHECK_ARG(c, in_feats && f_cluster && inv && out_point && out_group);
+  CHECK_ARG(c, (csr_offsets == nullptr) == (csr_order == nullptr));
+  CHECK_ARG(c, precision == SSTB200_PREC_FP32 || precision == SSTB200_PREC_BF16);
   CHECK_ARG(c, L->num_vfe >= 1 && L->num_vfe <= 2 && L->num_rel >= 0 && L->num_rel <= 4 && (L->act == 1 || L->act == 2));
   if (!L->mode_max) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIRLayer: only mode='max' is built");
   const int cin = L->in_channels, C0 = L->feat_channels[0], C1 = L->num_vfe > 1 ? L->feat_channels[1] : 0;
+  const int Clast = C1 ? C1 : C0;
+  if (out_point_ld <= 0) out_point_ld = Clast;
+  CHECK_ARG(c, out_point_ld >= Clast);
   if (cin > 32 * REL_MAXC || C0 > 256 || C1 > 256 || C0 % 32 || C1 % 32)
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIR dims (cin=%d, C0=%d, C1=%d) not supported", cin, C0, C1);
   if (L->num_rel > 0 && L->rel_dims[L->num_rel - 1] != cin) return sstb_fail(c, SSTB_ERR_ARG, "last rel-MLP layer must produce in_channels");
   for (int l = 0; l < L->num_rel; l++)
     if (L->rel_dims[l] > 32 * REL_MAXC) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "rel-MLP width %d", L->rel_dims[l]);
   const int Cmax = C0 > C1 ? C0 : C1;
+  const bool bf16 = precision == SSTB200_PREC_BF16;
+  if (!bf16 && out_point_ld != Clast) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIRLayer fp32 path writes dense point features (ld == C)");
   arena_reset(c);
   int rc = arena_reserve(c, csr_bytes(N, G) + al256((size_t)G * 4 + 8) + al256((size_t)N * cin * 4) + 2 * al256((size_t)N * Cmax * 4) +
-                                2 * al256((size_t)G * Cmax * 4) + 65536);
+                                2 * al256((size_t)G * Cmax * 4) + al256(((size_t)N + 4) * 4) + 65536);
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  // group CSR (once per layer; the group ids are the same for every block - callers may cache at a higher level)
-  int32_t* count = arena_alloc<int32_t>(c, (size_t)G + 2);
+  const int32_t* order = csr_order;
+  if (!order) {
+    int32_t* off = arena_alloc<int32_t>(c, (size_t)G + 2);
+    int32_t* ord = arena_alloc<int32_t>(c, (size_t)N + 1);
+    if (!off || !ord) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
+    rc = group_csr(c, (const long long*)inv, N, G, off, ord);
+    if (rc) return rc;
+    order = ord;
+  }
+  uint32_t* gord = arena_alloc<uint32_t>(c, (size_t)G * Cmax);
+  float* gterm = arena_alloc<float>(c, (size_t)G * Cmax);
+  if (!gord || !gterm) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
+  if (bf16) {
+    __nv_bfloat16* p0buf = arena_alloc<__nv_bfloat16>(c, ((size_t)N + 128) * 128);
+    if (!p0buf) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
+    rc = sstb_sir_layer_bf16(c, L, in_feats, f_cluster, (const long long*)inv, order, N, G, p0buf, gord, gterm, out_point, out_point_ld, out_group);
+    if (rc) return rc;
+    if (L->with_shortcut && cin - 3 == Clast) {
+      if (out_point_ld != Clast) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "shortcut with strided point features");
+      launch_pdl(shortcut_kernel, dim3((unsigned)(((size_t)N * Clast + 255) / 256)), dim3(256), (size_t)(0), st, out_point, in_feats, N, Clast, cin);
+    }
+    LAUNCH_CHECK(c);
+    return SSTB_OK;
+  }
   float* x0 = arena_alloc<float>(c, (size_t)N * cin);
   float* t = arena_alloc<float>(c, (size_t)N * Cmax);
   float* p0 = arena_alloc<float>(c, (size_t)N * Cmax);
-  uint32_t* gord = arena_alloc<uint32_t>(c, (size_t)G * Cmax);
-  float* gterm = arena_alloc<float>(c, (size_t)G * Cmax);
-  if (!count || !x0 || !t || !p0 || !gord || !gterm) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
-  CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)G + 2) * 4, st));
-  launch_pdl(count_index_kernel, dim3((N + 255) / 256), dim3(256), (size_t)(0), st, (const long long*)inv, N, G, count, count + G + 1);
-  Csr r;
-  rc = csr_build<long long>(c, r, (const long long*)inv, N, count, G, nullptr);
-  if (rc) return rc;
+  if (!x0 || !t || !p0) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
 
   // 1. relation MLP + gating
   const float* xin = in_feats;
@@ -243,7 +305,7 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
   const int Cg = C0 + C1;
   size_t gn = (size_t)G * C0;
   launch_pdl(fill_u32_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, gn, 0u);
-  launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, p0out, C0, r.order, (const long long*)inv, N, gord);
+  launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, p0out, C0, order, (const long long*)inv, N, gord);
   launch_pdl(segmax_finalize_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, G, C0, out_group, Cg, 0);
   if (C1) {
     CHECK_ARG(c, L->vfe_w[1] && L->vfe_ln_w[1] && L->vfe_ln_b[1]);
@@ -255,7 +317,7 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
     sstb_add_norm_act(st, t, nullptr, L->vfe_ln_w[1], L->vfe_ln_b[1], nullptr, nullptr, L->norm_eps, out_point, N, nullptr, C1, L->act);
     gn = (size_t)G * C1;
     launch_pdl(fill_u32_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, gn, 0u);
-    launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, out_point, C1, r.order, (const long long*)inv, N, gord);
+    launch_pdl(segmax_sorted_kernel, dim3((N + SEG_ROWS - 1) / SEG_ROWS), dim3(128), (size_t)(0), st, out_point, C1, order, (const long long*)inv, N, gord);
     launch_pdl(segmax_finalize_kernel, dim3((unsigned)((gn + 255) / 256)), dim3(256), (size_t)(0), st, gord, G, C1, out_group, Cg, C0);
   }
   {
@@ -265,4 +327,9 @@ extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer
   }
   LAUNCH_CHECK(c);
   return SSTB_OK;
+}
+
+extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster,
+                                         const int64_t* inv, int N, int G, float* out_point, float* out_group) {
+  return sstb200_sir_layer_forward_ex(c, L, in_feats, f_cluster, inv, N, G, nullptr, nullptr, SSTB200_PREC_FP32, out_point, 0, out_group);
 }

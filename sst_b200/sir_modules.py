@@ -28,6 +28,22 @@ class _SirLayer(C.Structure):
 
 L.SIGNATURES["sstb200_sir_layer_forward"] = (C.c_int, [L.vp, C.POINTER(_SirLayer), L.vp, L.vp, L.vp, C.c_int, C.c_int,
                                                        L.vp, L.vp])
+L.SIGNATURES["sstb200_sir_layer_forward_ex"] = (C.c_int, [L.vp, C.POINTER(_SirLayer), L.vp, L.vp, L.vp, C.c_int, C.c_int,
+                                                          L.vp, L.vp, C.c_int, L.vp, C.c_int, L.vp])
+L.SIGNATURES["sstb200_group_csr"] = (C.c_int, [L.vp, L.vp, C.c_int, C.c_int, L.vp, L.vp])
+_PREC = {"fp32": 0, "bf16": 1}
+
+
+def group_csr(unq_inv, num_groups):
+    """(offsets [G+1] int32, order [N] int32): points grouped by their group id - shared by the blocks of a SIR backbone."""
+    ops._need_cuda(unq_inv)
+    unq_inv = unq_inv.long().contiguous()
+    N, dev = unq_inv.shape[0], unq_inv.device
+    offsets = torch.empty((num_groups + 1,), dtype=torch.int32, device=dev)
+    order = torch.empty((N,), dtype=torch.int32, device=dev)
+    c = L.ctx(dev)
+    L.check(c, L.lib().sstb200_group_csr(c, unq_inv.data_ptr(), N, num_groups, offsets.data_ptr(), order.data_ptr()))
+    return offsets, order
 
 
 @VOXEL_ENCODERS.register_module()
@@ -99,8 +115,13 @@ class SIRLayer(nn.Module):
         s.rel_dist_scaler = float(self.rel_dist_scaler)
         return s
 
+    precision = "fp32"  # 'bf16': rel-MLP layer 3 and both VFE layers on tcgen05 (bf16 operands, fp32 accumulate / LN / pooling)
+
     def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_inv=False,
-                return_both=False, unq_inv_once=None, new_coors_once=None):
+                return_both=False, unq_inv_once=None, new_coors_once=None, csr_once=None, point_feats_out=None):
+        """`csr_once` = group_csr(unq_inv, G) shared between blocks; `point_feats_out` = a [N, >=C] fp32 view (last dim
+        contiguous) that receives the point features in place of a fresh tensor (bf16 path; SIR.forward uses it to write
+        block i's output straight into block i+1's [points || feats] input)."""
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("SIRLayer backward is not built yet; run under eval()/no_grad()")
         ops._need_cuda(features, coors)
@@ -115,15 +136,22 @@ class SIRLayer(nn.Module):
             f_cluster = features[:, :3] - mean[unq_inv]
         f_cluster = f_cluster.float().contiguous()
         C_last = self.feat_channels[-1]
-        point_feats = torch.empty((N, C_last), dtype=torch.float32, device=features.device)
+        if point_feats_out is not None:
+            point_feats = point_feats_out
+            assert point_feats.dtype == torch.float32 and point_feats.shape == (N, C_last) and point_feats.stride(1) == 1
+            ld = point_feats.stride(0)
+        else:
+            point_feats = torch.empty((N, C_last), dtype=torch.float32, device=features.device)
+            ld = C_last
         voxel_feats = torch.empty((G, sum(self.feat_channels)), dtype=torch.float32, device=features.device)
         s = self._struct()
         wants_shortcut = return_both or self.return_point_feats
         s.with_shortcut = int(bool(self.with_shortcut) and wants_shortcut)
+        off, order = csr_once if csr_once is not None else (None, None)
         c = L.ctx(features.device)
-        L.check(c, L.lib().sstb200_sir_layer_forward(c, C.byref(s), features.data_ptr(), f_cluster.data_ptr(),
-                                                     unq_inv.contiguous().data_ptr(), N, G, point_feats.data_ptr(),
-                                                     voxel_feats.data_ptr()))
+        L.check(c, L.lib().sstb200_sir_layer_forward_ex(
+            c, C.byref(s), features.data_ptr(), f_cluster.data_ptr(), unq_inv.contiguous().data_ptr(), N, G, L.ptr(off),
+            L.ptr(order), _PREC[self.precision], point_feats.data_ptr(), ld, voxel_feats.data_ptr()))
         if return_both:
             return point_feats, voxel_feats, new_coors
         if self.return_point_feats:
@@ -151,18 +179,34 @@ class SIR(nn.Module):
                      fusion_layer=None, return_point_feats=(i != num_blocks - 1), return_inv=False, rel_dist_scaler=10.0,
                      xyz_normalizer=xyz_normalizer, act=act, dropout=dropout) for i in range(num_blocks)])
 
+    precision = "fp32"  # forwarded to every block ('bf16' = tensor-core path, see SIRLayer.precision)
+
     def forward(self, points, features, coors, f_cluster=None):
-        # unique once regardless of the flag: the result is identical and the index is reused by every block
+        # unique + group CSR once regardless of the flag: the result is identical and both are reused by every block
         new_coors, unq_inv = ops.unique_rows(coors.long())
+        csr = group_csr(unq_inv, new_coors.shape[0]) if points.shape[0] and new_coors.shape[0] else None
         out_feats = features
         cluster_feat_list = []
         out_coors = new_coors
+        in_feats = torch.cat([points, out_feats], 1)
+        npt = points.shape[1]
         for i, block in enumerate(self.block_list):
-            in_feats = torch.cat([points, out_feats], 1)
-            if i < self.num_blocks - 1:
-                out_feats, out_cluster_feats = block(in_feats, coors, f_cluster, unq_inv_once=unq_inv, new_coors_once=new_coors)
+            block.precision = self.precision
+            last = i == self.num_blocks - 1
+            kw = dict(unq_inv_once=unq_inv, new_coors_once=new_coors, csr_once=csr)
+            nxt = None
+            if (not last and self.precision == "bf16" and block.feat_channels[-1] + npt == self.block_list[i + 1].in_channels
+                    and not (block.with_shortcut and block.in_channels - 3 == block.feat_channels[-1])):
+                # write this block's point features next to the raw points: no torch.cat between blocks
+                nxt = in_feats if in_feats.shape[1] == npt + block.feat_channels[-1] and i > 0 else \
+                    torch.empty((points.shape[0], npt + block.feat_channels[-1]), dtype=torch.float32, device=points.device)
+                if nxt is not in_feats:
+                    nxt[:, :npt] = points
+                kw["point_feats_out"] = nxt[:, npt:]
+            if not last:
+                out_feats, out_cluster_feats = block(in_feats, coors, f_cluster, **kw)
+                in_feats = nxt if nxt is not None else torch.cat([points, out_feats], 1)
             else:
-                out_feats, out_cluster_feats, out_coors = block(in_feats, coors, f_cluster, return_both=True,
-                                                                unq_inv_once=unq_inv, new_coors_once=new_coors)
+                out_feats, out_cluster_feats, out_coors = block(in_feats, coors, f_cluster, return_both=True, **kw)
             cluster_feat_list.append(out_cluster_feats)
         return out_feats, torch.cat(cluster_feat_list, dim=1), out_coors

@@ -77,3 +77,50 @@ def test_sir_layer_without_f_cluster_and_shortcut(cuda):
         a, b = m(x.to(cuda), coors.to(cuda))
     torch.testing.assert_close(a.cpu(), pf, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(b.cpu(), gf, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,G", [(20000, 64), (150000, 256), (300, 7), (129, 1)])
+def test_sir_config3_bf16_parity(cuda, N, G):
+    """Tensor-core path (tcgen05, bf16 operands / fp32 accumulate): 1e-2 of the fp32 oracle (north_star tolerance for bf16);
+    group coordinates stay bit-exact.  Also covers the in-place [points || feats] hand-over between blocks."""
+    g = torch.Generator().manual_seed(N + 1)
+    points = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1)
+    feats = torch.randn(N, 79, generator=g)
+    gid = torch.randint(0, G, (N,), generator=g)
+    coors = torch.stack([gid % 3, torch.zeros_like(gid), gid], 1)
+    fcl = torch.randn(N, 3, generator=g) * 2
+    m = _sir([84, 133, 133], 128, 3)
+    ref = O.sir_forward(points, feats, coors, fcl, dict(m.state_dict()), 3, 3, 2, [20, 20, 4])
+    m = m.to(cuda)
+    m.precision = "bf16"
+    with torch.no_grad():
+        a, b, c = m(points.to(cuda), feats.to(cuda), coors.to(cuda), fcl.to(cuda))
+    assert torch.equal(c.cpu(), ref[2])
+    for got, exp in ((a, ref[0]), (b, ref[1])):
+        assert torch.isfinite(got).all()
+        err = (got.cpu() - exp).abs().max().item() / exp.abs().max().item()
+        assert err < 1e-2, err
+
+
+def test_sir_bf16_unsupported_shape_fails_loudly(cuda):
+    from sst_b200._lib import SSTB200Error
+    m = _sir([32, 37, 37], 32, 3).to(cuda)
+    m.precision = "bf16"
+    N = 100
+    with pytest.raises(SSTB200Error), torch.no_grad():
+        m(torch.randn(N, 5, device=cuda), torch.randn(N, 27, device=cuda), torch.zeros(N, 3, dtype=torch.long, device=cuda),
+          torch.randn(N, 3, device=cuda))
+
+
+@pytest.mark.parametrize("N,G", [(150000, 256), (5000, 5000), (1000, 1), (77, 9000)])
+def test_group_csr(cuda, N, G):
+    """offsets = exclusive scan of the group sizes; order = a permutation grouping the points (small-G and large-G kernels)."""
+    from sst_b200.sir_modules import group_csr
+    g = torch.Generator().manual_seed(G)
+    inv = torch.randint(0, G, (N,), generator=g)
+    off, order = group_csr(inv.to(cuda), G)
+    off, order = off.cpu().long(), order.cpu().long()
+    cnt = torch.bincount(inv, minlength=G)
+    assert torch.equal(off, torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)]))
+    assert torch.equal(order.sort().values, torch.arange(N))
+    assert torch.equal(inv[order], inv.sort().values)

@@ -1,0 +1,77 @@
+"""The reference's OWN compiled voxel_layer (oracle/_ref/voxel_layer_ref.so: /root/reference/mmdet3d/ops/voxel/src/*.cpp,*.cu
+built unmodified for sm_100a by oracle/build_ref.py) as the checker:
+
+  * CPU (not gpu): pins oracle.dynamic_voxelize to the reference C++ `dynamic_voxelize` (voxelization_cpu.cpp:7-41).
+  * GPU: libsstb200 vs the reference CUDA kernels on the same B200 - `dynamic_voxelize_gpu` (voxelization_cuda.cu:332-375)
+    and `dynamic_point_to_voxel_forward/backward_gpu` (scatter_points_cuda.cu:183-303); indices bit-exact.
+
+Skipped when the prebuilt extension is absent (it is git-ignored, travels with gpurun, and is rebuilt by
+__graft_entry__.build() wherever /root/reference exists)."""
+import pytest
+import torch
+
+from oracle import build_ref, sst_oracle as O
+
+VS = (0.32, 0.32, 6)
+RNG = [-74.88, -74.88, -2, 74.88, 74.88, 4]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    try:
+        m = build_ref.load_module()
+    except Exception as e:  # e.g. a torch ABI mismatch
+        pytest.skip(f"oracle/_ref not loadable: {e}")
+    if m is None:
+        pytest.skip("oracle/_ref/voxel_layer_ref.so not built")
+    return m
+
+
+@pytest.mark.parametrize("voxel_size,rng", [(VS, RNG), ((0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4]),
+                                             ((0.1, 0.1, 0.15), [-51.2, -51.2, -5, 51.2, 51.2, 3])])
+def test_oracle_voxelize_equals_reference_cpp(ref, voxel_size, rng):
+    pts = O.synth_frame(11, 40000)
+    pts[::7, 0] += 200.0
+    pts[::11, 1] -= 300.0
+    co = torch.zeros((pts.shape[0], 3), dtype=torch.int32)
+    ref.dynamic_voxelize(pts, co, list(voxel_size), list(rng), 3)
+    assert torch.equal(co, O.dynamic_voxelize(pts, voxel_size, rng))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [1, 20000, 150000])
+def test_voxelize_vs_reference_cuda(cuda, ref, P):
+    from sst_b200 import ops
+    pts = O.synth_frame(77 + P, P).to(cuda)
+    pts[::5, 0] += 300.0
+    r = torch.zeros((P, 3), dtype=torch.int32, device=cuda)
+    ref.dynamic_voxelize(pts, r, list(VS), list(RNG), 3)
+    g = torch.zeros((P, 3), dtype=torch.int32, device=cuda)
+    ops.dynamic_voxelize(pts, g, VS, RNG, 3)
+    assert torch.equal(r, g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reduce", ["max", "mean", "sum"])
+@pytest.mark.parametrize("P,C,lo", [(150000, 128, 0), (200000, 3, -1), (5000, 64, -1), (17, 5, 0)])
+def test_dynamic_scatter_vs_reference_cuda(cuda, ref, reduce, P, C, lo):
+    """Forward + backward against the reference CUDA op (sorted unique + atomics) on identical device tensors."""
+    from sst_b200 import ops
+    g = torch.Generator().manual_seed(P + C)
+    feats = (torch.rand(P, C, generator=g) * 100 - 50).to(cuda)
+    if P >= 100000:
+        coors = ops.Voxelization(VS, RNG, -1)(O.synth_frame(5, P).to(cuda))
+    else:
+        coors = torch.randint(lo, 20, (P, 3), generator=g, dtype=torch.int32).to(cuda)
+    r_f, r_c, r_m, r_n = ref.dynamic_point_to_voxel_forward(feats, coors, reduce)
+    g_f, g_c, g_m, g_n = ops.dynamic_point_to_voxel_forward(feats, coors, reduce)
+    assert torch.equal(g_c, r_c) and torch.equal(g_m, r_m) and torch.equal(g_n, r_n)
+    if reduce == "max":
+        assert torch.equal(g_f, r_f)
+    else:  # the reference accumulates with fp32 atomics in arbitrary order
+        torch.testing.assert_close(g_f, r_f, rtol=1e-5, atol=2e-3 if reduce == "sum" else 1e-4)
+    grad = torch.randn(r_f.shape, generator=g).to(cuda)
+    r_g, g_g = torch.zeros_like(feats), torch.zeros_like(feats)
+    ref.dynamic_point_to_voxel_backward(r_g, grad, feats, r_f, r_m, r_n, reduce)
+    ops.dynamic_point_to_voxel_backward(g_g, grad, feats, r_f, r_m, r_n, reduce)
+    torch.testing.assert_close(g_g, r_g, rtol=1e-6, atol=1e-6)

@@ -21,6 +21,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true")
 ap.add_argument("--out", default=None)
+ap.add_argument("--with-reference", action="store_true",
+                help="also time the reference's own CUDA voxel_layer (oracle/_ref, built unmodified for sm_100a) on the same "
+                     "tensors: the in-tree GPU kernels to beat for V1/V2 (SURVEY.md 8d)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 P, C = 150000, 128
@@ -82,6 +85,17 @@ with torch.no_grad():
         ds = ops.DynamicScatter(fl.VOXEL_SIZE, fl.PC_RANGE, red == "mean")
         op(f"V2 DynamicScatter({red}, C={C})", "ops/voxel/scatter_points.py:52-110 -> src/scatter_points_cuda.cu:183-234",
            lambda ds=ds: ds(feats, coors3), bytes_=v2_bytes, note=f"M={M}")
+    if args.with_reference:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import build_ref  # measurement only: the reference kernels are timed, never used by the product
+        ref = build_ref.load_module()
+        if ref is not None:
+            rc = torch.zeros((P, 3), dtype=torch.int32, device=dev)
+            op("V1 REFERENCE CUDA dynamic_voxelize", "ops/voxel/src/voxelization_cuda.cu:332-375",
+               lambda: ref.dynamic_voxelize(pts, rc, list(fl.VOXEL_SIZE), list(fl.PC_RANGE), 3), bytes_=P * 24)
+            for red in ("max", "mean"):
+                op(f"V2 REFERENCE CUDA dynamic_point_to_voxel_forward({red}, C={C})", "ops/voxel/src/scatter_points_cuda.cu:183-234",
+                   lambda red=red: ref.dynamic_point_to_voxel_forward(feats, coors3, red), bytes_=v2_bytes)
     red_f, out_c, cmap, cnt = ops.dynamic_point_to_voxel_forward(feats, coors3, "max")
     gout = torch.randn_like(red_f)
     gin = torch.zeros_like(feats)
@@ -133,9 +147,11 @@ with torch.no_grad():
     sflops = 0
     for cin in (84, 133, 133):
         sflops += 2 * N * (3 * 16 + 16 * 32 + 32 * cin + cin * 128 + 256 * 128)
-    op("S2 SIR.forward (config 3: 150k pts, 256 groups, 3 blocks)", "models/backbones/sir.py:67-87",
-       lambda: sir(sp, sf, sc, fcl), flops=sflops, bytes_=N * (84 + 128) * 4 + 3 * G * 256 * 4,
-       note="bytes = read [points|feats] once + write point feats once; intermediates counted as on-chip")
+    for prec in ("fp32", "bf16"):
+        sir.precision = prec
+        op(f"S2 SIR.forward (config 3: 150k pts, 256 groups, 3 blocks, {prec})", "models/backbones/sir.py:67-87",
+           lambda: sir(sp, sf, sc, fcl), flops=sflops, bytes_=N * (84 + 128) * 4 + 3 * G * 256 * 4,
+           note="bytes = read [points|feats] once + write point feats once; intermediates counted as on-chip")
 
 if args.out and not args.once:
     json.dump({"peaks": pk, "rows": rows}, open(args.out, "w"), indent=1)
