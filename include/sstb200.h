@@ -275,9 +275,10 @@ int sstb200_sir_layer_forward(sstb200_ctx* ctx, const sstb200_sir_layer* layer, 
  * `precision` (SSTB200_PREC_BF16: the rel-MLP's last layer and both VFE layers run as tcgen05 GEMMs with bf16 operands and fp32
  * accumulation - needs feat_channels [128,128], rel-MLP [16,32,cin], cin <= 192, else SSTB200 "unsupported" error) and a row
  * pitch for out_point (>= C_last; lets SIR.forward write block i's point features straight into block i+1's [points || feats]
- * input; bf16 path only, 0 = dense). */
-int sstb200_sir_layer_forward_ex(sstb200_ctx* ctx, const sstb200_sir_layer* layer, const float* in_feats,
-                                 const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
+ * input; bf16 path only, 0 = dense).  in_feats may likewise be a pitched matrix (in_ld floats per row, 0 = dense) whose columns
+ * >= in_gap_at sit in_gap floats further right (the 16-byte aligned feature block of that hand-over buffer). */
+int sstb200_sir_layer_forward_ex(sstb200_ctx* ctx, const sstb200_sir_layer* layer, const float* in_feats, int in_ld,
+                                 int in_gap_at, int in_gap, const float* f_cluster, const int64_t* inv, int num_points, int num_groups,
                                  const int32_t* csr_offsets, const int32_t* csr_order, int precision, float* out_point,
                                  int out_point_ld, float* out_group);
 

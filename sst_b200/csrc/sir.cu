@@ -204,11 +204,12 @@ extern "C" int sstb200_group_csr(sstb200_ctx* c, const int64_t* inv, int N, int 
 
 int sstb_sir_layer_bf16(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster, const long long* inv,
                         const int32_t* order, int N, int G, __nv_bfloat16* p0buf, uint32_t* gord, float* gterm, float* out_point, int ldo,
-                        float* out_group);
+                        float* out_group, int in_ld, int gap_at, int gap);
 
-extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster,
-                                            const int64_t* inv, int N, int G, const int32_t* csr_offsets, const int32_t* csr_order,
-                                            int precision, float* out_point, int out_point_ld, float* out_group) {
+extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, int in_ld, int in_gap_at,
+                                            int in_gap, const float* f_cluster, const int64_t* inv, int N, int G,
+                                            const int32_t* csr_offsets, const int32_t* csr_order, int precision, float* out_point,
+                                            int out_point_ld, float* out_group) {
   CHECK_ARG(c, c && L && N >= 0 && G >= 0);
   if (N == 0 || G == 0) return SSTB_OK;
   CHECK_ARG(c, in_feats && f_cluster && inv && out_point && out_group);
@@ -227,7 +228,10 @@ extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_la
     if (L->rel_dims[l] > 32 * REL_MAXC) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "rel-MLP width %d", L->rel_dims[l]);
   const int Cmax = C0 > C1 ? C0 : C1;
   const bool bf16 = precision == SSTB200_PREC_BF16;
-  if (!bf16 && out_point_ld != Clast) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIRLayer fp32 path writes dense point features (ld == C)");
+  if (in_ld <= 0) in_ld = cin, in_gap_at = cin, in_gap = 0;
+  CHECK_ARG(c, in_gap >= 0 && in_gap_at >= 0 && in_gap_at <= cin && in_ld >= cin + in_gap);
+  if (!bf16 && (out_point_ld != Clast || in_ld != cin || in_gap != 0))
+    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "SIRLayer fp32 path works on dense point features (ld == C, no gap)");
   arena_reset(c);
   int rc = arena_reserve(c, csr_bytes(N, G) + al256((size_t)G * 4 + 8) + al256((size_t)N * cin * 4) + 2 * al256((size_t)N * Cmax * 4) +
                                 2 * al256((size_t)G * Cmax * 4) + al256(((size_t)N + 4) * 4) + 65536);
@@ -248,10 +252,11 @@ extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_la
   if (bf16) {
     __nv_bfloat16* p0buf = arena_alloc<__nv_bfloat16>(c, ((size_t)N + 128) * 128);
     if (!p0buf) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sir: arena");
-    rc = sstb_sir_layer_bf16(c, L, in_feats, f_cluster, (const long long*)inv, order, N, G, p0buf, gord, gterm, out_point, out_point_ld, out_group);
+    rc = sstb_sir_layer_bf16(c, L, in_feats, f_cluster, (const long long*)inv, order, N, G, p0buf, gord, gterm, out_point, out_point_ld, out_group, in_ld, in_gap_at,
+                             in_gap);
     if (rc) return rc;
     if (L->with_shortcut && cin - 3 == Clast) {
-      if (out_point_ld != Clast) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "shortcut with strided point features");
+      if (out_point_ld != Clast || in_ld != cin) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "shortcut with strided point features");
       launch_pdl(shortcut_kernel, dim3((unsigned)(((size_t)N * Clast + 255) / 256)), dim3(256), (size_t)(0), st, out_point, in_feats, N, Clast, cin);
     }
     LAUNCH_CHECK(c);
@@ -331,5 +336,5 @@ extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_la
 
 extern "C" int sstb200_sir_layer_forward(sstb200_ctx* c, const sstb200_sir_layer* L, const float* in_feats, const float* f_cluster,
                                          const int64_t* inv, int N, int G, float* out_point, float* out_group) {
-  return sstb200_sir_layer_forward_ex(c, L, in_feats, f_cluster, inv, N, G, nullptr, nullptr, SSTB200_PREC_FP32, out_point, 0, out_group);
+  return sstb200_sir_layer_forward_ex(c, L, in_feats, 0, 0, 0, f_cluster, inv, N, G, nullptr, nullptr, SSTB200_PREC_FP32, out_point, 0, out_group);
 }

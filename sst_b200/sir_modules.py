@@ -28,8 +28,8 @@ class _SirLayer(C.Structure):
 
 L.SIGNATURES["sstb200_sir_layer_forward"] = (C.c_int, [L.vp, C.POINTER(_SirLayer), L.vp, L.vp, L.vp, C.c_int, C.c_int,
                                                        L.vp, L.vp])
-L.SIGNATURES["sstb200_sir_layer_forward_ex"] = (C.c_int, [L.vp, C.POINTER(_SirLayer), L.vp, L.vp, L.vp, C.c_int, C.c_int,
-                                                          L.vp, L.vp, C.c_int, L.vp, C.c_int, L.vp])
+L.SIGNATURES["sstb200_sir_layer_forward_ex"] = (C.c_int, [L.vp, C.POINTER(_SirLayer), L.vp, C.c_int, C.c_int, C.c_int, L.vp, L.vp,
+                                                          C.c_int, C.c_int, L.vp, L.vp, C.c_int, L.vp, C.c_int, L.vp])
 L.SIGNATURES["sstb200_group_csr"] = (C.c_int, [L.vp, L.vp, C.c_int, C.c_int, L.vp, L.vp])
 _PREC = {"fp32": 0, "bf16": 1}
 
@@ -118,10 +118,11 @@ class SIRLayer(nn.Module):
     precision = "fp32"  # 'bf16': rel-MLP layer 3 and both VFE layers on tcgen05 (bf16 operands, fp32 accumulate / LN / pooling)
 
     def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_inv=False,
-                return_both=False, unq_inv_once=None, new_coors_once=None, csr_once=None, point_feats_out=None):
+                return_both=False, unq_inv_once=None, new_coors_once=None, csr_once=None, point_feats_out=None, feat_gap=None):
         """`csr_once` = group_csr(unq_inv, G) shared between blocks; `point_feats_out` = a [N, >=C] fp32 view (last dim
         contiguous) that receives the point features in place of a fresh tensor (bf16 path; SIR.forward uses it to write
-        block i's output straight into block i+1's [points || feats] input)."""
+        block i's output straight into block i+1's [points || feats] input).  `feat_gap` = (at, width): `features` is that
+        hand-over buffer, whose columns >= at sit `width` floats further right (bf16 path)."""
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("SIRLayer backward is not built yet; run under eval()/no_grad()")
         ops._need_cuda(features, coors)
@@ -149,9 +150,12 @@ class SIRLayer(nn.Module):
         s.with_shortcut = int(bool(self.with_shortcut) and wants_shortcut)
         off, order = csr_once if csr_once is not None else (None, None)
         c = L.ctx(features.device)
+        gap_at, gap = feat_gap if feat_gap is not None else (self.in_channels, 0)
+        assert features.shape[1] == self.in_channels + gap, (features.shape, self.in_channels, gap)
         L.check(c, L.lib().sstb200_sir_layer_forward_ex(
-            c, C.byref(s), features.data_ptr(), f_cluster.data_ptr(), unq_inv.contiguous().data_ptr(), N, G, L.ptr(off),
-            L.ptr(order), _PREC[self.precision], point_feats.data_ptr(), ld, voxel_feats.data_ptr()))
+            c, C.byref(s), features.data_ptr(), features.shape[1], gap_at, gap, f_cluster.data_ptr(),
+            unq_inv.contiguous().data_ptr(), N, G, L.ptr(off), L.ptr(order), _PREC[self.precision], point_feats.data_ptr(), ld,
+            voxel_feats.data_ptr()))
         if return_both:
             return point_feats, voxel_feats, new_coors
         if self.return_point_feats:
@@ -190,22 +194,30 @@ class SIR(nn.Module):
         out_coors = new_coors
         in_feats = torch.cat([points, out_feats], 1)
         npt = points.shape[1]
+        pad = (-npt) % 8  # the feature block of the hand-over buffer starts on a 32-byte boundary
+        gap = None
         for i, block in enumerate(self.block_list):
             block.precision = self.precision
             last = i == self.num_blocks - 1
-            kw = dict(unq_inv_once=unq_inv, new_coors_once=new_coors, csr_once=csr)
+            kw = dict(unq_inv_once=unq_inv, new_coors_once=new_coors, csr_once=csr, feat_gap=gap)
             nxt = None
-            if (not last and self.precision == "bf16" and block.feat_channels[-1] + npt == self.block_list[i + 1].in_channels
-                    and not (block.with_shortcut and block.in_channels - 3 == block.feat_channels[-1])):
-                # write this block's point features next to the raw points: no torch.cat between blocks
-                nxt = in_feats if in_feats.shape[1] == npt + block.feat_channels[-1] and i > 0 else \
-                    torch.empty((points.shape[0], npt + block.feat_channels[-1]), dtype=torch.float32, device=points.device)
-                if nxt is not in_feats:
+            Cb = block.feat_channels[-1]
+            if (not last and self.precision == "bf16" and Cb + npt == self.block_list[i + 1].in_channels and Cb % 4 == 0
+                    and not (block.with_shortcut and block.in_channels - 3 == Cb)):
+                # this block's point features land next to the raw points: no torch.cat between blocks.  Block i >= 1 reads
+                # and writes the same buffer (its kernel A has consumed the input before kernel B writes the output).
+                if gap is not None and in_feats.shape[1] == npt + pad + Cb:
+                    nxt = in_feats
+                else:
+                    nxt = torch.empty((points.shape[0], npt + pad + Cb), dtype=torch.float32, device=points.device)
                     nxt[:, :npt] = points
-                kw["point_feats_out"] = nxt[:, npt:]
+                kw["point_feats_out"] = nxt[:, npt + pad:]
             if not last:
                 out_feats, out_cluster_feats = block(in_feats, coors, f_cluster, **kw)
-                in_feats = nxt if nxt is not None else torch.cat([points, out_feats], 1)
+                if nxt is not None:
+                    in_feats, gap = nxt, (npt, pad)
+                else:
+                    in_feats, gap = torch.cat([points, out_feats], 1), None
             else:
                 out_feats, out_cluster_feats, out_coors = block(in_feats, coors, f_cluster, return_both=True, **kw)
             cluster_feat_list.append(out_cluster_feats)
