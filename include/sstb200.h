@@ -286,6 +286,12 @@ int sstb200_sir_layer_forward_ex(sstb200_ctx* ctx, const sstb200_sir_layer* laye
  * group unspecified).  What SIR.forward (models/backbones/sir.py:67-87, `unique_once`) shares between its blocks. */
 int sstb200_group_csr(sstb200_ctx* ctx, const int64_t* inv, int num_points, int num_groups, int32_t* offsets, int32_t* order);
 
+/* A4'  SSTv2.recover_bev (mmdet3d/models/backbones/sst_v2.py:161-196): voxel_feat [M,C] fp32 rows at coors [M,4] int64 (b,z,y,x)
+ * -> canvas [B,C,ny,nx] fp32, empty cells 0 (the canvas need not be zeroed by the caller: every element is written once).
+ * Synchronises the stream to report out-of-canvas coordinates as an error (the reference would raise an index error). */
+int sstb200_recover_bev(sstb200_ctx* ctx, const float* voxel_feat, const int64_t* coors, int num_voxels, int channels,
+                        int batch_size, int ny, int nx, float* canvas);
+
 /* A4  the whole encoder stack (SSTv2.forward's block loop, mmdet3d/models/backbones/sst_v2.py:129-133 with
  * BasicShiftBlockV2.forward, models/sst/sst_basic_block_v2.py:144-169): layer l uses the windows of shift l % 2.
  * x [n,d] input (not modified), y [n,d] output, tmp [n,d] scratch; all fp32, distinct buffers.  With precision BF16 and the

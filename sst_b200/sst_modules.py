@@ -232,6 +232,9 @@ class SSTInputLayerV2(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # SRA encoder
 # ------------------------------------------------------------------------------------------------
+L.SIGNATURES["sstb200_recover_bev"] = (C.c_int, [L.vp, L.vp, L.vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, L.vp])
+
+
 class _SraLayer(C.Structure):
     _fields_ = ([("d_model", C.c_int32), ("nhead", C.c_int32), ("dim_ff", C.c_int32), ("act", C.c_int32),
                  ("post_norm", C.c_int32), ("norm_eps", C.c_float)] +
@@ -460,9 +463,15 @@ class SSTv2(nn.Module):
         return y
 
     def recover_bev(self, voxel_feat, coors, batch_size):
-        """models/backbones/sst_v2.py:161-196 (dense canvas scatter; next-2, data movement only)."""
+        """models/backbones/sst_v2.py:161-196: sparse rows -> dense [B, C, ny, nx] canvas in one HBM-write-bound pass
+        (csrc/bev.cu; the canvas is written exactly once, zeros included)."""
         ny, nx = self.output_shape
-        C_ = voxel_feat.shape[-1]
-        canvas = voxel_feat.new_zeros((batch_size, C_, ny * nx))
-        canvas[coors[:, 0], :, coors[:, 2] * nx + coors[:, 3]] = voxel_feat
-        return canvas.view(batch_size, C_, ny, nx)
+        ops._need_cuda(voxel_feat, coors)
+        voxel_feat = voxel_feat.float().contiguous()
+        coors = coors.long().contiguous()
+        M, C_ = voxel_feat.shape
+        canvas = torch.empty((batch_size, C_, ny, nx), dtype=torch.float32, device=voxel_feat.device)
+        c = L.ctx(voxel_feat.device)
+        L.check(c, L.lib().sstb200_recover_bev(c, voxel_feat.data_ptr(), coors.data_ptr(), M, C_, batch_size, ny, nx,
+                                               canvas.data_ptr()))
+        return canvas

@@ -165,3 +165,49 @@ def test_sstv2_bf16_parity(cuda, P, blocks):
     with torch.no_grad():
         got32 = m(info_g)[0]["voxel_feats"].cpu()
     assert (got32 - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("B,C,ny,nx,M", [(2, 128, 468, 468, 40000), (1, 37, 50, 45, 700), (3, 64, 33, 32, 0), (1, 300, 40, 100, 1500)])
+def test_recover_bev_exact(cuda, B, C, ny, nx, M):
+    """SSTv2.recover_bev (sst_v2.py:161-196) is pure data movement: bit-exact against the oracle, including the zero fill."""
+    from sst_b200.sst_modules import SSTv2
+    g = torch.Generator().manual_seed(M + C)
+    cells = torch.randperm(B * ny * nx, generator=g)[:M]
+    b, rem = cells // (ny * nx), cells % (ny * nx)
+    coors = torch.stack([b, torch.zeros_like(b), rem // nx, rem % nx], 1)
+    feat = torch.randn(M, C, generator=g)
+    m = SSTv2(d_model=[C], nhead=[1], num_blocks=0, dim_feedforward=[C], output_shape=[ny, nx], num_attached_conv=0, to_bev=True)
+    got = m.recover_bev(feat.to(cuda), coors.to(cuda), B)
+    assert torch.equal(got.cpu(), O.recover_bev(feat, coors, B, (ny, nx)))
+
+
+def test_recover_bev_rejects_out_of_canvas(cuda):
+    from sst_b200._lib import SSTB200Error
+    from sst_b200.sst_modules import SSTv2
+    m = SSTv2(d_model=[8], nhead=[1], num_blocks=0, dim_feedforward=[8], output_shape=[10, 10], num_attached_conv=0, to_bev=True)
+    coors = torch.tensor([[0, 0, 3, 12]], device=cuda)
+    with pytest.raises(SSTB200Error):
+        m.recover_bev(torch.ones(1, 8, device=cuda), coors, 1)
+
+
+def test_sstv2_to_bev_with_attached_convs(cuda):
+    """Config 2 (ii): encoder stack -> BEV canvas -> the attached dense convs (cuDNN through torch; boundary layers, SURVEY 8f
+    next-2).  The canvas feeding the convs must equal the oracle's sparse output scattered by the oracle."""
+    from sst_b200.sst_modules import SSTInputLayerV2, SSTv2
+    feats, coors = _voxels((1000,), 8000, C=64)
+    torch.manual_seed(0)
+    m = SSTv2(d_model=[64], nhead=[4], num_blocks=1, dim_feedforward=[128], output_shape=[468, 468], num_attached_conv=2,
+              conv_in_channel=64, conv_out_channel=64, to_bev=True).eval()
+    il = SSTInputLayerV2((DROP_TRAIN, DROP_TEST), (12, 12, 1), (468, 468, 1), shuffle_voxels=False, mute=True).eval()
+    w = {k: v.clone() for k, v in m.state_dict().items()}
+    info_o = O.input_layer_v2(feats, coors, DROP_TEST, (12, 12, 1), (468, 468, 1))
+    w_o = {k: v for k, v in w.items() if not k.startswith("conv_layer")}
+    canvas = O.sstv2_forward(info_o, w_o, [4], 1, "gelu", {}, to_bev=True, output_shape=(468, 468))
+    cpu_m = torch.nn.Sequential(*[cl for cl in m.conv_layer])
+    with torch.no_grad():
+        ref = cpu_m(canvas)
+        m = m.to(cuda)
+        got = m(il(feats.to(cuda), coors.to(cuda), 1))[0].cpu()
+    assert got.shape == ref.shape == (1, 64, 468, 468)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-3, err

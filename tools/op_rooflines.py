@@ -132,6 +132,11 @@ with torch.no_grad():
         bb.precision = prec
         op(f"A4 SSTv2.forward (12 encoder layers, {prec})", "models/backbones/sst_v2.py:115-154", lambda: bb(info),
            flops=12 * lflops, bytes_=12 * 2 * M * C * 4)
+    bbv = fl.build_sst(fl.sst_cfg())[2].to(dev)
+    bbv.output_shape = [468, 468]
+    xs = bb(info)[0]["voxel_feats"]
+    op("A4' SSTv2.recover_bev (B=1, C=128, 468x468)", "models/backbones/sst_v2.py:161-196", lambda: bbv.recover_bev(xs, vc, 1),
+       bytes_=128 * 468 * 468 * 4 + M * 128 * 4, note="write-once canvas (zeros included) + one read of the rows")
     # config 3: SIR
     N, G = 150000, 256
     g = torch.Generator().manual_seed(3)
