@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SSTB200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("SSTB200_STREAMS", "4")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("SSTB200_STREAMS", "8")),
                     help="frames in flight per GPU (independent engines on their own CUDA streams); 1 = strictly serial")
     args = ap.parse_args()
     if args.impl == "reference":

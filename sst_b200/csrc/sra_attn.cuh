@@ -435,6 +435,12 @@ static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const in
 }
 
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // v4: batched ragged attention.  One CTA stages a *batch* of consecutive whole windows (<= 144 tokens, built by
 // win_batch_kernel) - K and V rows of the batch are one contiguous block in slot order, copied with cp.async - and its 8
 // warps sweep the batch's (16-query tile, head) items out of shared memory: K fragments by 32-bit LDS (conflict-free
@@ -564,27 +570,36 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      const float ms0 = m0 * scale, ms1 = m1 * scale;
-      // pass 2
+      // exp(x) = 2^(x log2 e): fold log2 e into the scale so that every probability is one FFMA + one MUFU.EX2
+      const float sl2 = scale * 1.4426950408889634f;
+      const float ms0 = m0 * sl2, ms1 = m1 * sl2;
+      // pass 2: full 16-key chunks need no masking; only the last (partial) chunk compares column indices with n
       float l0 = 0.f, l1 = 0.f;
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       const int nkc = (n + 15) >> 4;
+      const int nfull = n >> 4;
       for (int kc = 0; kc < nkc; kc++) {
         const uint32_t* kp0 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + g4) * LD);
         const uint32_t* kp1 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + 8 + g4) * LD);
         float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
         mma_f16_16816(sa, qa, kp0[t4], kp0[t4 + 4]);
         mma_f16_16816(sb, qa, kp1[t4], kp1[t4 + 4]);   // rows beyond the window are other windows' keys or zero padding: masked below
-        const int c0 = kc * 16 + 2 * t4;
         float p[8];
-        p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
-        p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
-        p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
-        p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
-        p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
-        p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
-        p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
-        p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
+        p[0] = fast_ex2(fmaf(sa[0], sl2, -ms0));
+        p[1] = fast_ex2(fmaf(sa[1], sl2, -ms0));
+        p[2] = fast_ex2(fmaf(sa[2], sl2, -ms1));
+        p[3] = fast_ex2(fmaf(sa[3], sl2, -ms1));
+        p[4] = fast_ex2(fmaf(sb[0], sl2, -ms0));
+        p[5] = fast_ex2(fmaf(sb[1], sl2, -ms0));
+        p[6] = fast_ex2(fmaf(sb[2], sl2, -ms1));
+        p[7] = fast_ex2(fmaf(sb[3], sl2, -ms1));
+        if (kc >= nfull) {  // warp-uniform: the tail chunk
+          const int c0 = kc * 16 + 2 * t4;
+          if (c0 >= n) p[0] = p[2] = 0.f;
+          if (c0 + 1 >= n) p[1] = p[3] = 0.f;
+          if (c0 + 8 >= n) p[4] = p[6] = 0.f;
+          if (c0 + 9 >= n) p[5] = p[7] = 0.f;
+        }
         l0 += (p[0] + p[1]) + (p[4] + p[5]);
         l1 += (p[2] + p[3]) + (p[6] + p[7]);
         uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
