@@ -95,17 +95,21 @@ __global__ void __launch_bounds__(64) emit_rows_kernel(const uint32_t* __restric
   pdl_wait();
   pdl_launch();
   int shift = (shift_if_no_invalid && flags[0] == 0) ? 1 : 0;
-  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w == 0) {
-    int t = (int)(*total) - shift;
-    *num_out = t < 0 ? 0 : t;
+  // four threads per bitmap word (one byte each): the serial decode loop is at most 8 cells long
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    int tot = (int)(*total) - shift;
+    *num_out = tot < 0 ? 0 : tot;
   }
-  for (; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
-    uint32_t bits = bitmap[w];
+  for (; t < nwords * 4; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t w = t >> 2;
+    const int part = (int)(t & 3);
+    const uint32_t word = bitmap[w];
+    uint32_t bits = (word >> (8 * part)) & 0xFFu;
     if (!bits) continue;
-    long long v = (long long)word_prefix[w] - shift;
+    long long v = (long long)word_prefix[w] + __popc(word & ((1u << (8 * part)) - 1u)) - shift;
     while (bits) {
-      int b = __ffs(bits) - 1;
+      int b = __ffs(bits) - 1 + 8 * part;
       bits &= bits - 1;
       if (v >= 0) {
         TO c[4];
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(64) emit_rows_kernel(const uint32_t* __restric
 template <typename TO>
 static void launch_emit_rows(sstb200_ctx* c, const KeyIndex& k, const Extents& e, int shift_if_no_invalid, TO* out_rows,
                              int32_t* num_out) {
-  size_t eg = (k.nwords + 63) / 64;
+  size_t eg = (k.nwords * 4 + 63) / 64;
   if (eg > (size_t)c->num_sms * 32) eg = (size_t)c->num_sms * 32;
   if (eg == 0) eg = 1;
   if (k.T < ((long long)1 << 31))
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
 // lane, lane+GROUP, ... (NV4 of them, C = 4*GROUP*NV4 at most), and FOUR points are in flight per lane (independent index and row
 // loads) - a 128-channel row is one 512-B warp transaction.  Same arithmetic as the scalar kernel (max with lowest-index tie
 // break for argmax; sum/mean in fp64, so independent of the CSR order).
-template <int GROUP, int NV4>
+template <int GROUP, int NV4, bool ARG>
 __global__ void __launch_bounds__(256) segment_reduce_v4_kernel(const float* __restrict__ src, int C,
                                                                 const uint32_t* __restrict__ offsets,
                                                                 const int32_t* __restrict__ order, int nseg_host,
@@ -290,89 +294,98 @@ __global__ void __launch_bounds__(256) segment_reduce_v4_kernel(const float* __r
                                                                 long long* __restrict__ argmax, int n_rows) {
   pdl_wait();
   pdl_launch();
+  constexpr int RIF = NV4 == 1 ? 8 : 4;  // rows in flight per lane (independent 16-byte loads)
   const int nseg = nseg_dev ? *nseg_dev : nseg_host;
   const int groups_per_block = blockDim.x / GROUP;
   const int g = threadIdx.x / GROUP, l = threadIdx.x % GROUP;
   const int C4 = C >> 2;
   const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+  // lanes of a group always run the same trip counts, but different groups of a warp do not: shuffles are group-masked
+  const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << ((threadIdx.x & 31) / GROUP * GROUP));
+  const float fill = mode == SSTB200_REDUCE_MAX ? -INFINITY : 0.f;  // value of a row slot past the end of the segment
   for (int s = blockIdx.x * groups_per_block + g; s < nseg; s += gridDim.x * groups_per_block) {
     const uint32_t b = offsets[s], e = offsets[s + 1];
-    if (mode == SSTB200_REDUCE_MAX) {
-      float4 m[NV4];
-      int am[NV4][4];
+    float4 m[NV4];
+    int am[NV4][4];
+    double acc[NV4][4];
 #pragma unroll
-      for (int j = 0; j < NV4; j++) {
-        m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        am[j][0] = am[j][1] = am[j][2] = am[j][3] = n_rows;
-      }
-      for (uint32_t k = b; k < e; k += 4) {
-        int p[4];
+    for (int j = 0; j < NV4; j++) {
+      m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      am[j][0] = am[j][1] = am[j][2] = am[j][3] = n_rows;
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    }
+    // the point ids of GROUP rows are fetched by ONE coalesced load and handed round by shuffles, so a long segment is a
+    // stream of independent row loads (RIF in flight) instead of a chain of index-load -> row-load round trips
+    for (uint32_t k0 = b; k0 < e; k0 += GROUP) {
+      const int mine = (k0 + l < e) ? order[k0 + l] : -1;
+      const int cnt = min((int)(e - k0), GROUP);
+      for (int r0 = 0; r0 < cnt; r0 += RIF) {
+        int p[RIF];
+        float4 v[RIF][NV4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) p[u] = (k + u < e) ? order[k + u] : -1;
-        float4 v[4][NV4];
+        for (int u = 0; u < RIF; u++) {
+          p[u] = __shfl_sync(gmask, mine, (r0 + u) % GROUP, GROUP);
+          if (r0 + u >= cnt) p[u] = -1;
+        }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < RIF; u++)
 #pragma unroll
           for (int j = 0; j < NV4; j++)
-            if (p[u] >= 0 && l + j * GROUP < C4) v[u][j] = __ldg(&src4[(size_t)p[u] * C4 + l + j * GROUP]);
+            v[u][j] = (p[u] >= 0 && l + j * GROUP < C4) ? __ldg(&src4[(size_t)p[u] * C4 + l + j * GROUP]) : make_float4(fill, fill, fill, fill);
+        if (mode == SSTB200_REDUCE_MAX && !ARG) {
+          // plain max: absent rows were loaded as -inf, one FMNMX per element
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (p[u] < 0) continue;
+          for (int u = 0; u < RIF; u++)
 #pragma unroll
-          for (int j = 0; j < NV4; j++) {
-            if (l + j * GROUP >= C4) continue;
-            const float x[4] = {v[u][j].x, v[u][j].y, v[u][j].z, v[u][j].w};
-            float* mm = &m[j].x;
+            for (int j = 0; j < NV4; j++) {
+              m[j].x = fmaxf(m[j].x, v[u][j].x);
+              m[j].y = fmaxf(m[j].y, v[u][j].y);
+              m[j].z = fmaxf(m[j].z, v[u][j].z);
+              m[j].w = fmaxf(m[j].w, v[u][j].w);
+            }
+        } else if (mode == SSTB200_REDUCE_MAX) {
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-              if (x[q] > mm[q] || (x[q] == mm[q] && p[u] < am[j][q])) {
-                mm[q] = x[q];
-                am[j][q] = p[u];
-              }
+          for (int u = 0; u < RIF; u++) {
+            if (p[u] < 0) continue;
+#pragma unroll
+            for (int j = 0; j < NV4; j++) {
+              const float x[4] = {v[u][j].x, v[u][j].y, v[u][j].z, v[u][j].w};
+              float* mm = &m[j].x;
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                if (x[q] > mm[q] || (x[q] == mm[q] && p[u] < am[j][q])) {
+                  mm[q] = x[q];
+                  am[j][q] = p[u];
+                }
+            }
           }
+        } else {
+          // fp64 accumulation: exact for these magnitudes, so the result does not depend on the CSR order
+#pragma unroll
+          for (int u = 0; u < RIF; u++)
+#pragma unroll
+            for (int j = 0; j < NV4; j++) {
+              acc[j][0] += (double)v[u][j].x;
+              acc[j][1] += (double)v[u][j].y;
+              acc[j][2] += (double)v[u][j].z;
+              acc[j][3] += (double)v[u][j].w;
+            }
         }
       }
+    }
 #pragma unroll
-      for (int j = 0; j < NV4; j++) {
-        int c4 = l + j * GROUP;
-        if (c4 >= C4) continue;
+    for (int j = 0; j < NV4; j++) {
+      const int c4 = l + j * GROUP;
+      if (c4 >= C4) continue;
+      if (mode == SSTB200_REDUCE_MAX) {
         if (b == e) m[j] = make_float4(empty_value, empty_value, empty_value, empty_value);
         reinterpret_cast<float4*>(out)[(size_t)s * C4 + c4] = m[j];
-        if (argmax) {
+        if (ARG) {
           longlong2* a2 = reinterpret_cast<longlong2*>(argmax + (size_t)s * C + 4 * c4);
           a2[0] = make_longlong2(am[j][0], am[j][1]);
           a2[1] = make_longlong2(am[j][2], am[j][3]);
         }
-      }
-    } else {
-      double acc[NV4][4];
-#pragma unroll
-      for (int j = 0; j < NV4; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-      for (uint32_t k = b; k < e; k += 4) {
-        int p[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) p[u] = (k + u < e) ? order[k + u] : -1;
-        float4 v[4][NV4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int j = 0; j < NV4; j++)
-            v[u][j] = (p[u] >= 0 && l + j * GROUP < C4) ? __ldg(&src4[(size_t)p[u] * C4 + l + j * GROUP])
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int j = 0; j < NV4; j++) {
-            acc[j][0] += (double)v[u][j].x;
-            acc[j][1] += (double)v[u][j].y;
-            acc[j][2] += (double)v[u][j].z;
-            acc[j][3] += (double)v[u][j].w;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < NV4; j++) {
-        int c4 = l + j * GROUP;
-        if (c4 >= C4) continue;
+      } else {
         float r[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -390,7 +403,15 @@ static void launch_segment_reduce(sstb200_ctx* c, const float* src, int C, const
                                   float empty_value, float* out, long long* argmax, int n_rows) {
   int grid = c->num_sms * 8;
   const bool vec = (C % 4 == 0) && C <= 256 && (((uintptr_t)src | (uintptr_t)out | (uintptr_t)argmax) & 15) == 0;
-#define SEGV4(G, NV) launch_pdl(segment_reduce_v4_kernel<G, NV>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, nseg_dev, mode, empty_value, out, argmax, n_rows)
+#define SEGV4(G, NV)                                                                                                                     \
+  do {                                                                                                                                  \
+    if (argmax)                                                                                                                         \
+      launch_pdl(segment_reduce_v4_kernel<G, NV, true>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, \
+                 nseg_dev, mode, empty_value, out, argmax, n_rows);                                                                     \
+    else                                                                                                                                \
+      launch_pdl(segment_reduce_v4_kernel<G, NV, false>, dim3(grid), dim3(256), (size_t)(0), c->stream, src, C, offsets, order, nseg_cap, \
+                 nseg_dev, mode, empty_value, out, argmax, n_rows);                                                                     \
+  } while (0)
   if (vec) {
     int c4 = C / 4;
     if (c4 > 32) SEGV4(32, 2);

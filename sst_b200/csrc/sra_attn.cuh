@@ -556,14 +556,19 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
         const uint32_t* kp = reinterpret_cast<const uint32_t*>(kbase + (j * 8 + g4) * LD);
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         mma_f16_16816(s, qa, kp[t4], kp[t4 + 4]);
-        const int c0 = j * 8 + 2 * t4;
-        if (c0 < n) {
-          m0 = fmaxf(m0, s[0]);
-          m1 = fmaxf(m1, s[2]);
-        }
-        if (c0 + 1 < n) {
-          m0 = fmaxf(m0, s[1]);
-          m1 = fmaxf(m1, s[3]);
+        if (j * 8 + 8 <= n) {  // warp-uniform: a full step
+          m0 = fmaxf(m0, fmaxf(s[0], s[1]));
+          m1 = fmaxf(m1, fmaxf(s[2], s[3]));
+        } else {
+          const int c0 = j * 8 + 2 * t4;
+          if (c0 < n) {
+            m0 = fmaxf(m0, s[0]);
+            m1 = fmaxf(m1, s[2]);
+          }
+          if (c0 + 1 < n) {
+            m0 = fmaxf(m0, s[1]);
+            m1 = fmaxf(m1, s[3]);
+          }
         }
       }
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
@@ -617,13 +622,13 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
       if (r0 < ke) {
-        const float i0 = 1.0f / l0;
+        const float i0 = __fdividef(1.0f, l0);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r0) * D + h * DH);
         op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
         op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
       }
       if (r1 < ke) {
-        const float i1 = 1.0f / l1;
+        const float i1 = __fdividef(1.0f, l1);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r1) * D + h * DH);
         op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
         op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);

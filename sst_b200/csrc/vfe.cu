@@ -108,17 +108,21 @@ __global__ void vfe_emit_kernel(const uint32_t* __restrict__ bitmap, const uint3
     }
     *num_out = (int32_t)t;
   }
-  for (; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
-    uint32_t bits = bitmap[w];
+  // four threads per bitmap word (one byte each): the serial decode loop is at most 8 cells long
+  for (size_t t = w; t < nwords * 4; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t ww = t >> 2;
+    const int part = (int)(t & 3);
+    const uint32_t word = bitmap[ww];
+    uint32_t bits = (word >> (8 * part)) & 0xFFu;
     if (!bits) continue;
-    long long rank = word_prefix[w];
-    int b = (w * 32 < cells_pad) ? 0 : (int)((w * 32) / cells_pad);
+    long long rank = (long long)word_prefix[ww] + __popc(word & ((1u << (8 * part)) - 1u));
+    int b = (ww * 32 < cells_pad) ? 0 : (int)((ww * 32) / cells_pad);
     while (bits) {
-      int bit = __ffs(bits) - 1;
+      int bit = __ffs(bits) - 1 + 8 * part;
       bits &= bits - 1;
       long long row = quirk_row(q, rank, b);
       if (row >= 0) {
-        long long local = (long long)(w * 32 + bit) - (long long)b * (long long)cells_pad;
+        long long local = (long long)(ww * 32 + bit) - (long long)b * (long long)cells_pad;
         long long x, y, z;
         if (cells_pad < ((size_t)1 << 31)) {  // 32-bit divisions (every real canvas)
           uint32_t lc = (uint32_t)local, q1 = lc / (uint32_t)X;
@@ -746,7 +750,7 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   launch_pdl(vfe_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
   key_index_scan(c, k);
   SampleQuirk q{k.word_prefix, cells_pad / 32, B, cfg->drop_first_voxel_per_sample != 0};
-  int eg = (int)((k.nwords + 63) / 64);
+  int eg = (int)((k.nwords * 4 + 63) / 64);
   if (eg > c->num_sms * 32) eg = c->num_sms * 32;
   launch_pdl(vfe_emit_kernel<TC>, dim3(eg), dim3(64), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
   Csr r;

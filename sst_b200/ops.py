@@ -227,14 +227,14 @@ class _SegmentReduce(Function):
     """torch_scatter.scatter / scatter_max, dim=0 (forward + backward)."""
 
     @staticmethod
-    def forward(ctx, src, index, num_segments, mode):
+    def forward(ctx, src, index, num_segments, mode, want_argmax=True):
         _need_cuda(src, index)
         assert src.dtype == torch.float32 and index.dtype == torch.int64
         src = src.contiguous()
         index = index.contiguous()
         P, Cc = src.shape
         out = torch.empty((num_segments, Cc), dtype=torch.float32, device=src.device)
-        arg = torch.empty((num_segments, Cc), dtype=torch.int64, device=src.device) if mode == "max" else None
+        arg = torch.empty((num_segments, Cc), dtype=torch.int64, device=src.device) if mode == "max" and want_argmax else None
         c = L.ctx(src.device)
         L.check(c, L.lib().sstb200_segment_reduce(c, src.data_ptr(), index.data_ptr(), P, Cc, num_segments,
                                                   _REDUCE[mode], out.data_ptr(), L.ptr(arg)))
@@ -253,19 +253,23 @@ class _SegmentReduce(Function):
         if ctx.mode == "max":
             gs = g.new_zeros((ctx.P + 1, g.shape[1]))
             gs.scatter_(0, arg, g)
-            return gs[:ctx.P], None, None, None
+            return gs[:ctx.P], None, None, None, None
         gv = g[index]
         if ctx.mode == "mean":
             cnt = torch.bincount(index, minlength=g.shape[0]).clamp(min=1)
             gv = gv / cnt[index][:, None].to(g.dtype)
-        return gv, None, None, None
+        return gv, None, None, None, None
 
 
-def segment_reduce(src, index, mode, num_segments=None):
+def segment_reduce(src, index, mode, num_segments=None, want_argmax=True):
+    """torch_scatter.scatter(src, index, dim=0, reduce=mode) / scatter_max -> (out, argmax or None).  `want_argmax=False`
+    skips the argmax output of 'max' (only valid when no gradient is needed): the kernel then runs one FMNMX per element."""
     if num_segments is None:
         num_segments = int(index.max()) + 1 if index.numel() else 0
-    out, arg = _SegmentReduce.apply(src, index, num_segments, mode)
-    return out, (arg if mode == "max" else None)
+    if mode == "max" and not want_argmax and src.requires_grad and torch.is_grad_enabled():
+        want_argmax = True
+    out, arg = _SegmentReduce.apply(src, index, num_segments, mode, want_argmax)
+    return out, (arg if mode == "max" and want_argmax else None)
 
 
 def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, new_coors=None):
@@ -285,7 +289,7 @@ def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, n
         feat = feat[valid_mask]
         coors = coors[valid_mask]
         new_coors, unq_inv, unq_cnt = unique_rows(coors.long(), return_counts=True)
-    new_feat, _ = segment_reduce(feat, unq_inv, mode, new_coors.shape[0])
+    new_feat, _ = segment_reduce(feat, unq_inv, mode, new_coors.shape[0], want_argmax=False)
     if not return_inv:
         return new_feat, new_coors
     return new_feat, new_coors, unq_inv
