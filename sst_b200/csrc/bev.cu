@@ -1,8 +1,8 @@
 // SSTv2.recover_bev (mmdet3d/models/backbones/sst_v2.py:161-196): sparse voxel rows [M, C] -> dense canvas [B, C, ny, nx].
 // The reference zero-fills one canvas per sample and index_puts the transposed rows; here ONE pass writes every output byte
 // exactly once (HBM-write bound: B*C*ny*nx*4 bytes): a cell -> row map (4 bytes per cell) is filled first, then each block
-// transposes the rows of 32 consecutive x cells through shared memory so that both the row reads (512-B rows) and the canvas
-// writes (128-B segments of one channel row) are coalesced; all-empty blocks only stream zeros.
+// transposes the rows of 128 consecutive x cells, 32 channels at a time, through shared memory so that the canvas is written
+// as 512-byte warp stores (float4 per lane, streaming); all-empty blocks only stream zeros.
 #include <stdarg.h>
 #include "common.cuh"
 
@@ -20,12 +20,14 @@ __global__ void bev_map_kernel(const long long* __restrict__ coors, int M, int B
   cell_map[((size_t)b * ny + y) * nx + x] = i;  // a duplicated cell keeps one of its rows (the reference: the last writer)
 }
 
-#define BEV_X 32
+#define BEV_X 128   // x cells per block
+#define BEV_CC 32    // channels per pass
+#define BEV_PITCH 132  // floats; == 4 (mod 32): 16-byte row reads by 32 lanes are conflict-free
 __global__ void __launch_bounds__(256) bev_fill_kernel(const float* __restrict__ feat, int C, const int32_t* __restrict__ cell_map, int ny,
                                                        int nx, float* __restrict__ out) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ float tile[];  // [BEV_X][C + 1]
+  __shared__ __align__(16) float tile[BEV_CC][BEV_PITCH];  // [channel][cell]
   __shared__ int sRow[BEV_X];
   __shared__ int any;
   const int x0 = blockIdx.x * BEV_X, y = blockIdx.y, b = blockIdx.z;
@@ -40,21 +42,35 @@ __global__ void __launch_bounds__(256) bev_fill_kernel(const float* __restrict__
   }
   __syncthreads();
   const bool some = any != 0;
-  if (some) {
-    for (int cx = warp; cx < BEV_X; cx += 8) {
-      int r = sRow[cx];
-      if (r < 0) continue;
-      const float* src = feat + (size_t)r * C;
-      for (int c = lane; c < C; c += 32) tile[cx * (C + 1) + c] = src[c];
-    }
-    __syncthreads();
-  }
-  const int x = x0 + lane;
-  if (x >= nx) return;
-  const bool occ = some && sRow[lane] >= 0;
-  float* o = out + (((size_t)b * C) * ny + y) * nx + x;
+  const int cell = threadIdx.x & (BEV_X - 1), chalf = threadIdx.x >> 7;  // phase A: thread = (cell, half of the channel pass)
+  const int myrow = sRow[cell];
+  const int x = x0 + lane * 4;
   const size_t cstride = (size_t)ny * nx;
-  for (int c = warp; c < C; c += 8) __stcs(o + (size_t)c * cstride, occ ? tile[lane * (C + 1) + c] : 0.f);
+  const bool vec = ((nx & 3) == 0) && x + 3 < nx;
+  for (int c0 = 0; c0 < C; c0 += BEV_CC) {
+    if (some) {
+      __syncthreads();  // previous pass read out
+      const float* src = myrow >= 0 ? feat + (size_t)myrow * C + c0 + chalf * (BEV_CC / 2) : nullptr;
+#pragma unroll
+      for (int k = 0; k < BEV_CC / 2; k++) {
+        int ch = chalf * (BEV_CC / 2) + k;
+        tile[ch][cell] = (src && c0 + ch < C) ? __ldg(src + k) : 0.f;
+      }
+      __syncthreads();
+    }
+    for (int c = warp; c < BEV_CC && c0 + c < C; c += 8) {
+      float4 v = some ? *reinterpret_cast<const float4*>(&tile[c][lane * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* o = out + (((size_t)b * C + c0 + c) * ny + y) * nx + x;
+      if (vec) {
+        __stcs(reinterpret_cast<float4*>(o), v);
+      } else {
+        if (x < nx) __stcs(o, v.x);
+        if (x + 1 < nx) __stcs(o + 1, v.y);
+        if (x + 2 < nx) __stcs(o + 2, v.z);
+        if (x + 3 < nx) __stcs(o + 3, v.w);
+      }
+    }
+  }
 }
 
 extern "C" int sstb200_recover_bev(sstb200_ctx* c, const float* voxel_feat, const int64_t* coors, int M, int C, int B, int ny, int nx,
@@ -73,13 +89,7 @@ extern "C" int sstb200_recover_bev(sstb200_ctx* c, const float* voxel_feat, cons
   CUDA_TRY(c, cudaMemsetAsync(err, 0, 4, c->stream));
   if (M > 0)
     launch_pdl(bev_map_kernel, dim3((M + 255) / 256), dim3(256), (size_t)0, c->stream, (const long long*)coors, M, B, ny, nx, cell_map, err);
-  const size_t smem = (size_t)BEV_X * (C + 1) * 4;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    CUDA_TRY(c, cudaFuncSetAttribute(bev_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  launch_pdl(bev_fill_kernel, dim3((nx + BEV_X - 1) / BEV_X, ny, B), dim3(256), smem, c->stream, voxel_feat, C, (const int32_t*)cell_map, ny, nx,
+  launch_pdl(bev_fill_kernel, dim3((nx + BEV_X - 1) / BEV_X, ny, B), dim3(256), (size_t)0, c->stream, voxel_feat, C, (const int32_t*)cell_map, ny, nx,
              canvas);
   LAUNCH_CHECK(c);
   CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, err, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -56,34 +56,74 @@ __device__ __forceinline__ void bitmap_set(uint32_t* __restrict__ bitmap, long l
   if ((__ldcg(w) & bit) == 0) atomicOr(w, bit);
 }
 
+// merge a block-private bitmap into the global one (skip words that are empty or already fully present)
+__device__ __forceinline__ void bitmap_merge(const uint32_t* sbm, uint32_t* __restrict__ bitmap, uint32_t nwords) {
+  __syncthreads();
+  for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) {
+    const uint32_t v = sbm[w];
+    if (v && (__ldcg(&bitmap[w]) & v) != v) atomicOr(&bitmap[w], v);
+  }
+}
+
 // ---- mark kernels --------------------------------------------------------------------------------
-template <typename TI>
-__global__ void mark_rows_kernel(const TI* __restrict__ rows, int n, Extents e, bool negative_is_invalid,
+// SM = true: each (large) block first ORs into a private shared-memory copy of the bitmap and then merges its non-zero words into
+// the global one.  Same-address global atomics serialise (~10 ns each, measured): a dense LiDAR ring puts > 1000 points into one
+// bitmap word, which made the plain kernel 4x slower than its traffic; privatised, a word sees at most one atomic per block.
+template <typename TI, bool SM>
+__global__ void __launch_bounds__(SM ? 1024 : 256) mark_rows_kernel(const TI* __restrict__ rows, int n, Extents e, bool negative_is_invalid,
                                  long long* __restrict__ keys, uint32_t* __restrict__ bitmap,
-                                 int32_t* __restrict__ flags, const int32_t* __restrict__ n_dev = nullptr) {
+                                 int32_t* __restrict__ flags, const int32_t* __restrict__ n_dev, uint32_t nwords) {
   pdl_wait();
   pdl_launch();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ uint32_t mark_sbm[];
   if (n_dev) n = *n_dev;
-  if (i >= n) return;
-  long long key = 0;
-  bool bad = false, neg = false;
+  if (SM) {
+    for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) mark_sbm[w] = 0u;
+    __syncthreads();
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long key = 0;
+    bool bad = false, neg = false;
 #pragma unroll 4
-  for (int d = 0; d < e.ndim; d++) {
-    long long v = (long long)rows[(size_t)i * e.ndim + d];
-    if (negative_is_invalid && v < 0) neg = true;
-    long long r = v - e.lo[d];
-    if (r < 0 || r >= e.ext[d]) bad = true;
-    key = key * e.ext[d] + r;
+    for (int d = 0; d < e.ndim; d++) {
+      long long v = (long long)rows[(size_t)i * e.ndim + d];
+      if (negative_is_invalid && v < 0) neg = true;
+      long long r = v - e.lo[d];
+      if (r < 0 || r >= e.ext[d]) bad = true;
+      key = key * e.ext[d] + r;
+    }
+    if (bad || neg) {
+      keys[i] = -1;
+      flags[0] = 1;
+      if (!neg) flags[1] = 1;  // a row outside the caller's bounds (not a "negative = invalid" row): the bounds were wrong
+      continue;
+    }
+    keys[i] = key;
+    if (SM) atomicOr(&mark_sbm[key >> 5], 1u << (key & 31));
+    else bitmap_set(bitmap, key);
   }
-  if (bad || neg) {
-    keys[i] = -1;
-    flags[0] = 1;
-    if (!neg) flags[1] = 1;  // a row outside the caller's bounds (not a "negative = invalid" row): the bounds were wrong
-    return;
+  if (SM) bitmap_merge(mark_sbm, bitmap, nwords);
+}
+#define MARK_SMEM_MAX_WORDS (24 * 1024)  // 96 KB of shared memory
+template <typename TI>
+static void launch_mark_rows(sstb200_ctx* c, const TI* rows, int n, const Extents& e, bool negative_is_invalid, KeyIndex& k,
+                             const int32_t* n_dev) {
+  if (k.nwords <= MARK_SMEM_MAX_WORDS) {
+    static size_t attr = 0;
+    size_t smem = k.nwords * 4;
+    if (smem > 48 * 1024 && smem > attr) {
+      cudaFuncSetAttribute(mark_rows_kernel<TI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MARK_SMEM_MAX_WORDS * 4);
+      attr = MARK_SMEM_MAX_WORDS * 4;
+    }
+    int grid = (n + 1023) / 1024;
+    if (grid > c->num_sms) grid = c->num_sms;
+    if (grid < 1) grid = 1;
+    launch_pdl(mark_rows_kernel<TI, true>, dim3(grid), dim3(1024), smem, c->stream, rows, n, e, negative_is_invalid, k.keys, k.bitmap, k.flags,
+               n_dev, (uint32_t)k.nwords);
+  } else {
+    launch_pdl(mark_rows_kernel<TI, false>, dim3((n + 255) / 256), dim3(256), (size_t)0, c->stream, rows, n, e, negative_is_invalid, k.keys,
+               k.bitmap, k.flags, n_dev, 0u);
   }
-  keys[i] = key;
-  bitmap_set(bitmap, key);
 }
 
 // ---- emit unique rows (decode keys of set bits) ----------------------------------------------------

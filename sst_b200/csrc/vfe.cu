@@ -53,23 +53,31 @@ __device__ __forceinline__ long long quirk_row(const SampleQuirk& q, long long r
   return rank - shift;
 }
 
-template <typename TC>
-__global__ void vfe_mark_kernel(const TC* __restrict__ coors, int P, int B, int Z, int Y, int X, size_t cells_pad,
-                                long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags) {
+template <typename TC, bool SM>
+__global__ void __launch_bounds__(SM ? 1024 : 256) vfe_mark_kernel(const TC* __restrict__ coors, int P, int B, int Z, int Y, int X, size_t cells_pad,
+                                long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags,
+                                uint32_t nwords) {
   pdl_wait();
   pdl_launch();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  long long b = (long long)coors[(size_t)i * 4], z = (long long)coors[(size_t)i * 4 + 1], y = (long long)coors[(size_t)i * 4 + 2],
-            x = (long long)coors[(size_t)i * 4 + 3];
-  if (b < 0 || b >= B || z < 0 || z >= Z || y < 0 || y >= Y || x < 0 || x >= X) {
-    keys[i] = -1;
-    flags[0] = 1;
-    return;
+  extern __shared__ uint32_t mark_sbm[];  // SM: block-private bitmap (see mark_rows_kernel in index.cuh)
+  if (SM) {
+    for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) mark_sbm[w] = 0u;
+    __syncthreads();
   }
-  long long key = b * (long long)cells_pad + (z * Y + y) * X + x;
-  keys[i] = key;
-  bitmap_set(bitmap, key);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    long long b = (long long)coors[(size_t)i * 4], z = (long long)coors[(size_t)i * 4 + 1], y = (long long)coors[(size_t)i * 4 + 2],
+              x = (long long)coors[(size_t)i * 4 + 3];
+    if (b < 0 || b >= B || z < 0 || z >= Z || y < 0 || y >= Y || x < 0 || x >= X) {
+      keys[i] = -1;
+      flags[0] = 1;
+      continue;
+    }
+    long long key = b * (long long)cells_pad + (z * Y + y) * X + x;
+    keys[i] = key;
+    if (SM) atomicOr(&mark_sbm[key >> 5], 1u << (key & 31));
+    else bitmap_set(bitmap, key);
+  }
+  if (SM) bitmap_merge(mark_sbm, bitmap, nwords);
 }
 
 template <typename TM>
@@ -747,7 +755,14 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   if (!count || !vmean || !vf0 || !fold || !y0buf) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)P + 2) * 4, c->stream));
   int nb = (P + 255) / 256;
-  launch_pdl(vfe_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags);
+  if (k.nwords <= 12 * 1024) {  // <= 48 KB: block-private bitmap
+    int mg = (P + 1023) / 1024;
+    if (mg > c->num_sms) mg = c->num_sms;
+    launch_pdl(vfe_mark_kernel<TC, true>, dim3(mg), dim3(1024), k.nwords * 4, c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags,
+               (uint32_t)k.nwords);
+  } else {
+    launch_pdl(vfe_mark_kernel<TC, false>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, B, Z, Y, X, cells_pad, k.keys, k.bitmap, k.flags, 0u);
+  }
   key_index_scan(c, k);
   SampleQuirk q{k.word_prefix, cells_pad / 32, B, cfg->drop_first_voxel_per_sample != 0};
   int eg = (int)((k.nwords * 4 + 63) / 64);

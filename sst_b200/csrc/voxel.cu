@@ -122,7 +122,7 @@ extern "C" int sstb200_dynamic_point_to_voxel_forward(sstb200_ctx* c, const floa
   if (rc) return rc;
   CUDA_TRY(c, cudaMemsetAsync(reduce_count, 0, (size_t)P * 4, c->stream));
   int nb = (P + 255) / 256;
-  launch_pdl(mark_rows_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, P, e, true, k.keys, k.bitmap, k.flags, nullptr);
+  launch_mark_rows<int32_t>(c, coors, P, e, true, k, nullptr);
   key_index_scan(c, k);
   launch_emit_rows<int32_t>(c, k, e, 1, out_coors, num_dev);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 1, k.flags, coors_map, reduce_count, nullptr);
@@ -248,7 +248,7 @@ extern "C" int sstb200_unique_rows_i64(sstb200_ctx* c, const int64_t* coors, int
   if (rc) return rc;
   if (counts) CUDA_TRY(c, cudaMemsetAsync(counts, 0, (size_t)P * 4, c->stream));
   int nb = (P + 255) / 256;
-  launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)coors, P, e, false, k.keys, k.bitmap, k.flags, nullptr);
+  launch_mark_rows<long long>(c, (const long long*)coors, P, e, false, k, nullptr);
   key_index_scan(c, k);
   launch_emit_rows<long long>(c, k, e, 0, (long long*)new_coors, num_dev);
   launch_pdl(map_count_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, 0, k.flags,
@@ -303,7 +303,7 @@ extern "C" int sstb200_ingroup_indices(sstb200_ctx* c, const int64_t* group, int
   const int32_t* ng = (const int32_t*)k.total;  // #distinct groups, written by the bitmap scan
   CUDA_TRY(c, cudaMemsetAsync(count, 0, ((size_t)N + 2) * 4, c->stream));
   int nb = (N + 255) / 256;
-  launch_pdl(mark_rows_kernel<long long>, dim3(nb), dim3(256), (size_t)(0), c->stream, (const long long*)group, N, e, false, k.keys, k.bitmap, k.flags, nullptr);
+  launch_mark_rows<long long>(c, (const long long*)group, N, e, false, k, nullptr);
   key_index_scan(c, k);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, N, k.bitmap, k.word_prefix, 0, k.flags, cid, count, nullptr);
   Csr r;

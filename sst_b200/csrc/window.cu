@@ -39,38 +39,45 @@ static void make_geom(const sstb200_window_cfg* cfg, int do_shift, WinGeom& g) {
   g.batch = cfg->batch_size;
 }
 
-template <typename TC>
-__global__ void win_mark_kernel(const TC* __restrict__ coors, int n, const int32_t* __restrict__ n_dev, WinGeom g,
+template <typename TC, bool SM>
+__global__ void __launch_bounds__(SM ? 1024 : 256) win_mark_kernel(const TC* __restrict__ coors, int n, const int32_t* __restrict__ n_dev, WinGeom g,
                                 long long* __restrict__ keys, uint32_t* __restrict__ bitmap, int32_t* __restrict__ flags,
                                 long long* __restrict__ batch_win_inds, long long* __restrict__ coors_in_win,
-                                int32_t* __restrict__ pos_code) {
+                                int32_t* __restrict__ pos_code, uint32_t nwords) {
   pdl_wait();
   pdl_launch();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ uint32_t mark_sbm[];  // SM: block-private bitmap (see mark_rows_kernel)
   if (n_dev) n = *n_dev;
-  if (i >= n) return;
-  long long b = (long long)coors[(size_t)i * 4 + 0];
-  long long x = (long long)coors[(size_t)i * 4 + 3] + g.sx;
-  long long y = (long long)coors[(size_t)i * 4 + 2] + g.sy;
-  long long z = (long long)coors[(size_t)i * 4 + 1] + g.sz;
-  long long wxi = x / g.wx, wyi = y / g.wy, wzi = z / g.wz;
-  long long key = b * ((long long)g.nx * g.ny * g.nz) + wxi * (g.ny * g.nz) + wyi * g.nz + wzi;
-  int cx = (int)(x - wxi * g.wx), cy = (int)(y - wyi * g.wy), cz = (int)(z - wzi * g.wz);
-  if (batch_win_inds) batch_win_inds[i] = key;
-  if (coors_in_win) {
-    coors_in_win[(size_t)i * 3 + 0] = cz;
-    coors_in_win[(size_t)i * 3 + 1] = cy;
-    coors_in_win[(size_t)i * 3 + 2] = cx;
+  if (SM) {
+    for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) mark_sbm[w] = 0u;
+    __syncthreads();
   }
-  if (pos_code) pos_code[i] = cx | (cy << 8) | (cz << 16);
-  bool bad = b < 0 || b >= g.batch || wxi < 0 || wxi >= g.nx || wyi < 0 || wyi >= g.ny || wzi < 0 || wzi >= g.nz;
-  if (bad) {
-    keys[i] = -1;
-    flags[0] = 1;
-    return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long b = (long long)coors[(size_t)i * 4 + 0];
+    long long x = (long long)coors[(size_t)i * 4 + 3] + g.sx;
+    long long y = (long long)coors[(size_t)i * 4 + 2] + g.sy;
+    long long z = (long long)coors[(size_t)i * 4 + 1] + g.sz;
+    long long wxi = x / g.wx, wyi = y / g.wy, wzi = z / g.wz;
+    long long key = b * ((long long)g.nx * g.ny * g.nz) + wxi * (g.ny * g.nz) + wyi * g.nz + wzi;
+    int cx = (int)(x - wxi * g.wx), cy = (int)(y - wyi * g.wy), cz = (int)(z - wzi * g.wz);
+    if (batch_win_inds) batch_win_inds[i] = key;
+    if (coors_in_win) {
+      coors_in_win[(size_t)i * 3 + 0] = cz;
+      coors_in_win[(size_t)i * 3 + 1] = cy;
+      coors_in_win[(size_t)i * 3 + 2] = cx;
+    }
+    if (pos_code) pos_code[i] = cx | (cy << 8) | (cz << 16);
+    bool bad = b < 0 || b >= g.batch || wxi < 0 || wxi >= g.nx || wyi < 0 || wyi >= g.ny || wzi < 0 || wzi >= g.nz;
+    if (bad) {
+      keys[i] = -1;
+      flags[0] = 1;
+      continue;
+    }
+    keys[i] = key;
+    if (SM) atomicOr(&mark_sbm[key >> 5], 1u << (key & 31));
+    else bitmap_set(bitmap, key);
   }
-  keys[i] = key;
-  bitmap_set(bitmap, key);
+  if (SM) bitmap_merge(mark_sbm, bitmap, nwords);
 }
 
 struct LevelCfg {
@@ -250,8 +257,15 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   if (!count) return sstb_fail(c, SSTB_ERR_WORKSPACE, "window plan: arena");
   CUDA_TRY(c, cudaMemsetAsync(count, 0, (nwcap + 2) * 4, c->stream));
   int nb = (n + 255) / 256;
-  launch_pdl(win_mark_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, n, n_dev, g, k.keys, k.bitmap, k.flags, (long long*)o->batch_win_inds,
-                                                 (long long*)o->coors_in_win, o->pos_code);
+  if (k.nwords <= 12 * 1024) {  // <= 48 KB: block-private bitmap
+    int mg = (n + 1023) / 1024;
+    if (mg > c->num_sms) mg = c->num_sms;
+    launch_pdl(win_mark_kernel<TC, true>, dim3(mg), dim3(1024), k.nwords * 4, c->stream, coors, n, n_dev, g, k.keys, k.bitmap, k.flags,
+               (long long*)o->batch_win_inds, (long long*)o->coors_in_win, o->pos_code, (uint32_t)k.nwords);
+  } else {
+    launch_pdl(win_mark_kernel<TC, false>, dim3(nb), dim3(256), (size_t)(0), c->stream, coors, n, n_dev, g, k.keys, k.bitmap, k.flags,
+               (long long*)o->batch_win_inds, (long long*)o->coors_in_win, o->pos_code, 0u);
+  }
   key_index_scan(c, k);
   launch_pdl(map_count_kernel<int32_t>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, n, k.bitmap, k.word_prefix, 0, k.flags, o->tok_win, count, n_dev);
   const int32_t* nwin = (const int32_t*)k.total;  // #distinct windows, written by the bitmap scan
