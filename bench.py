@@ -47,7 +47,15 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.windows = gpu_index, [], None, []
+
+    def begin(self):
+        """Open a timed window: only samples that arrive inside a window count (the sampler itself is started earlier,
+        because nvidia-smi needs tens of ms to produce its first line)."""
+        self.windows.append([time.time(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.time()
 
     def start(self):
         try:
@@ -61,7 +69,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -72,7 +80,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.windows and not any(a <= ts <= (b if b is not None else ts) for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -231,11 +241,12 @@ def main():
         e.load_frames_device(frames_d[i % NF], offs_d)
         return e.run()
 
+    sampler = ClockSampler(local)
+    sampler.start()   # before the warm-up; samples are kept only inside the timed windows (begin/end)
     for i in range(max(args.warmup, S)):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.begin()
     main = torch.cuda.current_stream(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
@@ -247,7 +258,7 @@ def main():
         main.wait_stream(e.stream)
     e1.record(main)
     barrier()
-    clocks = sampler.stop()
+    sampler.end()
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -293,9 +304,12 @@ def main():
 
     M = e2e_run(2 * S)
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     M = e2e_run(args.steps)
     e2e_s = time.perf_counter() - t0
+    sampler.end()
+    clocks = sampler.stop()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -646,7 +646,12 @@ static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const i
     CUDA_TRY(c, cudaFuncSetAttribute(win_attn_batch_kernel<NHL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(c->num_sms * 6), dim3(256), smem, c->stream, qkv, counters, win_offsets,
+  static int grid_mult = 0;
+  if (!grid_mult) {
+    const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)
+    grid_mult = e && atoi(e) > 0 ? atoi(e) : 6;
+  }
+  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(c->num_sms * grid_mult), dim3(256), smem, c->stream, qkv, counters, win_offsets,
                          win_batch, 0.25f, out));
   return SSTB_OK;
 }

@@ -1,5 +1,9 @@
+"""Not a test (not collected): prints the bf16 path's error against the oracle after 1 / 3 / 6 blocks at the full config-2 size.
+    python tests/probe_bf16_error.py   (GPU box)"""
 import sys, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from oracle import sst_oracle as O
 import test_gpu_sst as T
 from sst_b200.sst_modules import SSTInputLayerV2

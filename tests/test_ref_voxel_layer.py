@@ -75,3 +75,49 @@ def test_dynamic_scatter_vs_reference_cuda(cuda, ref, reduce, P, C, lo):
     ref.dynamic_point_to_voxel_backward(r_g, grad, feats, r_f, r_m, r_n, reduce)
     ops.dynamic_point_to_voxel_backward(g_g, grad, feats, r_f, r_m, r_n, reduce)
     torch.testing.assert_close(g_g, r_g, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_speed_vs_reference_cuda(cuda, ref):
+    """"also time the reference CUDA voxel_layer built for sm_100a - the in-tree GPU kernel to beat for V1/V2".
+    Same device tensors, CUDA events, L2 flushed before every call, median of 15.  The gate is deliberately loose (2x); the
+    measured ratios are printed (run with -s) and written to gpurun_out/ref_cuda_timing.json when that directory exists."""
+    import json
+    import os
+    from sst_b200 import ops
+    P, C = 150000, 128
+    pts = O.synth_frame(1000, P).to(cuda)
+    coors = ops.Voxelization(VS, RNG, -1)(pts)
+    feats = torch.randn(P, C, device=cuda)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=cuda)
+
+    def timed(fn, iters=15):
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b) * 1e3)
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    rc = torch.zeros((P, 3), dtype=torch.int32, device=cuda)
+    gc = torch.zeros((P, 3), dtype=torch.int32, device=cuda)
+    out["dynamic_voxelize"] = dict(reference_us=timed(lambda: ref.dynamic_voxelize(pts, rc, list(VS), list(RNG), 3)),
+                                   ours_us=timed(lambda: ops.dynamic_voxelize(pts, gc, VS, RNG, 3)))
+    for red in ("max", "mean"):
+        ds = ops.DynamicScatter(VS, RNG, red == "mean")
+        out[f"dynamic_scatter_{red}_C{C}"] = dict(
+            reference_us=timed(lambda: ref.dynamic_point_to_voxel_forward(feats, coors, red)),
+            ours_us=timed(lambda: ds(feats, coors)))
+    for k, v in out.items():
+        v["speedup"] = v["reference_us"] / v["ours_us"]
+        print(f"{k}: reference CUDA {v['reference_us']:.1f} us, libsstb200 {v['ours_us']:.1f} us, x{v['speedup']:.1f}")
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        json.dump(out, open(os.path.join(d, "ref_cuda_timing.json"), "w"), indent=1)
+    assert out["dynamic_scatter_max_C128"]["speedup"] > 2.0 and out["dynamic_scatter_mean_C128"]["speedup"] > 2.0

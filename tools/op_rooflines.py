@@ -1,7 +1,8 @@
 """Per-op latency + roofline table for every SURVEY.md 8(a) row, through the public Python ops / modules (the calls a
 reference user makes), on config-2 / config-3 shapes.  CUDA events on the current stream, L2 flushed before every call,
 median of `--iters`.  Ops that return data-dependent shapes read one int32 back (like the reference) - that sync is inside
-the timing, so these are API latencies, not kernel sums (kernel sums: ncu launch lists under profiles/).
+the timing, so these are API latencies, not kernel sums (kernel sums: ncu launch lists under profiles/).  The reference's own
+CUDA voxel_layer is timed on the same tensors by tests/test_ref_voxel_layer.py::test_speed_vs_reference_cuda.
 
     python tools/op_rooflines.py [--iters 20] [--out gpurun_out/op_rooflines.json]
     ncu ... python tools/op_rooflines.py --once        # one call per op, separated by marker kernels (torch.arange)
@@ -21,9 +22,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true")
 ap.add_argument("--out", default=None)
-ap.add_argument("--with-reference", action="store_true",
-                help="also time the reference's own CUDA voxel_layer (oracle/_ref, built unmodified for sm_100a) on the same "
-                     "tensors: the in-tree GPU kernels to beat for V1/V2 (SURVEY.md 8d)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 P, C = 150000, 128
@@ -85,17 +83,6 @@ with torch.no_grad():
         ds = ops.DynamicScatter(fl.VOXEL_SIZE, fl.PC_RANGE, red == "mean")
         op(f"V2 DynamicScatter({red}, C={C})", "ops/voxel/scatter_points.py:52-110 -> src/scatter_points_cuda.cu:183-234",
            lambda ds=ds: ds(feats, coors3), bytes_=v2_bytes, note=f"M={M}")
-    if args.with_reference:
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        from oracle import build_ref  # measurement only: the reference kernels are timed, never used by the product
-        ref = build_ref.load_module()
-        if ref is not None:
-            rc = torch.zeros((P, 3), dtype=torch.int32, device=dev)
-            op("V1 REFERENCE CUDA dynamic_voxelize", "ops/voxel/src/voxelization_cuda.cu:332-375",
-               lambda: ref.dynamic_voxelize(pts, rc, list(fl.VOXEL_SIZE), list(fl.PC_RANGE), 3), bytes_=P * 24)
-            for red in ("max", "mean"):
-                op(f"V2 REFERENCE CUDA dynamic_point_to_voxel_forward({red}, C={C})", "ops/voxel/src/scatter_points_cuda.cu:183-234",
-                   lambda red=red: ref.dynamic_point_to_voxel_forward(feats, coors3, red), bytes_=v2_bytes)
     red_f, out_c, cmap, cnt = ops.dynamic_point_to_voxel_forward(feats, coors3, "max")
     gout = torch.randn_like(red_f)
     gin = torch.zeros_like(feats)
