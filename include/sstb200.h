@@ -49,6 +49,16 @@ int sstb200_num_sms(sstb200_ctx* ctx);
 int sstb200_dynamic_voxelize(sstb200_ctx* ctx, const float* points, int num_points, int num_features,
                              const float voxel_size[3], const float coors_range[6], int32_t* coors);
 
+/* V1' voxel_layer.hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range, max_points, max_voxels)
+ *     (voxelization.h:51-70 -> voxelization_cpu.cpp:43-142 / voxelization_cuda.cu:68-330).  voxels
+ *     [max_voxels, max_points, F], coors [max_voxels,3] (z,y,x), num_points_per_voxel [max_voxels] are caller-allocated AND
+ *     zero-initialised, as ops/voxel/voxelize.py:46-53 does.  Voxels are numbered by first appearance in the point list; every
+ *     voxel keeps its first max_points points in input order.  Returns the voxel count in device memory and, if
+ *     voxel_num_host != NULL, on the host (one stream sync; the reference returns an int). */
+int sstb200_hard_voxelize(sstb200_ctx* ctx, const float* points, int num_points, int num_features, const float voxel_size[3],
+                          const float coors_range[6], int max_points, int max_voxels, float* voxels, int32_t* coors,
+                          int32_t* num_points_per_voxel, int32_t* voxel_num_dev, int32_t* voxel_num_host);
+
 /* V2  voxel_layer.dynamic_point_to_voxel_forward(feats, coors, reduce_type)
  *     (voxelization.h:96-108 -> scatter_points_cuda.cu:183-234).
  *     feats [P,C] fp32, coors [P,3] int32.  coor_lo/hi: inclusive bounds of the non-negative

@@ -28,6 +28,7 @@ SIGNATURES = {
     "sstb200_last_error": (C.c_char_p, [vp]),
     "sstb200_num_sms": (C.c_int, [vp]),
     "sstb200_dynamic_voxelize": (C.c_int, [vp, vp, C.c_int, C.c_int, P_f32, P_f32, vp]),
+    "sstb200_hard_voxelize": (C.c_int, [vp, vp, C.c_int, C.c_int, P_f32, P_f32, C.c_int, C.c_int, vp, vp, vp, vp, P_i32]),
     "sstb200_dynamic_point_to_voxel_forward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, P_i32, P_i32,
                                                            vp, vp, vp, vp, vp, P_i32]),
     "sstb200_dynamic_point_to_voxel_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,

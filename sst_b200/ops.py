@@ -44,14 +44,41 @@ def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
         L.arr(C.c_float, [float(v) for v in coors_range]), coors.data_ptr()))
 
 
+def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range, max_points, max_voxels, NDim=3):
+    """voxel_layer.hard_voxelize (ops/voxel/src/voxelization.h:51-70): fills the caller's zero-initialised buffers, returns the
+    number of voxels (int, one stream sync like the reference)."""
+    assert NDim == 3
+    _need_cuda(points, voxels, coors, num_points_per_voxel)
+    assert points.dtype == torch.float32 and voxels.dtype == torch.float32
+    assert coors.dtype == torch.int32 and num_points_per_voxel.dtype == torch.int32
+    for t in (points, voxels, coors, num_points_per_voxel):
+        assert t.is_contiguous()
+    assert voxels.shape == (max_voxels, max_points, points.shape[1]) and coors.shape == (max_voxels, 3)
+    num_dev = torch.empty((1,), dtype=torch.int32, device=points.device)
+    num = C.c_int32(0)
+    c = L.ctx(points.device)
+    L.check(c, L.lib().sstb200_hard_voxelize(
+        c, points.data_ptr(), points.shape[0], points.shape[1], L.arr(C.c_float, [float(v) for v in voxel_size]),
+        L.arr(C.c_float, [float(v) for v in coors_range]), int(max_points), int(max_voxels), voxels.data_ptr(), coors.data_ptr(),
+        num_points_per_voxel.data_ptr(), num_dev.data_ptr(), C.byref(num)))
+    return num.value
+
+
 class _Voxelization(Function):
+    """ops/voxel/voxelize.py:11-72."""
+
     @staticmethod
     def forward(ctx, points, voxel_size, coors_range, max_points=35, max_voxels=20000):
         if max_points == -1 or max_voxels == -1:
             coors = points.new_zeros(size=(points.size(0), 3), dtype=torch.int)
             dynamic_voxelize(points.contiguous(), coors, voxel_size, coors_range, 3)
             return coors
-        raise NotImplementedError("hard voxelization is outside the hot path (SURVEY.md 8f next-4)")
+        points = points.contiguous()
+        voxels = points.new_zeros(size=(max_voxels, max_points, points.size(1)))
+        coors = points.new_zeros(size=(max_voxels, 3), dtype=torch.int)
+        num_points_per_voxel = points.new_zeros(size=(max_voxels,), dtype=torch.int)
+        voxel_num = hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range, max_points, max_voxels, 3)
+        return voxels[:voxel_num], coors[:voxel_num], num_points_per_voxel[:voxel_num]
 
 
 voxelization = _Voxelization.apply

@@ -151,3 +151,16 @@ def test_ingroup_indices(cuda, n, ngroups):
     ref = O.ingroup_indices(grp)
     got = ops.get_inner_win_inds(grp.to(cuda))
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("P,F,mp,mv", [(20000, 4, 32, 20000), (20000, 4, 5, 300), (3000, 3, 1, 50), (1, 4, 3, 2)])
+def test_hard_voxelize_bitexact(cuda, P, F, mp, mv):
+    """`Voxelization(max_num_points > 0)` (hard voxelisation): voxel order = first appearance, first
+    max_points points per voxel in input order, max_voxels cap - bit-exact against the oracle (itself pinned to the reference
+    C++ in tests/test_ref_voxel_layer.py)."""
+    from sst_b200 import ops
+    pts = O.synth_frame(9 + P, P, extra_dims=F - 3)
+    pts[::13, 0] += 500.0
+    ov, oc, on = O.hard_voxelize(pts, VS, RNG, mp, mv)
+    gv, gc, gn = ops.Voxelization(VS, RNG, mp, mv).eval()(pts.to(cuda))
+    assert torch.equal(gc.cpu(), oc) and torch.equal(gn.cpu(), on) and torch.equal(gv.cpu(), ov)

@@ -121,3 +121,46 @@ def test_speed_vs_reference_cuda(cuda, ref):
     if os.path.isdir(d):
         json.dump(out, open(os.path.join(d, "ref_cuda_timing.json"), "w"), indent=1)
     assert out["dynamic_scatter_max_C128"]["speedup"] > 2.0 and out["dynamic_scatter_mean_C128"]["speedup"] > 2.0
+
+
+HV_CASES = [  # (P, F, voxel_size, range, max_points, max_voxels)
+    (20000, 4, (0.32, 0.32, 6), [-74.88, -74.88, -2, 74.88, 74.88, 4], 32, 20000),
+    (20000, 4, (0.32, 0.32, 6), [-74.88, -74.88, -2, 74.88, 74.88, 4], 5, 300),       # both caps bite
+    (30000, 5, (0.5, 0.5, 0.25), [-40, -40, -3, 40, 40, 1], 10, 16000),               # 3-D grid
+    (7, 3, (1.0, 1.0, 1.0), [0, 0, 0, 4, 4, 4], 2, 3),
+]
+
+
+def _hv_points(P, F):
+    pts = O.synth_frame(300 + P, P, extra_dims=F - 3)
+    pts[::13, 0] += 500.0  # out of range -> clamped by this fork's voxeliser
+    return pts
+
+
+@pytest.mark.parametrize("P,F,vs,rng,mp,mv", HV_CASES)
+def test_oracle_hard_voxelize_equals_reference_cpp(ref, P, F, vs, rng, mp, mv):
+    """Pins oracle.hard_voxelize to the reference's own `hard_voxelize_cpu` (voxelization_cpu.cpp:43-142)."""
+    pts = _hv_points(P, F)
+    voxels = torch.zeros((mv, mp, F))
+    coors = torch.zeros((mv, 3), dtype=torch.int32)
+    npts = torch.zeros((mv,), dtype=torch.int32)
+    n = ref.hard_voxelize(pts, voxels, coors, npts, list(vs), list(rng), mp, mv, 3)
+    ov, oc, on = O.hard_voxelize(pts, vs, rng, mp, mv)
+    assert n == ov.shape[0]
+    assert torch.equal(oc, coors[:n]) and torch.equal(on, npts[:n]) and torch.equal(ov, voxels[:n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,F,vs,rng,mp,mv", HV_CASES + [(150000, 4, (0.32, 0.32, 6), [-74.88, -74.88, -2, 74.88, 74.88, 4], 32, 32000)])
+def test_hard_voxelize_vs_reference(cuda, ref, P, F, vs, rng, mp, mv):
+    """libsstb200 `Voxelization(max_num_points > 0)` against the reference CPU implementation (bit-exact: pure data movement)."""
+    from sst_b200 import ops
+    pts = _hv_points(P, F)
+    voxels = torch.zeros((mv, mp, F))
+    coors = torch.zeros((mv, 3), dtype=torch.int32)
+    npts = torch.zeros((mv,), dtype=torch.int32)
+    n = ref.hard_voxelize(pts, voxels, coors, npts, list(vs), list(rng), mp, mv, 3)
+    layer = ops.Voxelization(vs, rng, mp, mv).eval()
+    gv, gc, gn = layer(pts.to(cuda))
+    assert gv.shape[0] == n
+    assert torch.equal(gc.cpu(), coors[:n]) and torch.equal(gn.cpu(), npts[:n]) and torch.equal(gv.cpu(), voxels[:n])

@@ -76,6 +76,9 @@ with torch.no_grad():
     vox = ops.Voxelization(fl.VOXEL_SIZE, fl.PC_RANGE, -1).to(dev)
     op("V1 Voxelization(dynamic)", "ops/voxel/voxelize.py:102-113", lambda: vox(pts), bytes_=P * (3 * 4 + 3 * 4))
     coors3 = vox(pts)
+    hvox = ops.Voxelization(fl.VOXEL_SIZE, fl.PC_RANGE, 32, 32000).to(dev).eval()
+    op("V1' Voxelization(hard, max_points=32, max_voxels=32000)", "ops/voxel/voxelize.py:45-57 -> src/voxelization_cuda.cu:188-330",
+       lambda: hvox(pts), bytes_=P * 12 + 32000 * 32 * 12, note="bytes = read points + the zero-filled [max_voxels, max_points, F] output")
     feats = torch.randn(P, C, device=dev)
     M = ops.dynamic_point_to_voxel_forward(feats, coors3, "max")[0].shape[0]
     v2_bytes = P * (4 * C + 12) + M * (4 * C + 12) + 4 * P + 4 * M
