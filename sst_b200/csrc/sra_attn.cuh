@@ -123,17 +123,9 @@ int sstb_win_attn(sstb200_ctx* c, const TI* qkv, int d, int nhead, int n_cap, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tensor-core ragged window attention (bf16 in/out, fp32 softmax): one CTA per window (persistent grid-stride),
-// K/V of the window staged once in shared memory, one warp per (16-query tile, head):
-//   S = Q_h K_h^T      mma.sync.m16n8k16 (dh = 16 is exactly one k-step), all key tiles kept in registers
-//   softmax            fp32, quad shuffles for the row max / sum
-//   O = P V_h          P re-used from the S accumulators as A fragments (no smem round trip), V via ldmatrix.trans
-// Windows hold <= 144 tokens on this path (12x12 pillars), i.e. <= 18 key tiles.
-// q/k/v and the output are in SLOT order (row s = token tok_perm[s]; the QKV GEMM's epilogue scatters into it), so a
-// window is a contiguous block of rows: K/V staging is a straight coalesced copy with no index indirection.
+// Tensor-core ragged window attention helpers (mma.sync.m16n8k16, fp32 accumulate) shared by the kernels below.
 // ------------------------------------------------------------------------------------------------
 #define ATT_MAXT 144
-#define ATT_LD 136  // bf16 elements per staged row (128 + 8 pad -> conflict-free fragment loads)
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -154,136 +146,6 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-static __global__ void __launch_bounds__(256) win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int nhead,
-                                                           const int32_t* __restrict__ nwin_dev,
-                                                           const int32_t* __restrict__ win_offsets, float scale,
-                                                           __nv_bfloat16* __restrict__ out) {
-  pdl_wait();
-  pdl_launch();
-  constexpr int D = 128, DH = 16, KT = ATT_MAXT / 8;
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sV = sK + ATT_MAXT * ATT_LD;
-  const int R = *nwin_dev;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g4 = lane >> 2, t4 = lane & 3;
-  for (int w = blockIdx.x; w < R; w += gridDim.x) {
-    const int kb = win_offsets[w];
-    const int n = min(win_offsets[w + 1] - kb, ATT_MAXT);
-    const int npad = (n + 15) & ~15;
-    __syncthreads();  // previous window fully consumed
-    // stage K and V rows (16-byte chunks; 16 chunks per row each)
-    for (int idx = threadIdx.x; idx < npad * 32; idx += blockDim.x) {
-      int r = idx >> 5, c = idx & 31;
-      int4 v = make_int4(0, 0, 0, 0);
-      if (r < n) v = *reinterpret_cast<const int4*>(qkv + (size_t)(kb + r) * 3 * D + D + c * 8);
-      __nv_bfloat16* dst = (c < 16 ? sK : sV) + r * ATT_LD + (c & 15) * 8;
-      *reinterpret_cast<int4*>(dst) = v;
-    }
-    __syncthreads();
-    const int ntile = npad >> 4;
-    const int nkt = (n + 7) >> 3;
-    for (int item = warp; item < ntile * nhead; item += 8) {
-      const int qt = item / nhead, h = item % nhead;
-      // Q fragment
-      const int r0 = qt * 16 + g4, r1 = r0 + 8;
-      const int tok0 = r0 < n ? kb + r0 : -1, tok1 = r1 < n ? kb + r1 : -1;
-      uint32_t qa[4] = {0, 0, 0, 0};
-      if (tok0 >= 0) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok0 * 3 * D + h * DH);
-        qa[0] = qp[t4];
-        qa[2] = qp[t4 + 4];
-      }
-      if (tok1 >= 0) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok1 * 3 * D + h * DH);
-        qa[1] = qp[t4];
-        qa[3] = qp[t4 + 4];
-      }
-      float s[KT][4];
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < KT; j++) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        if (j < nkt) {
-          const uint32_t* kp = reinterpret_cast<const uint32_t*>(sK + (j * 8 + g4) * ATT_LD + h * DH);
-          mma_bf16_16816(s[j], qa, kp[t4], kp[t4 + 4]);
-          const int c0 = j * 8 + 2 * t4;
-          s[j][0] = c0 < n ? s[j][0] * scale : -INFINITY;
-          s[j][1] = c0 + 1 < n ? s[j][1] * scale : -INFINITY;
-          s[j][2] = c0 < n ? s[j][2] * scale : -INFINITY;
-          s[j][3] = c0 + 1 < n ? s[j][3] * scale : -INFINITY;
-          m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
-          m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
-        }
-      }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < KT; j++) {
-        if (j < nkt) {
-          s[j][0] = __expf(s[j][0] - m0);
-          s[j][1] = __expf(s[j][1] - m0);
-          s[j][2] = __expf(s[j][2] - m1);
-          s[j][3] = __expf(s[j][3] - m1);
-          l0 += s[j][0] + s[j][1];
-          l1 += s[j][2] + s[j][3];
-        }
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      // O = P V
-      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int kc = 0; kc < KT / 2; kc++) {
-        if (kc * 16 < n) {
-          uint32_t pa[4];
-          pa[0] = pack2_bf16(s[2 * kc][0], s[2 * kc][1]);
-          pa[1] = pack2_bf16(s[2 * kc][2], s[2 * kc][3]);
-          pa[2] = pack2_bf16(s[2 * kc + 1][0], s[2 * kc + 1][1]);
-          pa[3] = pack2_bf16(s[2 * kc + 1][2], s[2 * kc + 1][3]);
-          // V^T fragments: 4 8x8 matrices (keys 0-7 / 8-15) x (dims 0-7 / 8-15) of this head
-          const __nv_bfloat16* vrow = sV + (kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + h * DH + (lane >> 4) * 8;
-          uint32_t vb[4];
-          uint32_t saddr = (uint32_t)__cvta_generic_to_shared(vrow);
-          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                       : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
-                       : "r"(saddr));
-          mma_bf16_16816(o[0], pa, vb[0], vb[1]);
-          mma_bf16_16816(o[1], pa, vb[2], vb[3]);
-        }
-      }
-      const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-      if (tok0 >= 0) {
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok0 * D + h * DH);
-        op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
-        op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
-      }
-      if (tok1 >= 0) {
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok1 * D + h * DH);
-        op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
-        op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
-      }
-    }
-  }
-}
-
-static inline int sstb_win_attn_mma(sstb200_ctx* c, const __nv_bfloat16* qkv, int nhead, const int32_t* nwin_dev,
-                                    const int32_t* win_offsets, __nv_bfloat16* out) {
-  size_t smem = (size_t)2 * ATT_MAXT * ATT_LD * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(c, cudaFuncSetAttribute(win_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  launch_pdl(win_attn_mma_kernel, dim3(c->num_sms * 2), dim3(256), (size_t)(smem), c->stream, qkv, nhead, nwin_dev, win_offsets, 0.25f, out);
-  CUDA_TRY(c, cudaGetLastError());
-  return SSTB_OK;
-}
 
 // ------------------------------------------------------------------------------------------------
 // v3: warp-autonomous ragged attention.  One warp owns one (window, head): K_h and V_h^T of the whole window live in

@@ -124,3 +124,14 @@ def test_group_csr(cuda, N, G):
     assert torch.equal(off, torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)]))
     assert torch.equal(order.sort().values, torch.arange(N))
     assert torch.equal(inv[order], inv.sort().values)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sir_empty_input(cuda, precision):
+    """No points: shapes are kept, nothing is launched (the reference returns empty tensors through torch.unique / scatter)."""
+    m = _sir([84, 133, 133], 128, 3).to(cuda)
+    m.precision = precision
+    with torch.no_grad():
+        a, b, c = m(torch.zeros(0, 5, device=cuda), torch.zeros(0, 79, device=cuda), torch.zeros(0, 3, dtype=torch.long, device=cuda),
+                    torch.zeros(0, 3, device=cuda))
+    assert a.shape == (0, 128) and b.shape == (0, 768) and c.shape == (0, 3)

@@ -164,3 +164,9 @@ def test_hard_voxelize_bitexact(cuda, P, F, mp, mv):
     ov, oc, on = O.hard_voxelize(pts, VS, RNG, mp, mv)
     gv, gc, gn = ops.Voxelization(VS, RNG, mp, mv).eval()(pts.to(cuda))
     assert torch.equal(gc.cpu(), oc) and torch.equal(gn.cpu(), on) and torch.equal(gv.cpu(), ov)
+
+
+def test_hard_voxelize_empty(cuda):
+    from sst_b200 import ops
+    v, c, n = ops.Voxelization(VS, RNG, 8, 100).eval()(torch.zeros(0, 4, device=cuda))
+    assert v.shape == (0, 8, 4) and c.shape == (0, 3) and n.shape == (0,)
