@@ -302,6 +302,16 @@ int sstb200_group_csr(sstb200_ctx* ctx, const int64_t* inv, int num_points, int 
 int sstb200_recover_bev(sstb200_ctx* ctx, const float* voxel_feat, const int64_t* coors, int num_voxels, int channels,
                         int batch_size, int ny, int nx, float* canvas);
 
+/* N1  Voxel2PointScatterNeck.forward (mmdet3d/models/necks/voxel2point_neck.py:28-62): points [N,Cp] fp32,
+ * pts_coors [N,4] int64 (b,z,y,x), voxel_feats [M,C] fp32 (rows of dropped voxels hold `padding`), voxel2point_inds [N] int64.
+ * out [<=N, C(+3)] receives, for every point whose voxel row is not all-padding and in input order, the voxel row followed (with_xyz)
+ * by the point's offset from its voxel centre; mask_out [N] (1 = kept).  The call synchronises once to return the row count (the
+ * reference's boolean indexing does the same) and to report out-of-range indices as an error. */
+int sstb200_voxel2point(sstb200_ctx* ctx, const float* points, int point_dims, const int64_t* pts_coors, const float* voxel_feats,
+                        int num_voxels, int channels, const int64_t* voxel2point_inds, int num_points, float padding,
+                        const float voxel_size[3], const float pc_min[3], int with_xyz, int normalize_local_xyz, float* out,
+                        uint8_t* mask_out, int32_t* num_out_dev, int32_t* num_out_host);
+
 /* A4  the whole encoder stack (SSTv2.forward's block loop, mmdet3d/models/backbones/sst_v2.py:129-133 with
  * BasicShiftBlockV2.forward, models/sst/sst_basic_block_v2.py:144-169): layer l uses the windows of shift l % 2.
  * x [n,d] input (not modified), y [n,d] output, tmp [n,d] scratch; all fp32, distinct buffers.  With precision BF16 and the

@@ -143,9 +143,9 @@ def load():
     mod("mmcv")
     mod("mmcv.runner", auto_fp16=_passthrough_deco, force_fp32=_passthrough_deco, BaseModule=nn.Module)
     mod("mmcv.cnn", build_norm_layer=_build_norm_layer, build_conv_layer=_build_conv_layer,
-        NORM_LAYERS=_Registry())
+        NORM_LAYERS=_Registry(), ConvModule=None)
     mod("mmdet")
-    mod("mmdet.models", BACKBONES=reg)
+    mod("mmdet.models", BACKBONES=reg, NECKS=reg)
     mod("torch_scatter", scatter=_ts_scatter, scatter_max=_ts_scatter_max)
     mod("ingroup_indices", forward=_ingroup_forward)
 
@@ -165,7 +165,8 @@ def load():
     bld = mod("mmdet3d.models.builder", MIDDLE_ENCODERS=reg, VOXEL_ENCODERS=reg, BACKBONES=reg,
               build_voxel_encoder=reg.build, build_fusion_layer=None)
     sys.modules["mmdet3d.models"].builder = bld
-    for sub in ("middle_encoders", "backbones", "sst", "voxel_encoders"):
+    ops.voxel = types.ModuleType("mmdet3d.ops.voxel")  # `from mmdet3d.ops import voxel` in necks/voxel2point_neck.py (unused there)
+    for sub in ("middle_encoders", "backbones", "sst", "voxel_encoders", "necks"):
         pkg(f"mmdet3d.models.{sub}", f"mmdet3d/models/{sub}")
 
     sst_ops = importlib.import_module("mmdet3d.ops.sst.sst_ops")
@@ -197,6 +198,7 @@ def load():
     sstv2 = importlib.import_module("mmdet3d.models.backbones.sst_v2")
     sir = importlib.import_module("mmdet3d.models.backbones.sir")
     cos = importlib.import_module("mmdet3d.models.sst.cosine_msa")
+    v2p = importlib.import_module("mmdet3d.models.necks.voxel2point_neck")
 
     ns = types.SimpleNamespace(
         sst_ops=sst_ops, voxel_encoder=ve, ve_utils=ve_utils, input_layer_v2=il2, block_v2=blk,
@@ -204,6 +206,7 @@ def load():
         DynamicVFE=ve.DynamicVFE, DynamicScatterVFE=ve.DynamicScatterVFE, SIRLayer=ve.SIRLayer,
         SSTInputLayerV2=il2.SSTInputLayerV2, SSTv2=sstv2.SSTv2, SIR=sir.SIR,
         EncoderLayer=blk.EncoderLayer, WindowAttention=blk.WindowAttention,
+        Voxel2PointScatterNeck=v2p.Voxel2PointScatterNeck,
     )
     _LOADED = ns
     return ns

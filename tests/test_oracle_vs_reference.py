@@ -59,3 +59,19 @@ def test_state_dict_keys_match_reference(R):
     o = SSTv2(d_model=[32], nhead=[4], num_blocks=1, dim_feedforward=[64], num_attached_conv=0, to_bev=False, layer_cfg=lc)
     r = R.SSTv2(d_model=[32], nhead=[4], num_blocks=1, dim_feedforward=[64], num_attached_conv=0, to_bev=False, layer_cfg=lc)
     assert {k: tuple(v.shape) for k, v in o.state_dict().items()} == {k: tuple(v.shape) for k, v in r.state_dict().items()}
+
+
+@pytest.mark.parametrize("with_xyz,norm", [(True, False), (True, True), (False, False)])
+def test_voxel2point_neck(R, with_xyz, norm):
+    """oracle.voxel2point_neck vs the unmodified reference Voxel2PointScatterNeck (necks/voxel2point_neck.py:28-62)."""
+    g = torch.Generator().manual_seed(5)
+    N, M, C = 5000, 700, 16
+    pts = O.synth_frame(3, N, extra_dims=1)
+    coors = torch.nn.functional.pad(O.dynamic_voxelize(pts, VS, RNG), (1, 0), value=0).long()
+    vf = torch.randn(M, C, generator=g)
+    vf[::7] = -1.0  # dropped voxels are padded rows
+    inds = torch.randint(0, M, (N,), generator=g)
+    neck = R.Voxel2PointScatterNeck(point_cloud_range=RNG, voxel_size=VS, with_xyz=with_xyz, normalize_local_xyz=norm).eval()
+    r_out, r_mask = neck(pts, coors, vf, inds)
+    o_out, o_mask = O.voxel2point_neck(pts, coors, vf, inds, VS, RNG, with_xyz, norm)
+    assert torch.equal(r_mask, o_mask) and torch.equal(r_out, o_out)
