@@ -154,8 +154,12 @@ __global__ void __launch_bounds__(256) add_norm_kernel(const float* __restrict__
   }
   if (bn_mean) {  // eval-mode BatchNorm1d (use_bn layers): per-channel affine
     cnt = 0;
-    for (int c = ln; c < d; c += 32, cnt++)
-      out[(size_t)row * d + c] = (v[cnt] - bn_mean[c]) * rsqrtf(bn_var[c] + eps) * gamma[c] + beta[c];
+    for (int c = ln; c < d; c += 32, cnt++) {
+      float o = (v[cnt] - bn_mean[c]) * rsqrtf(bn_var[c] + eps) * gamma[c] + beta[c];
+      if (act == 1) o = fmaxf(o, 0.f);
+      if (act == 2) o = gelu_erf(o);
+      out[(size_t)row * d + c] = o;
+    }
     return;
   }
   float mean = warp_sum(s) / (float)d;

@@ -7,6 +7,7 @@
 // registers - the per-point feature tensors are never materialised.
 #include <stdarg.h>
 #include "index.cuh"
+#include "sra.cuh"
 #include "umma.cuh"
 
 struct VfeDev {
@@ -716,6 +717,75 @@ static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const T
   return SSTB_OK;
 }
 
+// =====================================================================================================
+// Wide-input path (fp32): point dims beyond the fused kernels' register budget, e.g. FSDv2's virtual-voxel encoder
+// DynamicScatterVFE(in_channels=67, feat_channels=[64,128]) (configs/fsdv2, SURVEY config 5).  Same index / CSR as above, then the
+// layers as row GEMMs:  X = decorate(points)  ->  Y0 = relu(BN(X W0^T))  ->  V0 = segmax(Y0)
+//                       Y1 = relu(BN(Y0 W1a^T + (V0 W1b^T)[voxel]))      ->  V1 = segmax(Y1)      ([Y0 || V0[voxel]] never materialised)
+// =====================================================================================================
+template <typename TC, typename TM>
+__global__ void __launch_bounds__(256) vfe_decorate_wide_kernel(VfeDev v, const float* __restrict__ pts, const TC* __restrict__ coors,
+                                                                const TM* __restrict__ map, const float* __restrict__ vmean, int P,
+                                                                float* __restrict__ X, long long* __restrict__ row64) {
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31;
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= P) return;
+  const long long vox = (long long)map[p];
+  if (lane == 0) row64[p] = vox < 0 ? 0 : vox;  // dropped points (quirk Q1) are in no CSR segment: any valid row keeps the GEMM in bounds
+  const float* q = pts + (size_t)p * v.F;
+  float* x = X + (size_t)p * v.D0;
+  for (int k = lane; k < v.F; k += 32) x[k] = q[k];
+  int base = v.F;
+  if (v.with_cluster) {
+    if (lane < 3) x[base + lane] = vox >= 0 ? (q[lane] - vmean[(size_t)vox * 3 + lane]) / v.rel_dist_scaler : 0.f;
+    base += 3;
+  }
+  if (v.with_center) {
+    if (lane < 3) {
+      const float vs = lane == 0 ? v.vx : (lane == 1 ? v.vy : v.vz);
+      const float off = lane == 0 ? v.x_off : (lane == 1 ? v.y_off : v.z_off);
+      const float cc = (float)coors[(size_t)p * 4 + (3 - lane)];
+      x[base + lane] = q[lane] - __fadd_rn(__fmul_rn(cc, vs), off);
+    }
+    base += 3;
+  }
+}
+
+template <typename TC, typename TM>
+static int vfe_wide_path(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const VfeDev& v, const float* pts, const TC* coors, const TM* map,
+                         const Csr& r, int P, const int32_t* num_dev, float* vmean, float* out_feats) {
+  cudaStream_t st = c->stream;
+  const int D0 = v.D0, C0 = v.C0, C1 = v.C1;
+  const int Cmax = C0 > C1 ? C0 : C1;
+  float* X = arena_alloc<float>(c, (size_t)P * D0);
+  float* Y0 = arena_alloc<float>(c, (size_t)P * C0);
+  float* T1 = C1 ? arena_alloc<float>(c, (size_t)P * Cmax) : nullptr;
+  float* V0 = C1 ? arena_alloc<float>(c, (size_t)P * C0) : nullptr;
+  float* G = C1 ? arena_alloc<float>(c, (size_t)P * C1) : nullptr;
+  long long* row64 = arena_alloc<long long>(c, (size_t)P);
+  if (!X || !Y0 || !row64 || (C1 && (!T1 || !V0 || !G))) return sstb_fail(c, SSTB_ERR_WORKSPACE, "vfe (wide): arena");
+  const int mode = v.mode_max ? SSTB200_REDUCE_MAX : SSTB200_REDUCE_MEAN;
+  launch_pdl(vfe_mean_kernel, dim3(c->num_sms * 8), dim3(256), (size_t)0, st, pts, v.F, (const uint32_t*)r.offsets, (const int32_t*)r.order, num_dev,
+             vmean);
+  launch_pdl(vfe_decorate_wide_kernel<TC, TM>, dim3((unsigned)(((size_t)P * 32 + 255) / 256)), dim3(256), (size_t)0, st, v, pts, coors, map,
+             (const float*)vmean, P, X, row64);
+  sstb_gemm_rows_ex(st, X, D0, cfg->weight[0], D0, nullptr, nullptr, 0, nullptr, Y0, C0, P, nullptr, C0, D0, 0, nullptr, nullptr, 0, 0, 0, 0);
+  sstb_add_norm_act(st, Y0, nullptr, cfg->bn_weight[0], cfg->bn_bias[0], cfg->bn_mean[0], cfg->bn_var[0], cfg->bn_eps, Y0, P, nullptr, C0, 1);
+  launch_segment_reduce(c, Y0, C0, r.offsets, r.order, P, num_dev, mode, 0.f, C1 ? V0 : out_feats, nullptr, P);
+  if (C1) {
+    sstb_gemm_rows_ex(st, V0, C0, cfg->weight[1] + C0, 2 * C0, nullptr, nullptr, 0, nullptr, G, C1, P, num_dev, C1, C0, 0, nullptr, nullptr, 0, 0,
+                      0, 0);
+    sstb_gemm_rows_ex(st, Y0, C0, cfg->weight[1], 2 * C0, nullptr, G, C1, (const long long*)row64, T1, C1, P, nullptr, C1, C0, 0, nullptr, nullptr,
+                      0, 0, 0, 0);
+    sstb_add_norm_act(st, T1, nullptr, cfg->bn_weight[1], cfg->bn_bias[1], cfg->bn_mean[1], cfg->bn_var[1], cfg->bn_eps, T1, P, nullptr, C1, 1);
+    launch_segment_reduce(c, T1, C1, r.offsets, r.order, P, num_dev, mode, 0.f, out_feats, nullptr, P);
+  }
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
 template <typename TC>
 static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const float* pts, const TC* coors, int P,
                             float* out_feats, TC* out_coors, TC* inverse, int32_t* num_dev, int32_t* num_host) {
@@ -730,7 +800,8 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   int F = cfg->in_channels;
   int D0 = F + 3 * (cfg->with_cluster_center != 0) + 3 * (cfg->with_voxel_center != 0) + (cfg->with_distance != 0);
   int C0 = cfg->feat_channels[0], C1 = cfg->num_layers > 1 ? cfg->feat_channels[1] : 0;
-  if (D0 > VFE_MAXD || F > 32) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE input dim %d > %d", D0, VFE_MAXD);
+  const bool wide = D0 > VFE_MAXD || F > 32;  // beyond the fused kernels: row-GEMM path below (fp32)
+  if (wide && cfg->with_distance) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "VFE with_distance is not built");
   CHECK_ARG(c, cfg->weight[0] && cfg->bn_weight[0] && cfg->bn_bias[0] && cfg->bn_mean[0] && cfg->bn_var[0]);
   if (C1) CHECK_ARG(c, cfg->weight[1] && cfg->bn_weight[1] && cfg->bn_bias[1] && cfg->bn_mean[1] && cfg->bn_var[1]);
   int Z = cfg->grid_zyx[0], Y = cfg->grid_zyx[1], X = cfg->grid_zyx[2], B = cfg->batch_size;
@@ -741,7 +812,8 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   if (T > ((long long)1 << 34)) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "voxel grid too large for bitmap rank (%lld cells)", T);
   arena_reset(c);
   int rc = arena_reserve(c, key_index_bytes(P, T) + csr_bytes(P, P) + al256((size_t)P * 4) * 3 + al256((size_t)P * 3 * 4) +
-                                al256((size_t)P * C0 * 4) + al256((size_t)P * C0 * 2 + 128) + al256((size_t)(C0 + C1) * 8) + 8192);
+                                al256((size_t)P * C0 * 4) + al256((size_t)P * C0 * 2 + 128) + al256((size_t)(C0 + C1) * 8) + 8192 +
+                                (wide ? al256((size_t)P * D0 * 4) + 4 * al256((size_t)P * (C0 > C1 ? C0 : C1) * 4) + al256((size_t)P * 8) : 0));
   if (rc) return rc;
   KeyIndex k;
   rc = key_index_alloc(c, k, P, T);
@@ -800,6 +872,13 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   v.t0 = fold + C0;
   v.s1 = fold + 2 * C0;
   v.t1 = fold + 2 * C0 + C1;
+  if (wide) {
+    rc = inverse ? vfe_wide_path<TC, TC>(c, cfg, v, pts, coors, (const TC*)inverse, r, P, num_dev, vmean, out_feats)
+                 : vfe_wide_path<TC, int32_t>(c, cfg, v, pts, coors, (const int32_t*)map32, r, P, num_dev, vmean, out_feats);
+    if (rc) return rc;
+    if (num_host) return read_back_i32(c, num_dev, num_host);
+    return SSTB_OK;
+  }
   launch_pdl(fold_bn_kernel, dim3((C0 + 127) / 128), dim3(128), (size_t)(0), c->stream, cfg->bn_weight[0], cfg->bn_bias[0], cfg->bn_mean[0], cfg->bn_var[0],
                                                            cfg->bn_eps, C0, fold, fold + C0);
   if (C1)

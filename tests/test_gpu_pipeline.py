@@ -85,3 +85,28 @@ def test_engine_matches_oracle(cuda, precision, tol):
     got = feats[:M].cpu()
     err = (got - out_o).abs().max().item() / out_o.abs().max().item()
     assert err < tol, err
+
+
+@pytest.mark.parametrize("mode", ["max", "avg"])
+def test_dynamic_scatter_vfe_wide_input(cuda, mode):
+    """FSDv2's virtual-voxel encoder shape (configs/fsdv2: in_channels 67 -> [64, 128], SURVEY config 5): beyond the fused
+    kernels' 16 decorated dims, served by the row-GEMM path; coordinates / inverse bit-exact, features <= 1e-3."""
+    from sst_b200.voxel_modules import DynamicScatterVFE
+    vs, rng = (0.4, 0.4, 0.4), [-51.2, -51.2, -5, 51.2, 51.2, 3]
+    torch.manual_seed(0)
+    m = DynamicScatterVFE(in_channels=67, feat_channels=[64, 128], with_cluster_center=True, with_voxel_center=True, voxel_size=vs,
+                          point_cloud_range=rng, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), unique_once=True,
+                          rel_dist_scaler=10.0, mode=mode).eval()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.5)
+            mod.running_var.uniform_(0.5, 2)
+    n = 9000
+    pts = torch.cat([torch.cat([O.synth_frame(30 + b, n) * 0.6, torch.randn(n, 64)], 1) for b in range(2)])
+    co = torch.cat([torch.nn.functional.pad(O.dynamic_voxelize(pts[b * n:(b + 1) * n], vs, rng), (1, 0), value=b) for b in range(2)]).long()
+    ref = O.dynamic_scatter_vfe_forward(pts, co, dict(m.state_dict()), vs, rng, 2, rel_dist_scaler=10.0, mode=mode)
+    m = m.to(cuda)
+    got = m(pts.to(cuda), co.to(cuda), return_inv=True)
+    assert torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[2].cpu(), ref[2])
+    err = (got[0].cpu() - ref[0]).abs().max().item() / ref[0].abs().max().item()
+    assert err < 1e-3, err
