@@ -86,6 +86,20 @@ inline T* arena_alloc(sstb200_ctx* c, size_t n) {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remember the largest value applied per device
+// (one static SmemAttr per call site / kernel instantiation), so a process that drives several GPUs sets it on each of them.
+struct SmemAttr {
+  size_t set[64] = {0};
+};
+template <typename K>
+static inline cudaError_t ensure_smem(const sstb200_ctx* c, SmemAttr& a, K kern, size_t bytes) {
+  const int d = c->device & 63;
+  if (bytes <= a.set[d]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) a.set[d] = bytes;
+  return e;
+}
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------
 // Every kernel of the library starts with pdl_wait() (griddepcontrol.wait: block until the producer grid has completed
 // and its writes are visible) followed by pdl_launch() (griddepcontrol.launch_dependents: allow the next kernel of the

@@ -109,12 +109,9 @@ template <typename TI>
 static void launch_mark_rows(sstb200_ctx* c, const TI* rows, int n, const Extents& e, bool negative_is_invalid, KeyIndex& k,
                              const int32_t* n_dev) {
   if (k.nwords <= MARK_SMEM_MAX_WORDS) {
-    static size_t attr = 0;
+    static SmemAttr sa;
     size_t smem = k.nwords * 4;
-    if (smem > 48 * 1024 && smem > attr) {
-      cudaFuncSetAttribute(mark_rows_kernel<TI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MARK_SMEM_MAX_WORDS * 4);
-      attr = MARK_SMEM_MAX_WORDS * 4;
-    }
+    if (smem > 48 * 1024) ensure_smem(c, sa, mark_rows_kernel<TI, true>, (size_t)MARK_SMEM_MAX_WORDS * 4);
     int grid = (n + 1023) / 1024;
     if (grid > c->num_sms) grid = c->num_sms;
     if (grid < 1) grid = 1;

@@ -292,11 +292,8 @@ extern "C" int sstb200_sir_layer_forward_ex(sstb200_ctx* c, const sstb200_sir_la
     }
     for (int i = 0; i < 3; i++) rd.inv_norm[i] = L->xyz_normalizer[i];
     if (smem > 200 * 1024) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "rel-MLP weights do not fit shared memory");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      CUDA_TRY(c, cudaFuncSetAttribute(sir_rel_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_smem = 200 * 1024;
-    }
+    static SmemAttr sa;
+    CUDA_TRY(c, ensure_smem(c, sa, sir_rel_gate_kernel, (size_t)200 * 1024));
     launch_pdl(sir_rel_gate_kernel, dim3(c->num_sms * 4), dim3(256), (size_t)(smem), st, rd, in_feats, f_cluster, N, x0);
     xin = x0;
   } else {

@@ -568,11 +568,8 @@ int sstb_sir_layer_bf16(sstb200_ctx* c, const sstb200_sir_layer* L, const float*
   CUDA_TRY(c, cudaMemsetAsync(gord, 0, gn * 4, st));
 #define SIR_A(KPV, ACTV)                                                                                                          \
   do {                                                                                                                            \
-    static size_t attr = 0;                                                                                                       \
-    if (smemA > attr) {                                                                                                           \
-      CUDA_TRY(c, cudaFuncSetAttribute(sir_a_kernel<KPV, 16, 32, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)); \
-      attr = smemA;                                                                                                               \
-    }                                                                                                                             \
+    static SmemAttr sa;                                                                                                           \
+    CUDA_TRY(c, ensure_smem(c, sa, sir_a_kernel<KPV, 16, 32, ACTV>, smemA));                                                      \
     launch_pdl(sir_a_kernel<KPV, 16, 32, ACTV>, dim3(grid), dim3(NT), smemA, st, d, in_feats, f_cluster, inv, order, N, p0buf, gord, pitch_in, in_ld, gap_at, gap); \
   } while (0)
 #define SIR_A2(KPV)            \
@@ -588,11 +585,8 @@ int sstb_sir_layer_bf16(sstb200_ctx* c, const sstb200_sir_layer* L, const float*
   CUDA_TRY(c, cudaMemsetAsync(gord, 0, gn * 4, st));
 #define SIR_B(ACTV)                                                                                                     \
   do {                                                                                                                  \
-    static bool attr = false;                                                                                           \
-    if (!attr) {                                                                                                        \
-      CUDA_TRY(c, cudaFuncSetAttribute(sir_b_kernel<ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));   \
-      attr = true;                                                                                                      \
-    }                                                                                                                   \
+    static SmemAttr sa;                                                                                                 \
+    CUDA_TRY(c, ensure_smem(c, sa, sir_b_kernel<ACTV>, smemB));                                                         \
     launch_pdl(sir_b_kernel<ACTV>, dim3(grid), dim3(NT), smemB, st, d, (const __nv_bfloat16*)p0buf, (const float*)out_group, Cg, inv, order, N, out_point, ldo, gord); \
   } while (0)
   if (L->act == 2) SIR_B(2);

@@ -503,11 +503,8 @@ static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const i
                                       const int32_t* win_batch, __nv_bfloat16* out) {
   constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
   size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(c, cudaFuncSetAttribute(win_attn_batch_kernel<NHL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static SmemAttr sa;
+  CUDA_TRY(c, ensure_smem(c, sa, win_attn_batch_kernel<NHL>, smem));
   static int grid_mult = 0;
   if (!grid_mult) {
     const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)

@@ -363,11 +363,8 @@ int launch_umma(sstb200_ctx* c, const GemmArgs& g, int n_tiles_y) {
   size_t stage = (EPI == EPI_RES_LN) ? (size_t)TILE_M * NT * 4 : (size_t)TILE_M * NT * 2;
   size_t smem = (ops > stage ? ops : stage) + 1024;
   auto kern = umma_gemm_kernel<K, NT, PRO, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static SmemAttr sa;
+  CUDA_TRY(c, ensure_smem(c, sa, kern, smem));
   GemmArgs ga = g;
   ga.ny = n_tiles_y;
   int items_cap = ((g.M_cap + TILE_M - 1) / TILE_M) * n_tiles_y;

@@ -497,11 +497,8 @@ int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_b
   g.M_cap = n_cap;
   g.M_dev = n_dev;
   size_t smem = 6 * (size_t)SLOT + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(c, cudaFuncSetAttribute(sra_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static SmemAttr sa;
+  CUDA_TRY(c, ensure_smem(c, sa, sra_chain_kernel, smem));
   int tiles_cap = (n_cap + TM - 1) / TM;
   int grid = c->num_sms < tiles_cap ? c->num_sms : tiles_cap;
   CUDA_TRY(c, launch_pdl(sra_chain_kernel, dim3(grid), dim3(NTHR), smem, c->stream, g));

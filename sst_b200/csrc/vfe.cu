@@ -684,11 +684,8 @@ static int launch_vfe_tiles(sstb200_ctx* c, const VfeDev& v, const float* pts, c
     size_t opA = (size_t)VT * 2 * C0 * 2, opB = (size_t)C1s * 2 * C0 * 2, tile = (size_t)VT * (C1s + 1) * 4;
     size_t smem1 = opB + (opA > tile ? opA : tile) + 1024;
     auto kern = vfe_l1_umma_kernel<TC, TM, C0, C1s>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-      attr_set = true;
-    }
+    static SmemAttr sa;
+    CUDA_TRY(c, ensure_smem(c, sa, kern, smem1));
     launch_pdl(vfe_zero_edges_kernel<TM>, dim3(c->num_sms * 8), dim3(64), (size_t)(0), st, r.offsets, r.order, map, num_dev, C1s, out);
     launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem1), st, v, pts, coors, r.offsets, r.order, map, num_dev, vmean, vf0, out,
                (const __nv_bfloat16*)y0buf);
@@ -705,11 +702,8 @@ static int launch_vfe(sstb200_ctx* c, const VfeDev& v, const float* pts, const T
   size_t smem = ((size_t)v.D0 * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
   size_t smem_max = ((size_t)VFE_MAXD * C0 + 2 * C0 + 2 * (size_t)C0 * C1 + 2 * C1) * 4;
   auto kern = vfe_fused_kernel<TC, NC0, NC1>;
-  static bool attr_set = false;  // not a stream op, but keep it out of CUDA-graph capture after warm-up
-  if (!attr_set) {
-    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    attr_set = true;
-  }
+  static SmemAttr sa;  // not a stream op, but kept out of CUDA-graph capture after warm-up
+  CUDA_TRY(c, ensure_smem(c, sa, kern, smem_max));
   int grid = c->num_sms * 2;
   if (!skip_phase0) launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem), c->stream, v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 0);
   if (NC1 > 0) launch_pdl(kern, dim3(grid), dim3(256), (size_t)(smem), c->stream, v, pts, coors, r.offsets, r.order, num_dev, vmean, vf0, out, 1);
