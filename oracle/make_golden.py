@@ -143,6 +143,42 @@ def scatter_fixture():
     print("dynamic_scatter", ref_coors.shape)
 
 
+def neck_fixture(R):
+    """Voxel2PointScatterNeck (necks/voxel2point_neck.py:28-62) through the unmodified reference class."""
+    g = torch.Generator().manual_seed(5)
+    N, M, C = 3000, 400, 16
+    pts = O.synth_frame(3, N, extra_dims=1)
+    coors = torch.nn.functional.pad(O.dynamic_voxelize(pts, VS, RNG), (1, 0), value=0).long()
+    vf = torch.randn(M, C, generator=g)
+    vf[::7] = -1.0
+    inds = torch.randint(0, M, (N,), generator=g)
+    out = {"points": pts.numpy(), "coors": coors.numpy(), "voxel_feats": vf.numpy(), "inds": inds.numpy()}
+    for name, (xyz, norm) in {"xyz": (True, False), "xyznorm": (True, True), "noxyz": (False, False)}.items():
+        neck = R.Voxel2PointScatterNeck(point_cloud_range=RNG, voxel_size=VS, with_xyz=xyz, normalize_local_xyz=norm).eval()
+        r, m = neck(pts, coors, vf, inds)
+        out[f"out_{name}"], out[f"mask_{name}"] = r.numpy(), m.numpy()
+    np.savez_compressed(os.path.join(OUT, "neck_small.npz"), **out)
+    print("neck", out["out_xyz"].shape)
+
+
+def hard_voxelize_fixture():
+    """voxel_layer.hard_voxelize through the reference's own C++ (oracle/_ref, built from voxelization_cpu.cpp unmodified)."""
+    from oracle import build_ref
+    ref = build_ref.load_module() or (build_ref.build() and build_ref.load_module())
+    pts = O.synth_frame(41, 6000, extra_dims=1)
+    pts[::13, 0] += 500.0
+    out = {"points": pts.numpy()}
+    for name, (mp, mv) in {"roomy": (16, 6000), "capped": (3, 150)}.items():
+        voxels = torch.zeros((mv, mp, 4))
+        coors = torch.zeros((mv, 3), dtype=torch.int32)
+        npts = torch.zeros((mv,), dtype=torch.int32)
+        n = ref.hard_voxelize(pts, voxels, coors, npts, list(VS), list(RNG), mp, mv, 3)
+        out[f"voxels_{name}"], out[f"coors_{name}"], out[f"npts_{name}"] = voxels[:n].numpy(), coors[:n].numpy(), npts[:n].numpy()
+        out[f"cfg_{name}"] = np.array([mp, mv])
+    np.savez_compressed(os.path.join(OUT, "hard_voxelize.npz"), **out)
+    print("hard_voxelize", out["voxels_roomy"].shape, out["voxels_capped"].shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = ref_shim.load()
@@ -150,3 +186,5 @@ if __name__ == "__main__":
     sir_fixture(R)
     dsvfe_fixture(R)
     scatter_fixture()
+    neck_fixture(R)
+    hard_voxelize_fixture()

@@ -52,3 +52,18 @@ def test_reorder(cuda):
     temp[keep] = data
     ref[shuffle] = temp
     assert torch.equal(reorder(data.to(cuda), shuffle.to(cuda), keep.to(cuda)).cpu(), ref)
+
+
+@pytest.mark.parametrize("name,xyz,norm", [("xyz", True, False), ("xyznorm", True, True), ("noxyz", False, False)])
+def test_voxel2point_neck_reference_golden(cuda, name, xyz, norm):
+    """Fixture written by the unmodified reference class (tests/golden/neck_small.npz)."""
+    import os
+    import numpy as np
+    from sst_b200.neck_modules import Voxel2PointScatterNeck
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "neck_small.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(cuda)
+    neck = Voxel2PointScatterNeck(point_cloud_range=RNG, voxel_size=VS, with_xyz=xyz, normalize_local_xyz=norm).eval()
+    with torch.no_grad():
+        out, mask = neck(t("points"), t("coors"), t("voxel_feats"), t("inds"))
+    assert torch.equal(mask.cpu(), torch.from_numpy(z[f"mask_{name}"]))
+    assert torch.equal(out.cpu(), torch.from_numpy(z[f"out_{name}"]))

@@ -170,3 +170,17 @@ def test_hard_voxelize_empty(cuda):
     from sst_b200 import ops
     v, c, n = ops.Voxelization(VS, RNG, 8, 100).eval()(torch.zeros(0, 4, device=cuda))
     assert v.shape == (0, 8, 4) and c.shape == (0, 3) and n.shape == (0,)
+
+
+@pytest.mark.parametrize("name", ["roomy", "capped"])
+def test_hard_voxelize_reference_golden(cuda, name):
+    """Fixture written by the reference's own C++ hard_voxelize (tests/golden/hard_voxelize.npz, oracle/make_golden.py)."""
+    import os
+    import numpy as np
+    from sst_b200 import ops
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hard_voxelize.npz"))
+    mp, mv = [int(v) for v in z[f"cfg_{name}"]]
+    v, c, n = ops.Voxelization(VS, RNG, mp, mv).eval()(torch.from_numpy(z["points"]).to(cuda))
+    assert torch.equal(c.cpu(), torch.from_numpy(z[f"coors_{name}"]))
+    assert torch.equal(n.cpu(), torch.from_numpy(z[f"npts_{name}"]))
+    assert torch.equal(v.cpu(), torch.from_numpy(z[f"voxels_{name}"]))

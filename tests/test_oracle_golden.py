@@ -124,3 +124,20 @@ def test_ingroup_and_window_helpers():
     w, ciw = O.get_window_coors(co, (468, 468, 1), (12, 12, 1), False)
     # no shift: shift = window size (sst_ops.py:283-286) -> x=13+12=25 -> win 2 rem 1; y=5+12=17 -> win 1 rem 5
     assert w.tolist() == [2 * 80 + 1 * 2 + 0, 3200 + 39 * 80 + 39 * 2] and ciw.tolist() == [[0, 5, 1], [0, 11, 11]]
+
+
+@pytest.mark.parametrize("name,xyz,norm", [("xyz", True, False), ("xyznorm", True, True), ("noxyz", False, False)])
+def test_voxel2point_neck_golden(name, xyz, norm):
+    """Outputs of the unmodified reference Voxel2PointScatterNeck (tests/golden/neck_small.npz, oracle/make_golden.py)."""
+    z = _load("neck_small.npz")
+    out, mask = O.voxel2point_neck(z["points"], z["coors"], z["voxel_feats"], z["inds"], VS, RNG, xyz, norm)
+    assert torch.equal(mask, z[f"mask_{name}"]) and torch.equal(out, z[f"out_{name}"])
+
+
+@pytest.mark.parametrize("name", ["roomy", "capped"])
+def test_hard_voxelize_golden(name):
+    """Outputs of the reference's own C++ hard_voxelize (voxelization_cpu.cpp:43-142 compiled unmodified into oracle/_ref)."""
+    z = _load("hard_voxelize.npz")
+    mp, mv = [int(v) for v in z[f"cfg_{name}"]]
+    v, c, n = O.hard_voxelize(z["points"], VS, RNG, mp, mv)
+    assert torch.equal(c, z[f"coors_{name}"]) and torch.equal(n, z[f"npts_{name}"]) and torch.equal(v, z[f"voxels_{name}"])
