@@ -75,3 +75,60 @@ def test_voxel2point_neck(R, with_xyz, norm):
     r_out, r_mask = neck(pts, coors, vf, inds)
     o_out, o_mask = O.voxel2point_neck(pts, coors, vf, inds, VS, RNG, with_xyz, norm)
     assert torch.equal(r_mask, o_mask) and torch.equal(r_out, o_out)
+
+
+def test_oracle_gradients_match_reference(R):
+    """The oracle is differentiable torch code, so autograd through it is the checker for the (round-2) backward kernels: pin it
+    now - parameter and input gradients of DynamicVFE -> SSTInputLayerV2 -> SSTv2 (eval-mode BN, one block) against the reference."""
+    torch.manual_seed(0)
+    pts = O.synth_frame(1000, 6000)
+    coors = torch.nn.functional.pad(O.dynamic_voxelize(pts, VS, RNG), (1, 0), value=0)
+    vfe = R.DynamicVFE(in_channels=3, feat_channels=[32, 64], with_cluster_center=True, with_voxel_center=True, voxel_size=VS,
+                       point_cloud_range=RNG, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)).eval()
+    il = R.SSTInputLayerV2(DROP_TEST, (12, 12, 1), (468, 468, 1), shuffle_voxels=False, debug=True, mute=True).eval()
+    bb = R.SSTv2(d_model=[64], nhead=[4], num_blocks=1, dim_feedforward=[128], output_shape=[468, 468], num_attached_conv=0,
+                 to_bev=False).eval()
+    p_r = pts.clone().requires_grad_(True)
+    vf_r, vc_r = vfe(p_r, coors)
+    out_r = bb(il(vf_r, vc_r, 1))[0]["voxel_feats"]
+    out_r.square().mean().backward()
+    g_ref = {"vfe." + k: v.grad.clone() for k, v in vfe.named_parameters()}
+    g_ref.update({"bb." + k: v.grad.clone() for k, v in bb.named_parameters()})
+
+    wv = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k in dict(vfe.named_parameters()))
+          for k, v in vfe.state_dict().items()}
+    wb = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in bb.state_dict().items()}
+    p_o = pts.clone().requires_grad_(True)
+    vf_o, vc_o = O.dynamic_vfe_forward(p_o, coors, wv, VS, RNG, 2)
+    info_o = O.input_layer_v2(vf_o, vc_o, DROP_TEST, (12, 12, 1), (468, 468, 1))
+    out_o = O.sstv2_forward(info_o, wb, [4], 1)
+    out_o.square().mean().backward()
+    torch.testing.assert_close(p_o.grad, p_r.grad, rtol=1e-4, atol=1e-7)
+    for k, g in g_ref.items():
+        w = wv[k[4:]] if k.startswith("vfe.") else wb[k[3:]]
+        torch.testing.assert_close(w.grad, g, rtol=2e-4, atol=1e-7, msg=k)
+
+
+def test_oracle_sir_gradients_match_reference(R):
+    """Same for FSD's SIR (point-group MLP + pooling): oracle autograd == reference autograd."""
+    torch.manual_seed(1)
+    N, G = 3000, 40
+    g = torch.Generator().manual_seed(2)
+    points = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1)
+    feats = torch.randn(N, 27, generator=g)
+    gid = torch.randint(0, G, (N,), generator=g)
+    coors = torch.stack([gid % 3, torch.zeros_like(gid), gid], 1)
+    fcl = torch.randn(N, 3, generator=g) * 2
+    # distinct inner lists: the reference's SIRLayer appends in_channels to rel_mlp_hidden_dims in place (voxel_encoder.py:665)
+    m = R.SIR(num_blocks=2, in_channels=[32, 37], feat_channels=[[32, 32], [32, 32]], rel_mlp_hidden_dims=[[16, 32], [16, 32]],
+              norm_cfg=dict(type='LN', eps=1e-3), mode='max', xyz_normalizer=[20, 20, 4], act='gelu', unique_once=True).eval()
+    f_r = feats.clone().requires_grad_(True)
+    a, b, _ = m(points, f_r, coors, fcl)
+    (a.square().mean() + b.square().mean()).backward()
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    f_o = feats.clone().requires_grad_(True)
+    ao, bo, _ = O.sir_forward(points, f_o, coors, fcl, w, 2, 3, 2, [20, 20, 4])
+    (ao.square().mean() + bo.square().mean()).backward()
+    torch.testing.assert_close(f_o.grad, f_r.grad, rtol=1e-4, atol=1e-7)
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(w[k].grad, p.grad, rtol=2e-4, atol=1e-7, msg=k)
