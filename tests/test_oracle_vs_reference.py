@@ -132,3 +132,37 @@ def test_oracle_sir_gradients_match_reference(R):
     torch.testing.assert_close(f_o.grad, f_r.grad, rtol=1e-4, atol=1e-7)
     for k, p in m.named_parameters():
         torch.testing.assert_close(w[k].grad, p.grad, rtol=2e-4, atol=1e-7, msg=k)
+
+
+def test_training_mode_vfe_matches_reference(R):
+    """Config-4 groundwork: DynamicVFE in TRAIN mode (naiveSyncBN1d batch statistics, single process) - outputs, input / parameter
+    gradients and the running-buffer update of one step against the reference."""
+    torch.manual_seed(0)
+    pts = O.synth_frame(1000, 6000)
+    coors = torch.nn.functional.pad(O.dynamic_voxelize(pts, VS, RNG), (1, 0), value=0)
+    vfe = R.DynamicVFE(in_channels=3, feat_channels=[32, 64], with_cluster_center=True, with_voxel_center=True, voxel_size=VS,
+                       point_cloud_range=RNG, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)).train()
+    w0 = {k: v.detach().clone() for k, v in vfe.state_dict().items()}
+    p_r = pts.clone().requires_grad_(True)
+    vf_r, vc_r = vfe(p_r, coors)
+    vf_r.square().mean().backward()
+    w = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in w0.items()}
+    p_o = pts.clone().requires_grad_(True)
+    vf_o, vc_o = O.dynamic_vfe_forward(p_o, coors, w, VS, RNG, 2, training=True)
+    vf_o.square().mean().backward()
+    assert torch.equal(vc_o, vc_r)
+    torch.testing.assert_close(vf_o, vf_r, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(p_o.grad, p_r.grad, rtol=1e-4, atol=1e-7)
+    for k, p in vfe.named_parameters():
+        torch.testing.assert_close(w[k].grad, p.grad, rtol=2e-4, atol=1e-7, msg=k)
+    # running buffers after the step (layer 0 sees the decorated points): nn.BatchNorm1d update with the unbiased variance
+    with torch.no_grad():
+        ls = [pts]
+        vmean, mcoors = O.dynamic_scatter_module(pts, coors, True)
+        ls.append(pts[:, :3] - vmean[O._canvas_lookup(coors, mcoors, RNG, VS)][:, :3])
+        ls.append(O._center_offsets(pts, coors, VS, RNG))
+        y0 = torch.nn.functional.linear(torch.cat(ls, 1), w0["vfe_layers.0.linear.weight"])
+        rm, rv = O.bn_running_update(y0, w0["vfe_layers.0.norm.running_mean"], w0["vfe_layers.0.norm.running_var"], 0.01)
+    sd = vfe.state_dict()
+    torch.testing.assert_close(rm, sd["vfe_layers.0.norm.running_mean"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(rv, sd["vfe_layers.0.norm.running_var"], rtol=1e-5, atol=1e-7)
