@@ -129,8 +129,9 @@ def pick_threads():
     return _BEST_THREADS
 
 
-def cpu_oracle_frames(n_frames, warmup, threads=None):
-    """The reference's own CPU path (restated in oracle/, see oracle/sst_oracle.py header) on the host cores."""
+def cpu_oracle_frames(n_frames, warmup, threads=None, budget_s=None):
+    """The reference's own CPU path (restated in oracle/, see oracle/sst_oracle.py header) on the host cores.  `budget_s`
+    bounds the sample: no new frame is started once the timed frames have used that many seconds."""
     from oracle import sst_oracle as O
     from sst_b200 import flagship as fl
     threads = threads or pick_threads()
@@ -150,6 +151,8 @@ def cpu_oracle_frames(n_frames, warmup, threads=None):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+                if budget_s is not None and sum(times) >= budget_s:
+                    break
     return times, threads, out.shape[0]
 
 
@@ -158,16 +161,19 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    times, threads, M = cpu_oracle_frames(steps, min(args.warmup, 1))
+    # bounded sample: every step is one full frame (~1.5 s on this class of host); at most ~150 s of frames are timed so that
+    # the run ends within a few minutes whatever K the caller asks for
+    times, threads, M = cpu_oracle_frames(steps, min(args.warmup, 1), budget_s=float(os.environ.get("SSTB200_REF_BUDGET_S", "150")))
     tot = sum(times)
-    v = steps / tot
+    timed = len(times)
+    v = timed / tot
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot / timed, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config2: SST-6 fwd, 150k-pt Waymo-shaped sweep, 0.32m pillars, d=128 h=8 ff=256, batch 1, sparse output"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} frames (each = full config-2 forward) on {threads} host threads, torch CPU fp32; "
+                         "sample": f"{timed} frames timed (each step = one full config-2 forward; bounded to ~150 s of frames) on {threads} host threads, torch CPU fp32; "
                                    "the reference itself is Python and cannot travel to the GPU box, so its restatement oracle/sst_oracle.py (validated bit-exact against it) is timed"},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
