@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
             print(f"nvcc failed on {s}", file=sys.stderr)
     if failed:
         raise RuntimeError("libsstb200 build failed")
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart", "-lcuda"])
+    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"])
     return OUT
 
 

@@ -23,6 +23,9 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const int32_t* row_map, const float* x,
                         float* y, int n_cap, const int32_t* n_dev, const sstb200_sra_layer* next = nullptr,
                         const sstb200_sra_plan* next_plan = nullptr, void* next_qkv = nullptr);
+int sstb_sra_chain2_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const float* x, float* y, int n_cap,
+                         const int32_t* n_dev, const sstb200_sra_layer* next = nullptr, const sstb200_sra_plan* next_plan = nullptr,
+                         void* next_qkv = nullptr);
 int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans /*[2]*/,
                         const float* x, float* y, float* scratch, int n_cap, const int32_t* n_dev);
 

@@ -148,155 +148,6 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 
 // ------------------------------------------------------------------------------------------------
-// v3: warp-autonomous ragged attention.  One warp owns one (window, head): K_h and V_h^T of the whole window live in
-// REGISTERS as mma B-fragments (<= 72 registers for 144 keys), loaded once straight from the slot-ordered q/k/v rows,
-// then the warp sweeps the window's 16-query tiles.  No shared memory, no block-level barrier, no index indirection:
-// per-SM residency is bounded by registers only, which is what this latency-bound kernel needs.
-// Softmax is two-pass over S (QK^T is recomputed in pass 2 - tensor-core work is free here, registers are not).
-// ------------------------------------------------------------------------------------------------
-// one (window, head) unit with at most KT*8 keys; everything indexed by KT is fully unrolled, so small windows run a
-// short instruction stream (the K/V fragment prologue is ~6x shorter for KT=4 than for KT=18)
-template <int KT>
-__device__ __forceinline__ void attn_unit(const __half* __restrict__ base, int kb, int n, int h, float scale,
-                                          __nv_bfloat16* __restrict__ out, int g4, int t4) {
-  constexpr int D = 128, DH = 16;
-  const int nkt = (n + 7) >> 3;
-  uint32_t kf[KT][2];
-#pragma unroll
-  for (int j = 0; j < KT; j++) {
-    kf[j][0] = kf[j][1] = 0u;
-    int key = 8 * j + g4;
-    if (key < n) {
-      const uint32_t* kp = reinterpret_cast<const uint32_t*>(base + (size_t)key * 3 * D + D);
-      kf[j][0] = kp[t4];
-      kf[j][1] = kp[t4 + 4];
-    }
-  }
-  uint32_t vf[(KT + 1) / 2][4];
-#pragma unroll
-  for (int kc = 0; kc < (KT + 1) / 2; kc++) {
-    const unsigned short* vp = reinterpret_cast<const unsigned short*>(base + 2 * D);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int k0 = kc * 16 + 2 * t4 + (q & 1) * 8, dim = g4 + (q >> 1) * 8;
-      unsigned lo = k0 < n ? vp[(size_t)k0 * 3 * D + dim] : 0;
-      unsigned hi = k0 + 1 < n ? vp[(size_t)(k0 + 1) * 3 * D + dim] : 0;
-      vf[kc][q] = lo | (hi << 16);
-    }
-  }
-  const int ntile = (n + 15) >> 4;
-  for (int qt = 0; qt < ntile; qt++) {
-    const int r0 = qt * 16 + g4, r1 = r0 + 8;
-    uint32_t qa[4] = {0u, 0u, 0u, 0u};
-    if (r0 < n) {
-      const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 3 * D);
-      qa[0] = qp[t4];
-      qa[2] = qp[t4 + 4];
-    }
-    if (r1 < n) {
-      const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 3 * D);
-      qa[1] = qp[t4];
-      qa[3] = qp[t4 + 4];
-    }
-    // pass 1: row maxima
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < KT; j++) {
-      if (j < nkt) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16_16816(s, qa, kf[j][0], kf[j][1]);
-        const int c0 = j * 8 + 2 * t4;
-        if (c0 < n) {
-          m0 = fmaxf(m0, s[0]);
-          m1 = fmaxf(m1, s[2]);
-        }
-        if (c0 + 1 < n) {
-          m0 = fmaxf(m0, s[1]);
-          m1 = fmaxf(m1, s[3]);
-        }
-      }
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    const float ms0 = m0 * scale, ms1 = m1 * scale;  // scale > 0: max commutes with the scaling
-    // pass 2: P = exp(scale*S - max), O += P V
-    float l0 = 0.f, l1 = 0.f;
-    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int kc = 0; kc < (KT + 1) / 2; kc++) {
-      if (kc * 16 < n) {
-        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16_16816(sa, qa, kf[2 * kc][0], kf[2 * kc][1]);
-        if (2 * kc + 1 < KT) mma_f16_16816(sb, qa, kf[(2 * kc + 1 < KT) ? 2 * kc + 1 : 0][0], kf[(2 * kc + 1 < KT) ? 2 * kc + 1 : 0][1]);
-        const int c0 = kc * 16 + 2 * t4;
-        float p[8];
-        p[0] = c0 < n ? __expf(fmaf(sa[0], scale, -ms0)) : 0.f;
-        p[1] = c0 + 1 < n ? __expf(fmaf(sa[1], scale, -ms0)) : 0.f;
-        p[2] = c0 < n ? __expf(fmaf(sa[2], scale, -ms1)) : 0.f;
-        p[3] = c0 + 1 < n ? __expf(fmaf(sa[3], scale, -ms1)) : 0.f;
-        p[4] = c0 + 8 < n ? __expf(fmaf(sb[0], scale, -ms0)) : 0.f;
-        p[5] = c0 + 9 < n ? __expf(fmaf(sb[1], scale, -ms0)) : 0.f;
-        p[6] = c0 + 8 < n ? __expf(fmaf(sb[2], scale, -ms1)) : 0.f;
-        p[7] = c0 + 9 < n ? __expf(fmaf(sb[3], scale, -ms1)) : 0.f;
-        l0 += (p[0] + p[1]) + (p[4] + p[5]);
-        l1 += (p[2] + p[3]) + (p[6] + p[7]);
-        uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
-        mma_f16_16816(o[0], pa, vf[kc][0], vf[kc][1]);
-        mma_f16_16816(o[1], pa, vf[kc][2], vf[kc][3]);
-      }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    if (r0 < n) {
-      const float i0 = 1.0f / l0;
-      uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r0) * D + h * DH);
-      op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
-      op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
-    }
-    if (r1 < n) {
-      const float i1 = 1.0f / l1;
-      uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(kb + r1) * D + h * DH);
-      op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
-      op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
-    }
-  }
-}
-
-static __global__ void __launch_bounds__(128) win_attn_warp_kernel(const __half* __restrict__ qkv,
-                                                                   const int32_t* __restrict__ nwin_dev,
-                                                                   const int32_t* __restrict__ win_offsets, float scale,
-                                                                   __nv_bfloat16* __restrict__ out) {
-  pdl_wait();
-  pdl_launch();
-  constexpr int D = 128, DH = 16, NH = 8;
-  const int R = *nwin_dev;
-  const int lane = threadIdx.x & 31;
-  const int g4 = lane >> 2, t4 = lane & 3;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < R * NH; u += warps_total) {
-    const int w = u / NH, h = u % NH;
-    const int kb = win_offsets[w];
-    const int n = min(win_offsets[w + 1] - kb, ATT_MAXT);
-    const __half* base = qkv + (size_t)kb * 3 * D + h * DH;
-    if (n <= 32) attn_unit<4>(base, kb, n, h, scale, out, g4, t4);
-    else if (n <= 64) attn_unit<8>(base, kb, n, h, scale, out, g4, t4);
-    else attn_unit<ATT_MAXT / 8>(base, kb, n, h, scale, out, g4, t4);
-  }
-}
-
-static inline int sstb_win_attn_warp(sstb200_ctx* c, const __half* qkv, const int32_t* nwin_dev, const int32_t* win_offsets,
-                                     __nv_bfloat16* out) {
-  // 128 threads (4 warps) per CTA; ~120 registers -> 4 CTAs (16 warps) per SM
-  launch_pdl(win_attn_warp_kernel, dim3(c->num_sms * 4), dim3(128), (size_t)(0), c->stream, qkv, nwin_dev, win_offsets, 0.25f, out);
-  CUDA_TRY(c, cudaGetLastError());
-  return SSTB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -319,7 +170,8 @@ template <int NHL>
 static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half* __restrict__ qkv,
                                                                     const int32_t* __restrict__ counters,
                                                                     const int32_t* __restrict__ win_offsets,
-                                                                    const int32_t* __restrict__ win_batch, float scale,
+                                                                    const int32_t* __restrict__ win_batch,
+                                                                    const int32_t* __restrict__ tok_perm, float scale,
                                                                     __nv_bfloat16* __restrict__ out) {
   pdl_wait();
   pdl_launch();
@@ -331,6 +183,7 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
   __shared__ int sTileKb[ATT_BT];    // local key range of its window
   __shared__ int sTileKe[ATT_BT];
   __shared__ int sNumTiles;
+  __shared__ int sTok[ATT_BT];       // token row of local slot r (q|k|v rows and output rows are in flat token order)
   // batch b = the windows whose first slot lies in [b*ATT_CHUNK, (b+1)*ATT_CHUNK) (win_batch_kernel, csrc/window.cu); it holds
   // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows
   const int nbatch = counters[17];
@@ -344,7 +197,9 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
     const int nrow = min(s1 - s0, ATT_BT);
     const int npad = (nrow + 15) & ~15;
     __syncthreads();  // previous batch fully consumed
-    // stage K | V rows (contiguous in slot order): 32 x 16-byte pieces per row
+    for (int r = threadIdx.x; r < nrow; r += blockDim.x) sTok[r] = tok_perm[s0 + r];
+    __syncthreads();
+    // stage K | V rows (gathered through the window permutation): 16-byte pieces with cp.async
     {
       const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV);
       const int nfill = min(npad + 16, ATT_BT + 16);  // key chunks may run up to 15 rows past the batch: keep them finite (0)
@@ -354,7 +209,7 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
         const int pc = isv ? c - PPR : c;
         uint32_t dst = (isv ? v0 : k0) + (uint32_t)(r * LD + pc * 8) * 2;
         if (r < nrow) {
-          const __half* src = qkv + (size_t)(s0 + r) * 3 * D + (isv ? 2 * D : D) + hs * NHL * DH + pc * 8;
+          const __half* src = qkv + (size_t)sTok[r] * 3 * D + (isv ? 2 * D : D) + hs * NHL * DH + pc * 8;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
         } else {
           *reinterpret_cast<int4*>((isv ? sV : sK) + r * LD + pc * 8) = make_int4(0, 0, 0, 0);
@@ -400,13 +255,14 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
       const int n = ke - kb;
       const int r0 = row + g4, r1 = r0 + 8;
       uint32_t qa[4] = {0u, 0u, 0u, 0u};
+      const int tok0 = r0 < ke ? sTok[r0] : 0, tok1 = r1 < ke ? sTok[r1] : 0;
       if (r0 < ke) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)(s0 + r0) * 3 * D + h * DH);
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok0 * 3 * D + h * DH);
         qa[0] = qp[t4];
         qa[2] = qp[t4 + 4];
       }
       if (r1 < ke) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)(s0 + r1) * 3 * D + h * DH);
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok1 * 3 * D + h * DH);
         qa[1] = qp[t4];
         qa[3] = qp[t4 + 4];
       }
@@ -485,13 +341,13 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
       if (r0 < ke) {
         const float i0 = __fdividef(1.0f, l0);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r0) * D + h * DH);
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok0 * D + h * DH);
         op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
         op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
       }
       if (r1 < ke) {
         const float i1 = __fdividef(1.0f, l1);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(s0 + r1) * D + h * DH);
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok1 * D + h * DH);
         op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
         op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
       }
@@ -500,7 +356,7 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
 }
 
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                      const int32_t* win_batch, __nv_bfloat16* out) {
+                                      const int32_t* win_batch, const int32_t* tok_perm, __nv_bfloat16* out) {
   constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
   size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
   static SmemAttr sa;
@@ -511,6 +367,6 @@ static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const i
     grid_mult = e && atoi(e) > 0 ? atoi(e) : 6;
   }
   CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(c->num_sms * grid_mult), dim3(256), smem, c->stream, qkv, counters, win_offsets,
-                         win_batch, 0.25f, out));
+                         win_batch, tok_perm, 0.25f, out));
   return SSTB_OK;
 }

@@ -404,8 +404,8 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     dbg_skip = e ? atoi(e) : 0;
   }
   // tensor-core attention path: plain scaled-dot-product, 8 heads x 16, windows <= 144 tokens
-  const bool slot_order = !L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
-                          P->num_windows_dev && P->tok_slot;
+  const bool tc_attn = !L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
+                       P->num_windows_dev && P->win_batch;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M_cap = n_cap;
@@ -423,18 +423,16 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.pos_ntiles = 2;
   g.out_bf16 = qkv;
   g.ldo = 3 * d;
-  g.out_row_map = slot_order ? P->tok_slot : nullptr;  // rows land in window (slot) order for the tensor-core attention
+  g.out_row_map = nullptr;  // q|k|v, att and the residual stream all live in flat token order; attention gathers its windows
   // q/k/v for the tensor-core attention are written as fp16 (softmax logits need the mantissa: with bf16 q,k the logit
   // error dominates the layer's error budget); the SIMT fallback reads bf16.
-  rc = (dbg_skip & 1) ? 0 : (slot_order ? launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3) : launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3));
+  rc = (dbg_skip & 1) ? 0 : (tc_attn ? launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3) : launch_umma<128, 128, PRO_F32, EPI_BF16>(c, g, 3));
   if (rc) return rc;
   // 2. ragged window attention (fp32 math on bf16 q/k/v)
   if (dbg_skip & 2)
     rc = 0;
-  else if (slot_order && P->win_batch)
-    rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, P->win_batch, att);
-  else if (slot_order)
-    rc = sstb_win_attn_warp(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, att);
+  else if (tc_attn)
+    rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
@@ -444,10 +442,11 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     static int use_chain = -1;
     if (use_chain < 0) {
       const char* e = getenv("SSTB200_CHAIN");
-      use_chain = (e && e[0] == '0') ? 0 : 1;
+      use_chain = e ? atoi(e) : 2;   // 0: unfused GEMM launches, 1: round-1 chain kernel, 2: warp-specialised TMA chain (default)
     }
     if (dbg_skip & 4) return SSTB_OK;
-    if (use_chain) return sstb_sra_chain_bf16(c, L, att, slot_order ? P->tok_perm : nullptr, x, y, n_cap, n_dev);
+    if (use_chain == 1) return sstb_sra_chain_bf16(c, L, att, nullptr, x, y, n_cap, n_dev);
+    if (use_chain) return sstb_sra_chain2_bf16(c, L, att, x, y, n_cap, n_dev);
   }
   // 3. out-projection + residual + LayerNorm1 (unfused reference path, SSTB200_CHAIN=0)
   memset(&g, 0, sizeof(g));
@@ -464,7 +463,6 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.out_f32 = x1;
   g.out_bf16 = x1b;
   g.ldo = d;
-  g.out_row_map = slot_order ? P->tok_perm : nullptr;  // attention output rows are in slot order: scatter back to tokens
   rc = launch_umma<128, 128, PRO_BF16, EPI_RES_LN>(c, g, 1);
   if (rc) return rc;
   // 4. FFN1 + GELU
@@ -504,7 +502,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 static bool layer_supported_tc(const sstb200_sra_layer* L, const sstb200_sra_plan* P) {
   return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && !L->norm1_mean && L->act == 2 && !L->tau && L->nhead == 8 &&
          L->in_proj_w_bf16 && L->out_proj_w_bf16 && L->lin1_w_bf16 && L->lin2_w_bf16 && P->max_window_tokens > 0 &&
-         P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->tok_slot && P->win_batch && P->pos_table && P->pos_L % 32 == 0;
+         P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->win_batch && P->pos_table && P->pos_L % 32 == 0;
 }
 
 int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans, const float* x,
@@ -536,19 +534,27 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     g.pos_ntiles = 2;
     g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(qkv);
     g.ldo = 3 * d;
-    g.out_row_map = P->tok_slot;
     int rc = launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3);
     if (rc) return rc;
   }
   const float* xin = x;
   for (int l = 0; l < num_layers; l++) {
     const sstb200_sra_plan* P = &plans[l & 1];
-    int rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, att);
+    int rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
     if (rc) return rc;
     const bool has_next = l + 1 < num_layers;
+    static int use_chain = -1;
+    if (use_chain < 0) {
+      const char* e = getenv("SSTB200_CHAIN");
+      use_chain = e ? atoi(e) : 2;
+    }
     // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
-    rc = sstb_sra_chain_bf16(c, &layers[l], att, P->tok_perm, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
-                             has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
+    if (use_chain == 1)
+      rc = sstb_sra_chain_bf16(c, &layers[l], att, nullptr, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
+                               has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
+    else
+      rc = sstb_sra_chain2_bf16(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
+                                has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
     if (rc) return rc;
     xin = y;
   }

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain_kernel(ChainArgs g) {
         int tok = sRow[r];
         if (tok >= 0) {
           const uint8_t* st = nt < 2 ? sH + nt * SLOT : sWr;
-          *reinterpret_cast<int4*>(g.qkv_out + (size_t)g.next_slot[tok] * 384 + nt * 128 + ch * 8) =
+          *reinterpret_cast<int4*>(g.qkv_out + (size_t)(g.next_slot ? g.next_slot[tok] : tok) * 384 + nt * 128 + ch * 8) =
               *reinterpret_cast<const int4*>(st + (size_t)r * 256 + ((ch ^ (r & 15)) << 4));
         }
       }
@@ -467,11 +467,11 @@ int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_b
   ChainArgs g;
   memset(&g, 0, sizeof(g));
   if (next && next_plan && next_qkv) {
-    if (next_plan->pos_L % 32 != 0 || !next_plan->tok_slot || !next_plan->pos_code)
-      return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs pos_L %% 32 == 0 and the next plan's tok_slot / pos_code");
+    if (next_plan->pos_L % 32 != 0 || !next_plan->pos_code)
+      return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs pos_L %% 32 == 0 and the next plan's pos_code");
     g.Wqkv = (const __nv_bfloat16*)next->in_proj_w_bf16;
     g.bqkv = next->in_proj_b;
-    g.next_slot = next_plan->tok_slot;
+    g.next_slot = nullptr;   // q|k|v rows stay in flat token order (the attention kernel gathers its windows)
     g.next_pos_code = next_plan->pos_code;
     g.pos_tab = next_plan->pos_table;
     g.posL = next_plan->pos_L;
