@@ -33,7 +33,10 @@ typedef struct sstb200_ctx sstb200_ctx;
 #define SSTB200_REDUCE_MEAN 1
 #define SSTB200_REDUCE_MAX 2
 #define SSTB200_PREC_FP32 0 /* fp32 FFMA everywhere */
-#define SSTB200_PREC_BF16 1 /* bf16 tensor-core GEMMs, fp32 accumulate / softmax / LayerNorm / residual */
+#define SSTB200_PREC_BF16 1 /* 16-bit tensor-core GEMMs, fp32 accumulate / softmax / LayerNorm / residual.  The SRA encoder uses
+                             * IEEE fp16 operands (the reference's own mixed-precision mode, `fp16 = dict(loss_scale=32.0)`), the
+                             * VFE / SIR tensor paths bf16; the API name of the mode stays 'bf16'. */
+#define SSTB200_PREC_F16 1
 
 int sstb200_version(void);
 sstb200_ctx* sstb200_create(int device);
@@ -167,8 +170,8 @@ typedef struct {
   const float* tau; /* non-NULL: cosine attention; tau_n = 1 or nhead */
   int32_t tau_n;
   float tau_min;
-  /* optional bf16 copies of the four weight matrices (tensor-core path); NULL -> fp32 path only */
-  const void *in_proj_w_bf16, *out_proj_w_bf16, *lin1_w_bf16, *lin2_w_bf16;
+  /* optional IEEE fp16 copies of the four weight matrices (tensor-core path); NULL -> fp32 path only */
+  const void *in_proj_w_f16, *out_proj_w_f16, *lin1_w_f16, *lin2_w_f16;
 } sstb200_sra_layer;
 
 /* window CSR of one shift (produced by sstb200_window_plan) + positional-embedding table

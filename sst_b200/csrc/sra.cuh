@@ -1,5 +1,6 @@
 // internal declarations shared by the SRA translation units
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 void sstb_gemm_rows(cudaStream_t st, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr,
@@ -20,12 +21,9 @@ int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
                         int n_cap, const int32_t* n_dev);
 
-int sstb_sra_chain_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const int32_t* row_map, const float* x,
-                        float* y, int n_cap, const int32_t* n_dev, const sstb200_sra_layer* next = nullptr,
-                        const sstb200_sra_plan* next_plan = nullptr, void* next_qkv = nullptr);
-int sstb_sra_chain2_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const float* x, float* y, int n_cap,
-                         const int32_t* n_dev, const sstb200_sra_layer* next = nullptr, const sstb200_sra_plan* next_plan = nullptr,
-                         void* next_qkv = nullptr);
+int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* att, const float* x, float* y, int n_cap,
+                    const int32_t* n_dev, const sstb200_sra_layer* next = nullptr, const sstb200_sra_plan* next_plan = nullptr,
+                    void* next_qkv = nullptr);
 int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans /*[2]*/,
                         const float* x, float* y, float* scratch, int n_cap, const int32_t* n_dev);
 

@@ -24,6 +24,23 @@ __device__ __forceinline__ void load_vec<__nv_bfloat16, 8>(const __nv_bfloat16* 
     o[2 * i + 1] = f.y;
   }
 }
+template <>
+__device__ __forceinline__ void load_vec<__half, 8>(const __half* p, float* o) {
+  int4 v = *(const int4*)p;
+  const __half2* h = (const __half2*)&v;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 f = __half22float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store_vec8(__half* p, const float* v) {
+  __half2 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *(int4*)p = *(const int4*)h;
+}
 __device__ __forceinline__ void store_vec8(float* p, const float* v) {
   *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
   *(float4*)(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -172,7 +189,7 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
                                                                     const int32_t* __restrict__ win_offsets,
                                                                     const int32_t* __restrict__ win_batch,
                                                                     const int32_t* __restrict__ tok_perm, float scale,
-                                                                    __nv_bfloat16* __restrict__ out) {
+                                                                    __half* __restrict__ out) {
   pdl_wait();
   pdl_launch();
   constexpr int D = 128, DH = 16, LD = NHL * 16 + 8, HSPLIT = 8 / NHL, PPR = NHL * 2;  // PPR: 16-byte pieces per row per matrix
@@ -342,21 +359,21 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
       if (r0 < ke) {
         const float i0 = __fdividef(1.0f, l0);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok0 * D + h * DH);
-        op[t4] = pack2_bf16(o[0][0] * i0, o[0][1] * i0);
-        op[t4 + 4] = pack2_bf16(o[1][0] * i0, o[1][1] * i0);
+        op[t4] = pack2_f16(o[0][0] * i0, o[0][1] * i0);
+        op[t4 + 4] = pack2_f16(o[1][0] * i0, o[1][1] * i0);
       }
       if (r1 < ke) {
         const float i1 = __fdividef(1.0f, l1);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok1 * D + h * DH);
-        op[t4] = pack2_bf16(o[0][2] * i1, o[0][3] * i1);
-        op[t4 + 4] = pack2_bf16(o[1][2] * i1, o[1][3] * i1);
+        op[t4] = pack2_f16(o[0][2] * i1, o[0][3] * i1);
+        op[t4 + 4] = pack2_f16(o[1][2] * i1, o[1][3] * i1);
       }
     }
   }
 }
 
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                      const int32_t* win_batch, const int32_t* tok_perm, __nv_bfloat16* out) {
+                                      const int32_t* win_batch, const int32_t* tok_perm, __half* out) {
   constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
   size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
   static SmemAttr sa;

@@ -1,4 +1,6 @@
-// bf16 tensor-core path of the SRA encoder layer: tcgen05.mma (UMMA) GEMMs with TMEM accumulators.
+// 16-bit tensor-core path of the SRA encoder layer (precision 'bf16' of the API; operands are IEEE fp16 - same tensor
+// throughput, 8x smaller operand rounding than bf16, and the reference's own mixed-precision setting is fp16,
+// configs/sst_refactor/sst_waymoD5_1x_3class_8heads_v2.py:82): tcgen05.mma (UMMA) GEMMs with TMEM accumulators.
 //
 // Every dense op of the layer (QKV projection, attention out-projection, FFN1, FFN2) is one launch of the same
 // kernel template:  C[128-row tile, NT] = A[128, K] . W[NT, K]^T  with the whole K extent staged once in shared
@@ -42,7 +44,7 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_RES_LN = 2, EPI_F16 = 3 };
 struct GemmArgs {
   const void* A;        // [M, lda] bf16 or fp32; tile rows are consecutive rows of A
   int lda;
-  const __nv_bfloat16* W;  // [N_total, K] bf16
+  const __half* W;  // [N_total, K] bf16
   const float* bias;    // [N_total]
   int M_cap;
   const int32_t* M_dev;
@@ -53,7 +55,7 @@ struct GemmArgs {
   int ny;                                    // number of n tiles
   // epilogue
   const int32_t* out_row_map;  // nullable: output / residual row of tile row i is out_row_map[i] (scatter), else i
-  __nv_bfloat16* out_bf16;  // [M, ldo]
+  __half* out_h16;  // [M, ldo]
   int ldo;
   const float* res;     // [M, NT] fp32 residual (EPI_RES_LN)
   const float *gamma, *beta;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
     }
     // ---- stage W tile (rows n0..n0+NT of W[., K]) ----------------------------------------------------------------
     {
-      const __nv_bfloat16* wsrc = g.W + (size_t)n0 * K;
+      const __half* wsrc = g.W + (size_t)n0 * K;
       for (int i0 = tid; i0 < NT * CH; i0 += NTH * UNR) {
         int4 v[UNR];
 #pragma unroll
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
           int r = idx / CH, j = idx % CH;
           v[u] = make_int4(0, 0, 0, 0);
           if (idx < TILE_M * CH && row0 + r < M)
-            v[u] = *reinterpret_cast<const int4*>((const __nv_bfloat16*)g.A + (size_t)(row0 + r) * g.lda + j * 8);
+            v[u] = *reinterpret_cast<const int4*>((const __half*)g.A + (size_t)(row0 + r) * g.lda + j * 8);
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
@@ -183,10 +185,10 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
               }
             }
             int4 v;
-            v.x = (int)pack_bf16(f[0], f[1]);
-            v.y = (int)pack_bf16(f[2], f[3]);
-            v.z = (int)pack_bf16(f[4], f[5]);
-            v.w = (int)pack_bf16(f[6], f[7]);
+            v.x = (int)pack_f16(f[0], f[1]);
+            v.y = (int)pack_f16(f[2], f[3]);
+            v.z = (int)pack_f16(f[4], f[5]);
+            v.w = (int)pack_f16(f[6], f[7]);
             int c = j >> 3, jj = j & 7;
             *reinterpret_cast<int4*>(sA + (size_t)c * TILE_M * 128 + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
           }
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
 
     // ---- MMA issue: one thread ------------------------------------------------------------------------------------------
     if (tid == 0) {
-      const uint32_t idesc = umma_idesc(TILE_M, NT);
+      const uint32_t idesc = umma_idesc_f16(TILE_M, NT);
       const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
 #pragma unroll
       for (int c = 0; c < K / 64; c++) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
         for (int s = 0; s < 4; s++) {
           uint64_t ad = umma_desc_sw128(a0 + c * TILE_M * 128 + s * 32);
           uint64_t bd = umma_desc_sw128(w0 + c * NT * 128 + s * 32);
-          umma_bf16(tmem, ad, bd, idesc, (c | s) ? 1u : 0u);
+          umma_f16(tmem, ad, bd, idesc, (c | s) ? 1u : 0u);
         }
       }
       umma_commit(smem_u32(&mbar));  // implicit tcgen05.fence::before_thread_sync
@@ -245,8 +247,8 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
             a2 = gelu_fast(a2);
             a3 = gelu_fast(a3);
           }
-          pk[i >> 1] = (EPI == EPI_F16) ? pack_f16(a0, a1) : pack_bf16(a0, a1);
-          pk[(i >> 1) + 1] = (EPI == EPI_F16) ? pack_f16(a2, a3) : pack_bf16(a2, a3);
+          pk[i >> 1] = pack_f16(a0, a1);
+          pk[(i >> 1) + 1] = pack_f16(a2, a3);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
         int r = idx / ECH, ch = idx % ECH;
         int gr = sRow[r];
         if (gr >= 0)
-          *reinterpret_cast<int4*>(g.out_bf16 + (size_t)gr * g.ldo + n0 + ch * 8) =
+          *reinterpret_cast<int4*>(g.out_h16 + (size_t)gr * g.ldo + n0 + ch * 8) =
               *reinterpret_cast<const int4*>(sE + (size_t)r * NT * 2 + ((ch ^ (r & (ECH - 1))) << 4));
       }
     } else {  // EPI_RES_LN : NT == row width, fp32 staging tile [128][NT] (16-byte chunks XOR-swizzled by row)
@@ -337,15 +339,15 @@ __global__ void __launch_bounds__(256) umma_gemm_kernel(GemmArgs g) {
           *reinterpret_cast<float4*>(g.out_f32 + (size_t)gr * NT + ch * 4) =
               *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + ((ch ^ (r & 31)) << 4));
       }
-      if (g.out_bf16) {
+      if (g.out_h16) {
         for (int idx = tid; idx < TILE_M * (NT / 8); idx += NTH) {
           int r = idx / (NT / 8), c8 = idx % (NT / 8);
           int gr = sRow[r];
           if (gr >= 0) {
             float4 a = *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + (((2 * c8) ^ (r & 31)) << 4));
             float4 b = *reinterpret_cast<const float4*>(sE + (size_t)r * NT * 4 + (((2 * c8 + 1) ^ (r & 31)) << 4));
-            *reinterpret_cast<int4*>(g.out_bf16 + (size_t)gr * g.ldo + c8 * 8) =
-                make_int4((int)pack_bf16(a.x, a.y), (int)pack_bf16(a.z, a.w), (int)pack_bf16(b.x, b.y), (int)pack_bf16(b.z, b.w));
+            *reinterpret_cast<int4*>(g.out_h16 + (size_t)gr * g.ldo + c8 * 8) =
+                make_int4((int)pack_f16(a.x, a.y), (int)pack_f16(a.z, a.w), (int)pack_f16(b.x, b.y), (int)pack_f16(b.z, b.w));
           }
         }
       }
@@ -387,14 +389,14 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   if (d != 128 || ff != 256 || !L->post_norm || L->norm1_mean || L->act != 2)
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED,
                      "bf16 tensor-core path is built for d_model=128, dim_ff=256, post-norm LayerNorm, gelu (got d=%d ff=%d)", d, ff);
-  if (!L->in_proj_w_bf16 || !L->out_proj_w_bf16 || !L->lin1_w_bf16 || !L->lin2_w_bf16)
-    return sstb_fail(c, SSTB_ERR_ARG, "bf16 path needs the *_w_bf16 weight copies");
+  if (!L->in_proj_w_f16 || !L->out_proj_w_f16 || !L->lin1_w_f16 || !L->lin2_w_f16)
+    return sstb_fail(c, SSTB_ERR_ARG, "the tensor-core path needs the *_w_f16 weight copies");
   if (P->pos_table && P->pos_L % 8 != 0)
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "bf16 path needs the per-axis positional length (%d) to be a multiple of 8", P->pos_L);
-  __nv_bfloat16* qkv = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * 3 * d);
-  __nv_bfloat16* att = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
-  __nv_bfloat16* x1b = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
-  __nv_bfloat16* hid = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * ff);
+  __half* qkv = arena_alloc<__half>(c, (size_t)n_cap * 3 * d);
+  __half* att = arena_alloc<__half>(c, (size_t)n_cap * d);
+  __half* x1b = arena_alloc<__half>(c, (size_t)n_cap * d);
+  __half* hid = arena_alloc<__half>(c, (size_t)n_cap * ff);
   float* x1 = arena_alloc<float>(c, (size_t)n_cap * d);
   if (!qkv || !att || !x1b || !hid || !x1) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra bf16 layer: arena too small");
   int rc;
@@ -413,7 +415,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   // 1. QKV projection: q,k from bf16(x + pos), v from bf16(x)
   g.A = x;
   g.lda = d;
-  g.W = (const __nv_bfloat16*)L->in_proj_w_bf16;
+  g.W = (const __half*)L->in_proj_w_f16;
   g.bias = L->in_proj_b;
   g.pos_tab = P->pos_table;
   g.pos_code = P->pos_code;
@@ -421,7 +423,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.pos_maxw = P->pos_maxw;
   g.pos_ndim = P->pos_ndim;
   g.pos_ntiles = 2;
-  g.out_bf16 = qkv;
+  g.out_h16 = qkv;
   g.ldo = 3 * d;
   g.out_row_map = nullptr;  // q|k|v, att and the residual stream all live in flat token order; attention gathers its windows
   // q/k/v for the tensor-core attention are written as fp16 (softmax logits need the mantissa: with bf16 q,k the logit
@@ -432,9 +434,9 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   if (dbg_skip & 2)
     rc = 0;
   else if (tc_attn)
-    rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(qkv), P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
+    rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
-    rc = sstb_win_attn<__nv_bfloat16, __nv_bfloat16>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
+    rc = sstb_win_attn<__half, __half>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
   if (rc) return rc;
   // 3-5 fused: out-projection + LN1 + FFN1 + GELU + FFN2 + LN2 in one persistent tcgen05 kernel (csrc/sra_chain.cu)
@@ -442,11 +444,10 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     static int use_chain = -1;
     if (use_chain < 0) {
       const char* e = getenv("SSTB200_CHAIN");
-      use_chain = e ? atoi(e) : 2;   // 0: unfused GEMM launches, 1: round-1 chain kernel, 2: warp-specialised TMA chain (default)
+      use_chain = e ? atoi(e) : 1;   // 0: unfused GEMM launches (bring-up reference), else the warp-specialised TMA chain
     }
     if (dbg_skip & 4) return SSTB_OK;
-    if (use_chain == 1) return sstb_sra_chain_bf16(c, L, att, nullptr, x, y, n_cap, n_dev);
-    if (use_chain) return sstb_sra_chain2_bf16(c, L, att, x, y, n_cap, n_dev);
+    if (use_chain) return sstb_sra_chain2(c, L, att, x, y, n_cap, n_dev);
   }
   // 3. out-projection + residual + LayerNorm1 (unfused reference path, SSTB200_CHAIN=0)
   memset(&g, 0, sizeof(g));
@@ -454,14 +455,14 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.M_dev = n_dev;
   g.A = att;
   g.lda = d;
-  g.W = (const __nv_bfloat16*)L->out_proj_w_bf16;
+  g.W = (const __half*)L->out_proj_w_f16;
   g.bias = L->out_proj_b;
   g.res = x;
   g.gamma = L->norm1_w;
   g.beta = L->norm1_b;
   g.eps = L->norm_eps;
   g.out_f32 = x1;
-  g.out_bf16 = x1b;
+  g.out_h16 = x1b;
   g.ldo = d;
   rc = launch_umma<128, 128, PRO_BF16, EPI_RES_LN>(c, g, 1);
   if (rc) return rc;
@@ -471,9 +472,9 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.M_dev = n_dev;
   g.A = x1b;
   g.lda = d;
-  g.W = (const __nv_bfloat16*)L->lin1_w_bf16;
+  g.W = (const __half*)L->lin1_w_f16;
   g.bias = L->lin1_b;
-  g.out_bf16 = hid;
+  g.out_h16 = hid;
   g.ldo = ff;
   rc = launch_umma<128, 128, PRO_BF16, EPI_BF16_GELU>(c, g, 2);
   if (rc) return rc;
@@ -483,7 +484,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   g.M_dev = n_dev;
   g.A = hid;
   g.lda = ff;
-  g.W = (const __nv_bfloat16*)L->lin2_w_bf16;
+  g.W = (const __half*)L->lin2_w_f16;
   g.bias = L->lin2_b;
   g.res = x1;
   g.gamma = L->norm2_w;
@@ -501,7 +502,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 // ------------------------------------------------------------------------------------------------
 static bool layer_supported_tc(const sstb200_sra_layer* L, const sstb200_sra_plan* P) {
   return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && !L->norm1_mean && L->act == 2 && !L->tau && L->nhead == 8 &&
-         L->in_proj_w_bf16 && L->out_proj_w_bf16 && L->lin1_w_bf16 && L->lin2_w_bf16 && P->max_window_tokens > 0 &&
+         L->in_proj_w_f16 && L->out_proj_w_f16 && L->lin1_w_f16 && L->lin2_w_f16 && P->max_window_tokens > 0 &&
          P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->win_batch && P->pos_table && P->pos_L % 32 == 0;
 }
 
@@ -512,7 +513,7 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     if (!layer_supported_tc(&layers[l], &plans[l & 1])) return SSTB_ERR_UNSUPPORTED;  // caller falls back to per-layer calls
   const int d = 128;
   __half* qkv = arena_alloc<__half>(c, (size_t)n_cap * 3 * d);
-  __nv_bfloat16* att = arena_alloc<__nv_bfloat16>(c, (size_t)n_cap * d);
+  __half* att = arena_alloc<__half>(c, (size_t)n_cap * d);
   if (!qkv || !att) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
   // QKV of layer 0 (stand-alone GEMM, fp32 x + pos -> fp16 rows in slot order of shift 0)
   {
@@ -524,7 +525,7 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     g.M_dev = n_dev;
     g.A = x;
     g.lda = d;
-    g.W = (const __nv_bfloat16*)L->in_proj_w_bf16;
+    g.W = (const __half*)L->in_proj_w_f16;
     g.bias = L->in_proj_b;
     g.pos_tab = P->pos_table;
     g.pos_code = P->pos_code;
@@ -532,7 +533,7 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     g.pos_maxw = P->pos_maxw;
     g.pos_ndim = P->pos_ndim;
     g.pos_ntiles = 2;
-    g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(qkv);
+    g.out_h16 = qkv;
     g.ldo = 3 * d;
     int rc = launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3);
     if (rc) return rc;
@@ -543,17 +544,8 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     int rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
     if (rc) return rc;
     const bool has_next = l + 1 < num_layers;
-    static int use_chain = -1;
-    if (use_chain < 0) {
-      const char* e = getenv("SSTB200_CHAIN");
-      use_chain = e ? atoi(e) : 2;
-    }
     // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
-    if (use_chain == 1)
-      rc = sstb_sra_chain_bf16(c, &layers[l], att, nullptr, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
-                               has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
-    else
-      rc = sstb_sra_chain2_bf16(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
+    rc = sstb_sra_chain2(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
                                 has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
     if (rc) return rc;
     xin = y;

@@ -8,18 +8,23 @@
 // replaces mmdet3d/models/sst/sst_basic_block_v2.py:104-126 (+ the in-projection of the following layer's
 // nn.MultiheadAttention, :70) for one 128-token tile per iteration of a persistent CTA.
 //
-// Roles (18 warps):  warp 17 = TMA producer (one lane): every operand tile - att, the residual x, all weights - arrives by
-// cp.async.bulk.tensor into 128B-swizzled shared memory; weights + att stream through a ring of three 32 KB slots guarded by
-// full/empty mbarriers.  warp 16 = MMA issuer (one lane): tcgen05.mma with TMEM accumulators, tcgen05.commit -> mbarriers.
-// warps 0-15 = epilogue: TMEM -> registers (thread per row, 4 warps per TMEM lane quadrant each owning a column quarter),
-// bias / residual / LayerNorm / GELU, operands of the next GEMM written straight into the swizzled K-major layout, outputs
-// staged in the same swizzle and stored with TMA.  GEMM2 -> GELU -> GEMM3 is pipelined in 64-column chunks (double-buffered
-// accumulator chunks in TMEM, double-buffered hidden chunks in shared memory), so the tensor pipe works on chunk c+1 while
-// the epilogue warps run GELU on chunk c, and GEMM1 of the next tile is issued while the q|k|v epilogue of this one runs.
-// All rows are in flat token order: every tile of att / x / y / q|k|v is a plain 2-D box.
+// Roles (19 warps):
+//   warp 17  TMA loads (one lane): every operand tile - att, the residual x, all weights - arrives by cp.async.bulk.tensor
+//            into 128B-swizzled shared memory; weights + att stream through a ring of three 32 KB slots (full/empty mbarriers).
+//   warp 16  MMA issuer (one lane): tcgen05.mma (fp16 operands, fp32 accumulators in TMEM), tcgen05.commit -> mbarriers.
+//   warp 18  TMA stores (one lane): y (fp32) and q|k|v (fp16) tiles leave through swizzled staging buffers; the warp turns
+//            "staging written" mbarriers into bulk stores and "store has read its source" into "staging free" mbarriers, so the
+//            epilogue never executes a CTA-wide barrier.
+//   warps 0-15  epilogue: TMEM -> registers (thread per row, 4 warps per TMEM lane quadrant, each a column quarter); bias /
+//            residual / LayerNorm in packed fp32x2 arithmetic (FADD2 / FFMA2), GELU in half2 (tanh form, MUFU.TANH.F16); the
+//            operands of the next GEMM are written straight into the swizzled K-major layout.
+// GEMM2 -> GELU -> GEMM3 is pipelined in 64-column chunks: two accumulator chunks in TMEM, two hidden chunks in shared memory,
+// and two epilogue warp groups (8 warps each) that own the even / odd chunks, so GELU of chunk c overlaps the MMAs of c+1 and
+// the GELU of the other group.  GEMM1 of the next tile is issued while the q|k|v epilogue of this one runs.
+// All rows are in flat token order: every tile of att / x / y / q|k|v is a plain 2-D TMA box.
 //
 // TMEM columns: [0,128) acc1 / acc3, [128,256) two acc2 chunks (later k), [256,384) x1 fp32 (later v), [384,512) q.
-// Shared memory: ring 3 x 32 KB | A 32 KB (x1 operand, y staging lo, q/v staging) | B 32 KB (hidden ring, y staging hi,
+// Shared memory: ring 3 x 32 KB | A 32 KB (x1 operand, y staging lo, q / v staging) | B 32 KB (hidden chunks, y staging hi,
 // k staging) | C 64 KB (x fp32 tile, LN statistics exchange, then the (y+pos | y) operands) | mbarriers.
 #include <stdarg.h>
 #include <cuda_fp16.h>
@@ -30,9 +35,8 @@ namespace {
 
 constexpr int TM = 128, D = 128;
 constexpr int SLOT = 32768;
-constexpr int W_MMA = 16, W_TMA = 17;
-constexpr int NTHR = 18 * 32;
-constexpr int NEPI = 512;
+constexpr int W_MMA = 16, W_TMA = 17, W_ST = 18;
+constexpr int NTHR = 19 * 32;
 constexpr int OFF_RING = 0, OFF_A = 3 * SLOT, OFF_B = 4 * SLOT, OFF_C = 5 * SLOT, OFF_BAR = 7 * SLOT;
 constexpr int SMEM_BYTES = 7 * SLOT + 512;
 
@@ -42,16 +46,19 @@ enum {
   B_XFULL = 6,   // residual tile landed in C
   B_CFREE = 7,   // C may be overwritten by the next residual tile
   B_ACC1 = 8,    // GEMM1 retired
-  B_X1 = 9,      // x1 operand (A) + fp32 copy (TMEM) written             [16 warp arrivals]
+  B_X1 = 9,      // x1 operand (A) + fp32 copy (TMEM) written              [16 warp arrivals]
   B_ACC2F = 10,  // [2] GEMM2 chunk retired
-  B_ACC2E = 12,  // [2] acc2 chunk read back                              [16]
-  B_HIDF = 14,   // [2] hidden chunk written                              [16]
+  B_ACC2E = 12,  // [2] acc2 chunk read back                               [8]
+  B_HIDF = 14,   // [2] hidden chunk written                               [8]
   B_HIDE = 16,   // [2] hidden chunk consumed by GEMM3
   B_ACC3 = 18,   // GEMM3 retired
-  B_YFULL = 19,  // LN2 done: acc3 / x1 read, (y+pos | y) operands written [16]
+  B_YFULL = 19,  // LN2 done: acc3 / x1 read, y staging + (y+pos | y) operands written [16]
   B_QKVF = 20,   // [3] q / k / v chunk retired
-  B_QKVE = 23,   // [3] q / k / v chunk read back                         [16]
-  NBAR = 26
+  B_QKVE = 23,   // [3] q / k / v chunk read back                          [16]
+  B_QST = 26,    // [3] q / k / v staging written                          [16]
+  B_FREEA = 29,  // staging buffer A drained by its TMA store
+  B_FREEB = 30,  // staging buffer B drained
+  NBAR = 31
 };
 
 struct Chain2Maps {
@@ -68,48 +75,102 @@ struct Chain2Args {
   const int32_t* next_pos_code;  // [tokens]
   const float* pos_tab;          // [ndim][maxw][L]
   int posL, pos_maxw, pos_ndim;
+  long long* dbg;                // optional timeline buffer [grid][3 roles][2 tiles][32] (SSTB200_CHAIN_DBG), else nullptr
 };
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+#define DBG_T(role, it, ev)                                                                                   \
+  do {                                                                                                        \
+    if (g.dbg && (it) < 2) g.dbg[(((size_t)blockIdx.x * 3 + (role)) * 2 + (it)) * 32 + (ev)] = clock64();       \
+  } while (0)
+
+typedef unsigned long long u64;
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 - one issue slot for two lanes)
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 pk2u(uint32_t lo, uint32_t hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void up2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void up2u(u64 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// two fp32 -> packed half2 (lo in the low half)
+__device__ __forceinline__ uint32_t cvt_h2(u64 v) {
+  float lo, hi;
+  up2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// tanh-form GELU on two values in half2: 0.5 z (1 + tanh(z (c0 + c1 z^2))).  The argument of tanh is built from z clamped to
+// [-12, 12] (the function is z or 0 to fp16 precision beyond that), so no intermediate leaves the fp16 range.  Deviation from
+// the erf form plus the half2 arithmetic stays below 1e-3 relative - the fp16 rounding of the operand it feeds is 5e-4.
+__device__ __forceinline__ uint32_t gelu_h2(uint32_t z) {
+  const uint32_t C0 = 0x3A623A62u;   // half2(0.7978846)
+  const uint32_t C1 = 0x28912891u;   // half2(0.0356774) = 0.7978846 * 0.044715
+  const uint32_t HALF = 0x38003800u, LIM = 0x4A004A00u, NLIM = 0xCA00CA00u;   // 0.5, 12, -12
+  uint32_t zc, z2, p, u, t, hz, r;
+  asm("min.f16x2 %0, %1, %2;" : "=r"(zc) : "r"(z), "r"(LIM));
+  asm("max.f16x2 %0, %1, %2;" : "=r"(zc) : "r"(zc), "r"(NLIM));
+  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(z2) : "r"(zc));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(z2), "r"(C1), "r"(C0));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(u) : "r"(p), "r"(zc));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hz) : "r"(z), "r"(HALF));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(hz), "r"(t));
+  return r;
+}
+
+__device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
       "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
 
-// tanh-form GELU on the MUFU.TANH unit (see csrc/sra_chain.cu: deviation from the erf form is below the bf16 rounding
-// applied right after)
-__device__ __forceinline__ float gelu_t(float x) {
-  float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// 4 (K = 64) or 8 (K = 128) tcgen05.mma k-steps on K-major SWIZZLE_128B operands; chunk pitch = bytes between 64-wide K chunks
-__device__ __forceinline__ void mma_steps(uint32_t d_tmem, uint32_t a0, uint32_t a_chunk, uint32_t b0, uint32_t b_chunk, int kchunks,
-                                          uint32_t idesc, bool accum) {
-  for (int c = 0; c < kchunks; c++)
+// K-major SWIZZLE_128B descriptors differ only in the start address: build the constant part once, add (bytes >> 4)
+__device__ __forceinline__ void mma_steps(uint32_t d_tmem, u64 adesc, u64 bdesc, int ksteps, uint32_t idesc, bool accum) {
+  // ksteps = 4 (K = 64) or 8 (K = 128: the second 64-wide chunk lives 16 KB further in both operands)
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-      umma_bf16(d_tmem, umma_desc_sw128(a0 + c * a_chunk + s * 32), umma_desc_sw128(b0 + c * b_chunk + s * 32), idesc,
-                (accum || c || s) ? 1u : 0u);
+  for (int s = 0; s < 8; s++) {
+    if (s < ksteps) {
+      const u64 off = (u64)((s & 3) * 2 + (s >> 2) * 1024);   // 32 B per k-step, 16384 B per K chunk, in 16-byte units
+      umma_f16(d_tmem, adesc + off, bdesc + off, idesc, (accum || s) ? 1u : 0u);
     }
+  }
 }
 
 __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Args g) {
@@ -122,9 +183,10 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   if (tid == 0) {
     if (sbase & 1023u) __trap();   // SWIZZLE_128B operands / TMA boxes need the 1024-byte alignment
     for (int i = 0; i < NBAR; i++) {
-      const bool warps16 = (i == B_X1) || (i == B_ACC2E) || (i == B_ACC2E + 1) || (i == B_HIDF) || (i == B_HIDF + 1) || (i == B_YFULL) ||
-                           (i >= B_QKVE && i < B_QKVE + 3);
-      mbar_init(BAR(i), warps16 ? 16u : 1u);
+      uint32_t cnt = 1;
+      if (i == B_X1 || i == B_YFULL || (i >= B_QKVE && i < B_QKVE + 3) || (i >= B_QST && i < B_QST + 3)) cnt = 16;
+      if (i == B_ACC2E || i == B_ACC2E + 1 || i == B_HIDF || i == B_HIDF + 1) cnt = 8;
+      mbar_init(BAR(i), cnt);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -134,11 +196,11 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     tma_prefetch_desc(&maps.wo);
     tma_prefetch_desc(&maps.w1);
     tma_prefetch_desc(&maps.w2);
+    if (g.has_tail) tma_prefetch_desc(&maps.wqkv);
+  }
+  if (warp == W_ST && lane == 0) {
     tma_prefetch_desc(&maps.y);
-    if (g.has_tail) {
-      tma_prefetch_desc(&maps.wqkv);
-      tma_prefetch_desc(&maps.qkv);
-    }
+    if (g.has_tail) tma_prefetch_desc(&maps.qkv);
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -153,7 +215,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   const int NI = tail ? 9 : 6;   // ring items per tile: att, Wo, W1[0:128], W1[128:256], W2[:,0:128], W2[:,128:256], Wq, Wk, Wv
 
   if (warp == W_TMA) {
-    // ================================================= TMA producer =================================================
+    // ================================================== TMA loads ==================================================
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -166,20 +228,26 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           tma_load_2d(sbase + OFF_RING + s * SLOT, m, ca, ra, BAR(B_FULL + s));
           tma_load_2d(sbase + OFF_RING + s * SLOT + 16384, m, cb, rb, BAR(B_FULL + s));
         };
+        DBG_T(2, it, 0);
         load_item(0, &maps.att, 0, row0, 64, row0);
         load_item(1, &maps.wo, 0, 0, 64, 0);
+        DBG_T(2, it, 1);
         mbar_wait(BAR(B_CFREE), (uint32_t)((it + 1) & 1));   // previous tile's users of C are done
+        DBG_T(2, it, 2);
         mbar_expect_tx(BAR(B_XFULL), 4 * 16384);
 #pragma unroll
         for (int q = 0; q < 4; q++) tma_load_2d(sbase + OFF_C + q * 16384, &maps.x, q * 32, row0, BAR(B_XFULL));
         load_item(2, &maps.w1, 0, 0, 64, 0);
         load_item(3, &maps.w1, 0, 128, 64, 128);
+        DBG_T(2, it, 3);
         load_item(4, &maps.w2, 0, 0, 64, 0);
         load_item(5, &maps.w2, 128, 0, 192, 0);
+        DBG_T(2, it, 4);
         if (tail) {
           load_item(6, &maps.wqkv, 0, 0, 64, 0);
           load_item(7, &maps.wqkv, 0, 128, 64, 128);
           load_item(8, &maps.wqkv, 0, 256, 64, 256);
+          DBG_T(2, it, 5);
         }
       }
     }
@@ -187,50 +255,58 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   } else if (warp == W_MMA) {
     // ================================================== MMA issuer ==================================================
     if (lane == 0) {
-      const uint32_t idesc128 = umma_idesc(TM, 128), idesc64 = umma_idesc(TM, 64);
+      const uint32_t idesc128 = umma_idesc_f16(TM, 128), idesc64 = umma_idesc_f16(TM, 64);
+      const u64 dA = umma_desc_sw128(sbase + OFF_A), dB0 = umma_desc_sw128(sbase + OFF_B), dC = umma_desc_sw128(sbase + OFF_C);
+      const u64 dR = umma_desc_sw128(sbase + OFF_RING);
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int k0 = it * NI;
         const uint32_t par = (uint32_t)(it & 1);
-        auto slot = [&](int j) { return sbase + OFF_RING + (uint32_t)((k0 + j) % 3) * SLOT; };
+        auto slot = [&](int j) { return dR + (u64)(((k0 + j) % 3) * (SLOT >> 4)); };   // descriptor of ring item j
         auto wait_full = [&](int j) {
           const int kk = k0 + j;
           mbar_wait(BAR(B_FULL + kk % 3), (uint32_t)((kk / 3) & 1));
         };
         auto release = [&](int j) { umma_commit(BAR(B_EMPTY + (k0 + j) % 3)); };
         // ---- GEMM1: acc1 = att . Wo^T
+        DBG_T(1, it, 0);
         wait_full(0);
         wait_full(1);
         tc_fence_after();
-        mma_steps(tmem, slot(0), 16384, slot(1), 16384, 2, idesc128, false);
+        DBG_T(1, it, 1);
+        mma_steps(tmem, slot(0), slot(1), 8, idesc128, false);
         umma_commit(BAR(B_ACC1));
         release(0);
         release(1);
+        DBG_T(1, it, 2);
         // ---- GEMM2 (N chunks of 64) interleaved with GEMM3 (K chunks of 64)
         mbar_wait(BAR(B_X1), par);
         tc_fence_after();
+        DBG_T(1, it, 3);
         auto g2 = [&](int c) {
           if (c == 0) wait_full(2);
           if (c == 2) wait_full(3);
           mbar_wait(BAR(B_ACC2E + (c & 1)), (uint32_t)(((c >> 1) + 1) & 1));
           tc_fence_after();
-          mma_steps(tmem + 128 + (c & 1) * 64, sbase + OFF_A, 16384, slot(2 + (c >> 1)) + (c & 1) * 8192, 16384, 2, idesc64, false);
+          mma_steps(tmem + 128 + (c & 1) * 64, dA, slot(2 + (c >> 1)) + (u64)((c & 1) * (8192 >> 4)), 8, idesc64, false);
           umma_commit(BAR(B_ACC2F + (c & 1)));
           if (c == 1) release(2);
           if (c == 3) release(3);
+          DBG_T(1, it, 4 + c);
         };
         auto g3 = [&](int c) {
           if (c == 0) wait_full(4);
           if (c == 2) wait_full(5);
           mbar_wait(BAR(B_HIDF + (c & 1)), (uint32_t)((c >> 1) & 1));
           tc_fence_after();
-          mma_steps(tmem, sbase + OFF_B + (c & 1) * 16384, 0, slot(4 + (c >> 1)) + (c & 1) * 16384, 0, 1, idesc128, c > 0);
+          mma_steps(tmem, dB0 + (u64)((c & 1) * (16384 >> 4)), slot(4 + (c >> 1)) + (u64)((c & 1) * (16384 >> 4)), 4, idesc128, c > 0);
           umma_commit(BAR(B_HIDE + (c & 1)));
           if (c == 1) release(4);
           if (c == 3) {
             release(5);
             umma_commit(BAR(B_ACC3));
           }
+          DBG_T(1, it, 8 + c);
         };
         g2(0);
         g2(1);
@@ -243,6 +319,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         // ---- LN2 done: acc3 / x1 have been read, (y+pos | y) operands are in C
         mbar_wait(BAR(B_YFULL), par);
         tc_fence_after();
+        DBG_T(1, it, 12);
         if (!tail) mbar_arrive(BAR(B_CFREE));   // residual consumed and the LN2 statistics exchange (which lives in C) is over
         if (tail) {
 #pragma unroll 1
@@ -251,13 +328,56 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
             mbar_wait(BAR(B_QKVE + nt), par ^ 1u);
             tc_fence_after();
             const uint32_t dcol = nt == 0 ? 384u : (nt == 1 ? 128u : 256u);
-            mma_steps(tmem + dcol, sbase + OFF_C + (nt < 2 ? 0 : 32768), 16384, slot(6 + nt), 16384, 2, idesc128, false);
+            mma_steps(tmem + dcol, dC + (u64)(nt < 2 ? 0 : (32768 >> 4)), slot(6 + nt), 8, idesc128, false);
             umma_commit(BAR(B_QKVF + nt));
             release(6 + nt);
+            DBG_T(1, it, 13 + nt);
           }
           umma_commit(BAR(B_CFREE));
         }
       }
+    }
+    __syncwarp();
+  } else if (warp == W_ST) {
+    // ================================================== TMA stores ==================================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int row0 = tile * TM;
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait(BAR(B_YFULL), par);            // y staging (A | B) written and fenced by all epilogue warps
+        tma_store_2d(&maps.y, 0, row0, sbase + OFF_A);
+        tma_store_2d(&maps.y, 32, row0, sbase + OFF_A + 16384);
+        tma_store_commit();
+        tma_store_2d(&maps.y, 64, row0, sbase + OFF_B);
+        tma_store_2d(&maps.y, 96, row0, sbase + OFF_B + 16384);
+        tma_store_commit();
+        tma_store_wait_read<1>();
+        mbar_arrive(BAR(B_FREEA));               // y[:, 0:64] has left A
+        tma_store_wait_read<0>();
+        mbar_arrive(BAR(B_FREEB));               // y[:, 64:128] has left B
+        if (tail) {
+          mbar_wait(BAR(B_QST + 0), par);
+          tma_store_2d(&maps.qkv, 0, row0, sbase + OFF_A);
+          tma_store_2d(&maps.qkv, 64, row0, sbase + OFF_A + 16384);
+          tma_store_commit();
+          mbar_wait(BAR(B_QST + 1), par);
+          tma_store_2d(&maps.qkv, 128, row0, sbase + OFF_B);
+          tma_store_2d(&maps.qkv, 192, row0, sbase + OFF_B + 16384);
+          tma_store_commit();
+          tma_store_wait_read<1>();
+          mbar_arrive(BAR(B_FREEA));             // q has left A
+          mbar_wait(BAR(B_QST + 2), par);
+          tma_store_2d(&maps.qkv, 256, row0, sbase + OFF_A);
+          tma_store_2d(&maps.qkv, 320, row0, sbase + OFF_A + 16384);
+          tma_store_commit();
+          tma_store_wait_read<1>();
+          mbar_arrive(BAR(B_FREEB));             // k has left B
+          tma_store_wait_read<0>();
+          mbar_arrive(BAR(B_FREEA));             // v has left A
+        }
+      }
+      tma_store_wait_all<0>();
     }
     __syncwarp();
   } else {
@@ -271,37 +391,50 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     uint8_t* const rowC = smem + OFF_C + lrow * 128;
     // LN statistics exchange: each thread parks (sum, sumsq) in the first 8 bytes of its own (dead) residual span
     float2* const stat_own = reinterpret_cast<float2*>(rowC + cq * 16384 + (sw << 4));
+    const int ge = cq >> 1, hf = cq & 1;                   // GELU group (owns acc2 / hidden buffer ge) and column half inside a chunk
+    int nA = 0, nB = 0;                                    // phases of FREEA / FREEB consumed so far
     int it = 0;
+#define DBG_E(ev) do { if (tid == 0) DBG_T(0, it, ev); } while (0)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * TM;
       const uint32_t par = (uint32_t)(it & 1);
-      if (tid == 0) tma_store_wait_read<0>();   // the previous tile's stores have drained A / B
-      named_bar_sync(1, NEPI);
-      float t[32];
-      // ---------------- epilogue 1: x1 = LN1(x + acc1 + bo) -> fp32 in TMEM[256..384), bf16 operand in A ----------------
-      mbar_wait(BAR(B_XFULL), par);
-      mbar_wait(BAR(B_ACC1), par);
-      tc_fence_after();
+      DBG_E(0);
+      u64 t2[16];   // the row slice as fp32 pairs: x + acc1 + bo, then x1, later y
+      float4 ga[8];
+      // ---------------- epilogue 1: x1 = LN1(x + acc1 + bo) -> fp32 in TMEM[256..384), fp16 operand in A ----------------
       {
-        float v[32];
-        tmem_ld32(tlane + c0, v);
-        float sum = 0.f, sq = 0.f;
+        float4 b4[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) b4[q] = __ldg(reinterpret_cast<const float4*>(g.bo + c0) + q);
+        mbar_wait(BAR(B_XFULL), par);
+        DBG_E(1);
+        mbar_wait(BAR(B_ACC1), par);
+        tc_fence_after();
+        DBG_E(2);
+        uint32_t v[32];
+        tmem_ld32u(tlane + c0, v);
+        tmem_wait_ld();
+        u64 sum2 = 0ull, sq2 = 0ull;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float4 r4 = *reinterpret_cast<const float4*>(rowC + cq * 16384 + (((uint32_t)q ^ sw) << 4));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bo + c0) + q);
-          const float a0 = v[4 * q] + b4.x + r4.x, a1 = v[4 * q + 1] + b4.y + r4.y, a2 = v[4 * q + 2] + b4.z + r4.z,
-                      a3 = v[4 * q + 3] + b4.w + r4.w;
-          t[4 * q] = a0;
-          t[4 * q + 1] = a1;
-          t[4 * q + 2] = a2;
-          t[4 * q + 3] = a3;
-          sum += (a0 + a1) + (a2 + a3);
-          sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          const u64 a = add2(add2(pk2u(v[4 * q], v[4 * q + 1]), pk2(b4[q].x, b4[q].y)), pk2(r4.x, r4.y));
+          const u64 b = add2(add2(pk2u(v[4 * q + 2], v[4 * q + 3]), pk2(b4[q].z, b4[q].w)), pk2(r4.z, r4.w));
+          t2[2 * q] = a;
+          t2[2 * q + 1] = b;
+          sum2 = add2(sum2, add2(a, b));
+          sq2 = fma2(a, a, sq2);
+          sq2 = fma2(b, b, sq2);
         }
-        *stat_own = make_float2(sum, sq);
+        float s0, s1, q0, q1;
+        up2(sum2, s0, s1);
+        up2(sq2, q0, q1);
+        *stat_own = make_float2(s0 + s1, q0 + q1);
       }
+#pragma unroll
+      for (int q = 0; q < 8; q++) ga[q] = __ldg(reinterpret_cast<const float4*>(g.g1 + c0) + q);
       named_bar_sync(2 + qd, 128);
+      DBG_E(3);
       {
         const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
         const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
@@ -310,79 +443,109 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
         const float mean = sum * (1.0f / D);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
+        const u64 rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+        uint32_t xo[32];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(g.g1 + c0) + q), e4 = __ldg(reinterpret_cast<const float4*>(g.be1 + c0) + q);
-          t[4 * q] = (t[4 * q] - mean) * rstd * g4.x + e4.x;
-          t[4 * q + 1] = (t[4 * q + 1] - mean) * rstd * g4.y + e4.y;
-          t[4 * q + 2] = (t[4 * q + 2] - mean) * rstd * g4.z + e4.z;
-          t[4 * q + 3] = (t[4 * q + 3] - mean) * rstd * g4.w + e4.w;
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(g.be1 + c0) + q);
+          const u64 a = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
+          const u64 b = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
+          t2[2 * q] = a;
+          t2[2 * q + 1] = b;
+          up2u(a, xo[4 * q], xo[4 * q + 1]);
+          up2u(b, xo[4 * q + 2], xo[4 * q + 3]);
         }
-        tmem_st32(tlane + 256 + c0, t);
+        tmem_st32u(tlane + 256 + c0, xo);   // fp32 x1 stays in TMEM for the second residual
+        if (it > 0) {                       // the previous tile's v chunk has left A
+          mbar_wait(BAR(B_FREEA), (uint32_t)(nA & 1));
+          nA++;
+        }
         const int kc = cq >> 1, j0 = (cq & 1) * 4;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const float* s = &t[q * 8];
+        for (int q = 0; q < 4; q++)
           *reinterpret_cast<int4*>(rowA + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4)) =
-              make_int4((int)pack_bf16(s[0], s[1]), (int)pack_bf16(s[2], s[3]), (int)pack_bf16(s[4], s[5]), (int)pack_bf16(s[6], s[7]));
-        }
+              make_int4((int)cvt_h2(t2[4 * q]), (int)cvt_h2(t2[4 * q + 1]), (int)cvt_h2(t2[4 * q + 2]), (int)cvt_h2(t2[4 * q + 3]));
       }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_X1));
+      DBG_E(4);
 
-      // ---------------- epilogue 2: hidden chunk c = GELU(acc2 chunk + b1) -> bf16 K-chunk of GEMM3's A operand in B ----------------
+      // ---------------- epilogue 2: hidden chunk c = GELU(acc2 chunk + b1) -> fp16 K-chunk of GEMM3's A operand in B ----------------
+      // group ge owns chunks ge and ge + 2 (accumulator buffer ge, hidden buffer ge); a thread covers 32 of the chunk's 64 columns
+      if (it > 0) {   // the previous tile's k chunk has left B
+        mbar_wait(BAR(B_FREEB), (uint32_t)(nB & 1));
+        nB++;
+      }
 #pragma unroll 1
-      for (int c = 0; c < 4; c++) {
-        const int b = c & 1;
-        mbar_wait(BAR(B_ACC2F + b), (uint32_t)((c >> 1) & 1));
+      for (int u = 0; u < 2; u++) {
+        const int c = ge + 2 * u;
+        float4 b4[8];
+        const float4* bp = reinterpret_cast<const float4*>(g.b1 + c * 64 + hf * 32);
+#pragma unroll
+        for (int q = 0; q < 8; q++) b4[q] = __ldg(bp + q);
+        mbar_wait(BAR(B_ACC2F + ge), (uint32_t)u);
         tc_fence_after();
-        float v[16];
-        tmem_ld16(tlane + 128 + b * 64 + cq * 16, v);
+        DBG_E(5 + u);
+        uint32_t v[32];
+        tmem_ld32u(tlane + 128 + ge * 64 + hf * 32, v);
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_ACC2E + b));
-        const float4* bp = reinterpret_cast<const float4*>(g.b1 + c * 64 + cq * 16);
-        uint32_t pk[8];
+        if (lane == 0) mbar_arrive(BAR(B_ACC2E + ge));
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(bp + (i >> 2));
-          pk[i >> 1] = pack_bf16(gelu_t(v[i] + b4.x), gelu_t(v[i + 1] + b4.y));
-          pk[(i >> 1) + 1] = pack_bf16(gelu_t(v[i + 2] + b4.z), gelu_t(v[i + 3] + b4.w));
+        for (int q = 0; q < 8; q++) {
+          pk[2 * q] = gelu_h2(cvt_h2(add2(pk2u(v[4 * q], v[4 * q + 1]), pk2(b4[q].x, b4[q].y))));
+          pk[2 * q + 1] = gelu_h2(cvt_h2(add2(pk2u(v[4 * q + 2], v[4 * q + 3]), pk2(b4[q].z, b4[q].w))));
         }
-        mbar_wait(BAR(B_HIDE + b), (uint32_t)(((c >> 1) + 1) & 1));   // GEMM3 has consumed the chunk that lived here
-        uint8_t* hb = smem + OFF_B + b * 16384 + lrow * 128;
-        *reinterpret_cast<int4*>(hb + (((uint32_t)(cq * 2) ^ sw) << 4)) = make_int4((int)pk[0], (int)pk[1], (int)pk[2], (int)pk[3]);
-        *reinterpret_cast<int4*>(hb + (((uint32_t)(cq * 2 + 1) ^ sw) << 4)) = make_int4((int)pk[4], (int)pk[5], (int)pk[6], (int)pk[7]);
+        mbar_wait(BAR(B_HIDE + ge), (uint32_t)((u + 1) & 1));   // GEMM3 has consumed the chunk that lived in this buffer
+        uint8_t* hb = smem + OFF_B + ge * 16384 + lrow * 128;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          *reinterpret_cast<int4*>(hb + (((uint32_t)(hf * 4 + q) ^ sw) << 4)) =
+              make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_HIDF + b));
+        if (lane == 0) mbar_arrive(BAR(B_HIDF + ge));
+        DBG_E(7 + u);
       }
 
       // ---------------- epilogue 3: y = LN2(x1 + acc3 + b2) -> fp32 staging (TMA store) + operands of GEMM4 ----------------
-      mbar_wait(BAR(B_ACC3), par);
-      tc_fence_after();
+      int pcode = 0;
+      if (tail && row0 + lrow < M) pcode = g.next_pos_code[row0 + lrow];
       {
-        float v[32], r[32];
-        tmem_ld32(tlane + c0, v);
-        tmem_ld32(tlane + 256 + c0, r);
-        float sum = 0.f, sq = 0.f;
+        float4 b4[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) b4[q] = __ldg(reinterpret_cast<const float4*>(g.b2 + c0) + q);
+        mbar_wait(BAR(B_ACC3), par);
+        tc_fence_after();
+        DBG_E(9);
+        uint32_t v[32], r[32];
+        tmem_ld32u(tlane + c0, v);
+        tmem_ld32u(tlane + 256 + c0, r);
+        tmem_wait_ld();
+        u64 sum2 = 0ull, sq2 = 0ull;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.b2 + c0) + q);
-          const float a0 = v[4 * q] + b4.x + r[4 * q], a1 = v[4 * q + 1] + b4.y + r[4 * q + 1];
-          const float a2 = v[4 * q + 2] + b4.z + r[4 * q + 2], a3 = v[4 * q + 3] + b4.w + r[4 * q + 3];
-          t[4 * q] = a0;
-          t[4 * q + 1] = a1;
-          t[4 * q + 2] = a2;
-          t[4 * q + 3] = a3;
-          sum += (a0 + a1) + (a2 + a3);
-          sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          const u64 a = add2(add2(pk2u(v[4 * q], v[4 * q + 1]), pk2(b4[q].x, b4[q].y)), pk2u(r[4 * q], r[4 * q + 1]));
+          const u64 b = add2(add2(pk2u(v[4 * q + 2], v[4 * q + 3]), pk2(b4[q].z, b4[q].w)), pk2u(r[4 * q + 2], r[4 * q + 3]));
+          t2[2 * q] = a;
+          t2[2 * q + 1] = b;
+          sum2 = add2(sum2, add2(a, b));
+          sq2 = fma2(a, a, sq2);
+          sq2 = fma2(b, b, sq2);
         }
-        *stat_own = make_float2(sum, sq);
+        float s0, s1, q0, q1;
+        up2(sum2, s0, s1);
+        up2(sq2, q0, q1);
+        *stat_own = make_float2(s0 + s1, q0 + q1);
       }
+#pragma unroll
+      for (int q = 0; q < 8; q++) ga[q] = __ldg(reinterpret_cast<const float4*>(g.g2 + c0) + q);
       named_bar_sync(2 + qd, 128);
+      DBG_E(10);
       {
         const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
         const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
@@ -391,87 +554,78 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
         const float mean = sum * (1.0f / D);
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
+        const u64 rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
         named_bar_sync(2 + qd, 128);   // every statistic of this quadrant has been read: C may now receive the operands
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(g.g2 + c0) + q), e4 = __ldg(reinterpret_cast<const float4*>(g.be2 + c0) + q);
-          float4 o;
-          o.x = (t[4 * q] - mean) * rstd * g4.x + e4.x;
-          o.y = (t[4 * q + 1] - mean) * rstd * g4.y + e4.y;
-          o.z = (t[4 * q + 2] - mean) * rstd * g4.z + e4.z;
-          o.w = (t[4 * q + 3] - mean) * rstd * g4.w + e4.w;
-          *reinterpret_cast<float4*>(rowA + cq * 16384 + (((uint32_t)q ^ sw) << 4)) = o;   // y staging spans A | B (4 boxes of 32 columns)
-          t[4 * q] = o.x;
-          t[4 * q + 1] = o.y;
-          t[4 * q + 2] = o.z;
-          t[4 * q + 3] = o.w;
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(g.be2 + c0) + q);
+          const u64 a = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
+          const u64 b = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
+          t2[2 * q] = a;
+          t2[2 * q + 1] = b;
+          uint4 o;
+          up2u(a, o.x, o.y);
+          up2u(b, o.z, o.w);
+          *reinterpret_cast<uint4*>(rowA + cq * 16384 + (((uint32_t)q ^ sw) << 4)) = o;   // y staging spans A | B (4 boxes of 32 columns)
         }
       }
+      DBG_E(11);
       if (tail) {
-        const int tok = row0 + lrow;
-        float pe[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) pe[i] = 0.f;
         const int axis = c0 / g.posL;   // posL % 32 == 0 (host check): the 32-column span lies inside one axis
-        if (tok < M && axis < g.pos_ndim) {
-          const int cv = (g.next_pos_code[tok] >> (8 * axis)) & 255;
-          const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)axis * g.pos_maxw + cv) * g.posL + (c0 - axis * g.posL));
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const float4 p4 = __ldg(tp + q);
-            pe[4 * q] = p4.x;
-            pe[4 * q + 1] = p4.y;
-            pe[4 * q + 2] = p4.z;
-            pe[4 * q + 3] = p4.w;
-          }
-        }
+        const bool has_pos = (row0 + lrow < M) && axis < g.pos_ndim;
+        const int cv = (pcode >> (8 * axis)) & 255;
+        const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)(has_pos ? axis : 0) * g.pos_maxw + (has_pos ? cv : 0)) * g.posL +
+                                                           (has_pos ? c0 - axis * g.posL : 0));
         const int kc = cq >> 1, j0 = (cq & 1) * 4;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const float* sy = &t[q * 8];
-          const float* sp = &pe[q * 8];
+          float4 p0 = __ldg(tp + 2 * q), p1 = __ldg(tp + 2 * q + 1);
+          if (!has_pos) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
           uint8_t* dst = rowC + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4);
-          *reinterpret_cast<int4*>(dst) = make_int4((int)pack_bf16(sy[0] + sp[0], sy[1] + sp[1]), (int)pack_bf16(sy[2] + sp[2], sy[3] + sp[3]),
-                                                    (int)pack_bf16(sy[4] + sp[4], sy[5] + sp[5]), (int)pack_bf16(sy[6] + sp[6], sy[7] + sp[7]));
-          *reinterpret_cast<int4*>(dst + 32768) = make_int4((int)pack_bf16(sy[0], sy[1]), (int)pack_bf16(sy[2], sy[3]),
-                                                            (int)pack_bf16(sy[4], sy[5]), (int)pack_bf16(sy[6], sy[7]));
+          *reinterpret_cast<int4*>(dst) =
+              make_int4((int)cvt_h2(add2(t2[4 * q], pk2(p0.x, p0.y))), (int)cvt_h2(add2(t2[4 * q + 1], pk2(p0.z, p0.w))),
+                        (int)cvt_h2(add2(t2[4 * q + 2], pk2(p1.x, p1.y))), (int)cvt_h2(add2(t2[4 * q + 3], pk2(p1.z, p1.w))));
+          *reinterpret_cast<int4*>(dst + 32768) =
+              make_int4((int)cvt_h2(t2[4 * q]), (int)cvt_h2(t2[4 * q + 1]), (int)cvt_h2(t2[4 * q + 2]), (int)cvt_h2(t2[4 * q + 3]));
         }
       }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_YFULL));
-      named_bar_sync(1, NEPI);
-      if (tid == 0) {
-        tma_store_2d(&maps.y, 0, row0, sbase + OFF_A);
-        tma_store_2d(&maps.y, 32, row0, sbase + OFF_A + 16384);
-        tma_store_commit();
-        tma_store_2d(&maps.y, 64, row0, sbase + OFF_B);
-        tma_store_2d(&maps.y, 96, row0, sbase + OFF_B + 16384);
-        tma_store_commit();
-      }
+      DBG_E(12);
 
-      // ---------------- epilogue 4: q | k | v chunk + bias -> fp16 staging (q, v in A; k in B) -> TMA store ----------------
+      // ---------------- epilogue 4: q | k | v chunk + bias -> fp16 staging (q, v in A; k in B) -> TMA store (warp 18) ----------------
       if (tail) {
 #pragma unroll 1
         for (int nt = 0; nt < 3; nt++) {
+          float4 b4[8];
+          const float4* bp = reinterpret_cast<const float4*>(g.bqkv + nt * 128 + c0);
+#pragma unroll
+          for (int q = 0; q < 8; q++) b4[q] = __ldg(bp + q);
           mbar_wait(BAR(B_QKVF + nt), par);
           tc_fence_after();
-          float v[32];
-          tmem_ld32(tlane + (nt == 0 ? 384 : (nt == 1 ? 128 : 256)) + c0, v);
+          DBG_E(13 + nt);
+          uint32_t v[32];
+          tmem_ld32u(tlane + (nt == 0 ? 384 : (nt == 1 ? 128 : 256)) + c0, v);
+          tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_QKVE + nt));
-          const float4* bp = reinterpret_cast<const float4*>(g.bqkv + nt * 128 + c0);
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(bp + (i >> 2));
-            pk[i >> 1] = pack_h2(v[i] + b4.x, v[i + 1] + b4.y);
-            pk[(i >> 1) + 1] = pack_h2(v[i + 2] + b4.z, v[i + 3] + b4.w);
+          for (int q = 0; q < 8; q++) {
+            pk[2 * q] = cvt_h2(add2(pk2u(v[4 * q], v[4 * q + 1]), pk2(b4[q].x, b4[q].y)));
+            pk[2 * q + 1] = cvt_h2(add2(pk2u(v[4 * q + 2], v[4 * q + 3]), pk2(b4[q].z, b4[q].w)));
           }
-          if (tid == 0) tma_store_wait_read<1>();   // the store that last read this staging buffer has drained
-          named_bar_sync(1, NEPI);
+          // the store that last read this staging buffer has drained it
+          if (nt == 1) {
+            mbar_wait(BAR(B_FREEB), (uint32_t)(nB & 1));
+            nB++;
+          } else {
+            mbar_wait(BAR(B_FREEA), (uint32_t)(nA & 1));
+            nA++;
+          }
           uint8_t* st = smem + (nt == 1 ? OFF_B : OFF_A) + (cq >> 1) * 16384 + lrow * 128;
           const int j0 = (cq & 1) * 4;
 #pragma unroll
@@ -479,17 +633,12 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
             *reinterpret_cast<int4*>(st + (((uint32_t)(j0 + q) ^ sw) << 4)) =
                 make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]);
           fence_async_smem();
-          named_bar_sync(1, NEPI);
-          if (tid == 0) {
-            const uint32_t sa = sbase + (nt == 1 ? OFF_B : OFF_A);
-            tma_store_2d(&maps.qkv, nt * 128, row0, sa);
-            tma_store_2d(&maps.qkv, nt * 128 + 64, row0, sa + 16384);
-            tma_store_commit();
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_QST + nt));
+          DBG_E(16 + nt);
         }
       }
     }
-    if (tid == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -499,8 +648,8 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
 
 }  // namespace
 
-int sstb_sra_chain2_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_bfloat16* att, const float* x, float* y, int n_cap,
-                         const int32_t* n_dev, const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv) {
+int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* att, const float* x, float* y, int n_cap, const int32_t* n_dev,
+                    const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv) {
   Chain2Maps maps;
   Chain2Args g;
   memset(&g, 0, sizeof(g));
@@ -509,14 +658,14 @@ int sstb_sra_chain2_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_
   if (tail && (next_plan->pos_L % 32 != 0 || !next_plan->pos_code || !next_plan->pos_table))
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs pos_L %% 32 == 0 and the next plan's pos_code / pos_table");
   int rc = 0;
-  rc |= tmap_2d_sw128(&maps.att, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, att, 128, (uint64_t)n_cap, 256, 64, 128);
+  rc |= tmap_2d_sw128(&maps.att, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, att, 128, (uint64_t)n_cap, 256, 64, 128);
   rc |= tmap_2d_sw128(&maps.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, 128, (uint64_t)n_cap, 512, 32, 128);
   rc |= tmap_2d_sw128(&maps.y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, 128, (uint64_t)n_cap, 512, 32, 128);
-  rc |= tmap_2d_sw128(&maps.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L->out_proj_w_bf16, 128, 128, 256, 64, 128);
-  rc |= tmap_2d_sw128(&maps.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L->lin1_w_bf16, 128, 256, 256, 64, 128);
-  rc |= tmap_2d_sw128(&maps.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L->lin2_w_bf16, 256, 128, 512, 64, 128);
+  rc |= tmap_2d_sw128(&maps.wo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L->out_proj_w_f16, 128, 128, 256, 64, 128);
+  rc |= tmap_2d_sw128(&maps.w1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L->lin1_w_f16, 128, 256, 256, 64, 128);
+  rc |= tmap_2d_sw128(&maps.w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L->lin2_w_f16, 256, 128, 512, 64, 128);
   if (tail) {
-    rc |= tmap_2d_sw128(&maps.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, next->in_proj_w_bf16, 128, 384, 256, 64, 128);
+    rc |= tmap_2d_sw128(&maps.wqkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next->in_proj_w_f16, 128, 384, 256, 64, 128);
     rc |= tmap_2d_sw128(&maps.qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next_qkv, 384, (uint64_t)n_cap, 768, 64, 128);
     g.has_tail = 1;
     g.bqkv = next->in_proj_b;
@@ -541,6 +690,37 @@ int sstb_sra_chain2_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const __nv_
   CUDA_TRY(c, ensure_smem(c, sa, sra_chain2_kernel, (size_t)SMEM_BYTES));
   const int tiles_cap = (n_cap + TM - 1) / TM;
   const int grid = c->num_sms < tiles_cap ? c->num_sms : tiles_cap;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("SSTB200_CHAIN_DBG") ? atoi(getenv("SSTB200_CHAIN_DBG")) : 0;
+  static long long* dbg_buf = nullptr;
+  const size_t dbg_n = (size_t)grid * 3 * 2 * 32;
+  if (dbg_on) {   // timeline dump of CTA 0 and one mid CTA (profiling aid; synchronises)
+    if (!dbg_buf) CUDA_TRY(c, cudaMalloc(&dbg_buf, (size_t)1024 * 3 * 2 * 32 * 8));
+    CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, c->stream));
+    g.dbg = dbg_buf;
+  }
   CUDA_TRY(c, launch_pdl(sra_chain2_kernel, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
+  if (dbg_on) {
+    std::vector<long long> h(dbg_n);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(h.data(), dbg_buf, dbg_n * 8, cudaMemcpyDeviceToHost));
+    static int dumps = 0;
+    if (dumps++ % dbg_on == 0) {
+      const char* roles[3] = {"epi", "mma", "tma"};
+      for (int cta : {0, grid / 2}) {
+        long long t0 = h[(((size_t)cta * 3 + 2) * 2 + 0) * 32 + 0];
+        for (int role = 0; role < 3; role++)
+          for (int it = 0; it < 2; it++) {
+            printf("[chain2 dbg] cta %3d %s tile %d:", cta, roles[role], it);
+            for (int e = 0; e < 20; e++) {
+              long long v = h[(((size_t)cta * 3 + role) * 2 + it) * 32 + e];
+              printf(" %d:%lld", e, v ? v - t0 : -1);
+            }
+            printf("\n");
+          }
+      }
+      fflush(stdout);
+    }
+  }
   return SSTB_OK;
 }

@@ -72,10 +72,7 @@ class SSTEngine:
                               for p in self.plans]
         self.vfe_cfg = self.vfe._cfg(self.B)
         self.vfe_cfg.precision = PRECISIONS[precision]
-        prec = PRECISIONS[precision]
-        self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]
-        from .sst_modules import _SraLayer
-        self._layer_array = (_SraLayer * max(len(self._layers), 1))(*[ls for ls, _ in self._layers])
+        self._build_layer_structs()
         self._vs_arr, self._rng_arr = L.arr(C.c_float, self.vs), L.arr(C.c_float, self.rng)
         self.stream = torch.cuda.Stream(device=dev)
         self.graph = None
@@ -97,6 +94,29 @@ class SSTEngine:
                 self.launches_per_frame = nk.value   # kernel nodes of OUR library in one frame
                 self.other_nodes_per_frame = no.value
             self.stream.synchronize()
+
+    def _build_layer_structs(self):
+        """Layer descriptors for the C ABI.  The engine OWNS the fp16 weight copies whose addresses go into the descriptors (and
+        from there into the captured graph): they stay alive as long as the engine does, whatever the modules do later."""
+        from .sst_modules import _SraLayer
+        prec = PRECISIONS[self.precision]
+        layers = [layer for blk in self.bb.block_list for layer in blk.encoder_list]
+        assert all(l.d_model == self.d for l in layers), "engine assumes a constant d_model"
+        self._half_refs = [l.half_weights(refresh=True) for l in layers] if prec == 1 else []
+        self._layers = [(layer._struct(prec), i) for blk in self.bb.block_list for i, layer in enumerate(blk.encoder_list)]
+        self._layer_array = (_SraLayer * max(len(self._layers), 1))(*[ls for ls, _ in self._layers])
+
+    def refresh_weights(self):
+        """Call after the modules' parameters changed (optimizer step, load_state_dict): fp32 parameters are read in place by
+        the graph, the fp16 copies of the tensor-core path are re-cast INTO the buffers the graph already points at."""
+        if PRECISIONS[self.precision] != 1:
+            return
+        layers = [layer for blk in self.bb.block_list for layer in blk.encoder_list]
+        with torch.no_grad():
+            for l, refs in zip(layers, self._half_refs):
+                sa = l.win_attn.self_attn
+                for dst, src in zip(refs, (sa.in_proj_weight, sa.out_proj.weight, l.linear1.weight, l.linear2.weight)):
+                    dst.copy_(src)
 
     # everything below is stream-ordered and sync-free
     def _enqueue(self):

@@ -242,7 +242,7 @@ class _SraLayer(C.Structure):
                                            "lin2_w", "lin2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b",
                                            "norm1_mean", "norm1_var", "norm2_mean", "norm2_var", "tau")] +
                 [("tau_n", C.c_int32), ("tau_min", C.c_float)] +
-                [(k, C.c_void_p) for k in ("in_proj_w_bf16", "out_proj_w_bf16", "lin1_w_bf16", "lin2_w_bf16")])
+                [(k, C.c_void_p) for k in ("in_proj_w_f16", "out_proj_w_f16", "lin1_w_f16", "lin2_w_f16")])
 
 
 class _SraPlan(C.Structure):
@@ -331,13 +331,20 @@ class EncoderLayer(nn.Module):
         if self.win_attn.cosine:
             s.tau, s.tau_n, s.tau_min = f(sa.tau), sa.tau.numel(), float(self.win_attn.tau_min)
         if precision == 1:
-            if self._bf16 is None or self._bf16[0] is not sa.in_proj_weight._version:
-                ws = [w.detach().to(torch.bfloat16).contiguous() for w in
-                      (sa.in_proj_weight, sa.out_proj.weight, self.linear1.weight, self.linear2.weight)]
-                self._bf16 = (sa.in_proj_weight._version, ws)
-            ws = self._bf16[1]
-            s.in_proj_w_bf16, s.out_proj_w_bf16, s.lin1_w_bf16, s.lin2_w_bf16 = [w.data_ptr() for w in ws]
+            ws = self.half_weights()
+            s.in_proj_w_f16, s.out_proj_w_f16, s.lin1_w_f16, s.lin2_w_f16 = [w.data_ptr() for w in ws]
         return s
+
+    def half_weights(self, refresh=False):
+        """fp16 copies of the four weight matrices for the tensor-core path, re-cast whenever any of the four parameters
+        changed (version counter, storage or device).  Callers that bake the pointers into a CUDA graph (SSTEngine) keep the
+        returned tensors alive themselves and call `SSTEngine.refresh_weights()` after an update."""
+        sa = self.win_attn.self_attn
+        srcs = (sa.in_proj_weight, sa.out_proj.weight, self.linear1.weight, self.linear2.weight)
+        key = tuple((w._version, w.data_ptr(), str(w.device)) for w in srcs)
+        if refresh or self._bf16 is None or self._bf16[0] != key:
+            self._bf16 = (key, [w.detach().to(torch.float16).contiguous() for w in srcs])
+        return self._bf16[1]
 
     def forward(self, src, sra_plan, precision="fp32"):
         """src [n,d] fp32 flat voxel order; sra_plan: voxel_info['sra_plan_shift{i}']."""

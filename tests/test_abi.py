@@ -56,7 +56,8 @@ def test_product_never_imports_oracle():
 
 def test_sass_carries_the_blackwell_instructions():
     """The built library really contains the sm_100a tensor-core path (no silent SIMT-only build): tcgen05.mma -> UTCHMMA,
-    tcgen05.ld/st -> LDTM/STTM, tcgen05.commit -> UTCBAR, cp.async -> LDGSTS, mma.sync -> HMMA, redux.sync -> REDUX."""
+    tcgen05.ld/st -> LDTM/STTM, tcgen05.commit -> UTCBAR, cp.async -> LDGSTS, mma.sync -> HMMA, redux.sync -> REDUX, cp.async.bulk.tensor (TMA) ->
+    UTMALDG / UTMASTG, packed fp32x2 -> FFMA2."""
     import shutil
     import pytest
     from sst_b200 import build
@@ -66,8 +67,9 @@ def test_sass_carries_the_blackwell_instructions():
     so = build.build()
     sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100a" in sass.upper() or "arch = sm_100" in sass
-    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "LDGSTS", "HMMA.16816.F32", "REDUX"):
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR", "LDGSTS", "HMMA.16816.F32", "REDUX", "UTMALDG", "UTMASTG",
+                     "FFMA2", "MUFU.TANH.F16"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS of {so}"
     # every tensor-core kernel family is present
-    for kern in ("sra_chain_kernel", "umma_gemm_kernel", "vfe_l1_umma_kernel", "sir_a_kernel", "sir_b_kernel"):
+    for kern in ("sra_chain2_kernel", "umma_gemm_kernel", "vfe_l1_umma_kernel", "sir_a_kernel", "sir_b_kernel"):
         assert kern in sass, kern

@@ -1,4 +1,4 @@
-"""A/B of the SRA stack under SSTB200_CHAIN=1 (round-1 chain kernel) and =2 (warp-specialised TMA chain): each variant runs in
+"""A/B of the SRA stack under SSTB200_CHAIN=0 (unfused GEMM launches) and =1 (warp-specialised TMA chain): each variant runs in
 its own process (the switch is read once), dumps the 12-layer output, and the parent compares them and prints the timings.
     python tools/chain_ab.py            (parent)      python tools/chain_ab.py child <variant> <out.pt>"""
 import os
@@ -59,7 +59,7 @@ def child(variant, out):
 def main():
     import torch
     outs = {}
-    for v in ("1", "2"):
+    for v in ("0", "1"):
         env = dict(os.environ, SSTB200_CHAIN=v)
         out = f"/tmp/chain_ab_{v}.pt"
         r = subprocess.run([sys.executable, __file__, "child", v, out], env=env, timeout=600)
@@ -68,9 +68,9 @@ def main():
             continue
         outs[v] = torch.load(out)
     if len(outs) == 2:
-        a, b = outs["1"]["feats"], outs["2"]["feats"]
+        a, b = outs["0"]["feats"], outs["1"]["feats"]
         d = (a - b).abs().max().item()
-        print(f"max |chain1 - chain2| = {d:.3e} (max |chain1| = {a.abs().max().item():.3e}); bit-equal: {torch.equal(a, b)}")
+        print(f"max |unfused - chain| = {d:.3e} (max |unfused| = {a.abs().max().item():.3e}); bit-equal: {torch.equal(a, b)}")
 
 
 if __name__ == "__main__":
