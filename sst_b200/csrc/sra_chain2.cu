@@ -1,9 +1,9 @@
 // Fused post-attention chain of one SRA encoder layer, warp-specialised (d_model = 128, dim_ff = 256, post-norm LayerNorm, GELU):
 //
 //     x1 = LayerNorm1(x + att . Wo^T + bo)          GEMM1  [128 x 128] x [128 x 128]
-//     h  = GELU(x1 . W1^T + b1)                     GEMM2  [128 x 128] x [128 x 256]   four N = 64 chunks
+//     h  = GELU(x1 . W1^T + b1)                     GEMM2  [128 x 128] x [128 x 256]   two N = 128 chunks
 //     y  = LayerNorm2(x1 + h . W2^T + b2)           GEMM3  [128 x 256] x [256 x 128]   four K = 64 chunks
-//     q|k|v (next layer) = (y + pos | y) . Wqkv^T   GEMM4  [128 x 128] x [128 x 384]   three N = 128 chunks (optional tail)
+//     q|k|v (next layer) = (y + pos | y) . Wqkv^T   GEMM4  [128 x 128] x [128 x 384]   q|k as one N = 256 GEMM, v N = 128 (optional tail)
 //
 // replaces mmdet3d/models/sst/sst_basic_block_v2.py:104-126 (+ the in-projection of the following layer's
 // nn.MultiheadAttention, :70) for one 128-token tile per iteration of a persistent CTA.
@@ -18,12 +18,12 @@
 //   warps 0-15  epilogue: TMEM -> registers (thread per row, 4 warps per TMEM lane quadrant, each a column quarter); bias /
 //            residual / LayerNorm in packed fp32x2 arithmetic (FADD2 / FFMA2), GELU in half2 (tanh form, MUFU.TANH.F16); the
 //            operands of the next GEMM are written straight into the swizzled K-major layout.
-// GEMM2 -> GELU -> GEMM3 is pipelined in 64-column chunks: two accumulator chunks in TMEM, two hidden chunks in shared memory,
-// and two epilogue warp groups (8 warps each) that own the even / odd chunks, so GELU of chunk c overlaps the MMAs of c+1 and
-// the GELU of the other group.  GEMM1 of the next tile is issued while the q|k|v epilogue of this one runs.
+// GEMM2 -> GELU -> GEMM3 is pipelined: two 128-column accumulator chunks in TMEM, two 64-column hidden chunks in shared memory,
+// and two epilogue warp groups (8 warps each) that own one accumulator chunk each and feed GEMM3 its K-chunks as they finish
+// them, so GELU overlaps the MMAs and the other group.  GEMM1 of the next tile is issued while the q|k|v epilogue of this one runs.
 // All rows are in flat token order: every tile of att / x / y / q|k|v is a plain 2-D TMA box.
 //
-// TMEM columns: [0,128) acc1 / acc3, [128,256) two acc2 chunks (later k), [256,384) x1 fp32 (later v), [384,512) q.
+// TMEM columns: [0,128) acc1 / acc3, [128,256) acc2 chunk 0 (later q), [256,384) acc2 chunk 1 (later k), [384,512) x1 fp32 (later v).
 // Shared memory: ring 3 x 32 KB | A 32 KB (x1 operand, y staging lo, q / v staging) | B 32 KB (hidden chunks, y staging hi,
 // k staging) | C 64 KB (x fp32 tile, LN statistics exchange, then the (y+pos | y) operands) | mbarriers.
 #include <stdarg.h>
@@ -53,8 +53,8 @@ enum {
   B_HIDE = 16,   // [2] hidden chunk consumed by GEMM3
   B_ACC3 = 18,   // GEMM3 retired
   B_YFULL = 19,  // LN2 done: acc3 / x1 read, y staging + (y+pos | y) operands written [16]
-  B_QKVF = 20,   // [3] q / k / v chunk retired
-  B_QKVE = 23,   // [3] q / k / v chunk read back                          [16]
+  B_QKVF = 20,   // [2] q|k / v GEMM retired                               (slot 22 unused)
+  B_QKVE = 23,   // [2] q|k / v accumulator read back                      [16] (slot 25 unused)
   B_QST = 26,    // [3] q / k / v staging written                          [16]
   B_FREEA = 29,  // staging buffer A drained by its TMA store
   B_FREEB = 30,  // staging buffer B drained
@@ -62,7 +62,7 @@ enum {
 };
 
 struct Chain2Maps {
-  CUtensorMap att, x, y, qkv, wo, w1, w2, wqkv;
+  CUtensorMap att, x, y, qkv, wo, w1, w2, wqkv, wqk;
 };
 
 struct Chain2Args {
@@ -116,19 +116,17 @@ __device__ __forceinline__ uint32_t cvt_h2(u64 v) {
   return r;
 }
 
-// tanh-form GELU on two values in half2: 0.5 z (1 + tanh(z (c0 + c1 z^2))).  The argument of tanh is built from z clamped to
-// [-12, 12] (the function is z or 0 to fp16 precision beyond that), so no intermediate leaves the fp16 range.  Deviation from
-// the erf form plus the half2 arithmetic stays below 1e-3 relative - the fp16 rounding of the operand it feeds is 5e-4.
+// tanh-form GELU on two values in half2: 0.5 z (1 + tanh(z (c0 + c1 z^2))).  No clamp is needed: if z^2 overflows fp16 the
+// argument becomes +-inf and tanh returns +-1, which is the right limit (z or 0).  Deviation from the erf form plus the half2
+// arithmetic stays below 1e-3 relative - the fp16 rounding of the operand it feeds is 5e-4.
 __device__ __forceinline__ uint32_t gelu_h2(uint32_t z) {
   const uint32_t C0 = 0x3A623A62u;   // half2(0.7978846)
   const uint32_t C1 = 0x28912891u;   // half2(0.0356774) = 0.7978846 * 0.044715
-  const uint32_t HALF = 0x38003800u, LIM = 0x4A004A00u, NLIM = 0xCA00CA00u;   // 0.5, 12, -12
-  uint32_t zc, z2, p, u, t, hz, r;
-  asm("min.f16x2 %0, %1, %2;" : "=r"(zc) : "r"(z), "r"(LIM));
-  asm("max.f16x2 %0, %1, %2;" : "=r"(zc) : "r"(zc), "r"(NLIM));
-  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(z2) : "r"(zc));
+  const uint32_t HALF = 0x38003800u;   // 0.5
+  uint32_t z2, p, u, t, hz, r;
+  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(z2) : "r"(z));
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(z2), "r"(C1), "r"(C0));
-  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(u) : "r"(p), "r"(zc));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(u) : "r"(p), "r"(z));
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(u));
   asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hz) : "r"(z), "r"(HALF));
   asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(hz), "r"(t));
@@ -161,16 +159,35 @@ __device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
 
-// K-major SWIZZLE_128B descriptors differ only in the start address: build the constant part once, add (bytes >> 4)
-__device__ __forceinline__ void mma_steps(uint32_t d_tmem, u64 adesc, u64 bdesc, int ksteps, uint32_t idesc, bool accum) {
-  // ksteps = 4 (K = 64) or 8 (K = 128: the second 64-wide chunk lives 16 KB further in both operands)
+// One tcgen05.mma; ACC is an immediate so that the accumulate predicate folds to a constant.
+template <int ACC>
+__device__ __forceinline__ void mma1(uint32_t d_tmem, u64 adesc, u64 bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+// K-major SWIZZLE_128B descriptors differ only in the start address: constant part once, then + (bytes >> 4).
+// KSTEPS = 4 (K = 64) or 8 (K = 128: operand K-chunk c lives a_chunk / b_chunk 16-byte units further).
+template <int KSTEPS, bool ACCUM>
+__device__ __forceinline__ void mma_steps(uint32_t d_tmem, u64 adesc, u64 bdesc, uint32_t idesc, uint32_t a_chunk = 1024, uint32_t b_chunk = 1024) {
 #pragma unroll
-  for (int s = 0; s < 8; s++) {
-    if (s < ksteps) {
-      const u64 off = (u64)((s & 3) * 2 + (s >> 2) * 1024);   // 32 B per k-step, 16384 B per K chunk, in 16-byte units
-      umma_f16(d_tmem, adesc + off, bdesc + off, idesc, (accum || s) ? 1u : 0u);
-    }
+  for (int s = 0; s < KSTEPS; s++) {
+    const u64 ao = (u64)((s & 3) * 2) + (u64)((s >> 2) * a_chunk), bo = (u64)((s & 3) * 2) + (u64)((s >> 2) * b_chunk);
+    if (ACCUM || s > 0) mma1<1>(d_tmem, adesc + ao, bdesc + bo, idesc);
+    else mma1<0>(d_tmem, adesc + ao, bdesc + bo, idesc);
   }
+}
+// hot spin for the single MMA-issuing thread (mbarrier.test_wait does not suspend: the wake-up is immediate)
+__device__ __forceinline__ void mbar_spin(uint32_t saddr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done)
+                 : "r"(saddr), "r"(parity)
+                 : "memory");
+  } while (!done);
 }
 
 __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Args g) {
@@ -184,7 +201,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     if (sbase & 1023u) __trap();   // SWIZZLE_128B operands / TMA boxes need the 1024-byte alignment
     for (int i = 0; i < NBAR; i++) {
       uint32_t cnt = 1;
-      if (i == B_X1 || i == B_YFULL || (i >= B_QKVE && i < B_QKVE + 3) || (i >= B_QST && i < B_QST + 3)) cnt = 16;
+      if (i == B_X1 || i == B_YFULL || (i >= B_QKVE && i < B_QKVE + 2) || (i >= B_QST && i < B_QST + 3)) cnt = 16;
       if (i == B_ACC2E || i == B_ACC2E + 1 || i == B_HIDF || i == B_HIDF + 1) cnt = 8;
       mbar_init(BAR(i), cnt);
     }
@@ -196,7 +213,10 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     tma_prefetch_desc(&maps.wo);
     tma_prefetch_desc(&maps.w1);
     tma_prefetch_desc(&maps.w2);
-    if (g.has_tail) tma_prefetch_desc(&maps.wqkv);
+    if (g.has_tail) {
+      tma_prefetch_desc(&maps.wqkv);
+      tma_prefetch_desc(&maps.wqk);
+    }
   }
   if (warp == W_ST && lane == 0) {
     tma_prefetch_desc(&maps.y);
@@ -244,8 +264,15 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         load_item(5, &maps.w2, 128, 0, 192, 0);
         DBG_T(2, it, 4);
         if (tail) {
-          load_item(6, &maps.wqkv, 0, 0, 64, 0);
-          load_item(7, &maps.wqkv, 0, 128, 64, 128);
+          // Wq|Wk as ONE N = 256 operand: a slot per 64-wide K chunk (256 rows x 128 B), then Wv (two K chunks of 128 rows)
+          auto load_qk = [&](int j, int col) {
+            const int kk = k0 + j, s2 = kk % 3;
+            mbar_wait(BAR(B_EMPTY + s2), (uint32_t)(((kk / 3) + 1) & 1));
+            mbar_expect_tx(BAR(B_FULL + s2), SLOT);
+            tma_load_2d(sbase + OFF_RING + s2 * SLOT, &maps.wqk, col, 0, BAR(B_FULL + s2));
+          };
+          load_qk(6, 0);
+          load_qk(7, 64);
           load_item(8, &maps.wqkv, 0, 256, 64, 256);
           DBG_T(2, it, 5);
         }
@@ -255,7 +282,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   } else if (warp == W_MMA) {
     // ================================================== MMA issuer ==================================================
     if (lane == 0) {
-      const uint32_t idesc128 = umma_idesc_f16(TM, 128), idesc64 = umma_idesc_f16(TM, 64);
+      const uint32_t idesc128 = umma_idesc_f16(TM, 128), idesc256 = umma_idesc_f16(TM, 256);
       const u64 dA = umma_desc_sw128(sbase + OFF_A), dB0 = umma_desc_sw128(sbase + OFF_B), dC = umma_desc_sw128(sbase + OFF_C);
       const u64 dR = umma_desc_sw128(sbase + OFF_RING);
       int it = 0;
@@ -265,7 +292,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         auto slot = [&](int j) { return dR + (u64)(((k0 + j) % 3) * (SLOT >> 4)); };   // descriptor of ring item j
         auto wait_full = [&](int j) {
           const int kk = k0 + j;
-          mbar_wait(BAR(B_FULL + kk % 3), (uint32_t)((kk / 3) & 1));
+          mbar_spin(BAR(B_FULL + kk % 3), (uint32_t)((kk / 3) & 1));
         };
         auto release = [&](int j) { umma_commit(BAR(B_EMPTY + (k0 + j) % 3)); };
         // ---- GEMM1: acc1 = att . Wo^T
@@ -274,66 +301,69 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         wait_full(1);
         tc_fence_after();
         DBG_T(1, it, 1);
-        mma_steps(tmem, slot(0), slot(1), 8, idesc128, false);
+        mma_steps<8, false>(tmem, slot(0), slot(1), idesc128);
         umma_commit(BAR(B_ACC1));
         release(0);
         release(1);
         DBG_T(1, it, 2);
-        // ---- GEMM2 (N chunks of 64) interleaved with GEMM3 (K chunks of 64)
-        mbar_wait(BAR(B_X1), par);
+        // ---- GEMM2: two N = 128 chunks (W1 rows 0..127 / 128..255) into acc2 buffers 0 / 1
+        mbar_spin(BAR(B_X1), par);
         tc_fence_after();
         DBG_T(1, it, 3);
-        auto g2 = [&](int c) {
-          if (c == 0) wait_full(2);
-          if (c == 2) wait_full(3);
-          mbar_wait(BAR(B_ACC2E + (c & 1)), (uint32_t)(((c >> 1) + 1) & 1));
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          wait_full(2 + j);
+          mbar_spin(BAR(B_ACC2E + j), par ^ 1u);
           tc_fence_after();
-          mma_steps(tmem + 128 + (c & 1) * 64, dA, slot(2 + (c >> 1)) + (u64)((c & 1) * (8192 >> 4)), 8, idesc64, false);
-          umma_commit(BAR(B_ACC2F + (c & 1)));
-          if (c == 1) release(2);
-          if (c == 3) release(3);
-          DBG_T(1, it, 4 + c);
-        };
-        auto g3 = [&](int c) {
+          mma_steps<8, false>(tmem + 128 + j * 128, dA, slot(2 + j), idesc128);
+          umma_commit(BAR(B_ACC2F + j));
+          release(2 + j);
+          DBG_T(1, it, 4 + j);
+        }
+        // ---- GEMM3: K chunks of 64 as the GELU groups deliver them (chunks 0,1 from group 0, 2,3 from group 1)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
           if (c == 0) wait_full(4);
           if (c == 2) wait_full(5);
-          mbar_wait(BAR(B_HIDF + (c & 1)), (uint32_t)((c >> 1) & 1));
+          mbar_spin(BAR(B_HIDF + (c >> 1)), (uint32_t)(c & 1));
           tc_fence_after();
-          mma_steps(tmem, dB0 + (u64)((c & 1) * (16384 >> 4)), slot(4 + (c >> 1)) + (u64)((c & 1) * (16384 >> 4)), 4, idesc128, c > 0);
-          umma_commit(BAR(B_HIDE + (c & 1)));
+          const u64 ad = dB0 + (u64)((c >> 1) * (16384 >> 4)), bd = slot(4 + (c >> 1)) + (u64)((c & 1) * (16384 >> 4));
+          if (c == 0) mma_steps<4, false>(tmem, ad, bd, idesc128);
+          else mma_steps<4, true>(tmem, ad, bd, idesc128);
+          umma_commit(BAR(B_HIDE + (c >> 1)));
           if (c == 1) release(4);
           if (c == 3) {
             release(5);
             umma_commit(BAR(B_ACC3));
           }
           DBG_T(1, it, 8 + c);
-        };
-        g2(0);
-        g2(1);
-        g3(0);
-        g2(2);
-        g3(1);
-        g2(3);
-        g3(2);
-        g3(3);
+        }
         // ---- LN2 done: acc3 / x1 have been read, (y+pos | y) operands are in C
-        mbar_wait(BAR(B_YFULL), par);
+        mbar_spin(BAR(B_YFULL), par);
         tc_fence_after();
         DBG_T(1, it, 12);
         if (!tail) mbar_arrive(BAR(B_CFREE));   // residual consumed and the LN2 statistics exchange (which lives in C) is over
         if (tail) {
-#pragma unroll 1
-          for (int nt = 0; nt < 3; nt++) {
-            wait_full(6 + nt);
-            mbar_wait(BAR(B_QKVE + nt), par ^ 1u);
-            tc_fence_after();
-            const uint32_t dcol = nt == 0 ? 384u : (nt == 1 ? 128u : 256u);
-            mma_steps(tmem + dcol, dC + (u64)(nt < 2 ? 0 : (32768 >> 4)), slot(6 + nt), 8, idesc128, false);
-            umma_commit(BAR(B_QKVF + nt));
-            release(6 + nt);
-            DBG_T(1, it, 13 + nt);
-          }
+          // q|k = (y + pos) . [Wq; Wk]^T as one N = 256 GEMM into TMEM [128, 384): B K-chunk kc is ring item 6 + kc
+          wait_full(6);
+          wait_full(7);
+          mbar_spin(BAR(B_QKVE + 0), par ^ 1u);
+          tc_fence_after();
+          mma_steps<4, false>(tmem + 128, dC, slot(6), idesc256);
+          mma_steps<4, true>(tmem + 128, dC + 1024, slot(7), idesc256);
+          umma_commit(BAR(B_QKVF + 0));
+          release(6);
+          release(7);
+          DBG_T(1, it, 13);
+          // v = y . Wv^T into TMEM [384, 512)
+          wait_full(8);
+          mbar_spin(BAR(B_QKVE + 1), par ^ 1u);
+          tc_fence_after();
+          mma_steps<8, false>(tmem + 384, dC + (u64)(32768 >> 4), slot(8), idesc128);
+          umma_commit(BAR(B_QKVF + 1));
+          release(8);
           umma_commit(BAR(B_CFREE));
+          DBG_T(1, it, 14);
         }
       }
     }
@@ -455,7 +485,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           up2u(a, xo[4 * q], xo[4 * q + 1]);
           up2u(b, xo[4 * q + 2], xo[4 * q + 3]);
         }
-        tmem_st32u(tlane + 256 + c0, xo);   // fp32 x1 stays in TMEM for the second residual
+        tmem_st32u(tlane + 384 + c0, xo);   // fp32 x1 stays in TMEM for the second residual
         if (it > 0) {                       // the previous tile's v chunk has left A
           mbar_wait(BAR(B_FREEA), (uint32_t)(nA & 1));
           nA++;
@@ -472,28 +502,33 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
       if (lane == 0) mbar_arrive(BAR(B_X1));
       DBG_E(4);
 
-      // ---------------- epilogue 2: hidden chunk c = GELU(acc2 chunk + b1) -> fp16 K-chunk of GEMM3's A operand in B ----------------
-      // group ge owns chunks ge and ge + 2 (accumulator buffer ge, hidden buffer ge); a thread covers 32 of the chunk's 64 columns
+      // ---------------- epilogue 2: hidden K-chunk = GELU(acc2 + b1) -> fp16 K-chunk of GEMM3's A operand in B ----------------
+      // group ge owns accumulator chunk ge (hidden columns [128 ge, 128 ge + 128)) and hidden buffer ge: it delivers K-chunks
+      // 2 ge and 2 ge + 1 one after the other; a thread covers 32 of a K-chunk's 64 columns
       if (it > 0) {   // the previous tile's k chunk has left B
         mbar_wait(BAR(B_FREEB), (uint32_t)(nB & 1));
         nB++;
       }
 #pragma unroll 1
       for (int u = 0; u < 2; u++) {
-        const int c = ge + 2 * u;
+        const int c = 2 * ge + u;
         float4 b4[8];
         const float4* bp = reinterpret_cast<const float4*>(g.b1 + c * 64 + hf * 32);
 #pragma unroll
         for (int q = 0; q < 8; q++) b4[q] = __ldg(bp + q);
-        mbar_wait(BAR(B_ACC2F + ge), (uint32_t)u);
-        tc_fence_after();
+        if (u == 0) {
+          mbar_wait(BAR(B_ACC2F + ge), par);
+          tc_fence_after();
+        }
         DBG_E(5 + u);
         uint32_t v[32];
-        tmem_ld32u(tlane + 128 + ge * 64 + hf * 32, v);
+        tmem_ld32u(tlane + 128 + ge * 128 + u * 64 + hf * 32, v);
         tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_ACC2E + ge));
+        if (u == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_ACC2E + ge));
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -524,7 +559,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         DBG_E(9);
         uint32_t v[32], r[32];
         tmem_ld32u(tlane + c0, v);
-        tmem_ld32u(tlane + 256 + c0, r);
+        tmem_ld32u(tlane + 384 + c0, r);
         tmem_wait_ld();
         u64 sum2 = 0ull, sq2 = 0ull;
 #pragma unroll
@@ -556,16 +591,18 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
         const u64 rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
         named_bar_sync(2 + qd, 128);   // every statistic of this quadrant has been read: C may now receive the operands
+        // (global loads are kept out of the loops that store to shared memory: the compiler will not move them across the stores)
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float4 e4 = __ldg(reinterpret_cast<const float4*>(g.be2 + c0) + q);
-          const u64 a = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
-          const u64 b = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
-          t2[2 * q] = a;
-          t2[2 * q + 1] = b;
+          t2[2 * q] = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
+          t2[2 * q + 1] = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
           uint4 o;
-          up2u(a, o.x, o.y);
-          up2u(b, o.z, o.w);
+          up2u(t2[2 * q], o.x, o.y);
+          up2u(t2[2 * q + 1], o.z, o.w);
           *reinterpret_cast<uint4*>(rowA + cq * 16384 + (((uint32_t)q ^ sw) << 4)) = o;   // y staging spans A | B (4 boxes of 32 columns)
         }
       }
@@ -577,25 +614,32 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)(has_pos ? axis : 0) * g.pos_maxw + (has_pos ? cv : 0)) * g.posL +
                                                            (has_pos ? c0 - axis * g.posL : 0));
         const int kc = cq >> 1, j0 = (cq & 1) * 4;
+        uint32_t yp[16];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          float4 p4 = __ldg(tp + q);
+          if (!has_pos) p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          yp[2 * q] = cvt_h2(add2(t2[2 * q], pk2(p4.x, p4.y)));
+          yp[2 * q + 1] = cvt_h2(add2(t2[2 * q + 1], pk2(p4.z, p4.w)));
+        }
+        if (tid == 0 && g.dbg && it < 2) g.dbg[(((size_t)blockIdx.x * 3 + 0) * 2 + it) * 32 + 19] = clock64() + (yp[15] == 0x12345678u);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          float4 p0 = __ldg(tp + 2 * q), p1 = __ldg(tp + 2 * q + 1);
-          if (!has_pos) p0 = p1 = make_float4(0.f, 0.f, 0.f, 0.f);
           uint8_t* dst = rowC + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4);
-          *reinterpret_cast<int4*>(dst) =
-              make_int4((int)cvt_h2(add2(t2[4 * q], pk2(p0.x, p0.y))), (int)cvt_h2(add2(t2[4 * q + 1], pk2(p0.z, p0.w))),
-                        (int)cvt_h2(add2(t2[4 * q + 2], pk2(p1.x, p1.y))), (int)cvt_h2(add2(t2[4 * q + 3], pk2(p1.z, p1.w))));
+          *reinterpret_cast<int4*>(dst) = make_int4((int)yp[4 * q], (int)yp[4 * q + 1], (int)yp[4 * q + 2], (int)yp[4 * q + 3]);
           *reinterpret_cast<int4*>(dst + 32768) =
               make_int4((int)cvt_h2(t2[4 * q]), (int)cvt_h2(t2[4 * q + 1]), (int)cvt_h2(t2[4 * q + 2]), (int)cvt_h2(t2[4 * q + 3]));
         }
       }
+      DBG_E(20);
       fence_async_smem();
+      DBG_E(21);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_YFULL));
       DBG_E(12);
 
-      // ---------------- epilogue 4: q | k | v chunk + bias -> fp16 staging (q, v in A; k in B) -> TMA store (warp 18) ----------------
+      // ---------------- epilogue 4: q | k | v + bias -> fp16 staging (q, v in A; k in B) -> TMA store (warp 18) ----------------
       if (tail) {
 #pragma unroll 1
         for (int nt = 0; nt < 3; nt++) {
@@ -603,15 +647,19 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           const float4* bp = reinterpret_cast<const float4*>(g.bqkv + nt * 128 + c0);
 #pragma unroll
           for (int q = 0; q < 8; q++) b4[q] = __ldg(bp + q);
-          mbar_wait(BAR(B_QKVF + nt), par);
-          tc_fence_after();
+          if (nt != 1) {   // q|k retire together (one N = 256 GEMM), v on its own
+            mbar_wait(BAR(B_QKVF + (nt >> 1)), par);
+            tc_fence_after();
+          }
           DBG_E(13 + nt);
           uint32_t v[32];
-          tmem_ld32u(tlane + (nt == 0 ? 384 : (nt == 1 ? 128 : 256)) + c0, v);
+          tmem_ld32u(tlane + 128 + nt * 128 + c0, v);
           tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_QKVE + nt));
+          if (nt != 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_QKVE + (nt >> 1)));
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 8; q++) {
@@ -666,6 +714,7 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
   rc |= tmap_2d_sw128(&maps.w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L->lin2_w_f16, 256, 128, 512, 64, 128);
   if (tail) {
     rc |= tmap_2d_sw128(&maps.wqkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next->in_proj_w_f16, 128, 384, 256, 64, 128);
+    rc |= tmap_2d_sw128(&maps.wqk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next->in_proj_w_f16, 128, 256, 256, 64, 256);
     rc |= tmap_2d_sw128(&maps.qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next_qkv, 384, (uint64_t)n_cap, 768, 64, 128);
     g.has_tail = 1;
     g.bqkv = next->in_proj_b;
@@ -712,7 +761,7 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
         for (int role = 0; role < 3; role++)
           for (int it = 0; it < 2; it++) {
             printf("[chain2 dbg] cta %3d %s tile %d:", cta, roles[role], it);
-            for (int e = 0; e < 20; e++) {
+            for (int e = 0; e < 22; e++) {
               long long v = h[(((size_t)cta * 3 + role) * 2 + it) * 32 + e];
               printf(" %d:%lld", e, v ? v - t0 : -1);
             }
