@@ -165,74 +165,142 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 
 // ------------------------------------------------------------------------------------------------
+
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t ex2_h2(float a, float b) {
+  uint32_t h, r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
 
-// v4: batched ragged attention.  One CTA stages a *batch* of consecutive whole windows (<= 144 tokens, built by
-// win_batch_kernel) - K and V rows of the batch are one contiguous block in slot order, copied with cp.async - and its 8
-// warps sweep the batch's (16-query tile, head) items out of shared memory: K fragments by 32-bit LDS (conflict-free
-// 272-byte pitch), V^T fragments by ldmatrix.trans, two-pass softmax with QK^T recomputed (no S array in registers).
-// Compared with one-window-per-CTA this amortises the staging round trip and the barrier over ~5 windows, and compared
-// with the register-resident warp kernel every inner-loop operand comes from shared memory instead of L2.
+// ------------------------------------------------------------------------------------------------
+// v5: batched ragged attention on mma.sync tiles, single-pass softmax.
+// One CTA stages a *batch* of consecutive whole windows (<= 144 tokens each, built by win_batch_kernel): the K and V columns
+// of its NHL heads, gathered row by row through the window permutation with cp.async (q|k|v and the output live in flat token
+// order, SURVEY 8a B6: flat2window / window2flat never materialise).  Its 8 warps sweep the batch's 16-query tiles; a tile is
+// processed for all NHL heads in turn.  Per (tile, head) the window is walked in chunks of <= 64 keys (one chunk for most
+// windows, up to three for the 65..144-token ones): S = Q K^T of the chunk stays in REGISTERS (KT key tiles of 8, fully
+// unrolled, no inner branches; K fragments by ldmatrix.x4), row maxima by shuffles, P = 2^(scale' S - max) computed two at a
+// time on the half2 MUFU path - which is exactly the fp16 A fragment of P V - V^T fragments by ldmatrix.trans, and the row
+// sums come out of the tensor core as well (a constant "ones" B fragment).  A further chunk rescales the running accumulators
+// by 2^(old max - new max).  ~0.15 instructions per score; the two-pass form this replaces needed ~0.7.
 // ------------------------------------------------------------------------------------------------
 #define ATT_CHUNK 112
 #define ATT_BT 256   // >= ATT_CHUNK - 1 + 144 rows per batch
+#define ATT_KCHUNK 64
 
-// NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which halves
+// m0 / m1: running row maxima in log2 units; o / ol: running numerators / denominators.  kaddr / vaddr: this lane's ldmatrix
+// row addresses for the chunk's first key (shared-memory byte addresses); n = keys of the window inside this chunk
+// (8 * KT - 16 < n <= 8 * KT, so only the last two key tiles can be partial).
+template <int KT, int LD>
+__device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, uint32_t vaddr, int n, int t4, bool ones_lane, float sl2,
+                                           bool first, float& m0, float& m1, float (*o)[4], float* ol) {
+  float s[KT][4];
+#pragma unroll
+  for (int jj = 0; jj < KT / 2; jj++) {
+    uint32_t kf[4];
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(kf[0]), "=r"(kf[1]), "=r"(kf[2]), "=r"(kf[3])
+                 : "r"(kaddr + (uint32_t)(jj * 16 * LD * 2)));
+    s[2 * jj][0] = s[2 * jj][1] = s[2 * jj][2] = s[2 * jj][3] = 0.f;
+    s[2 * jj + 1][0] = s[2 * jj + 1][1] = s[2 * jj + 1][2] = s[2 * jj + 1][3] = 0.f;
+    mma_f16_16816(s[2 * jj], qa, kf[0], kf[1]);
+    mma_f16_16816(s[2 * jj + 1], qa, kf[2], kf[3]);
+  }
+  // columns past the window hold other windows' keys or zero fill: -inf (only the last two tiles can be affected)
+#pragma unroll
+  for (int j = KT - 2; j < KT; j++) {
+    const int c0 = j * 8 + 2 * t4;
+    if (c0 >= n) s[j][0] = s[j][2] = -INFINITY;
+    if (c0 + 1 >= n) s[j][1] = s[j][3] = -INFINITY;
+  }
+  float c0m = fmaxf(s[0][0], s[0][1]), c1m = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+  for (int j = 1; j < KT; j++) {
+    c0m = fmaxf(c0m, fmaxf(s[j][0], s[j][1]));
+    c1m = fmaxf(c1m, fmaxf(s[j][2], s[j][3]));
+  }
+  c0m = fmaxf(c0m, __shfl_xor_sync(0xffffffffu, c0m, 1));
+  c0m = fmaxf(c0m, __shfl_xor_sync(0xffffffffu, c0m, 2));
+  c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 1));
+  c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 2));
+  const float n0 = fmaxf(m0, c0m * sl2), n1 = fmaxf(m1, c1m * sl2);
+  if (!first) {   // rescale what the earlier chunks accumulated (warp-uniform)
+    const float f0 = fast_ex2(m0 - n0), f1 = fast_ex2(m1 - n1);
+    o[0][0] *= f0, o[0][1] *= f0, o[1][0] *= f0, o[1][1] *= f0, ol[0] *= f0, ol[1] *= f0;
+    o[0][2] *= f1, o[0][3] *= f1, o[1][2] *= f1, o[1][3] *= f1, ol[2] *= f1, ol[3] *= f1;
+  }
+  m0 = n0;
+  m1 = n1;
+  const uint32_t ones = ones_lane ? 0x3C003C00u : 0u;   // B fragment whose column 0 is 1: the row sums of P
+#pragma unroll
+  for (int kc = 0; kc < KT / 2; kc++) {
+    uint32_t pa[4];
+    pa[0] = ex2_h2(fmaf(s[2 * kc][0], sl2, -n0), fmaf(s[2 * kc][1], sl2, -n0));
+    pa[1] = ex2_h2(fmaf(s[2 * kc][2], sl2, -n1), fmaf(s[2 * kc][3], sl2, -n1));
+    pa[2] = ex2_h2(fmaf(s[2 * kc + 1][0], sl2, -n0), fmaf(s[2 * kc + 1][1], sl2, -n0));
+    pa[3] = ex2_h2(fmaf(s[2 * kc + 1][2], sl2, -n1), fmaf(s[2 * kc + 1][3], sl2, -n1));
+    uint32_t vb[4];
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
+                 : "r"(vaddr + (uint32_t)(kc * 16 * LD * 2)));
+    mma_f16_16816(o[0], pa, vb[0], vb[1]);
+    mma_f16_16816(o[1], pa, vb[2], vb[3]);
+    mma_f16_16816(ol, pa, ones, ones);
+  }
+}
+
+// NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which shortens
 // the critical path of batches that hold one big window and raises the number of resident warps per SM.
 template <int NHL>
-static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half* __restrict__ qkv,
-                                                                    const int32_t* __restrict__ counters,
-                                                                    const int32_t* __restrict__ win_offsets,
-                                                                    const int32_t* __restrict__ win_batch,
-                                                                    const int32_t* __restrict__ tok_perm, float scale,
-                                                                    __half* __restrict__ out) {
+static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __half* __restrict__ qkv,
+                                                                       const int32_t* __restrict__ counters,
+                                                                       const int32_t* __restrict__ win_offsets,
+                                                                       const int32_t* __restrict__ win_batch,
+                                                                       const int32_t* __restrict__ tok_perm, float scale,
+                                                                       __half* __restrict__ out, long long* dbg) {
   pdl_wait();
   pdl_launch();
+  int dbg_n = 0;
   constexpr int D = 128, DH = 16, LD = NHL * 16 + 8, HSPLIT = 8 / NHL, PPR = NHL * 2;  // PPR: 16-byte pieces per row per matrix
+  constexpr int NROW = ATT_BT + 16;
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* sK = reinterpret_cast<__half*>(att_smem);
-  __half* sV = sK + (ATT_BT + 16) * LD;
-  __shared__ int sTileRow[ATT_BT];   // first local row of q-tile k
-  __shared__ int sTileKb[ATT_BT];    // local key range of its window
-  __shared__ int sTileKe[ATT_BT];
+  __half* sV = sK + NROW * LD;
+  __shared__ int sTok[NROW];           // token row of local slot r, -1 beyond the batch
+  __shared__ short sTileRow[ATT_BT];   // first local row of q-tile k
+  __shared__ short sTileKb[ATT_BT];    // local key range of its window
+  __shared__ short sTileKe[ATT_BT];
   __shared__ int sNumTiles;
-  __shared__ int sTok[ATT_BT];       // token row of local slot r (q|k|v rows and output rows are in flat token order)
   // batch b = the windows whose first slot lies in [b*ATT_CHUNK, (b+1)*ATT_CHUNK) (win_batch_kernel, csrc/window.cu); it holds
   // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows
   const int nbatch = counters[17];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 2, t4 = lane & 3;
+  const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV);
+  // this lane's ldmatrix row offsets (bytes) inside a 16-key block: K fragments (non-transposed) / V^T fragments (.trans)
+  const uint32_t klane = (uint32_t)((((lane & 7) + ((lane >> 4) & 1) * 8) * LD + ((lane >> 3) & 1) * 8) * 2);
+  const uint32_t vlane = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8) * 2);
+  const float sl2 = scale * 1.4426950408889634f;   // exp(x) = 2^(x log2 e)
+  // staging role of this thread: piece c of a row (K pieces first, then V), rows tid / (2 PPR), + 256 / (2 PPR), ...
+  const int sc = threadIdx.x % (2 * PPR), sr0 = threadIdx.x / (2 * PPR);
+  const bool s_isv = sc >= PPR;
+  const int s_pc = s_isv ? sc - PPR : sc;
   for (int unit = blockIdx.x; unit < nbatch * HSPLIT; unit += gridDim.x) {
     const int b = unit / HSPLIT, hs = unit % HSPLIT;
     const int wb = win_batch[b], we = win_batch[b + 1];
     if (wb == we) continue;  // a big window covers this chunk entirely (uniform per CTA)
     const int s0 = win_offsets[wb], s1 = win_offsets[we];
     const int nrow = min(s1 - s0, ATT_BT);
-    const int npad = (nrow + 15) & ~15;
+    const int nfill = min(((nrow + 15) & ~15) + 16, NROW);  // key chunks may run up to 15 rows past the batch: keep them finite (0)
+    if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 0] = clock64();
     __syncthreads();  // previous batch fully consumed
-    for (int r = threadIdx.x; r < nrow; r += blockDim.x) sTok[r] = tok_perm[s0 + r];
-    __syncthreads();
-    // stage K | V rows (gathered through the window permutation): 16-byte pieces with cp.async
-    {
-      const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV);
-      const int nfill = min(npad + 16, ATT_BT + 16);  // key chunks may run up to 15 rows past the batch: keep them finite (0)
-      for (int idx = threadIdx.x; idx < nfill * 2 * PPR; idx += blockDim.x) {
-        int r = idx / (2 * PPR), c = idx % (2 * PPR);
-        const bool isv = c >= PPR;
-        const int pc = isv ? c - PPR : c;
-        uint32_t dst = (isv ? v0 : k0) + (uint32_t)(r * LD + pc * 8) * 2;
-        if (r < nrow) {
-          const __half* src = qkv + (size_t)sTok[r] * 3 * D + (isv ? 2 * D : D) + hs * NHL * DH + pc * 8;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-        } else {
-          *reinterpret_cast<int4*>((isv ? sV : sK) + r * LD + pc * 8) = make_int4(0, 0, 0, 0);
-        }
-      }
-    }
+    for (int r = threadIdx.x; r < nfill; r += blockDim.x) sTok[r] = r < nrow ? tok_perm[s0 + r] : -1;
     // q-tile table (warp 0): windows of the batch -> tiles
     if (warp == 0) {
       int cnt = 0;
@@ -247,127 +315,84 @@ static __global__ void __launch_bounds__(256) win_attn_batch_kernel(const __half
         int nt = (n + 15) >> 4;
         int x = nt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int y = __shfl_up_sync(0xffffffffu, x, o);
-          if (lane >= o) x += y;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+          int y = __shfl_up_sync(0xffffffffu, x, o2);
+          if (lane >= o2) x += y;
         }
         int base = cnt + x - nt;
         for (int k = 0; k < nt; k++) {
           if (base + k < ATT_BT) {
-            sTileRow[base + k] = kb + 16 * k;
-            sTileKb[base + k] = kb;
-            sTileKe[base + k] = kb + n;
+            sTileRow[base + k] = (short)(kb + 16 * k);
+            sTileKb[base + k] = (short)kb;
+            sTileKe[base + k] = (short)(kb + n);
           }
         }
         cnt += __shfl_sync(0xffffffffu, x, 31);
       }
       if (lane == 0) sNumTiles = min(cnt, ATT_BT);
     }
+    __syncthreads();
+    // stage K | V rows (gathered through the window permutation): 16-byte pieces with cp.async, zero fill beyond the batch
+    {
+      const __half* gsrc = qkv + (s_isv ? 2 * D : D) + (hs * NHL) * DH + s_pc * 8;
+      const uint32_t dst0 = (s_isv ? v0 : k0) + (uint32_t)(s_pc * 16);
+      for (int r = sr0; r < nfill; r += 256 / (2 * PPR)) {
+        const int tok = sTok[r];
+        const uint32_t dst = dst0 + (uint32_t)(r * LD * 2);
+        if (tok >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc + (size_t)tok * (3 * D)) : "memory");
+        else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(dst), "r"(0) : "memory");
+      }
+    }
+    if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 1] = clock64();
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
-    const int nitems = sNumTiles * NHL;
-    for (int item = warp; item < nitems; item += 8) {
-      const int tk = item / NHL, hl = item % NHL, h = hs * NHL + hl;
+    if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 2] = clock64();
+    const int ntiles = sNumTiles;
+    for (int tk = warp; tk < ntiles; tk += 8) {
       const int row = sTileRow[tk], kb = sTileKb[tk], ke = sTileKe[tk];
       const int n = ke - kb;
       const int r0 = row + g4, r1 = r0 + 8;
-      uint32_t qa[4] = {0u, 0u, 0u, 0u};
-      const int tok0 = r0 < ke ? sTok[r0] : 0, tok1 = r1 < ke ? sTok[r1] : 0;
-      if (r0 < ke) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok0 * 3 * D + h * DH);
-        qa[0] = qp[t4];
-        qa[2] = qp[t4 + 4];
-      }
-      if (r1 < ke) {
-        const uint32_t* qp = reinterpret_cast<const uint32_t*>(qkv + (size_t)tok1 * 3 * D + h * DH);
-        qa[1] = qp[t4];
-        qa[3] = qp[t4 + 4];
-      }
-      const int nkt = (n + 7) >> 3;
-      const __half* kbase = sK + (size_t)kb * LD + hl * DH;
-      // pass 1: row maxima
-      float m0 = -INFINITY, m1 = -INFINITY;
-      for (int j = 0; j < nkt; j++) {
-        const uint32_t* kp = reinterpret_cast<const uint32_t*>(kbase + (j * 8 + g4) * LD);
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16_16816(s, qa, kp[t4], kp[t4 + 4]);
-        if (j * 8 + 8 <= n) {  // warp-uniform: a full step
-          m0 = fmaxf(m0, fmaxf(s[0], s[1]));
-          m1 = fmaxf(m1, fmaxf(s[2], s[3]));
-        } else {
-          const int c0 = j * 8 + 2 * t4;
-          if (c0 < n) {
-            m0 = fmaxf(m0, s[0]);
-            m1 = fmaxf(m1, s[2]);
-          }
-          if (c0 + 1 < n) {
-            m0 = fmaxf(m0, s[1]);
-            m1 = fmaxf(m1, s[3]);
-          }
+      const int tok0 = r0 < ke ? sTok[r0] : -1, tok1 = r1 < ke ? sTok[r1] : -1;
+      const uint32_t kwin = k0 + (uint32_t)(kb * LD * 2) + klane, vwin = v0 + (uint32_t)(kb * LD * 2) + vlane;
+      const uint32_t* qp0 = reinterpret_cast<const uint32_t*>(qkv + (size_t)max(tok0, 0) * (3 * D) + hs * NHL * DH);
+      const uint32_t* qp1 = reinterpret_cast<const uint32_t*>(qkv + (size_t)max(tok1, 0) * (3 * D) + hs * NHL * DH);
+      uint32_t* op0 = reinterpret_cast<uint32_t*>(out + (size_t)max(tok0, 0) * D + hs * NHL * DH);
+      uint32_t* op1 = reinterpret_cast<uint32_t*>(out + (size_t)max(tok1, 0) * D + hs * NHL * DH);
+#pragma unroll 1
+      for (int hl = 0; hl < NHL; hl++) {
+        uint32_t qa[4];
+        qa[0] = tok0 >= 0 ? qp0[hl * 8 + t4] : 0u;
+        qa[2] = tok0 >= 0 ? qp0[hl * 8 + t4 + 4] : 0u;
+        qa[1] = tok1 >= 0 ? qp1[hl * 8 + t4] : 0u;
+        qa[3] = tok1 >= 0 ? qp1[hl * 8 + t4 + 4] : 0u;
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float ol[4] = {0.f, 0.f, 0.f, 0.f};
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+        for (int off = 0; off < n; off += ATT_KCHUNK) {
+          const int rem = n - off;   // warp-uniform
+          const uint32_t ka = kwin + (uint32_t)((off * LD + hl * DH) * 2), va = vwin + (uint32_t)((off * LD + hl * DH) * 2);
+          if (rem > 48) attn_chunk<8, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+          else if (rem > 32) attn_chunk<6, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+          else if (rem > 16) attn_chunk<4, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+          else attn_chunk<2, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+        }
+        const float l0 = __shfl_sync(0xffffffffu, ol[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, ol[2], lane & ~3);
+        if (tok0 >= 0) {
+          const float i0 = __fdividef(1.0f, l0);
+          op0[hl * 8 + t4] = pack2_f16(o[0][0] * i0, o[0][1] * i0);
+          op0[hl * 8 + t4 + 4] = pack2_f16(o[1][0] * i0, o[1][1] * i0);
+        }
+        if (tok1 >= 0) {
+          const float i1 = __fdividef(1.0f, l1);
+          op1[hl * 8 + t4] = pack2_f16(o[0][2] * i1, o[0][3] * i1);
+          op1[hl * 8 + t4 + 4] = pack2_f16(o[1][2] * i1, o[1][3] * i1);
         }
       }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      // exp(x) = 2^(x log2 e): fold log2 e into the scale so that every probability is one FFMA + one MUFU.EX2
-      const float sl2 = scale * 1.4426950408889634f;
-      const float ms0 = m0 * sl2, ms1 = m1 * sl2;
-      // pass 2: full 16-key chunks need no masking; only the last (partial) chunk compares column indices with n
-      float l0 = 0.f, l1 = 0.f;
-      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      const int nkc = (n + 15) >> 4;
-      const int nfull = n >> 4;
-      for (int kc = 0; kc < nkc; kc++) {
-        const uint32_t* kp0 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + g4) * LD);
-        const uint32_t* kp1 = reinterpret_cast<const uint32_t*>(kbase + (kc * 16 + 8 + g4) * LD);
-        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16_16816(sa, qa, kp0[t4], kp0[t4 + 4]);
-        mma_f16_16816(sb, qa, kp1[t4], kp1[t4 + 4]);   // rows beyond the window are other windows' keys or zero padding: masked below
-        float p[8];
-        p[0] = fast_ex2(fmaf(sa[0], sl2, -ms0));
-        p[1] = fast_ex2(fmaf(sa[1], sl2, -ms0));
-        p[2] = fast_ex2(fmaf(sa[2], sl2, -ms1));
-        p[3] = fast_ex2(fmaf(sa[3], sl2, -ms1));
-        p[4] = fast_ex2(fmaf(sb[0], sl2, -ms0));
-        p[5] = fast_ex2(fmaf(sb[1], sl2, -ms0));
-        p[6] = fast_ex2(fmaf(sb[2], sl2, -ms1));
-        p[7] = fast_ex2(fmaf(sb[3], sl2, -ms1));
-        if (kc >= nfull) {  // warp-uniform: the tail chunk
-          const int c0 = kc * 16 + 2 * t4;
-          if (c0 >= n) p[0] = p[2] = 0.f;
-          if (c0 + 1 >= n) p[1] = p[3] = 0.f;
-          if (c0 + 8 >= n) p[4] = p[6] = 0.f;
-          if (c0 + 9 >= n) p[5] = p[7] = 0.f;
-        }
-        l0 += (p[0] + p[1]) + (p[4] + p[5]);
-        l1 += (p[2] + p[3]) + (p[6] + p[7]);
-        uint32_t pa[4] = {pack2_f16(p[0], p[1]), pack2_f16(p[2], p[3]), pack2_f16(p[4], p[5]), pack2_f16(p[6], p[7])};
-        const __half* vrow = sV + (size_t)(kb + kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + hl * DH + (lane >> 4) * 8;
-        uint32_t vb[4];
-        uint32_t saddr = (uint32_t)__cvta_generic_to_shared(vrow);
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                     : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
-                     : "r"(saddr));
-        mma_f16_16816(o[0], pa, vb[0], vb[1]);
-        mma_f16_16816(o[1], pa, vb[2], vb[3]);
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      if (r0 < ke) {
-        const float i0 = __fdividef(1.0f, l0);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok0 * D + h * DH);
-        op[t4] = pack2_f16(o[0][0] * i0, o[0][1] * i0);
-        op[t4 + 4] = pack2_f16(o[1][0] * i0, o[1][1] * i0);
-      }
-      if (r1 < ke) {
-        const float i1 = __fdividef(1.0f, l1);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)tok1 * D + h * DH);
-        op[t4] = pack2_f16(o[0][2] * i1, o[0][3] * i1);
-        op[t4 + 4] = pack2_f16(o[1][2] * i1, o[1][3] * i1);
-      }
+    }
+    if (dbg && threadIdx.x == 0 && dbg_n < 4) {
+      dbg[(blockIdx.x * 4 + dbg_n) * 4 + 3] = clock64() * 1000 + ntiles;
+      dbg_n++;
     }
   }
 }
@@ -383,7 +408,34 @@ static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const i
     const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)
     grid_mult = e && atoi(e) > 0 ? atoi(e) : 6;
   }
-  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(c->num_sms * grid_mult), dim3(256), smem, c->stream, qkv, counters, win_offsets,
-                         win_batch, tok_perm, 0.25f, out));
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("SSTB200_ATT_DBG") ? atoi(getenv("SSTB200_ATT_DBG")) : 0;
+  static long long* dbg_buf = nullptr;
+  const int grid = c->num_sms * grid_mult;
+  if (dbg_on && !dbg_buf) CUDA_TRY(c, cudaMalloc(&dbg_buf, (size_t)4096 * 16 * 8));
+  if (dbg_on) CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, (size_t)grid * 16 * 8, c->stream));
+  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch, tok_perm,
+                         0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
+  if (dbg_on) {
+    static int dumps = 0;
+    std::vector<long long> h((size_t)grid * 16);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    if (dumps++ % dbg_on == 0) {
+      long long tmin = 1LL << 62;
+      for (int b = 0; b < grid; b++) if (h[b * 16]) tmin = std::min(tmin, h[b * 16]);
+      for (int b : {0, 1, 147, 148, 300, 443, 444, 600, 887}) {
+        if (b >= grid) continue;
+        printf("[attn dbg] cta %3d:", b);
+        for (int u = 0; u < 4; u++) {
+          const long long* e = &h[(b * 4 + u) * 4];
+          if (!e[0]) continue;
+          printf("  unit%d start %lld staged+%lld sync+%lld done+%lld tiles %lld |", u, e[0] - tmin, e[1] - e[0], e[2] - e[0], e[3] / 1000 - e[0], e[3] % 1000);
+        }
+        printf("\n");
+      }
+      fflush(stdout);
+    }
+  }
   return SSTB_OK;
 }

@@ -538,12 +538,15 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     int rc = launch_umma<128, 128, PRO_F32, EPI_F16>(c, g, 3);
     if (rc) return rc;
   }
+  static int skip = -1;   // SSTB200_STACK_SKIP bitmask (timing experiments only): 2 attention, 4 chain
+  if (skip < 0) skip = getenv("SSTB200_STACK_SKIP") ? atoi(getenv("SSTB200_STACK_SKIP")) : 0;
   const float* xin = x;
   for (int l = 0; l < num_layers; l++) {
     const sstb200_sra_plan* P = &plans[l & 1];
-    int rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
+    int rc = (skip & 2) ? 0 : sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
     if (rc) return rc;
     const bool has_next = l + 1 < num_layers;
+    if (skip & 4) continue;
     // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
     rc = sstb_sra_chain2(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
                                 has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);

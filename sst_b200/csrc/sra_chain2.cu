@@ -179,17 +179,7 @@ __device__ __forceinline__ void mma_steps(uint32_t d_tmem, u64 adesc, u64 bdesc,
     else mma1<0>(d_tmem, adesc + ao, bdesc + bo, idesc);
   }
 }
-// hot spin for the single MMA-issuing thread (mbarrier.test_wait does not suspend: the wake-up is immediate)
-__device__ __forceinline__ void mbar_spin(uint32_t saddr, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done)
-                 : "r"(saddr), "r"(parity)
-                 : "memory");
-  } while (!done);
-}
-
+template <bool TAIL>
 __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Args g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -213,14 +203,14 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     tma_prefetch_desc(&maps.wo);
     tma_prefetch_desc(&maps.w1);
     tma_prefetch_desc(&maps.w2);
-    if (g.has_tail) {
+    if (TAIL) {
       tma_prefetch_desc(&maps.wqkv);
       tma_prefetch_desc(&maps.wqk);
     }
   }
   if (warp == W_ST && lane == 0) {
     tma_prefetch_desc(&maps.y);
-    if (g.has_tail) tma_prefetch_desc(&maps.qkv);
+    if (TAIL) tma_prefetch_desc(&maps.qkv);
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -231,7 +221,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   pdl_launch();
   const int M = g.M_dev ? *g.M_dev : g.M_cap;
   const int n_tiles = (M + TM - 1) / TM;
-  const bool tail = g.has_tail != 0;
+  constexpr bool tail = TAIL;
   const int NI = tail ? 9 : 6;   // ring items per tile: att, Wo, W1[0:128], W1[128:256], W2[:,0:128], W2[:,128:256], Wq, Wk, Wv
 
   if (warp == W_TMA) {
@@ -292,7 +282,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         auto slot = [&](int j) { return dR + (u64)(((k0 + j) % 3) * (SLOT >> 4)); };   // descriptor of ring item j
         auto wait_full = [&](int j) {
           const int kk = k0 + j;
-          mbar_spin(BAR(B_FULL + kk % 3), (uint32_t)((kk / 3) & 1));
+          mbar_wait(BAR(B_FULL + kk % 3), (uint32_t)((kk / 3) & 1));
         };
         auto release = [&](int j) { umma_commit(BAR(B_EMPTY + (k0 + j) % 3)); };
         // ---- GEMM1: acc1 = att . Wo^T
@@ -307,13 +297,13 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         release(1);
         DBG_T(1, it, 2);
         // ---- GEMM2: two N = 128 chunks (W1 rows 0..127 / 128..255) into acc2 buffers 0 / 1
-        mbar_spin(BAR(B_X1), par);
+        mbar_wait(BAR(B_X1), par);
         tc_fence_after();
         DBG_T(1, it, 3);
 #pragma unroll
         for (int j = 0; j < 2; j++) {
           wait_full(2 + j);
-          mbar_spin(BAR(B_ACC2E + j), par ^ 1u);
+          mbar_wait(BAR(B_ACC2E + j), par ^ 1u);
           tc_fence_after();
           mma_steps<8, false>(tmem + 128 + j * 128, dA, slot(2 + j), idesc128);
           umma_commit(BAR(B_ACC2F + j));
@@ -325,7 +315,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         for (int c = 0; c < 4; c++) {
           if (c == 0) wait_full(4);
           if (c == 2) wait_full(5);
-          mbar_spin(BAR(B_HIDF + (c >> 1)), (uint32_t)(c & 1));
+          mbar_wait(BAR(B_HIDF + (c >> 1)), (uint32_t)(c & 1));
           tc_fence_after();
           const u64 ad = dB0 + (u64)((c >> 1) * (16384 >> 4)), bd = slot(4 + (c >> 1)) + (u64)((c & 1) * (16384 >> 4));
           if (c == 0) mma_steps<4, false>(tmem, ad, bd, idesc128);
@@ -339,7 +329,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           DBG_T(1, it, 8 + c);
         }
         // ---- LN2 done: acc3 / x1 have been read, (y+pos | y) operands are in C
-        mbar_spin(BAR(B_YFULL), par);
+        mbar_wait(BAR(B_YFULL), par);
         tc_fence_after();
         DBG_T(1, it, 12);
         if (!tail) mbar_arrive(BAR(B_CFREE));   // residual consumed and the LN2 statistics exchange (which lives in C) is over
@@ -347,7 +337,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           // q|k = (y + pos) . [Wq; Wk]^T as one N = 256 GEMM into TMEM [128, 384): B K-chunk kc is ring item 6 + kc
           wait_full(6);
           wait_full(7);
-          mbar_spin(BAR(B_QKVE + 0), par ^ 1u);
+          mbar_wait(BAR(B_QKVE + 0), par ^ 1u);
           tc_fence_after();
           mma_steps<4, false>(tmem + 128, dC, slot(6), idesc256);
           mma_steps<4, true>(tmem + 128, dC + 1024, slot(7), idesc256);
@@ -357,7 +347,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           DBG_T(1, it, 13);
           // v = y . Wv^T into TMEM [384, 512)
           wait_full(8);
-          mbar_spin(BAR(B_QKVE + 1), par ^ 1u);
+          mbar_wait(BAR(B_QKVE + 1), par ^ 1u);
           tc_fence_after();
           mma_steps<8, false>(tmem + 384, dC + (u64)(32768 >> 4), slot(8), idesc128);
           umma_commit(BAR(B_QKVF + 1));
@@ -622,7 +612,6 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           yp[2 * q] = cvt_h2(add2(t2[2 * q], pk2(p4.x, p4.y)));
           yp[2 * q + 1] = cvt_h2(add2(t2[2 * q + 1], pk2(p4.z, p4.w)));
         }
-        if (tid == 0 && g.dbg && it < 2) g.dbg[(((size_t)blockIdx.x * 3 + 0) * 2 + it) * 32 + 19] = clock64() + (yp[15] == 0x12345678u);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           uint8_t* dst = rowC + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4);
@@ -631,9 +620,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
               make_int4((int)cvt_h2(t2[4 * q]), (int)cvt_h2(t2[4 * q + 1]), (int)cvt_h2(t2[4 * q + 2]), (int)cvt_h2(t2[4 * q + 3]));
         }
       }
-      DBG_E(20);
       fence_async_smem();
-      DBG_E(21);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_YFULL));
@@ -735,8 +722,8 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
   g.eps = L->norm_eps;
   g.M_cap = n_cap;
   g.M_dev = n_dev;
-  static SmemAttr sa;
-  CUDA_TRY(c, ensure_smem(c, sa, sra_chain2_kernel, (size_t)SMEM_BYTES));
+  static SmemAttr sa0, sa1;
+  CUDA_TRY(c, tail ? ensure_smem(c, sa1, sra_chain2_kernel<true>, (size_t)SMEM_BYTES) : ensure_smem(c, sa0, sra_chain2_kernel<false>, (size_t)SMEM_BYTES));
   const int tiles_cap = (n_cap + TM - 1) / TM;
   const int grid = c->num_sms < tiles_cap ? c->num_sms : tiles_cap;
   static int dbg_on = -1;
@@ -748,7 +735,8 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
     CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, c->stream));
     g.dbg = dbg_buf;
   }
-  CUDA_TRY(c, launch_pdl(sra_chain2_kernel, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
+  if (tail) CUDA_TRY(c, launch_pdl(sra_chain2_kernel<true>, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
+  else CUDA_TRY(c, launch_pdl(sra_chain2_kernel<false>, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
   if (dbg_on) {
     std::vector<long long> h(dbg_n);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));

@@ -41,13 +41,21 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar_saddr) {
 __device__ __forceinline__ void mbar_init(uint32_t saddr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr), "r"(count) : "memory");
 }
+// try_wait suspends the thread in hardware for a bounded time per attempt; the attempt counter turns a lost arrival
+// (a protocol bug) into a trap - i.e. a CUDA error the caller sees - instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t saddr, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(saddr),
-      "r"(parity)
-      : "memory");
+  uint32_t done = 0, tries = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(done)
+        : "r"(saddr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++tries > (1u << 24)) __trap();
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
