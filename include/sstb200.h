@@ -138,7 +138,8 @@ typedef struct {
   int32_t* tok_perm;       /* [n]   token indices grouped by window, stable order inside */
   int32_t* win_level;      /* [n]   level slot (0..num_levels-1) per window, R valid */
   int32_t* win_rank;       /* [n]   rank of the window among the windows of its level */
-  int32_t* counters;       /* [18]  R, windows per level slot [8], tokens per level slot [8], number of window batches */
+  int32_t* counters;       /* [20]  R, windows per level slot [8], tokens per level slot [8], number of window batches,
+                            *       [18] status bits (bit0 token outside the window grid, bit1 window count not covered), [19] spare */
   int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
   int32_t* win_batch;      /* opt [n+1] batch b = windows [win_batch[b], win_batch[b+1]) whose first slot lies in [112b, 112b+112) */
 } sstb200_window_shift;

@@ -91,6 +91,53 @@ def sst_fixture(R):
     print("sst_small", len(out), "arrays", vf.shape)
 
 
+def vfe_fixture(R):
+    """DynamicVFE alone at a channel pair the fused CUDA kernels are instantiated for (multiples of 32)."""
+    torch.manual_seed(0)
+    pts = torch.cat([O.synth_frame(25, 3000), O.synth_frame(26, 2000)])
+    pts[:, :2] *= 0.3
+    c3 = O.dynamic_voxelize(pts, VS, RNG)
+    coors = torch.cat([torch.nn.functional.pad(c3[:3000], (1, 0), value=0), torch.nn.functional.pad(c3[3000:], (1, 0), value=1)])
+    vfe = R.DynamicVFE(in_channels=3, feat_channels=[32, 64], with_cluster_center=True, with_voxel_center=True, voxel_size=VS,
+                       point_cloud_range=RNG, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)).eval()
+    _rand_norm(vfe, 31)
+    with torch.no_grad():
+        vf, vc = vfe(pts, coors)
+    np.savez_compressed(os.path.join(OUT, "vfe_small.npz"), points=pts.numpy(), coors=coors.numpy(), feats=vf.numpy(), vcoors=vc.numpy(),
+                        **_sd(vfe, "w."))
+    print("vfe_small", vf.shape)
+
+
+def sst_v1_fixture(R):
+    """configs/sst names: SSTInputLayer (v1) + SSTv1 through the unmodified reference classes.  The dense BEV output is stored
+    as its rows at the occupied cells plus its total absolute sum (everything else must be zero)."""
+    torch.manual_seed(0)
+    pts = torch.cat([O.synth_frame(15, 2500), O.synth_frame(16, 1500)])
+    pts[:, :2] *= 0.2
+    c3 = O.dynamic_voxelize(pts, VS, RNG)
+    c4 = torch.cat([torch.nn.functional.pad(c3[:2500], (1, 0), value=0), torch.nn.functional.pad(c3[2500:], (1, 0), value=1)])
+    vc = torch.unique(c4, dim=0).long()
+    g = torch.Generator().manual_seed(21)
+    vf = torch.randn(vc.shape[0], 32, generator=g)
+    il = R.SSTInputLayer(drop_info=(DROP_TRAIN, DROP_TEST), shifts_list=[(0, 0), (6, 6)], window_shape=(12, 12), point_cloud_range=RNG,
+                         voxel_size=VS, shuffle_voxels=False, debug=True).eval()
+    bb = R.SSTv1(d_model=[32] * 2, nhead=[4] * 2, num_blocks=2, dim_feedforward=[64] * 2, output_shape=[468, 468], num_attached_conv=0,
+                 debug=True, drop_info=(DROP_TRAIN, DROP_TEST), pos_temperature=10000, normalize_pos=False, window_shape=(12, 12)).eval()
+    _rand_norm(bb, 14)
+    with torch.no_grad():
+        feat, f2w, info = il(vf, vc)
+        bev = bb((feat, f2w, info))[0]
+    co = info["coors"]
+    rows = bev[co[:, 0], :, co[:, 2], co[:, 3]]
+    out = dict(voxel_feats=vf.numpy(), voxel_coors=vc.numpy(), keep=info["voxel_keep_inds"].numpy(), coors=co.numpy(),
+               bev_rows=rows.numpy(), bev_abs_sum=np.array(bev.abs().double().sum().item()), bev_shape=np.array(bev.shape),
+               **{f"bwi{i}": info[f"batch_win_inds_shift{i}"].numpy() for i in range(2)},
+               **{f"ciw{i}": info[f"coors_in_win_shift{i}"].numpy() for i in range(2)},
+               **{f"lvl{i}": info[f"voxel_drop_level_shift{i}"].numpy() for i in range(2)}, **_sd(bb, "w."))
+    np.savez_compressed(os.path.join(OUT, "sst_v1_small.npz"), **out)
+    print("sst_v1_small", rows.shape, float(out["bev_abs_sum"]))
+
+
 def sir_fixture(R):
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(11)
@@ -183,6 +230,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = ref_shim.load()
     sst_fixture(R)
+    sst_v1_fixture(R)
+    vfe_fixture(R)
     sir_fixture(R)
     dsvfe_fixture(R)
     scatter_fixture()

@@ -199,6 +199,9 @@ def load():
     sir = importlib.import_module("mmdet3d.models.backbones.sir")
     cos = importlib.import_module("mmdet3d.models.sst.cosine_msa")
     v2p = importlib.import_module("mmdet3d.models.necks.voxel2point_neck")
+    il1 = importlib.import_module("mmdet3d.models.middle_encoders.sst_input_layer")
+    blk1 = importlib.import_module("mmdet3d.models.sst.sst_basic_block")
+    sstv1 = importlib.import_module("mmdet3d.models.backbones.sst_v1")
 
     ns = types.SimpleNamespace(
         sst_ops=sst_ops, voxel_encoder=ve, ve_utils=ve_utils, input_layer_v2=il2, block_v2=blk,
@@ -207,6 +210,7 @@ def load():
         SSTInputLayerV2=il2.SSTInputLayerV2, SSTv2=sstv2.SSTv2, SIR=sir.SIR,
         EncoderLayer=blk.EncoderLayer, WindowAttention=blk.WindowAttention,
         Voxel2PointScatterNeck=v2p.Voxel2PointScatterNeck,
+        input_layer_v1=il1, block_v1=blk1, sst_v1=sstv1, SSTInputLayer=il1.SSTInputLayer, SSTv1=sstv1.SSTv1,
     )
     _LOADED = ns
     return ns

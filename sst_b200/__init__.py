@@ -7,7 +7,7 @@ from .registry import BACKBONES, MIDDLE_ENCODERS, MODELS, VOXEL_ENCODERS, build_
 from . import norm  # noqa: F401
 from . import ops  # noqa: F401
 from . import sst_modules, voxel_modules, sir_modules, neck_modules  # noqa: F401
-from .sst_modules import SSTInputLayerV2, SSTv2, PseudoMiddleEncoderForSpconvFSD  # noqa: F401
+from .sst_modules import SSTInputLayer, SSTInputLayerV2, SSTv1, SSTv2, SST, PseudoMiddleEncoderForSpconvFSD  # noqa: F401
 from .voxel_modules import DynamicVFE, DynamicScatterVFE  # noqa: F401
 from .sir_modules import SIR, SIRLayer  # noqa: F401
 from .neck_modules import Voxel2PointScatterNeck  # noqa: F401

@@ -46,8 +46,17 @@ class Config(dict):
         return Config(v) if isinstance(v, dict) and not isinstance(v, Config) else v
 
 
-def find_hot_path_modules(cfg, registry):
-    """All sub-dicts of `cfg` whose `type` is registered here (voxel encoders, middle encoders, backbones)."""
+# every type name the reference registers from a hot-path file - voxel_encoders/voxel_encoder.py,
+# middle_encoders/sst_input_layer{,_v2}.py, backbones/{sst,sst_v1,sst_v2,sir}.py, necks/voxel2point_neck.py, ops/norm.py.
+# A config that names one of these must find it in this package: "configs load unchanged" cannot pass by skipping.
+REFERENCE_HOT_PATH_TYPES = frozenset((
+    "DynamicVFE", "DynamicScatterVFE", "SIRLayer", "SSTInputLayer", "SSTInputLayerV2", "PseudoMiddleEncoderForSpconvFSD",
+    "SST", "SSTv1", "SSTv2", "SIR", "Voxel2PointScatterNeck", "naiveSyncBN1d", "naiveSyncBN2d", "naiveSyncBN3d"))
+
+
+def find_hot_path_modules(cfg, registry, strict=True):
+    """All sub-dicts of `cfg` whose `type` is registered here (voxel encoders, middle encoders, backbones, necks).
+    strict: a `type` that the reference registers from a hot-path file but this package does not is an error."""
     found = []
 
     def walk(node, path):
@@ -55,6 +64,8 @@ def find_hot_path_modules(cfg, registry):
             t = node.get("type")
             if isinstance(t, str) and t in registry:
                 found.append((path, node))
+            elif strict and isinstance(t, str) and t in REFERENCE_HOT_PATH_TYPES and not t.startswith("naiveSyncBN"):
+                raise KeyError(f"{path}: hot-path type {t!r} of the reference is not registered in sst_b200")
             for k, v in node.items():
                 walk(v, f"{path}.{k}" if path else str(k))
         elif isinstance(node, (list, tuple)):

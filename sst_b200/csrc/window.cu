@@ -193,7 +193,7 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
 // batch_win[b] = lower_bound(offsets[0..R), b*chunk) - one binary search per thread; counters[17] = number of batches.
 // A batch holds at most chunk - 1 + max_window_tokens rows.
 __global__ void win_batch_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ nwin_dev, int chunk,
-                                 int32_t* __restrict__ batch_win, int32_t* __restrict__ counters) {
+                                 int32_t* __restrict__ batch_win, int32_t* __restrict__ counters, const int32_t* __restrict__ flags) {
   pdl_wait();
   pdl_launch();
   const int R = *nwin_dev;
@@ -212,13 +212,14 @@ __global__ void win_batch_kernel(const uint32_t* __restrict__ offsets, const int
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     counters[17] = nb;
     counters[0] = R;
+    counters[18] = flags[0] | (flags[1] << 1);   // status word for sync-free callers (bit0: token outside the window grid)
   }
 }
 
 __global__ void zero_counters_kernel(int32_t* c) {
   pdl_wait();
   pdl_launch();
-  if (threadIdx.x < 18) c[threadIdx.x] = 0;
+  if (threadIdx.x < 20) c[threadIdx.x] = 0;
 }
 
 template <typename TC>
@@ -286,7 +287,7 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   }
   if (o->win_batch)
     launch_pdl(win_batch_kernel, dim3((n / 112 + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
-               112, o->win_batch, o->counters);
+               112, o->win_batch, o->counters, (const int32_t*)k.flags);
   LAUNCH_CHECK(c);
   if (err_host) {
     CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, k.flags, 8, cudaMemcpyDeviceToHost, c->stream));

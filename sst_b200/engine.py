@@ -36,6 +36,9 @@ class SSTEngine:
         self.d = backbone.d_model[0]
         assert all(d == self.d for d in backbone.d_model), "engine assumes a constant d_model"
         assert not hasattr(backbone, "linear0"), "linear0 not wired into the engine"
+        if voxel_encoder.feat_channels[-1] != self.d:
+            raise ValueError(f"voxel encoder emits {voxel_encoder.feat_channels[-1]} channels but the backbone expects d_model = {self.d} "
+                             "(no linear0 in the engine path)")
         self.il.set_drop_info()
         if self.il._may_drop():
             raise NotImplementedError("the sync-free engine covers drop_info settings that cannot drop voxels "
@@ -54,7 +57,7 @@ class SSTEngine:
             p = {k: torch.empty((cap + 1,) if k in ("win_offsets", "win_batch") else (cap,), **i32)
                  for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "tok_slot",
                            "win_batch")}
-            p["counters"] = torch.zeros((18,), **i32)
+            p["counters"] = torch.zeros((20,), **i32)
             self.plans.append(p)
         self.wcfg, _ = ops._window_cfg(self.il.sparse_shape, self.il.window_shape, self.il.drop_info, self.B)
         tab, ndim, maxw, Lp = self.il._pos(self.d, dev)
@@ -143,12 +146,26 @@ class SSTEngine:
         Stream-ordered D2D copy into the engine's input buffer (no sync)."""
         n = points_dev.shape[0]
         assert n <= self.cap and offsets_dev.numel() == self.B + 1
+        # the caller produced points_dev / offsets_dev on ITS current stream: order the copies after that work
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.stream):
             self.points[:n].copy_(points_dev, non_blocking=True)
             self.offsets.copy_(offsets_dev, non_blocking=True)
 
+    def status(self):
+        """Synchronises the engine stream and raises if the last frame hit a condition the module path would have raised on:
+        a voxel outside the window grid (window-plan status word, one per shift).  The sync-free path itself never reads it."""
+        self.stream.synchronize()
+        for s, p in enumerate(self.plans):
+            flag = int(p["counters"][18].item())
+            if flag & 1:
+                raise L.SSTB200Error(f"shift {s}: a voxel coordinate lies outside the window grid (sparse_shape too small for the input)")
+        return True
+
     def run(self):
-        """Enqueue one forward over the resident frames (graph replay).  Returns (feats_buf, coors_buf, num_dev)."""
+        """Enqueue one forward over the resident frames (graph replay).  Returns (feats_buf, coors_buf, num_dev) - PERSISTENT
+        buffers of the engine: they are valid until the next run() on this engine; a consumer on another stream must order
+        itself after `engine.stream` (e.g. `torch.cuda.current_stream().wait_stream(engine.stream)`) and finish before then."""
         with torch.cuda.stream(self.stream):
             if self.graph is not None:
                 c = L.ctx(self.dev)

@@ -1,4 +1,4 @@
-"""naiveSyncBN1d/2d (mmdet3d/ops/norm.py:28-143): BatchNorm whose training statistics are averaged over ranks.
+"""naiveSyncBN1d/2d/3d (mmdet3d/ops/norm.py:28-199): BatchNorm whose training statistics are averaged over ranks.
 Eval mode == plain BatchNorm on running stats.  The reference does one all_gather per layer
 (ops/norm.py:9-24); here the [mean ‖ meansqr] vector is all-reduced once (NCCL sum) - same numbers."""
 import torch
@@ -71,3 +71,19 @@ class NaiveSyncBatchNorm2d(nn.BatchNorm2d):
         if r is None:
             return super().forward(input)
         return input * r[0].reshape(1, -1, 1, 1) + r[1].reshape(1, -1, 1, 1)
+
+
+@NORM_LAYERS.register_module("naiveSyncBN3d")
+class NaiveSyncBatchNorm3d(nn.BatchNorm3d):
+    """mmdet3d/ops/norm.py:145-199."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.fp16_enabled = False
+
+    def forward(self, input):
+        input = input.float()
+        r = _sync_bn_forward(self, input, [0, 2, 3, 4])
+        if r is None:
+            return super().forward(input)
+        return input * r[0].reshape(1, -1, 1, 1, 1) + r[1].reshape(1, -1, 1, 1, 1)

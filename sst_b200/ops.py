@@ -426,7 +426,7 @@ def window_plan(coors, sparse_shape, window_shape, drop_info, do_shift, batch_si
     p.tok_perm = torch.empty((n,), **i32)
     p.win_level = torch.empty((n,), **i32)
     p.win_rank = torch.empty((n,), **i32)
-    p.counters = torch.empty((18,), **i32)
+    p.counters = torch.zeros((20,), **i32)
     p.tok_slot = torch.empty((n,), **i32)
     p.win_batch = torch.empty((n + 1,), **i32)
     out = _WindowShift(*[getattr(p, k).data_ptr() for k, _ in _WindowShift._fields_])

@@ -293,7 +293,9 @@ class EncoderLayer(nn.Module):
                  layer_id=None, mlp_dropout=0, layer_cfg=dict()):
         super().__init__()
         assert not batch_first
-        assert dropout == 0 and mlp_dropout == 0 or True  # dropout is identity in eval; training path: see DESIGN.md
+        # the reference applies nn.Dropout(mlp_dropout) three times and attention dropout inside nn.MultiheadAttention
+        # (sst_basic_block_v2.py:85-98): identity in eval; a non-zero rate in training is refused, not silently ignored
+        self.dropout_p, self.mlp_dropout_p = float(dropout), float(mlp_dropout)
         self.win_attn = WindowAttention(d_model, nhead, dropout, layer_id=layer_id, layer_cfg=layer_cfg)
         self.linear1 = nn.Linear(d_model, dim_feedforward)
         self.linear2 = nn.Linear(dim_feedforward, d_model)
@@ -346,11 +348,19 @@ class EncoderLayer(nn.Module):
             self._bf16 = (key, [w.detach().to(torch.float16).contiguous() for w in srcs])
         return self._bf16[1]
 
+    def _check_input(self, src):
+        if src.dim() != 2 or src.shape[1] != self.d_model:
+            raise RuntimeError(f"EncoderLayer expects [n, {self.d_model}] features, got {tuple(src.shape)} "
+                               "(the kernels only receive the row count: a width mismatch would read out of bounds)")
+        if self.training and (self.dropout_p > 0 or self.mlp_dropout_p > 0):
+            raise NotImplementedError("dropout > 0 in training mode is not built (the reference's configs use dropout = 0)")
+
     def forward(self, src, sra_plan, precision="fp32"):
         """src [n,d] fp32 flat voxel order; sra_plan: voxel_info['sra_plan_shift{i}']."""
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("SRA backward not built yet (round 2); run under eval()/no_grad()")
         ops._need_cuda(src)
+        self._check_input(src)
         src = src.float().contiguous()
         out = torch.empty_like(src)
         prec = PRECISIONS[precision]
@@ -459,6 +469,10 @@ class SSTv2(nn.Module):
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("SRA backward not built yet (round 2); run under eval()/no_grad()")
         ops._need_cuda(x)
+        if len({l.d_model for l in layers}) != 1:
+            raise NotImplementedError("per-block d_model lists with different widths are not built (the reference's configs use one width)")
+        for l in layers:
+            l._check_input(x)
         x = x.float().contiguous()
         prec = PRECISIONS[precision]
         arr = (_SraLayer * len(layers))(*[l._struct(prec) for l in layers])
@@ -482,3 +496,151 @@ class SSTv2(nn.Module):
         L.check(c, L.lib().sstb200_recover_bev(c, voxel_feat.data_ptr(), coors.data_ptr(), M, C_, batch_size, ny, nx,
                                                canvas.data_ptr()))
         return canvas
+
+
+# ------------------------------------------------------------------------------------------------
+# v1 names (configs/sst/*.py): SSTInputLayer + SSTv1.  Same maths as v2 (models/middle_encoders/sst_input_layer.py:14-364,
+# models/backbones/sst_v1.py:17-270, models/sst/sst_basic_block.py:13-140): 2-D windows given as (num_x, num_y), the shift
+# written as an explicit (shift_x, shift_y) list, the positional embedding computed inside the backbone, and a TUPLE
+# (voxel_feat, flat2win_inds_list, voxel_info) handed from the input layer to the backbone.  Both classes drive the same
+# window-plan / SRA kernels as their v2 counterparts.
+# ------------------------------------------------------------------------------------------------
+@MIDDLE_ENCODERS.register_module()
+class SSTInputLayer(nn.Module):
+    """models/middle_encoders/sst_input_layer.py:14-364.  `forward` also accepts the `batch_size` third argument that
+    DynamicVoxelNet.extract_feat passes (detectors/dynamic_voxelnet.py:43; the reference's v1 signature rejects it)."""
+
+    def __init__(self, drop_info, shifts_list, window_shape, point_cloud_range, voxel_size, shuffle_voxels=True, debug=True):
+        super().__init__()
+        self.fp16_enabled = False
+        self.meta_drop_info = drop_info
+        self.shifts_list = shifts_list
+        self.point_cloud_range = point_cloud_range
+        self.voxel_size = voxel_size
+        self.shuffle_voxels = shuffle_voxels
+        self.debug = debug
+        self.window_shape = window_shape
+        wx, wy = window_shape
+        for i, (sx, sy) in enumerate(shifts_list):
+            if (sx, sy) != ((0, 0) if i == 0 else (wx // 2, wy // 2)) or i > 1:
+                raise NotImplementedError(f"shifts_list {shifts_list}: only [(0, 0), (win_x // 2, win_y // 2)] (the reference's own "
+                                          "assertion, sst_input_layer.py:312) is built")
+        if len(shifts_list) > 1 and (wx % 2 or wy % 2):
+            raise NotImplementedError("odd window sizes shift by win - win // 2 in v1 (sst_input_layer.py:313): not built")
+        import math
+        bev_x = int(math.ceil((point_cloud_range[3] - point_cloud_range[0]) / voxel_size[0]))
+        bev_y = int(math.ceil((point_cloud_range[4] - point_cloud_range[1]) / voxel_size[1]))
+        self._bev = (bev_x, bev_y)
+        # the shared machinery: v2 layer over the same grid (z collapsed), never shuffling by itself
+        self._v2 = SSTInputLayerV2(drop_info, (wx, wy, 1), (bev_x, bev_y, 1), shuffle_voxels=False, debug=debug, mute=True)
+
+    def set_drop_info(self):
+        if hasattr(self, "drop_info"):
+            return
+        self._v2.train(self.training)
+        self._v2.set_drop_info()
+        self.drop_info = self._v2.drop_info
+        print(f"drop_info is set to {self.drop_info}, in input_layer")
+
+    def window_partition(self, coors, voxel_info):
+        """sst_input_layer.py:298-330 (API parity: the v1 window ids / in-window coordinates, elementwise)."""
+        wx, wy = self.window_shape
+        bev_x, bev_y = self._bev
+        ny_win = -(-bev_y // wy) + 1
+        per_sample = (-(-bev_x // wx) + 1) * ny_win
+        for i, (sx, sy) in enumerate(self.shifts_list):
+            x = coors[:, 3] + (wx - sx if sx > 0 else 0)
+            y = coors[:, 2] + (wy - sy if sy > 0 else 0)
+            voxel_info[f"batch_win_inds_shift{i}"] = coors[:, 0] * per_sample + (x // wx) * ny_win + y // wy
+            voxel_info[f"coors_in_win_shift{i}"] = torch.stack([x % wx, y % wy], dim=-1)
+        return voxel_info
+
+    def forward(self, voxel_feat, coors, batch_size=None):
+        self.set_drop_info()
+        coors = coors.long()
+        if self.shuffle_voxels:
+            shuffle_inds = torch.randperm(len(voxel_feat), device=voxel_feat.device)
+            voxel_feat, coors = voxel_feat[shuffle_inds], coors[shuffle_inds]
+        coors = coors.contiguous()
+        if batch_size is None:
+            batch_size = int(coors[:, 0].max()) + 1 if len(coors) else 1
+        plans = self._v2._plans(coors, batch_size)
+        num_shifts = len(self.shifts_list)
+        p0, p1, keep = plans
+        if keep is not None:
+            voxel_feat, coors = voxel_feat[keep], coors[keep]
+        voxel_info = {"coors": coors,
+                      "voxel_keep_inds": keep if keep is not None else torch.arange(len(coors), device=coors.device)}
+        self.window_partition(coors, voxel_info)
+        tab, ndim, maxw, Lp = self._v2._pos(voxel_feat.size(1), voxel_feat.device)
+        flat2win = []
+        for i, p in enumerate((p0, p1)[:num_shifts]):
+            voxel_info[f"voxel_drop_level_shift{i}"] = p.drop_level
+            voxel_info[f"sra_plan_shift{i}"] = dict(plan=p, pos_table=tab, pos_ndim=ndim, pos_maxw=maxw, pos_L=Lp,
+                                                    max_tokens=max(v["max_tokens"] for v in self.drop_info.values()))
+            flat2win.append(_LazyDict(lambda p=p: {k: v for k, v in self._v2._flat2win_dict(p).items() if not isinstance(k, str)}))
+        if self.shuffle_voxels:
+            voxel_info["shuffle_inds"] = shuffle_inds
+        return voxel_feat, flat2win, voxel_info
+
+
+@BACKBONES.register_module()
+class SSTv1(SSTv2):
+    """models/backbones/sst_v1.py:17-270: v1 constructor / forward(input_tuple) on the v2 kernels."""
+
+    def __init__(self, d_model=[], nhead=[], num_blocks=6, dim_feedforward=[], dropout=0.0, activation="gelu", output_shape=None,
+                 num_attached_conv=2, conv_in_channel=64, conv_out_channel=64,
+                 norm_cfg=dict(type="naiveSyncBN2d", eps=1e-3, momentum=0.01), conv_cfg=dict(type="Conv2d", bias=False), debug=True,
+                 drop_info=None, normalize_pos=False, pos_temperature=10000, window_shape=None, in_channel=None,
+                 conv_kwargs=dict(kernel_size=3, dilation=2, padding=2, stride=1), checkpoint_blocks=[], precision=None):
+        assert drop_info is not None
+        super().__init__(d_model=d_model, nhead=nhead, num_blocks=num_blocks, dim_feedforward=dim_feedforward, dropout=dropout,
+                         activation=activation, output_shape=output_shape, num_attached_conv=num_attached_conv,
+                         conv_in_channel=conv_in_channel, conv_out_channel=conv_out_channel, norm_cfg=norm_cfg, conv_cfg=conv_cfg,
+                         debug=debug, in_channel=in_channel, to_bev=True, conv_kwargs=conv_kwargs, checkpoint_blocks=checkpoint_blocks,
+                         precision=precision)
+        self.meta_drop_info = drop_info
+        self.pos_temperature = pos_temperature
+        self.window_shape = window_shape
+        self.normalize_pos = normalize_pos
+
+    def set_drop_info(self):
+        if hasattr(self, "drop_info"):
+            return
+        meta = self.meta_drop_info
+        self.drop_info = (meta[0] if self.training else meta[1]) if isinstance(meta, tuple) else meta
+        print(f"drop_info is set to {self.drop_info}, in backbone")
+
+    def forward(self, input_tuple):
+        voxel_feat, ind_dict_list, voxel_info = input_tuple
+        assert voxel_info["coors"].dtype == torch.int64, "data type of coors should be torch.int64!"
+        self.set_drop_info()
+        if "sra_plan_shift0" not in voxel_info:
+            raise L.SSTB200Error("voxel_info lacks 'sra_plan_shift0': build it with sst_b200's SSTInputLayer")
+        plans = [voxel_info[f"sra_plan_shift{i}"] for i in range(len(ind_dict_list))]
+        for sp in plans:   # the positional table belongs to the backbone in v1 (pos_temperature / normalize_pos are ITS kwargs)
+            tab, ndim, maxw, Lp = _pos_table(tuple(self.window_shape) + (1,), self.d_model[0], self.pos_temperature, self.normalize_pos)
+            sp.update(pos_table=tab.to(voxel_feat.device).contiguous(), pos_ndim=ndim, pos_maxw=maxw, pos_L=Lp)
+        if len(plans) == 1:
+            plans = plans * 2
+        precision = self.precision or ("bf16" if self.fp16_enabled else "fp32")
+        out = voxel_feat
+        if hasattr(self, "linear0"):
+            out = ops.linear(out, self.linear0.weight, self.linear0.bias)
+        out = self._run_stack(out, plans, precision)
+        batch_size = int(voxel_info["coors"][:, 0].max()) + 1
+        out = self.recover_bev(out, voxel_info["coors"], batch_size)
+        if self.num_attached_conv > 0:
+            for conv in self.conv_layer:
+                out = conv(out)
+        return [out]
+
+
+@BACKBONES.register_module()
+class SST(nn.Module):
+    """models/backbones/sst.py: registered in the reference but dead code ("Do not use this file", sst.py:1; it needs the
+    undefined SRATensor, sst.py:142, and no config names it).  The name resolves; constructing it says why it cannot run."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("SST (models/backbones/sst.py) is dead code in the reference - use SSTv1 / SSTv2")

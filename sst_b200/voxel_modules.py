@@ -100,8 +100,15 @@ class DynamicVFE(nn.Module):
         return DynamicVFELayer(cin, cout, norm_cfg)
 
     def _canvas(self):
+        """Canvas of map_voxel_center_to_point (voxel_encoder.py:199-204: round() in double) - but never smaller than the grid
+        the voxeliser emits coordinates on, which is ceil((max-min)/vs) evaluated in FLOAT32 (voxelization_cuda.cu:355-357,
+        DESIGN quirk Q2): with a non-integer ratio the two differ by one cell and the last voxel row would fall off the canvas."""
+        import numpy as np
         r = self.point_cloud_range
-        return (round((r[5] - r[2]) / self.vz), round((r[4] - r[1]) / self.vy), round((r[3] - r[0]) / self.vx))
+        rnd = (round((r[5] - r[2]) / self.vz), round((r[4] - r[1]) / self.vy), round((r[3] - r[0]) / self.vx))
+        f32 = np.float32
+        cel = tuple(int(np.ceil((f32(r[3 + i]) - f32(r[i])) / f32(v))) for i, v in ((2, self.vz), (1, self.vy), (0, self.vx)))
+        return tuple(max(a, b) for a, b in zip(rnd, cel))
 
     precision = "fp32"  # 'bf16': second VFE layer on tensor cores (bf16 operands, fp32 accumulate)
 

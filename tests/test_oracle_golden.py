@@ -141,3 +141,27 @@ def test_hard_voxelize_golden(name):
     mp, mv = [int(v) for v in z[f"cfg_{name}"]]
     v, c, n = O.hard_voxelize(z["points"], VS, RNG, mp, mv)
     assert torch.equal(c, z[f"coors_{name}"]) and torch.equal(n, z[f"npts_{name}"]) and torch.equal(v, z[f"voxels_{name}"])
+
+
+def test_sst_v1_golden():
+    """configs/sst names: the v1 SSTInputLayer + SSTv1 of the reference (tests/golden/sst_v1_small.npz) are the same maths as v2 -
+    the oracle's v2 restatement reproduces the v1 output rows, the window ids up to v1's own numbering and the drop levels."""
+    z = _load("sst_v1_small.npz")
+    info = O.input_layer_v2(z["voxel_feats"], z["voxel_coors"], DROP_TEST, (12, 12, 1), (468, 468, 1))
+    assert torch.equal(info["voxel_keep_inds"], z["keep"]) and torch.equal(info["voxel_coors"], z["coors"])
+    for i in range(2):
+        assert torch.equal(info[f"voxel_drop_level_shift{i}"], z[f"lvl{i}"])
+        assert torch.equal(info[f"coors_in_win_shift{i}"][:, [2, 1]], z[f"ciw{i}"])          # v1 stacks (x, y)
+        # v1 numbers its windows differently (no +1 window offset, no z): the PARTITION is the same
+        a, b = info[f"batch_win_inds_shift{i}"], z[f"bwi{i}"]
+        assert torch.equal(torch.unique(a, return_inverse=True)[1], torch.unique(b, return_inverse=True)[1])
+    out = O.sstv2_forward(info, _w(z, "w."), [4, 4], 2, "gelu", {})
+    torch.testing.assert_close(out, z["bev_rows"], rtol=1e-4, atol=1e-5)
+    assert abs(float(out.abs().double().sum()) - float(z["bev_abs_sum"])) < 1e-3 * float(z["bev_abs_sum"])
+
+
+def test_vfe_small_golden():
+    z = _load("vfe_small.npz")
+    vf, vc = O.dynamic_vfe_forward(z["points"], z["coors"], _w(z, "w."), VS, RNG, 2)
+    assert torch.equal(vc, z["vcoors"])
+    torch.testing.assert_close(vf, z["feats"], rtol=1e-5, atol=1e-5)
