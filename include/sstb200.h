@@ -22,6 +22,7 @@
  */
 #ifndef SSTB200_H_
 #define SSTB200_H_
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -324,6 +325,33 @@ int sstb200_voxel2point(sstb200_ctx* ctx, const float* points, int point_dims, c
 int sstb200_sra_stack_forward(sstb200_ctx* ctx, const sstb200_sra_layer* layers, int num_layers,
                               const sstb200_sra_plan* plan_shift0, const sstb200_sra_plan* plan_shift1, const float* x,
                               float* y, float* tmp, int n, const int32_t* n_dev, int precision);
+
+/* ---- training (BASELINE config 4): SSTv2's encoder stack with everything the backward pass needs kept in `workspace`, and the
+ * backward pass (the autograd graph torch builds over sst_basic_block_v2.py:100-126 / backbones/sst_v2.py:129-133 in the reference).
+ * Shape: d_model 128, 8 heads, dim_ff 256, post-norm LayerNorm, GELU, windows <= 144 tokens (all configs/sst_refactor models).
+ * GEMM operands and saved activations are bf16, accumulation / softmax / LayerNorm / residual stream / gradients of the
+ * parameters fp32.  For these two entry points the `*_w_f16` fields of sstb200_sra_layer hold BF16 copies of the weights. */
+typedef struct {
+  const void *in_proj_wt, *out_proj_wt, *lin1_wt, *lin2_wt; /* bf16 TRANSPOSED copies, [in, out] row-major */
+} sstb200_sra_layer_wt;
+typedef struct { /* fp32 accumulators in the layout of the parameters; the call ADDS to them */
+  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b, *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+} sstb200_sra_layer_grads;
+
+size_t sstb200_sra_train_workspace_bytes(int n, int num_layers);
+/* x [n,128] fp32 (not modified) -> y_out [n,128]; workspace: device buffer of sstb200_sra_train_workspace_bytes() */
+int sstb200_sra_stack_forward_train(sstb200_ctx* ctx, const sstb200_sra_layer* layers, int num_layers,
+                                    const sstb200_sra_plan* plan_shift0, const sstb200_sra_plan* plan_shift1, const float* x,
+                                    float* y_out, void* workspace, int n);
+/* dy [n,128] = d loss / d y_out  ->  dx [n,128] = d loss / d x, parameter gradients accumulated into `grads` */
+int sstb200_sra_stack_backward(sstb200_ctx* ctx, const sstb200_sra_layer* layers, const sstb200_sra_layer_wt* wt,
+                               const sstb200_sra_layer_grads* grads, int num_layers, const sstb200_sra_plan* plan_shift0,
+                               const sstb200_sra_plan* plan_shift1, const float* x, void* workspace, const float* dy, float* dx,
+                               int n);
+/* torch.optim.AdamW step over a flat fp32 buffer (decoupled weight decay, bias-corrected moments); the gradient is read as
+ * grads[i] * grad_scale (1 / world_size after a summing all-reduce).  step counts from 1. */
+int sstb200_adamw_step(sstb200_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -11,5 +11,6 @@ from .sst_modules import SSTInputLayer, SSTInputLayerV2, SSTv1, SSTv2, SST, Pseu
 from .voxel_modules import DynamicVFE, DynamicScatterVFE  # noqa: F401
 from .sir_modules import SIR, SIRLayer  # noqa: F401
 from .neck_modules import Voxel2PointScatterNeck  # noqa: F401
+from . import train  # noqa: F401  (training entry points: autograd bridge, FlatAdamW)
 
 __version__ = "0.1.0"

@@ -257,7 +257,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
 
 // NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which shortens
 // the critical path of batches that hold one big window and raises the number of resident warps per SM.
-template <int NHL>
+template <int NHL, bool OUT_BF16>
 static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __half* __restrict__ qkv,
                                                                        const int32_t* __restrict__ counters,
                                                                        const int32_t* __restrict__ win_offsets,
@@ -380,13 +380,13 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
         const float l0 = __shfl_sync(0xffffffffu, ol[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, ol[2], lane & ~3);
         if (tok0 >= 0) {
           const float i0 = __fdividef(1.0f, l0);
-          op0[hl * 8 + t4] = pack2_f16(o[0][0] * i0, o[0][1] * i0);
-          op0[hl * 8 + t4 + 4] = pack2_f16(o[1][0] * i0, o[1][1] * i0);
+          op0[hl * 8 + t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][0] * i0, o[0][1] * i0);
+          op0[hl * 8 + t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][0] * i0, o[1][1] * i0);
         }
         if (tok1 >= 0) {
           const float i1 = __fdividef(1.0f, l1);
-          op1[hl * 8 + t4] = pack2_f16(o[0][2] * i1, o[0][3] * i1);
-          op1[hl * 8 + t4 + 4] = pack2_f16(o[1][2] * i1, o[1][3] * i1);
+          op1[hl * 8 + t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][2] * i1, o[0][3] * i1);
+          op1[hl * 8 + t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][2] * i1, o[1][3] * i1);
         }
       }
     }
@@ -397,12 +397,14 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
   }
 }
 
+// out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                      const int32_t* win_batch, const int32_t* tok_perm, __half* out) {
+                                      const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
+  __half* out = reinterpret_cast<__half*>(out_v);
   constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
   size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
-  static SmemAttr sa;
-  CUDA_TRY(c, ensure_smem(c, sa, win_attn_batch_kernel<NHL>, smem));
+  static SmemAttr sa, sb;
+  CUDA_TRY(c, out_bf16 ? ensure_smem(c, sb, win_attn_batch_kernel<NHL, true>, smem) : ensure_smem(c, sa, win_attn_batch_kernel<NHL, false>, smem));
   static int grid_mult = 0;
   if (!grid_mult) {
     const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)
@@ -414,8 +416,12 @@ static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const i
   const int grid = c->num_sms * grid_mult;
   if (dbg_on && !dbg_buf) CUDA_TRY(c, cudaMalloc(&dbg_buf, (size_t)4096 * 16 * 8));
   if (dbg_on) CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, (size_t)grid * 16 * 8, c->stream));
-  CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch, tok_perm,
-                         0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
+  if (out_bf16)
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, true>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch,
+                           tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
+  else
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch,
+                           tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
   if (dbg_on) {
     static int dumps = 0;
     std::vector<long long> h((size_t)grid * 16);

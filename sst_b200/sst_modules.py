@@ -357,8 +357,9 @@ class EncoderLayer(nn.Module):
 
     def forward(self, src, sra_plan, precision="fp32"):
         """src [n,d] fp32 flat voxel order; sra_plan: voxel_info['sra_plan_shift{i}']."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("SRA backward not built yet (round 2); run under eval()/no_grad()")
+        if torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("gradients flow through the stack-level path (SSTv2.forward); a single EncoderLayer call is "
+                                      "inference-only - run it under torch.no_grad()")
         ops._need_cuda(src)
         self._check_input(src)
         src = src.float().contiguous()
@@ -466,9 +467,17 @@ class SSTv2(nn.Module):
         layers = [l for blk in self.block_list for l in blk.encoder_list]
         if not layers:
             return x
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("SRA backward not built yet (round 2); run under eval()/no_grad()")
         ops._need_cuda(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for l in layers for p in l.parameters())):
+            # training step: forward that keeps the activations + hand-written backward (csrc/sra_train.cu), bf16 operands
+            from .train import SraStackFunction, layer_params
+            for l in layers:
+                l._check_input(x)
+            if precision != "bf16":
+                raise NotImplementedError("the training path runs with precision='bf16' (bf16 GEMM operands, fp32 accumulation / "
+                                          "LayerNorm / gradients) - set SSTv2(precision='bf16') or fp16_enabled")
+            flat = [p for l in layers for p in layer_params(l)]
+            return SraStackFunction.apply(x, layers, plans, make_sra_plan, *flat)
         if len({l.d_model for l in layers}) != 1:
             raise NotImplementedError("per-block d_model lists with different widths are not built (the reference's configs use one width)")
         for l in layers:
