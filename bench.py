@@ -180,6 +180,53 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_bench(args, world, rank, dev, frames_d):
+    """BASELINE config 4 on this node: `--train-frames` config-2 sweeps per GPU and step (4 per GPU = 32 frames on 8 GPUs),
+    training-mode modules (train drop_info, voxel shuffle, batch-statistics naiveSyncBN with its all-reduce, bf16 GEMM operands),
+    loss = mean(out^2), backward through the library's own kernels, ONE NCCL all-reduce over the flat gradient buffer, fused AdamW.
+    Timed with CUDA events over the whole step, MAX over ranks; the all-reduce is timed by its own event pair."""
+    import torch.distributed as dist
+    from sst_b200 import flagship as fl
+    from sst_b200.train import TrainStep
+    cfg = fl.sst_cfg()
+    cfg["backbone"]["precision"] = "bf16"
+    cfg["middle_encoder"]["shuffle_voxels"] = True
+    vfe, il, bb = fl.build_sst(cfg, seed=0)        # same init on every rank (DDP broadcasts rank 0's weights)
+    ts = TrainStep(vfe.to(dev), il, bb.to(dev), fl.VOXEL_SIZE, fl.PC_RANGE)
+    B = max(1, args.train_frames)
+    K, W = max(2, min(args.steps, 6)), 2
+    batches = [[frames_d[(i * B + j) % len(frames_d)] for j in range(B)] for i in range(K + W)]
+    for i in range(W):
+        ts.step(batches[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ts.ar_events.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for i in range(K):
+        loss = ts.step(batches[W + i], time_allreduce=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    ar_ms = sum(a.elapsed_time(b) for a, b in ts.ar_events)
+    t = torch.tensor([ms, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0]), float(t[1])
+    nbytes = ts.grad_bytes
+    return {"metric": "lidar_frames_per_sec_sst6_train_150k", "value": world * B * K / (ms / 1e3), "unit": "frames/s",
+            "frames_per_gpu_per_step": B, "steps": K, "warmup": W, "ms_per_step": ms / K, "dtype": "bf16 operands, fp32 accumulate / master weights",
+            "allreduce_ms_per_step": ar_ms / K, "allreduce_share": ar_ms / ms if ms > 0 else None,
+            "nccl_gradient_bytes_per_step": nbytes, "nccl_wire_bytes_per_rank_per_step": int(2 * (world - 1) / world * nbytes),
+            "collectives_per_step": "1 flat gradient all-reduce + 2 naiveSyncBN statistic all-reduces (fwd) + 2 (bwd)" if world > 1 else "none (1 GPU)",
+            "loss": float(loss), "optimizer": "AdamW (fused kernel over one flat buffer)", "scaling": "weak"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +235,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SSTB200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE config 4)")
+    ap.add_argument("--train-frames", type=int, default=4, help="frames per GPU and training step (config 4: 32 frames / 8 GPUs)")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SSTB200_STREAMS", "8")),
                     help="frames in flight per GPU (independent engines on their own CUDA streams); 1 = strictly serial")
     args = ap.parse_args()
@@ -365,6 +414,14 @@ def main():
                 "flops_per_launch": flops, "ms_per_launch": layer_ms, "M": Mv, "sum_n2": sum_n2,
                 "layer_share_of_step": 12 * layer_ms / latency_ms}
 
+    # ---- training step (BASELINE config 4): fwd + bwd + ONE flat NCCL gradient all-reduce + fused AdamW, weak scaling ----
+    train = None
+    if not args.no_train:
+        try:
+            train = train_bench(args, world, rank, dev, frames_d)
+        except Exception as e:   # the inference record must not be lost to a training-side failure; say so loudly instead
+            train = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times, threads, _ = cpu_oracle_frames(2, 1)
@@ -385,7 +442,7 @@ def main():
             "gpu_graph_other_nodes_per_step": int(getattr(eng, "other_nodes_per_frame", 0) or 0),
             "gpu_launches_per_step": int(eng.launches_per_frame or 0),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "train": train,
         }
         print(json.dumps(line))
     if world > 1:

@@ -141,3 +141,58 @@ class FlatAdamW:
         L.check(c, L.lib().sstb200_adamw_step(c, self.flat.data_ptr(), self.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                               self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t,
                                               float(grad_scale)))
+
+
+class TrainStep:
+    """One data-parallel training step of the SST hot path (BASELINE config 4), per rank:
+
+        points of B frames -> dynamic_voxelize -> DynamicVFE (train) -> SSTInputLayerV2 (train drop_info, shuffle) -> SSTv2 (bf16)
+        -> loss = mean(out^2) (the stand-in head of SURVEY 8d) -> backward -> ONE flat NCCL all-reduce of every gradient
+        -> fused AdamW (gradient averaged over the ranks inside the kernel).
+
+    mirrors the reference's DynamicVoxelNet.forward_train under MMDistributedDataParallel + Fp16OptimizerHook + AdamW
+    (detectors/dynamic_voxelnet.py:38-71, tools/dist_train.sh:7-9, configs/_base_/schedules/cosine_2x.py) for the part of the
+    model that is on the hot path.  naiveSyncBN exchanges its statistics inside the forward (sst_b200/norm.py)."""
+
+    def __init__(self, vfe, il, bb, voxel_size, pc_range, lr=1e-4, weight_decay=0.05):
+        import torch.distributed as dist
+        self.vfe, self.il, self.bb = vfe.train(), il.train(), bb.train()
+        self.vs, self.rng = voxel_size, pc_range
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.opt = FlatAdamW(list(vfe.parameters()) + list(bb.parameters()), lr=lr, weight_decay=weight_decay)
+        self.ar_events = []
+
+    def voxelize(self, frames):
+        """DynamicVoxelNet.voxelize (dynamic_voxelnet.py:49-71): per-frame dynamic_voxelize, batch index prepended."""
+        from . import ops
+        pts, coors = [], []
+        for b, p in enumerate(frames):
+            c = torch.zeros((p.shape[0], 3), dtype=torch.int32, device=p.device)
+            ops.dynamic_voxelize(p.contiguous(), c, self.vs, self.rng)
+            coors.append(torch.nn.functional.pad(c, (1, 0), value=b))
+            pts.append(p)
+        return torch.cat(pts), torch.cat(coors)
+
+    def step(self, frames, time_allreduce=False):
+        import torch.distributed as dist
+        self.opt.zero_grad()
+        pts, coors = self.voxelize(frames)
+        vf, vc = self.vfe(pts, coors)
+        info = self.il(vf, vc, len(frames))
+        out = self.bb(info)[0]["voxel_feats"]
+        loss = out.float().square().mean()
+        loss.backward()
+        if self.world > 1:
+            if time_allreduce:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            dist.all_reduce(self.opt.flat_grad)           # ONE collective over the flat gradient buffer (NCCL over NVLink)
+            if time_allreduce:
+                b.record()
+                self.ar_events.append((a, b))
+        self.opt.step(grad_scale=1.0 / self.world)
+        return loss.detach()
+
+    @property
+    def grad_bytes(self):
+        return self.opt.flat_grad.numel() * 4

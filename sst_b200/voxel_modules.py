@@ -4,8 +4,11 @@
     DynamicScatterVFE   mmdet3d/models/voxel_encoders/voxel_encoder.py:502-612
     DynamicVFELayer(V2) mmdet3d/models/voxel_encoders/utils.py:107-189   (parameter containers)
 
-Eval-mode forward is ONE fused libsstb200 call (csrc/vfe.cu).  Training-mode BatchNorm (batch statistics over
-all points, naiveSyncBN across ranks) is round-2 work and raises.
+Eval-mode forward is ONE fused libsstb200 call (csrc/vfe.cu).  In training mode (batch-statistics BatchNorm, naiveSyncBN
+across ranks, gradients) DynamicVFE runs the reference's own composition (voxel_encoder.py:229-298): the three scatters and
+their gradients are libsstb200's DynamicScatter forward / backward kernels (csrc/voxel.cu), the two small Linear layers
+(9->64, 128->128; 5 GFLOP, fp32 like the reference's @force_fp32), naiveSyncBN (sst_b200/norm.py, ONE all-reduce per layer) and
+ReLU are torch layers under autograd.
 """
 import ctypes as C
 
@@ -146,14 +149,54 @@ class DynamicVFE(nn.Module):
         return cfg
 
     def _check(self, features, coors):
-        if self.training:
-            raise NotImplementedError("training-mode VFE (batch-stat BN + backward) is not built yet; call .eval()")
         ops._need_cuda(features, coors)
         assert features.dtype == torch.float32 and features.shape[1] == self.raw_in_channels
         assert coors.shape[1] == 4
 
+    # ---- training mode: the reference's composition on libsstb200's DynamicScatter ---------------------------------
+    def _map_voxel_center_to_point(self, pts_coors, voxel_mean, voxel_coors):
+        """voxel_encoder.py:185-225 (dense canvas of row indices; cells of dropped voxels keep index 0 like the reference)."""
+        cz, cy, cx = self._canvas()
+        batch_size = int(pts_coors[-1, 0]) + 1
+        canvas = torch.zeros((cz * cy * cx * batch_size,), dtype=torch.long, device=voxel_mean.device)
+        vc = voxel_coors.long()
+        canvas[vc[:, 0] * cz * cy * cx + vc[:, 1] * cy * cx + vc[:, 2] * cx + vc[:, 3]] = torch.arange(voxel_mean.size(0), device=voxel_mean.device)
+        pc = pts_coors.long()
+        return voxel_mean[canvas[pc[:, 0] * cz * cy * cx + pc[:, 1] * cy * cx + pc[:, 2] * cx + pc[:, 3]]]
+
+    def _forward_train(self, features, coors):
+        """voxel_encoder.py:229-298 verbatim in structure; see the module docstring for what runs where."""
+        if self._with_distance or self.return_point_feats:
+            raise NotImplementedError("with_distance / return_point_feats in training mode")
+        vs, pr = (self.vx, self.vy, self.vz), self.point_cloud_range
+        if not hasattr(self, "_scatters"):
+            self._scatters = (ops.DynamicScatter(vs, pr, self.mode != "max"), ops.DynamicScatter(vs, pr, True))
+        vfe_scatter, cluster_scatter = self._scatters
+        coors = coors.int()
+        feats = [features]
+        if self._with_cluster_center:
+            voxel_mean, mean_coors = cluster_scatter(features, coors)
+            points_mean = self._map_voxel_center_to_point(coors, voxel_mean, mean_coors)
+            feats.append(features[:, :3] - points_mean[:, :3])
+        if self._with_voxel_center:
+            f_center = features.new_zeros((features.size(0), 3))
+            f_center[:, 0] = features[:, 0] - (coors[:, 3].type_as(features) * self.vx + self.x_offset)
+            f_center[:, 1] = features[:, 1] - (coors[:, 2].type_as(features) * self.vy + self.y_offset)
+            f_center[:, 2] = features[:, 2] - (coors[:, 1].type_as(features) * self.vz + self.z_offset)
+            feats.append(f_center)
+        x = torch.cat(feats, dim=-1)
+        voxel_feats = voxel_coors = None
+        for i, vfe in enumerate(self.vfe_layers):
+            point_feats = torch.relu(vfe.norm(vfe.linear(x)))      # utils.py:129-144
+            voxel_feats, voxel_coors = vfe_scatter(point_feats, coors)
+            if i != len(self.vfe_layers) - 1:
+                x = torch.cat([point_feats, self._map_voxel_center_to_point(coors, voxel_feats, voxel_coors)], dim=1)
+        return voxel_feats, voxel_coors
+
     def forward(self, features, coors, points=None, img_feats=None, img_metas=None):
         self._check(features, coors)
+        if self.training:
+            return self._forward_train(features.contiguous(), coors)
         features, coors = features.contiguous(), coors.int().contiguous()
         P, dev = features.shape[0], features.device
         if P == 0:
@@ -186,6 +229,8 @@ class DynamicScatterVFE(DynamicVFE):
 
     def forward(self, features, coors, points=None, img_feats=None, img_metas=None, return_inv=False):
         self._check(features, coors)
+        if self.training:
+            raise NotImplementedError("DynamicScatterVFE training mode (FSD) is not built; BASELINE config 4 trains the SST path")
         features, coors = features.contiguous(), coors.long().contiguous()
         P, dev = features.shape[0], features.device
         if P == 0:

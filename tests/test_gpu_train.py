@@ -79,3 +79,47 @@ def test_flat_adamw_matches_torch(cuda):
         ob.step()
     for x, y in zip(a, b):
         torch.testing.assert_close(x.detach(), y.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_full_model_train_step_gradients(cuda):
+    """DynamicVFE (training-mode batch-stat BN) -> SSTInputLayerV2 (training drop_info, shuffle off) -> SSTv2 (2 blocks): loss
+    and every parameter gradient against autograd through the oracle (training=True restatement, pinned to the reference by
+    tests/test_oracle_vs_reference.py)."""
+    from sst_b200 import flagship as fl
+    cfg = fl.sst_cfg(num_blocks=2)
+    cfg["backbone"]["precision"] = "bf16"
+    vfe, il, bb = fl.build_sst(cfg, seed=3)
+    pts = torch.cat([O.synth_frame(41, 12000), O.synth_frame(42, 9000)])
+    c3 = O.dynamic_voxelize(pts, VS, RNG)
+    coors = torch.cat([torch.nn.functional.pad(c3[:12000], (1, 0), value=0), torch.nn.functional.pad(c3[12000:], (1, 0), value=1)])
+    # oracle
+    wv = {k: v.detach().clone().requires_grad_(k in dict(vfe.named_parameters())) for k, v in vfe.state_dict().items()}
+    wb = {k: v.detach().clone().requires_grad_(True) for k, v in bb.state_dict().items()}
+    vf_o, vc_o = O.dynamic_vfe_forward(pts, coors, wv, VS, RNG, 2, training=True)
+    info_o = O.input_layer_v2(vf_o, vc_o, fl.DROP_TRAIN, (12, 12, 1), (468, 468, 1))
+    out_o = O.sstv2_forward(info_o, wb, [8, 8], 2)
+    loss_o = out_o.square().mean()
+    loss_o.backward()
+    # CUDA
+    vfe, bb = vfe.to(cuda).train(), bb.to(cuda).train()
+    il.train()
+    il.shuffle_voxels = False
+    vf, vc = vfe(pts.to(cuda), coors.to(cuda))
+    assert torch.equal(vc.cpu().long(), vc_o.long())
+    info = il(vf, vc, 2)
+    assert torch.equal(info["voxel_keep_inds"].cpu(), info_o["voxel_keep_inds"])
+    out = bb(info)[0]["voxel_feats"]
+    loss = out.float().square().mean()
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) < 2e-2 * abs(loss_o.item())
+
+    def rel(a, b):
+        return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+    bad = {}
+    for name, p in list(vfe.named_parameters()) + list(bb.named_parameters()):
+        ref = (wv if name in wv and wv[name].grad is not None and p.shape == wv[name].shape and name.startswith("vfe_layers") else wb)[name].grad
+        r = rel(p.grad.cpu(), ref)
+        if r > 3e-2:
+            bad[name] = r
+    assert not bad, bad
