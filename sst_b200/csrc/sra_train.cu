@@ -15,7 +15,7 @@
 //                       y  = LN2(x1 + h W2^T + b2)       tcgen05 GEMM + LN epilogue, keeps t2
 // backward:  LN2' -> dW2, dz = (dt2 W2) * gelu'(z) -> dW1, dx1 = dt2 + dz W1 -> LN1' -> dWo, datt = dt1 Wo -> attention' ->
 //            dWqkv, dx = dt1 + dqkv Wqkv.  dX-type GEMMs run on tcgen05 (transposed bf16 weight copies), dW-type GEMMs (reduction
-//            over the ~30 k tokens) on mma.sync tiles with fp32 atomics, attention' as a two-pass SIMT kernel per window batch.
+//            over the ~30 k tokens) on mma.sync tiles (per-split partial blocks + a deterministic reduce), attention' as a two-pass SIMT kernel per window batch.
 #include <stdarg.h>
 #include <cuda_fp16.h>
 #include "sra.cuh"
@@ -117,23 +117,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
-// column sums of a bf16 matrix [n, C] (bias gradients of the GEMMs whose output gradient only exists in bf16)
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, int n, int C, float* __restrict__ out) {
-  pdl_wait();
-  pdl_launch();
-  // thread = (column pair, row phase); 256 threads cover 64 column pairs x 4 row phases per pass over C
-  for (int c2 = (threadIdx.x & 63); c2 < C / 2; c2 += 64) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int r = blockIdx.x * 4 + (threadIdx.x >> 6); r < n; r += gridDim.x * 4) {
-      const float2 f = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(a + (size_t)r * C)[c2]);
-      s0 += f.x;
-      s1 += f.y;
-    }
-    atomicAdd(out + 2 * c2, s0);
-    atomicAdd(out + 2 * c2 + 1, s1);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // dW[bn*128 + 0..127, bk*128 + 0..127] += dY[:, bn*128 + ..]^T . X[:, bk*128 + ..]   (reduction over the rows)
 // Work item = (output block, row split).  A CTA walks its rows in slabs of 64 (cp.async double buffer); 8 warps, warp w owns
@@ -150,7 +133,10 @@ struct DwArgs {
   const float* pos_tab;
   const int32_t* pos_code;
   int posL, pos_maxw, pos_ndim;
-  float* dW;                // [N_out, K_in] fp32, +=
+  float* dW;                // [N_out, K_in] fp32, += (by dw_reduce_kernel)
+  float* part;              // [splits][nb * kb][128 x 128] fp32 partial blocks
+  float* part_b;            // [splits][nb][128] column sums of dY (bias gradient), written by the bk == 0 blocks; or nullptr
+  float* db;                // [N_out] fp32, += ; or nullptr
   int K_in;
   int nb, kb, splits, n;
 };
@@ -172,6 +158,8 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(DwArgs g) {
   float acc[16][4];
 #pragma unroll
   for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const bool want_b = g.part_b != nullptr && bk == 0;
+  float bsum = 0.f;
   if (r_begin < r_end) {
     auto stage = [&](int buf, int r0) {
       // dY slab: 64 rows x 128 cols bf16 = 16 pieces of 16 B per row
@@ -232,6 +220,10 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(DwArgs g) {
       __syncthreads();
       const __nv_bfloat16* y0 = sY + buf * DW_ROWS * DW_PITCH;
       const __nv_bfloat16* x0 = sX + buf * DW_ROWS * DW_PITCH;
+      if (want_b) {   // bias gradient: column tid & 127 over half of the slab's rows
+#pragma unroll 8
+        for (int r = (tid >> 7) * 32; r < (tid >> 7) * 32 + 32; r++) bsum += __bfloat162float(y0[r * DW_PITCH + (tid & 127)]);
+      }
 #pragma unroll
       for (int ks = 0; ks < DW_ROWS / 16; ks++) {
         uint32_t a[4];
@@ -255,21 +247,60 @@ __global__ void __launch_bounds__(256) dw_gemm_kernel(DwArgs g) {
       buf ^= 1;
     }
   }
-  // accumulator (row g4 / g4+8 of the warp's 16 rows, columns 8 nt + 2 t4 ..) -> global, fp32 atomics
+  // accumulator (row g4 / g4+8 of the warp's 16 rows, columns 8 nt + 2 t4 ..) -> this split's partial block
   const int g4 = lane >> 2, t4 = lane & 3;
-  float* base = g.dW + (size_t)(bn * 128 + warp * 16) * g.K_in + bk * 128;
+  float* base = g.part + ((size_t)sp * (g.nb * g.kb) + blk) * (128 * 128) + (size_t)(warp * 16) * 128;
 #pragma unroll
   for (int nt = 0; nt < 16; nt++) {
     const int col = nt * 8 + 2 * t4;
-    atomicAdd(base + (size_t)g4 * g.K_in + col, acc[nt][0]);
-    atomicAdd(base + (size_t)g4 * g.K_in + col + 1, acc[nt][1]);
-    atomicAdd(base + (size_t)(g4 + 8) * g.K_in + col, acc[nt][2]);
-    atomicAdd(base + (size_t)(g4 + 8) * g.K_in + col + 1, acc[nt][3]);
+    *reinterpret_cast<float2*>(base + (size_t)g4 * 128 + col) = make_float2(acc[nt][0], acc[nt][1]);
+    *reinterpret_cast<float2*>(base + (size_t)(g4 + 8) * 128 + col) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+  if (want_b) {
+    __shared__ float sb2[256];
+    sb2[tid] = bsum;
+    __syncthreads();
+    if (tid < 128) g.part_b[((size_t)sp * g.nb + bn) * 128 + tid] = sb2[tid] + sb2[tid + 128];
+  }
+}
+
+// dW[block] += sum over the row splits of the partial blocks (deterministic order); same for the bias partials
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_b, int splits, int nb, int kb,
+                                                        int K_in, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_wait();
+  pdl_launch();
+  const int blocks = nb * kb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < blocks * 128 * 32; i += gridDim.x * blockDim.x) {
+    const int blk = i / (128 * 32), e = i % (128 * 32), r = e / 32, c4 = e % 32;
+    const float4* src = reinterpret_cast<const float4*>(part + (size_t)blk * (128 * 128) + (size_t)r * 128) + c4;
+    const size_t stride = (size_t)blocks * (128 * 128) / 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      const float4 v0 = src[(size_t)sp * stride], v1 = src[(size_t)(sp + 1) * stride], v2 = src[(size_t)(sp + 2) * stride], v3 = src[(size_t)(sp + 3) * stride];
+      s.x += (v0.x + v1.x) + (v2.x + v3.x), s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z), s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; sp < splits; sp++) {
+      const float4 v = src[(size_t)sp * stride];
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(dW + (size_t)((blk / kb) * 128 + r) * K_in + (blk % kb) * 128) + c4;
+    float4 d = *dst;
+    d.x += s.x, d.y += s.y, d.z += s.z, d.w += s.w;
+    *dst = d;
+  }
+  if (db && part_b) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * 128; i += gridDim.x * blockDim.x) {
+      float sum = 0.f;
+      for (int sp = 0; sp < splits; sp++) sum += part_b[(size_t)sp * nb * 128 + i];
+      db[i] += sum;
+    }
   }
 }
 
 static int launch_dw(sstb200_ctx* c, const __nv_bfloat16* dY, int ldy, int n_out, const __nv_bfloat16* X, const float* Xf, int ldx, int k_in,
-                     const sstb200_sra_plan* pos, float* dW, int n) {
+                     const sstb200_sra_plan* pos, float* dW, int n, float* db = nullptr) {
   DwArgs g;
   memset(&g, 0, sizeof(g));
   g.dY = dY, g.ldy = ldy, g.X = X, g.Xf = Xf, g.ldx = ldx, g.dW = dW, g.K_in = k_in, g.n = n;
@@ -278,13 +309,22 @@ static int launch_dw(sstb200_ctx* c, const __nv_bfloat16* dY, int ldy, int n_out
   }
   g.nb = n_out / 128, g.kb = k_in / 128;
   const int blocks = g.nb * g.kb;
-  g.splits = (2 * c->num_sms + blocks - 1) / blocks;
+  g.splits = (2 * c->num_sms + blocks - 1) / blocks;   // two CTAs per SM (88 KB of shared memory each)
   const int max_splits = (n + DW_ROWS - 1) / DW_ROWS;
   if (g.splits > max_splits) g.splits = max_splits < 1 ? 1 : max_splits;
+  arena_reset(c);
+  int rc = arena_reserve(c, (size_t)g.splits * blocks * 128 * 128 * 4 + (size_t)g.splits * g.nb * 128 * 4 + 8192);
+  if (rc) return rc;
+  g.part = arena_alloc<float>(c, (size_t)g.splits * blocks * 128 * 128);
+  g.part_b = db ? arena_alloc<float>(c, (size_t)g.splits * g.nb * 128) : nullptr;
+  g.db = db;
+  if (!g.part || (db && !g.part_b)) return sstb_fail(c, SSTB_ERR_WORKSPACE, "dW partials: arena");
   const size_t smem = (size_t)4 * DW_ROWS * DW_PITCH * 2;
   static SmemAttr sa;
   CUDA_TRY(c, ensure_smem(c, sa, dw_gemm_kernel, smem));
   CUDA_TRY(c, launch_pdl(dw_gemm_kernel, dim3(blocks * g.splits), dim3(256), smem, c->stream, g));
+  CUDA_TRY(c, launch_pdl(dw_reduce_kernel, dim3(blocks * 16), dim3(256), (size_t)0, c->stream, (const float*)g.part, (const float*)g.part_b, g.splits,
+                         g.nb, g.kb, k_in, dW, db));
   return SSTB_OK;
 }
 
@@ -589,9 +629,8 @@ extern "C" int sstb200_sra_stack_backward(sstb200_ctx* c, const sstb200_sra_laye
     memset(&g, 0, sizeof(g));
     g.M_cap = n, g.A = dtb, g.lda = DM, g.W = T->lin2_wt, g.out_h16 = dzb, g.aux16 = lw + w.z, g.ldo = DFF;
     if ((rc = launch_umma<128, 128, PRO_H16, EPI_GELUGRAD, FMT_BF16>(c, g, 2))) return rc;
-    CUDA_TRY(c, launch_pdl(colsum_bf16_kernel, dim3(c->num_sms), dim3(256), (size_t)0, c->stream, (const __nv_bfloat16*)dzb, n, DFF, G->lin1_b));
-    // dW1 += dz^T x1
-    if ((rc = launch_dw(c, dzb, DFF, DFF, reinterpret_cast<const __nv_bfloat16*>(lw + w.x1b), nullptr, DM, DM, nullptr, G->lin1_w, n))) return rc;
+    // dW1 += dz^T x1, d b1 += colsum(dz)
+    if ((rc = launch_dw(c, dzb, DFF, DFF, reinterpret_cast<const __nv_bfloat16*>(lw + w.x1b), nullptr, DM, DM, nullptr, G->lin1_w, n, G->lin1_b))) return rc;
     // dx1 = dt2 + dz W1
     memset(&g, 0, sizeof(g));
     g.M_cap = n, g.A = dzb, g.lda = DFF, g.W = T->lin1_wt, g.res = dt, g.out_f32 = dx1;
@@ -607,10 +646,10 @@ extern "C" int sstb200_sra_stack_backward(sstb200_ctx* c, const sstb200_sra_laye
     // attention'
     if ((rc = launch_attn_bwd(c, reinterpret_cast<const __half*>(lw + w.qkv), reinterpret_cast<const __nv_bfloat16*>(lw + w.att), dattb, P, dqkv)))
       return rc;
-    CUDA_TRY(c, launch_pdl(colsum_bf16_kernel, dim3(c->num_sms), dim3(256), (size_t)0, c->stream, (const __nv_bfloat16*)dqkv, n, 3 * DM, G->in_proj_b));
-    // dWq|k += [dq|dk]^T (x + pos) ;  dWv += dv^T x
-    if ((rc = launch_dw(c, dqkv, 3 * DM, 2 * DM, nullptr, xin, DM, DM, P->pos_table ? P : nullptr, G->in_proj_w, n))) return rc;
-    if ((rc = launch_dw(c, dqkv + 2 * DM, 3 * DM, DM, nullptr, xin, DM, DM, nullptr, G->in_proj_w + (size_t)2 * DM * DM, n))) return rc;
+    // dWq|k += [dq|dk]^T (x + pos) ;  dWv += dv^T x ;  d bqkv += colsum(dqkv)
+    if ((rc = launch_dw(c, dqkv, 3 * DM, 2 * DM, nullptr, xin, DM, DM, P->pos_table ? P : nullptr, G->in_proj_w, n, G->in_proj_b))) return rc;
+    if ((rc = launch_dw(c, dqkv + 2 * DM, 3 * DM, DM, nullptr, xin, DM, DM, nullptr, G->in_proj_w + (size_t)2 * DM * DM, n, G->in_proj_b + 2 * DM)))
+      return rc;
     // dx = dt1 + dqkv Wqkv
     memset(&g, 0, sizeof(g));
     g.M_cap = n, g.A = dqkv, g.lda = 3 * DM, g.W = T->in_proj_wt, g.res = dt, g.out_f32 = dxo;
