@@ -397,18 +397,28 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
   }
 }
 
+template <int NHL>
+static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
+                                        const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16);
 // out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
                                       const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
+  static int nhl_env = -1;
+  if (nhl_env < 0) nhl_env = getenv("SSTB200_ATT_NHL") ? atoi(getenv("SSTB200_ATT_NHL")) : 2;
+  if (nhl_env == 4) return sstb_win_attn_batch_t<4>(c, qkv, counters, win_offsets, win_batch, tok_perm, out_v, out_bf16);
+  return sstb_win_attn_batch_t<2>(c, qkv, counters, win_offsets, win_batch, tok_perm, out_v, out_bf16);
+}
+template <int NHL>   // heads per CTA -> 8 / NHL CTAs per window batch
+static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
+                                        const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16) {
   __half* out = reinterpret_cast<__half*>(out_v);
-  constexpr int NHL = 2;  // heads per CTA -> 4 CTAs per window batch
   size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
   static SmemAttr sa, sb;
   CUDA_TRY(c, out_bf16 ? ensure_smem(c, sb, win_attn_batch_kernel<NHL, true>, smem) : ensure_smem(c, sa, win_attn_batch_kernel<NHL, false>, smem));
   static int grid_mult = 0;
   if (!grid_mult) {
     const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)
-    grid_mult = e && atoi(e) > 0 ? atoi(e) : 6;
+    grid_mult = e && atoi(e) > 0 ? atoi(e) : 9;
   }
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("SSTB200_ATT_DBG") ? atoi(getenv("SSTB200_ATT_DBG")) : 0;
