@@ -142,7 +142,8 @@ typedef struct {
   int32_t* counters;       /* [20]  R, windows per level slot [8], tokens per level slot [8], number of window batches,
                             *       [18] status bits (bit0 token outside the window grid, bit1 window count not covered), [19] spare */
   int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
-  int32_t* win_batch;      /* opt [n+1] batch b = windows [win_batch[b], win_batch[b+1]) whose first slot lies in [112b, 112b+112) */
+  int32_t* win_batch;      /* opt [n+16], 16-byte aligned: one record of 4 ints per batch b = the windows whose first slot lies in
+                              [112b, 112b+112): {first window, end window, first slot, end slot}; at most n/112 + 2 records */
 } sstb200_window_shift;
 
 /* status_host (opt, int32[18]): if non-NULL the call synchronises and returns

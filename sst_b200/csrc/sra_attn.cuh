@@ -255,16 +255,21 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
   }
 }
 
-// NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' K/V columns), which shortens
+// NHL = heads handled by one CTA: a batch is split over 8/NHL CTAs (each stages only its heads' Q/K/V columns), which shortens
 // the critical path of batches that hold one big window and raises the number of resident warps per SM.
+// A CTA's life is a chain of dependent global loads (batch record -> window permutation -> q|k|v rows), so the kernel is built
+// to keep that chain short and off the producer's critical path: (1) one int4 record per batch from win_batch_kernel instead of
+// win_batch -> win_offsets, (2) everything that depends only on the window plan (record, token list, q-tile table) happens
+// BEFORE griddepcontrol.wait, i.e. while the tail of the kernel that produces q|k|v is still running (the plan was written by
+// kernels that completed before that producer started: every kernel of the library waits before it triggers its dependents),
+// (3) Q is staged with K and V by cp.async, so the compute phase never waits on global memory.
 template <int NHL, bool OUT_BF16>
 static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __half* __restrict__ qkv,
                                                                        const int32_t* __restrict__ counters,
                                                                        const int32_t* __restrict__ win_offsets,
-                                                                       const int32_t* __restrict__ win_batch,
+                                                                       const int4* __restrict__ batch_rec, int rec_cap,
                                                                        const int32_t* __restrict__ tok_perm, float scale,
                                                                        __half* __restrict__ out, long long* dbg) {
-  pdl_wait();
   pdl_launch();
   int dbg_n = 0;
   constexpr int D = 128, DH = 16, LD = NHL * 16 + 8, HSPLIT = 8 / NHL, PPR = NHL * 2;  // PPR: 16-byte pieces per row per matrix
@@ -272,35 +277,45 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* sK = reinterpret_cast<__half*>(att_smem);
   __half* sV = sK + NROW * LD;
+  __half* sQ = sV + NROW * LD;
   __shared__ int sTok[NROW];           // token row of local slot r, -1 beyond the batch
   __shared__ short sTileRow[ATT_BT];   // first local row of q-tile k
   __shared__ short sTileKb[ATT_BT];    // local key range of its window
   __shared__ short sTileKe[ATT_BT];
   __shared__ int sNumTiles;
   // batch b = the windows whose first slot lies in [b*ATT_CHUNK, (b+1)*ATT_CHUNK) (win_batch_kernel, csrc/window.cu); it holds
-  // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows
+  // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows.  record = {first window, end window, first slot, end slot}
+  int4 rc = batch_rec[min((int)blockIdx.x / HSPLIT, rec_cap - 1)];
   const int nbatch = counters[17];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 2, t4 = lane & 3;
-  const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV);
-  // this lane's ldmatrix row offsets (bytes) inside a 16-key block: K fragments (non-transposed) / V^T fragments (.trans)
+  const uint32_t k0 = (uint32_t)__cvta_generic_to_shared(sK), v0 = (uint32_t)__cvta_generic_to_shared(sV),
+                 q0 = (uint32_t)__cvta_generic_to_shared(sQ);
+  // this lane's ldmatrix row offsets (bytes) inside a 16-row block: K fragments (non-transposed) / V^T fragments (.trans); the
+  // Q (A operand) fragment uses the V pattern without .trans
   const uint32_t klane = (uint32_t)((((lane & 7) + ((lane >> 4) & 1) * 8) * LD + ((lane >> 3) & 1) * 8) * 2);
   const uint32_t vlane = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8) * 2);
   const float sl2 = scale * 1.4426950408889634f;   // exp(x) = 2^(x log2 e)
-  // staging role of this thread: piece c of a row (K pieces first, then V), rows tid / (2 PPR), + 256 / (2 PPR), ...
-  const int sc = threadIdx.x % (2 * PPR), sr0 = threadIdx.x / (2 * PPR);
-  const bool s_isv = sc >= PPR;
-  const int s_pc = s_isv ? sc - PPR : sc;
+  bool waited = false;
   for (int unit = blockIdx.x; unit < nbatch * HSPLIT; unit += gridDim.x) {
     const int b = unit / HSPLIT, hs = unit % HSPLIT;
-    const int wb = win_batch[b], we = win_batch[b + 1];
+    if (unit != (int)blockIdx.x) rc = batch_rec[b];
+    const int wb = rc.x, we = rc.y, s0 = rc.z, s1 = rc.w;
     if (wb == we) continue;  // a big window covers this chunk entirely (uniform per CTA)
-    const int s0 = win_offsets[wb], s1 = win_offsets[we];
     const int nrow = min(s1 - s0, ATT_BT);
     const int nfill = min(((nrow + 15) & ~15) + 16, NROW);  // key chunks may run up to 15 rows past the batch: keep them finite (0)
     if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 0] = clock64();
     __syncthreads();  // previous batch fully consumed
-    for (int r = threadIdx.x; r < nfill; r += blockDim.x) sTok[r] = r < nrow ? tok_perm[s0 + r] : -1;
+    // staging role: lane = (row of an 8-row group, 16-byte piece p of the NHL heads' columns); a warp covers 8 rows x {K, V, Q} per
+    // step, the CTA 64 rows -> <= 5 steps, all of whose token loads are in flight together
+    constexpr int SROWS = 256 / PPR, SSTEPS = (NROW + SROWS - 1) / SROWS;
+    const int s_r = threadIdx.x / PPR, s_p = threadIdx.x % PPR;
+    int stok[SSTEPS];
+#pragma unroll
+    for (int j = 0; j < SSTEPS; j++) {
+      const int r = s_r + j * SROWS;
+      stok[j] = r < nrow ? tok_perm[s0 + r] : -1;
+    }
     // q-tile table (warp 0): windows of the batch -> tiles
     if (warp == 0) {
       int cnt = 0;
@@ -331,16 +346,28 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
       }
       if (lane == 0) sNumTiles = min(cnt, ATT_BT);
     }
-    __syncthreads();
-    // stage K | V rows (gathered through the window permutation): 16-byte pieces with cp.async, zero fill beyond the batch
-    {
-      const __half* gsrc = qkv + (s_isv ? 2 * D : D) + (hs * NHL) * DH + s_pc * 8;
-      const uint32_t dst0 = (s_isv ? v0 : k0) + (uint32_t)(s_pc * 16);
-      for (int r = sr0; r < nfill; r += 256 / (2 * PPR)) {
-        const int tok = sTok[r];
-        const uint32_t dst = dst0 + (uint32_t)(r * LD * 2);
-        if (tok >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gsrc + (size_t)tok * (3 * D)) : "memory");
-        else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(dst), "r"(0) : "memory");
+    if (!waited) {   // q|k|v of this layer are complete and visible from here on
+      pdl_wait();
+      waited = true;
+    }
+    // K | V | Q rows (gathered through the window permutation): 16-byte pieces with cp.async, zero fill beyond the batch
+#pragma unroll
+    for (int j = 0; j < SSTEPS; j++) {
+      const int r = s_r + j * SROWS;
+      if (r < nfill) {
+        const int tok = stok[j];
+        if (s_p == 0) sTok[r] = tok;
+        const uint32_t doff = (uint32_t)(r * LD * 2 + s_p * 16);
+        if (tok >= 0) {
+          const __half* src = qkv + (size_t)tok * (3 * D) + (hs * NHL) * DH + s_p * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(q0 + doff), "l"(src) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(k0 + doff), "l"(src + D) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(v0 + doff), "l"(src + 2 * D) : "memory");
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(q0 + doff), "r"(0) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(k0 + doff), "r"(0) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(v0 + doff), "r"(0) : "memory");
+        }
       }
     }
     if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 1] = clock64();
@@ -348,46 +375,42 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
     __syncthreads();
     if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 2] = clock64();
     const int ntiles = sNumTiles;
-    for (int tk = warp; tk < ntiles; tk += 8) {
+#pragma unroll 1
+    for (int item = warp; item < ntiles * NHL; item += 8) {   // (q-tile, head) items, round-robin over the warps
+      const int tk = item / NHL, hl = item - tk * NHL;
       const int row = sTileRow[tk], kb = sTileKb[tk], ke = sTileKe[tk];
       const int n = ke - kb;
       const int r0 = row + g4, r1 = r0 + 8;
       const int tok0 = r0 < ke ? sTok[r0] : -1, tok1 = r1 < ke ? sTok[r1] : -1;
-      const uint32_t kwin = k0 + (uint32_t)(kb * LD * 2) + klane, vwin = v0 + (uint32_t)(kb * LD * 2) + vlane;
-      const uint32_t* qp0 = reinterpret_cast<const uint32_t*>(qkv + (size_t)max(tok0, 0) * (3 * D) + hs * NHL * DH);
-      const uint32_t* qp1 = reinterpret_cast<const uint32_t*>(qkv + (size_t)max(tok1, 0) * (3 * D) + hs * NHL * DH);
-      uint32_t* op0 = reinterpret_cast<uint32_t*>(out + (size_t)max(tok0, 0) * D + hs * NHL * DH);
-      uint32_t* op1 = reinterpret_cast<uint32_t*>(out + (size_t)max(tok1, 0) * D + hs * NHL * DH);
+      const uint32_t kwin = k0 + (uint32_t)((kb * LD + hl * DH) * 2) + klane, vwin = v0 + (uint32_t)((kb * LD + hl * DH) * 2) + vlane;
+      uint32_t qa[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(qa[0]), "=r"(qa[1]), "=r"(qa[2]), "=r"(qa[3])
+                   : "r"(q0 + (uint32_t)((row * LD + hl * DH) * 2) + vlane));
+      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float ol[4] = {0.f, 0.f, 0.f, 0.f};
+      float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 1
-      for (int hl = 0; hl < NHL; hl++) {
-        uint32_t qa[4];
-        qa[0] = tok0 >= 0 ? qp0[hl * 8 + t4] : 0u;
-        qa[2] = tok0 >= 0 ? qp0[hl * 8 + t4 + 4] : 0u;
-        qa[1] = tok1 >= 0 ? qp1[hl * 8 + t4] : 0u;
-        qa[3] = tok1 >= 0 ? qp1[hl * 8 + t4 + 4] : 0u;
-        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        float ol[4] = {0.f, 0.f, 0.f, 0.f};
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
-        for (int off = 0; off < n; off += ATT_KCHUNK) {
-          const int rem = n - off;   // warp-uniform
-          const uint32_t ka = kwin + (uint32_t)((off * LD + hl * DH) * 2), va = vwin + (uint32_t)((off * LD + hl * DH) * 2);
-          if (rem > 48) attn_chunk<8, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-          else if (rem > 32) attn_chunk<6, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-          else if (rem > 16) attn_chunk<4, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-          else attn_chunk<2, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-        }
-        const float l0 = __shfl_sync(0xffffffffu, ol[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, ol[2], lane & ~3);
-        if (tok0 >= 0) {
-          const float i0 = __fdividef(1.0f, l0);
-          op0[hl * 8 + t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][0] * i0, o[0][1] * i0);
-          op0[hl * 8 + t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][0] * i0, o[1][1] * i0);
-        }
-        if (tok1 >= 0) {
-          const float i1 = __fdividef(1.0f, l1);
-          op1[hl * 8 + t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][2] * i1, o[0][3] * i1);
-          op1[hl * 8 + t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][2] * i1, o[1][3] * i1);
-        }
+      for (int off = 0; off < n; off += ATT_KCHUNK) {
+        const int rem = n - off;   // warp-uniform
+        const uint32_t ka = kwin + (uint32_t)(off * LD * 2), va = vwin + (uint32_t)(off * LD * 2);
+        if (rem > 48) attn_chunk<8, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+        else if (rem > 32) attn_chunk<6, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+        else if (rem > 16) attn_chunk<4, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+        else attn_chunk<2, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+      }
+      const float l0 = __shfl_sync(0xffffffffu, ol[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, ol[2], lane & ~3);
+      if (tok0 >= 0) {
+        uint32_t* op0 = reinterpret_cast<uint32_t*>(out + (size_t)tok0 * D + (hs * NHL + hl) * DH);
+        const float i0 = __fdividef(1.0f, l0);
+        op0[t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][0] * i0, o[0][1] * i0);
+        op0[t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][0] * i0, o[1][1] * i0);
+      }
+      if (tok1 >= 0) {
+        uint32_t* op1 = reinterpret_cast<uint32_t*>(out + (size_t)tok1 * D + (hs * NHL + hl) * DH);
+        const float i1 = __fdividef(1.0f, l1);
+        op1[t4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[0][2] * i1, o[0][3] * i1);
+        op1[t4 + 4] = (OUT_BF16 ? pack2_bf16 : pack2_f16)(o[1][2] * i1, o[1][3] * i1);
       }
     }
     if (dbg && threadIdx.x == 0 && dbg_n < 4) {
@@ -399,20 +422,23 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
 
 template <int NHL>
 static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                        const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16);
-// out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
+                                        const int32_t* win_batch, int rec_cap, const int32_t* tok_perm, void* out_v, bool out_bf16);
+// win_batch: the per-batch records of win_batch_kernel ({first window, end window, first slot, end slot}), n_cap = the token
+// capacity the window plan was built for (bounds the record array).  out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                      const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
+                                      const int32_t* win_batch, int n_cap, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
+  const int rec_cap = n_cap / ATT_CHUNK + 2;
   static int nhl_env = -1;
   if (nhl_env < 0) nhl_env = getenv("SSTB200_ATT_NHL") ? atoi(getenv("SSTB200_ATT_NHL")) : 2;
-  if (nhl_env == 4) return sstb_win_attn_batch_t<4>(c, qkv, counters, win_offsets, win_batch, tok_perm, out_v, out_bf16);
-  return sstb_win_attn_batch_t<2>(c, qkv, counters, win_offsets, win_batch, tok_perm, out_v, out_bf16);
+  if (nhl_env == 4) return sstb_win_attn_batch_t<4>(c, qkv, counters, win_offsets, win_batch, rec_cap, tok_perm, out_v, out_bf16);
+  return sstb_win_attn_batch_t<2>(c, qkv, counters, win_offsets, win_batch, rec_cap, tok_perm, out_v, out_bf16);
 }
 template <int NHL>   // heads per CTA -> 8 / NHL CTAs per window batch
 static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                        const int32_t* win_batch, const int32_t* tok_perm, void* out_v, bool out_bf16) {
+                                        const int32_t* win_batch, int rec_cap, const int32_t* tok_perm, void* out_v, bool out_bf16) {
   __half* out = reinterpret_cast<__half*>(out_v);
-  size_t smem = (size_t)2 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
+  const int4* recs = reinterpret_cast<const int4*>(win_batch);
+  size_t smem = (size_t)3 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
   static SmemAttr sa, sb;
   CUDA_TRY(c, out_bf16 ? ensure_smem(c, sb, win_attn_batch_kernel<NHL, true>, smem) : ensure_smem(c, sa, win_attn_batch_kernel<NHL, false>, smem));
   static int grid_mult = 0;
@@ -427,10 +453,10 @@ static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const
   if (dbg_on && !dbg_buf) CUDA_TRY(c, cudaMalloc(&dbg_buf, (size_t)4096 * 16 * 8));
   if (dbg_on) CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, (size_t)grid * 16 * 8, c->stream));
   if (out_bf16)
-    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, true>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch,
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, true>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
                            tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
   else
-    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, win_batch,
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
                            tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
   if (dbg_on) {
     static int dumps = 0;

@@ -74,7 +74,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   if (dbg_skip & 2)
     rc = 0;
   else if (tc_attn)
-    rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
+    rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__half, __half>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
@@ -183,7 +183,7 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
   const float* xin = x;
   for (int l = 0; l < num_layers; l++) {
     const sstb200_sra_plan* P = &plans[l & 1];
-    int rc = (skip & 2) ? 0 : sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm, att);
+    int rc = (skip & 2) ? 0 : sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att);
     if (rc) return rc;
     const bool has_next = l + 1 < num_layers;
     if (skip & 4) continue;

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) win_attn_bwd_kernel(const __half* __restr
   const int nbatch = counters[17];
   for (int unit = blockIdx.x; unit < nbatch * HSPLIT; unit += gridDim.x) {
     const int b = unit / HSPLIT, hs = unit % HSPLIT;
-    const int wb = win_batch[b], we = win_batch[b + 1];
+    const int wb = win_batch[4 * b], we = win_batch[4 * b + 1];   // batch record {first window, end window, first slot, end slot}
     if (wb == we) continue;
     const int s0 = win_offsets[wb], s1 = win_offsets[we];
     const int nrow = min(s1 - s0, NROW);
@@ -568,7 +568,7 @@ extern "C" int sstb200_sra_stack_forward_train(sstb200_ctx* c, const sstb200_sra
     g.out_h16 = lw + w.qkv, g.ldo = 3 * DM;
     if ((rc = launch_umma<128, 128, PRO_F32, EPI_F16, FMT_BF16>(c, g, 3))) return rc;
     // 2. attention (bf16 output)
-    if ((rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(lw + w.qkv), P->num_windows_dev, P->win_offsets, P->win_batch, P->tok_perm,
+    if ((rc = sstb_win_attn_batch(c, reinterpret_cast<const __half*>(lw + w.qkv), P->num_windows_dev, P->win_offsets, P->win_batch, n, P->tok_perm,
                                   lw + w.att, /*out_bf16=*/true)))
       return rc;
     // 3. x1 = LN1(x + att Wo^T + bo), keep t1

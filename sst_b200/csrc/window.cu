@@ -190,24 +190,30 @@ __global__ void tok_finish_kernel(int n, const int32_t* __restrict__ n_dev, cons
 }
 
 // Window batches for the batched attention kernel: batch b = the windows whose first slot lies in [b*chunk, (b+1)*chunk).
-// batch_win[b] = lower_bound(offsets[0..R), b*chunk) - one binary search per thread; counters[17] = number of batches.
+// One int4 record per batch {first window, end window, first slot, end slot} (two lower bounds over offsets[0..R) per thread), so
+// that a consumer CTA learns everything about its batch from ONE load; counters[17] = number of batches.
 // A batch holds at most chunk - 1 + max_window_tokens rows.
 __global__ void win_batch_kernel(const uint32_t* __restrict__ offsets, const int32_t* __restrict__ nwin_dev, int chunk,
-                                 int32_t* __restrict__ batch_win, int32_t* __restrict__ counters, const int32_t* __restrict__ flags) {
+                                 int4* __restrict__ batch_rec, int rec_cap, int32_t* __restrict__ counters, const int32_t* __restrict__ flags) {
   pdl_wait();
   pdl_launch();
   const int R = *nwin_dev;
   const int ntok = (int)offsets[R];
   const int nb = (ntok + chunk - 1) / chunk;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += gridDim.x * blockDim.x) {
-    const uint32_t t0 = (uint32_t)b * (uint32_t)chunk;
-    int lo = 0, hi = R;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (offsets[mid] < t0) lo = mid + 1;
-      else hi = mid;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb && b < rec_cap; b += gridDim.x * blockDim.x) {
+    int w[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const uint32_t t0 = (uint32_t)(b + e) * (uint32_t)chunk;
+      int lo = 0, hi = R;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (offsets[mid] < t0) lo = mid + 1;
+        else hi = mid;
+      }
+      w[e] = lo;
     }
-    batch_win[b] = lo;
+    batch_rec[b] = make_int4(w[0], w[1], (int)offsets[w[0]], (int)offsets[w[1]]);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     counters[17] = nb;
@@ -228,6 +234,7 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   CHECK_ARG(c, c && cfg && o && n >= 0);
   CHECK_ARG(c, cfg->num_levels >= 1 && cfg->num_levels <= 8 && cfg->batch_size >= 1);
   CHECK_ARG(c, o->tok_win && o->tok_inner && o->win_offsets && o->tok_perm && o->win_level && o->win_rank && o->counters);
+  CHECK_ARG(c, ((uintptr_t)o->win_batch & 15) == 0);   // int4 records
   WinGeom g;
   make_geom(cfg, do_shift, g);
   CHECK_ARG(c, g.wx > 0 && g.wy > 0 && g.wz > 0 && g.wx < 256 && g.wy < 256 && g.wz < 256);
@@ -287,7 +294,7 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
   }
   if (o->win_batch)
     launch_pdl(win_batch_kernel, dim3((n / 112 + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
-               112, o->win_batch, o->counters, (const int32_t*)k.flags);
+               112, reinterpret_cast<int4*>(o->win_batch), n / 112 + 2, o->counters, (const int32_t*)k.flags);
   LAUNCH_CHECK(c);
   if (err_host) {
     CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, k.flags, 8, cudaMemcpyDeviceToHost, c->stream));

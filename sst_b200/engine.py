@@ -54,7 +54,7 @@ class SSTEngine:
         self.x = [torch.empty((cap, self.d), **f32) for _ in range(2)]
         self.plans = []
         for _ in range(2):
-            p = {k: torch.empty((cap + 1,) if k in ("win_offsets", "win_batch") else (cap,), **i32)
+            p = {k: torch.empty((cap + 16,) if k in ("win_offsets", "win_batch") else (cap,), **i32)
                  for k in ("pos_code", "tok_win", "tok_inner", "win_offsets", "tok_perm", "win_level", "win_rank", "tok_slot",
                            "win_batch")}
             p["counters"] = torch.zeros((20,), **i32)

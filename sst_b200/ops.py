@@ -428,7 +428,7 @@ def window_plan(coors, sparse_shape, window_shape, drop_info, do_shift, batch_si
     p.win_rank = torch.empty((n,), **i32)
     p.counters = torch.zeros((20,), **i32)
     p.tok_slot = torch.empty((n,), **i32)
-    p.win_batch = torch.empty((n + 1,), **i32)
+    p.win_batch = torch.empty((n + 16,), **i32)   # int4 records, n/112 + 2 of them
     out = _WindowShift(*[getattr(p, k).data_ptr() for k, _ in _WindowShift._fields_])
     status = (C.c_int32 * 18)()
     if token_level is not None:

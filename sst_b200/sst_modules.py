@@ -468,7 +468,11 @@ class SSTv2(nn.Module):
         if not layers:
             return x
         ops._need_cuda(x)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for l in layers for p in l.parameters())):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for l in layers for p in l.parameters()))
+        if needs_grad and not self.training and x.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the input in eval() mode are not built: call .train() (the eval-mode forward runs "
+                                      "the inference kernels, which keep no activations)")
+        if needs_grad and self.training:
             # training step: forward that keeps the activations + hand-written backward (csrc/sra_train.cu), bf16 operands
             from .train import SraStackFunction, layer_params
             for l in layers:

@@ -160,11 +160,50 @@ def test_sstv2_bf16_parity(cuda, P, blocks):
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err
-    # and the fp32 path on the same inputs agrees with it to bf16 accuracy
+    # element-wise as well: every output within 1e-2 relative, small outputs within 1e-2 of the output scale
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    # mean error is an order of magnitude below the bound (catches a systematically biased path that max-norm would pass)
+    assert (got - ref).abs().mean().item() / ref.abs().mean().item() < 2e-3
+    # and the fp32 path on the same inputs agrees with the oracle to fp32 accuracy
     m.precision = "fp32"
     with torch.no_grad():
         got32 = m(info_g)[0]["voxel_feats"].cpu()
     assert (got32 - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+
+
+def test_sstv2_tensor_path_cosine_variant(cuda):
+    """precision='bf16' with cosine attention (learned tau): tcgen05 GEMMs + the SIMT cosine window attention on fp16 q|k|v;
+    same <= 1e-2 bound as the plain path."""
+    from sst_b200.sst_modules import SSTInputLayerV2
+    feats, coors = _voxels((1000,), 6000, C=128)
+    lc = dict(cosine=True, tau_min=0.01)
+    m = _sst_pair(128, 8, 256, 1, lc)
+    il = SSTInputLayerV2((DROP_TRAIN, DROP_TEST), (12, 12, 1), (468, 468, 1), shuffle_voxels=False, mute=True).eval()
+    w = {k: v.clone() for k, v in m.state_dict().items()}
+    info_o = O.input_layer_v2(feats, coors, DROP_TEST, (12, 12, 1), (468, 468, 1))
+    ref = O.sstv2_forward(info_o, w, [8], 1, "gelu", lc)
+    m = m.to(cuda)
+    m.precision = "bf16"
+    with torch.no_grad():
+        got = m(il(feats.to(cuda), coors.to(cuda), 1))[0]["voxel_feats"].cpu()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("layer_cfg,act,d,ff", [(dict(use_bn=True), "relu", 128, 256), (dict(post_norm=False), "gelu", 128, 256),
+                                                ({}, "gelu", 64, 128)])
+def test_sstv2_tensor_path_refuses_other_variants(cuda, layer_cfg, act, d, ff):
+    """The tensor-core path is built for the reference's shipped shape (d_model 128, dim_ff 256, post-norm LayerNorm, gelu).
+    Asking for it with BatchNorm / pre-norm / another width fails loudly - it never silently runs the fp32 kernels instead."""
+    from sst_b200._lib import SSTB200Error
+    from sst_b200.sst_modules import SSTInputLayerV2
+    feats, coors = _voxels((1000,), 3000, C=d)
+    m = _sst_pair(d, 8, ff, 1, layer_cfg, act).to(cuda)
+    m.precision = "bf16"
+    il = SSTInputLayerV2((DROP_TRAIN, DROP_TEST), (12, 12, 1), (468, 468, 1), shuffle_voxels=False, mute=True).eval()
+    with torch.no_grad(), pytest.raises(SSTB200Error, match="tensor-core path"):
+        m(il(feats.to(cuda), coors.to(cuda), 1))
 
 
 @pytest.mark.parametrize("B,C,ny,nx,M", [(2, 128, 468, 468, 40000), (1, 37, 50, 45, 700), (3, 64, 33, 32, 0), (1, 300, 40, 100, 1500)])

@@ -16,11 +16,16 @@ feats = torch.randn(P, C, device=dev)
 c64 = torch.cat([torch.zeros(P, 1, dtype=torch.int64, device=dev), coors.long()], 1)
 for avg in (False, True):
     ds = ops.DynamicScatter(fl.VOXEL_SIZE, fl.PC_RANGE, avg)
-    for _ in range(2):
+    for it in range(2):
+        if it == 1:
+            torch.cuda.profiler.start()   # `ncu --profile-from-start off`: warm passes only
         ds(feats, coors)
         torch.cuda.synchronize()
         torch.arange(7, device=dev)
-for _ in range(2):
+        torch.cuda.profiler.stop()
+for it in range(2):
+    if it == 1:
+        torch.cuda.profiler.start()
     ops.scatter_v2(feats, c64, "max")
     torch.cuda.synchronize()
     torch.arange(7, device=dev)

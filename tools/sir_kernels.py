@@ -22,7 +22,9 @@ sir = SIR(num_blocks=3, in_channels=[84, 133, 133], feat_channels=[[128, 128]] *
           norm_cfg=dict(type="LN", eps=1e-3), mode="max", xyz_normalizer=[20, 20, 4], act="gelu", unique_once=True).eval().to(dev)
 sir.precision = prec
 with torch.no_grad():
-    for _ in range(2):
+    for it in range(2):
+        if it == 1:
+            torch.cuda.profiler.start()   # `ncu --profile-from-start off`: the warm pass only
         sir(sp, sf, sc, fcl)
         torch.cuda.synchronize()
 print("done")
