@@ -364,7 +364,7 @@ def main():
         m = 0
         for i in range(nsteps + S - 1):     # software pipeline of depth S over the engine pool, one host thread
             if i < nsteps:
-                engs[i % S].submit_host(pin[i % len(pin)], offs_pin)
+                engs[i % S].submit_host(pin[i % len(pin)], offs_pin, *outs[i % S])
             j = i - (S - 1)
             if j >= 0:
                 m = engs[j % S].collect_host(*outs[j % S])
@@ -384,7 +384,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / float(t.item())
     h2d = P_POINTS * eng.F * 4 + 8
-    d2h = M * eng.d * 4 + M * 16 + 4
+    d2h = engs[0].d2h_rows * (eng.d * 4 + 16) + 4   # rows that actually crossed PCIe (predicted count >= M, see SSTEngine.submit_host)
 
     # ---- roofline of the dominant kernel group: the SRA encoder layers (attention + fused chain), timed as the 12-layer stack
     roof = None

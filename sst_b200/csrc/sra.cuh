@@ -21,9 +21,14 @@ int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
                         int n_cap, const int32_t* n_dev);
 
+#define SSTB_MAX_STACK 64   // encoder layers per stack call (kernel-parameter arrays of per-layer pointers)
+// next / next_plan / next_qkv / next_pos_qk: fuse the NEXT layer's q|k|v projection into the chain (next_pos_qk = that layer's
+// [256][64] fp16 block written by sstb_sra_pos_qk)
 int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* att, const float* x, float* y, int n_cap,
                     const int32_t* n_dev, const sstb200_sra_layer* next = nullptr, const sstb200_sra_plan* next_plan = nullptr,
-                    void* next_qkv = nullptr);
+                    void* next_qkv = nullptr, const __half* next_pos_qk = nullptr);
+// out [num_layers][256][64] fp16: pos_table . [Wq; Wk]^T per (axis, in-window coordinate) for every layer of the stack
+int sstb_sra_pos_qk(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plan, __half* out);
 int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans /*[2]*/,
                         const float* x, float* y, float* scratch, int n_cap, const int32_t* n_dev);
 

@@ -143,7 +143,8 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 static bool layer_supported_tc(const sstb200_sra_layer* L, const sstb200_sra_plan* P) {
   return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && !L->norm1_mean && L->act == 2 && !L->tau && L->nhead == 8 &&
          L->in_proj_w_f16 && L->out_proj_w_f16 && L->lin1_w_f16 && L->lin2_w_f16 && P->max_window_tokens > 0 &&
-         P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->win_batch && P->pos_table && P->pos_L % 32 == 0;
+         P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->win_batch && P->pos_table && P->pos_code && P->pos_L % 32 == 0 &&
+         P->pos_ndim >= 1 && P->pos_ndim <= 3 && P->pos_ndim * P->pos_maxw <= 32 && P->pos_ndim * P->pos_L <= 128;
 }
 
 int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plans, const float* x,
@@ -152,9 +153,17 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
   for (int l = 0; l < num_layers; l++)
     if (!layer_supported_tc(&layers[l], &plans[l & 1])) return SSTB_ERR_UNSUPPORTED;  // caller falls back to per-layer calls
   const int d = 128;
+  if (num_layers > SSTB_MAX_STACK) return SSTB_ERR_UNSUPPORTED;
   __half* qkv = arena_alloc<__half>(c, (size_t)n_cap * 3 * d);
   __half* att = arena_alloc<__half>(c, (size_t)n_cap * d);
-  if (!qkv || !att) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
+  __half* pos_qk = arena_alloc<__half>(c, (size_t)num_layers * 256 * 64);
+  if (!qkv || !att || !pos_qk) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
+  // the positional term of every layer's q|k projection, tabulated per (axis, coordinate): B operand of the chain's one-hot K chunk
+  // (both shifts share the table: it depends on the window shape only)
+  {
+    int rc = sstb_sra_pos_qk(c, layers, num_layers, &plans[0], pos_qk);
+    if (rc) return rc;
+  }
   // QKV of layer 0 (stand-alone GEMM, fp32 x + pos -> fp16 rows in slot order of shift 0)
   {
     const sstb200_sra_layer* L = &layers[0];
@@ -189,7 +198,8 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
     if (skip & 4) continue;
     // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
     rc = sstb_sra_chain2(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
-                                has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr);
+                                has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr,
+                                has_next ? pos_qk + (size_t)(l + 1) * 256 * 64 : nullptr);
     if (rc) return rc;
     xin = y;
   }

@@ -62,7 +62,7 @@ enum {
 };
 
 struct Chain2Maps {
-  CUtensorMap att, x, y, qkv, wo, w1, w2, wqkv, wqk;
+  CUtensorMap att, x, y, qkv, wo, w1, w2, wqkv, wqk, wpos;
 };
 
 struct Chain2Args {
@@ -73,8 +73,7 @@ struct Chain2Args {
   int has_tail;                  // GEMM4: q|k|v of the next layer
   const float* bqkv;             // [384]
   const int32_t* next_pos_code;  // [tokens]
-  const float* pos_tab;          // [ndim][maxw][L]
-  int posL, pos_maxw, pos_ndim;
+  int pos_maxw, pos_ndim;        // one-hot column of (axis, in-window coordinate) = axis * maxw + coordinate (< 32)
   long long* dbg;                // optional timeline buffer [grid][3 roles][2 tiles][32] (SSTB200_CHAIN_DBG), else nullptr
 };
 
@@ -206,6 +205,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
     if (TAIL) {
       tma_prefetch_desc(&maps.wqkv);
       tma_prefetch_desc(&maps.wqk);
+      tma_prefetch_desc(&maps.wpos);
     }
   }
   if (warp == W_ST && lane == 0) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
   const int M = g.M_dev ? *g.M_dev : g.M_cap;
   const int n_tiles = (M + TM - 1) / TM;
   constexpr bool tail = TAIL;
-  const int NI = tail ? 9 : 6;   // ring items per tile: att, Wo, W1[0:128], W1[128:256], W2[:,0:128], W2[:,128:256], Wq, Wk, Wv
+  const int NI = tail ? 10 : 6;   // ring items per tile: att, Wo, W1[0:128], W1[128:256], W2[:,0:128], W2[:,128:256], Wqk K-chunks 0 / 1, Wpos, Wv
 
   if (warp == W_TMA) {
     // ================================================== TMA loads ==================================================
@@ -255,15 +255,17 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
         DBG_T(2, it, 4);
         if (tail) {
           // Wq|Wk as ONE N = 256 operand: a slot per 64-wide K chunk (256 rows x 128 B), then Wv (two K chunks of 128 rows)
-          auto load_qk = [&](int j, int col) {
+          // + the positional term as a third K chunk: pos . [Wq; Wk]^T tabulated per (axis, coordinate) (256 rows x 64 columns)
+          auto load_qk = [&](int j, const CUtensorMap* m, int col) {
             const int kk = k0 + j, s2 = kk % 3;
             mbar_wait(BAR(B_EMPTY + s2), (uint32_t)(((kk / 3) + 1) & 1));
             mbar_expect_tx(BAR(B_FULL + s2), SLOT);
-            tma_load_2d(sbase + OFF_RING + s2 * SLOT, &maps.wqk, col, 0, BAR(B_FULL + s2));
+            tma_load_2d(sbase + OFF_RING + s2 * SLOT, m, col, 0, BAR(B_FULL + s2));
           };
-          load_qk(6, 0);
-          load_qk(7, 64);
-          load_item(8, &maps.wqkv, 0, 256, 64, 256);
+          load_qk(6, &maps.wqk, 0);
+          load_qk(7, &maps.wqk, 64);
+          load_qk(8, &maps.wpos, 0);
+          load_item(9, &maps.wqkv, 0, 256, 64, 256);
           DBG_T(2, it, 5);
         }
       }
@@ -328,30 +330,34 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           }
           DBG_T(1, it, 8 + c);
         }
-        // ---- LN2 done: acc3 / x1 have been read, (y+pos | y) operands are in C
+        // ---- LN2 done: acc3 / x1 have been read, the y operand and the one-hot position columns are in C
         mbar_wait(BAR(B_YFULL), par);
         tc_fence_after();
         DBG_T(1, it, 12);
         if (!tail) mbar_arrive(BAR(B_CFREE));   // residual consumed and the LN2 statistics exchange (which lives in C) is over
         if (tail) {
-          // q|k = (y + pos) . [Wq; Wk]^T as one N = 256 GEMM into TMEM [128, 384): B K-chunk kc is ring item 6 + kc
+          // q|k = (y + pos) . [Wq; Wk]^T = y . [Wq; Wk]^T + onehot(axis, coordinate) . (pos_table . [Wq; Wk]^T) as one N = 256 GEMM
+          // with K = 128 + 32 into TMEM [128, 384): B K-chunk kc is ring item 6 + kc, item 8 the tabulated positional term
           wait_full(6);
           wait_full(7);
+          wait_full(8);
           mbar_wait(BAR(B_QKVE + 0), par ^ 1u);
           tc_fence_after();
           mma_steps<4, false>(tmem + 128, dC, slot(6), idesc256);
+          release(6);   // as early as possible: Wv (item 9) takes this slot and must land before the q|k GEMM retires
           mma_steps<4, true>(tmem + 128, dC + 1024, slot(7), idesc256);
+          mma_steps<2, true>(tmem + 128, dC + (u64)(32768 >> 4), slot(8), idesc256);
           umma_commit(BAR(B_QKVF + 0));
-          release(6);
           release(7);
+          release(8);
           DBG_T(1, it, 13);
           // v = y . Wv^T into TMEM [384, 512)
-          wait_full(8);
+          wait_full(9);
           mbar_wait(BAR(B_QKVE + 1), par ^ 1u);
           tc_fence_after();
-          mma_steps<8, false>(tmem + 384, dC + (u64)(32768 >> 4), slot(8), idesc128);
+          mma_steps<8, false>(tmem + 384, dC, slot(9), idesc128);
           umma_commit(BAR(B_QKVF + 1));
-          release(8);
+          release(9);
           umma_commit(BAR(B_CFREE));
           DBG_T(1, it, 14);
         }
@@ -598,27 +604,26 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
       }
       DBG_E(11);
       if (tail) {
-        const int axis = c0 / g.posL;   // posL % 32 == 0 (host check): the 32-column span lies inside one axis
-        const bool has_pos = (row0 + lrow < M) && axis < g.pos_ndim;
-        const int cv = (pcode >> (8 * axis)) & 255;
-        const float4* tp = reinterpret_cast<const float4*>(g.pos_tab + ((size_t)(has_pos ? axis : 0) * g.pos_maxw + (has_pos ? cv : 0)) * g.posL +
-                                                           (has_pos ? c0 - axis * g.posL : 0));
+        // operands of GEMM4: y as fp16 (K chunks 0, 1 of C) and this row's one-hot position columns (third K chunk, 32 columns:
+        // column axis * maxw + coordinate is 1) - the positional embedding enters q|k through the tensor core, not through a gather
         const int kc = cq >> 1, j0 = (cq & 1) * 4;
-        uint32_t yp[16];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          float4 p4 = __ldg(tp + q);
-          if (!has_pos) p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          yp[2 * q] = cvt_h2(add2(t2[2 * q], pk2(p4.x, p4.y)));
-          yp[2 * q + 1] = cvt_h2(add2(t2[2 * q + 1], pk2(p4.z, p4.w)));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          uint8_t* dst = rowC + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4);
-          *reinterpret_cast<int4*>(dst) = make_int4((int)yp[4 * q], (int)yp[4 * q + 1], (int)yp[4 * q + 2], (int)yp[4 * q + 3]);
-          *reinterpret_cast<int4*>(dst + 32768) =
+        for (int q = 0; q < 4; q++)
+          *reinterpret_cast<int4*>(rowC + kc * 16384 + (((uint32_t)(j0 + q) ^ sw) << 4)) =
               make_int4((int)cvt_h2(t2[4 * q]), (int)cvt_h2(t2[4 * q + 1]), (int)cvt_h2(t2[4 * q + 2]), (int)cvt_h2(t2[4 * q + 3]));
+        uint32_t oh[4] = {0u, 0u, 0u, 0u};
+        if (row0 + lrow < M) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const int rel = a * g.pos_maxw + ((pcode >> (8 * a)) & 255) - 8 * cq;   // position inside this thread's 8 columns
+            if (a < g.pos_ndim && rel >= 0 && rel < 8) {
+              const uint32_t one = 0x3C00u << ((rel & 1) << 4);
+#pragma unroll
+              for (int w = 0; w < 4; w++) oh[w] |= (rel >> 1) == w ? one : 0u;
+            }
+          }
         }
+        *reinterpret_cast<int4*>(rowC + 32768 + (((uint32_t)cq ^ sw) << 4)) = make_int4((int)oh[0], (int)oh[1], (int)oh[2], (int)oh[3]);
       }
       fence_async_smem();
       tc_fence_before();
@@ -681,17 +686,61 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
 #undef BAR
 }
 
+// pos_qk[l][n][axis * maxw + coordinate] = sum_j Wqk_l[n][axis * L + j] * pos_table[axis][coordinate][j]  (n < 256: q and k rows of
+// in_proj; fp32 accumulation, fp16 result, columns >= ndim * maxw zero): the B operand of the one-hot K chunk in the chain's q|k
+// GEMM.  32 blocks per layer; recomputed every frame (0.4 MFLOP per layer) so that in-place weight updates are always seen.
+struct PosQkArgs {
+  const __half* w[SSTB_MAX_STACK];   // in_proj weights [384][128] fp16 per layer
+  int num_layers;
+};
+__global__ void __launch_bounds__(256) pos_qk_kernel(PosQkArgs a, const float* __restrict__ pos_tab, int L, int maxw, int ndim,
+                                                       __half* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  // block = 8 of a layer's 256 rows (one per warp); lane = output column (axis, coordinate); table transposed in shared memory
+  __shared__ float sT[128][33];      // [j][column], j < L <= 128
+  __shared__ __half sW[8][128];
+  const int l = blockIdx.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (blockIdx.x & 31) * 8 + warp;
+  const int ncol = ndim * maxw;      // <= 32 (host check)
+  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
+    const int j = i >> 5, col = i & 31;
+    sT[j][col] = (col < ncol && j < L) ? pos_tab[(size_t)col * L + j] : 0.f;   // pos_tab is [axis][coordinate][L] = [column][L]
+  }
+  reinterpret_cast<uint2*>(sW[warp])[lane] = reinterpret_cast<const uint2*>(a.w[l] + (size_t)n * 128)[lane];
+  __syncthreads();
+  const int axis = min(lane / maxw, ndim - 1);
+  float acc = 0.f;
+  if ((axis + 1) * L <= 128)
+    for (int j = 0; j < L; j++) acc = fmaf(__half2float(sW[warp][axis * L + j]), sT[j][lane], acc);
+  __half* o = out + ((size_t)l * 256 + n) * 64;
+  o[lane] = __float2half_rn(lane < ncol ? acc : 0.f);
+  o[32 + lane] = __float2half_rn(0.f);
+}
+
 }  // namespace
 
+int sstb_sra_pos_qk(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plan, __half* out) {
+  if (num_layers > SSTB_MAX_STACK) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "encoder stacks deeper than %d layers are not built", SSTB_MAX_STACK);
+  PosQkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.num_layers = num_layers;
+  for (int l = 0; l < num_layers; l++) a.w[l] = reinterpret_cast<const __half*>(layers[l].in_proj_w_f16);
+  CUDA_TRY(c, launch_pdl(pos_qk_kernel, dim3(num_layers * 32), dim3(256), (size_t)0, c->stream, a, (const float*)plan->pos_table, plan->pos_L, plan->pos_maxw,
+                         plan->pos_ndim, out));
+  return SSTB_OK;
+}
+
 int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* att, const float* x, float* y, int n_cap, const int32_t* n_dev,
-                    const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv) {
+                    const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv, const __half* next_pos_qk) {
   Chain2Maps maps;
   Chain2Args g;
   memset(&g, 0, sizeof(g));
   memset(&maps, 0, sizeof(maps));
   const bool tail = next && next_plan && next_qkv;
-  if (tail && (next_plan->pos_L % 32 != 0 || !next_plan->pos_code || !next_plan->pos_table))
-    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs pos_L %% 32 == 0 and the next plan's pos_code / pos_table");
+  if (tail && (!next_pos_qk || !next_plan->pos_code || next_plan->pos_ndim < 1 || next_plan->pos_ndim > 3 ||
+               next_plan->pos_ndim * next_plan->pos_maxw > 32))
+    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "fused QKV tail needs the next plan's pos_code and ndim * max window extent <= 32");
   int rc = 0;
   rc |= tmap_2d_sw128(&maps.att, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, att, 128, (uint64_t)n_cap, 256, 64, 128);
   rc |= tmap_2d_sw128(&maps.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, 128, (uint64_t)n_cap, 512, 32, 128);
@@ -702,12 +751,11 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
   if (tail) {
     rc |= tmap_2d_sw128(&maps.wqkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next->in_proj_w_f16, 128, 384, 256, 64, 128);
     rc |= tmap_2d_sw128(&maps.wqk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next->in_proj_w_f16, 128, 256, 256, 64, 256);
+    rc |= tmap_2d_sw128(&maps.wpos, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next_pos_qk, 64, 256, 128, 64, 256);
     rc |= tmap_2d_sw128(&maps.qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, next_qkv, 384, (uint64_t)n_cap, 768, 64, 128);
     g.has_tail = 1;
     g.bqkv = next->in_proj_b;
     g.next_pos_code = next_plan->pos_code;
-    g.pos_tab = next_plan->pos_table;
-    g.posL = next_plan->pos_L;
     g.pos_maxw = next_plan->pos_maxw;
     g.pos_ndim = next_plan->pos_ndim;
   }

@@ -177,27 +177,45 @@ class SSTEngine:
     def forward_host(self, pinned_points, offsets_pinned, out_feats_pinned, out_coors_pinned):
         """End-to-end call on HOST buffers: H2D(points) -> forward -> D2H(num) -> D2H(feats[:M], coors[:M]).
         Returns M; the output copies are stream-ordered (synchronise the engine stream before reading them)."""
-        self.submit_host(pinned_points, offsets_pinned)
+        self.submit_host(pinned_points, offsets_pinned, out_feats_pinned, out_coors_pinned)
         return self.collect_host(out_feats_pinned, out_coors_pinned)
 
-    def submit_host(self, pinned_points, offsets_pinned):
+    def submit_host(self, pinned_points, offsets_pinned, out_feats_pinned=None, out_coors_pinned=None):
         """Asynchronous half of forward_host: enqueue H2D + forward + D2H of the row count; returns immediately, so
-        several engines (streams) can be kept in flight by one host thread."""
+        several engines (streams) can be kept in flight by one host thread.
+
+        With the pinned output buffers given here, the D2H of the result is enqueued right behind the forward for a predicted
+        row count (the largest of the recent frames + 2 %): the data-dependent size then costs no host round trip on the
+        stream's critical path; `collect_host` copies the few missing rows in the rare case the prediction was short."""
         n = pinned_points.shape[0]
         if not hasattr(self, "_num_pinned"):
             self._num_pinned = torch.zeros((1,), dtype=torch.int32).pin_memory()
             self._done = torch.cuda.Event()
+            self._rows_guess = 0
+        self._rows_sent = 0
         with torch.cuda.stream(self.stream):
             self.points[:n].copy_(pinned_points, non_blocking=True)
             self.offsets.copy_(offsets_pinned, non_blocking=True)
             self.run()
             self._num_pinned.copy_(self.num, non_blocking=True)
+            if out_feats_pinned is not None and self._rows_guess > 0:
+                g = min(self._rows_guess, self.cap, out_feats_pinned.shape[0])
+                out_feats_pinned[:g].copy_(self._last[:g], non_blocking=True)
+                out_coors_pinned[:g].copy_(self.vc[:g], non_blocking=True)
+                self._rows_sent = g
             self._done.record(self.stream)
 
     def collect_host(self, out_feats_pinned, out_coors_pinned):
+        """Rows [0, M) of the pinned buffers receive the frame's voxel features / coordinates (rows beyond M are unspecified).
+        They are complete on return when the prediction made at submit time covered M; otherwise the missing rows are copied
+        stream-ordered (synchronise the engine stream before reading).  `d2h_rows` = rows that cross PCIe for this frame."""
         self._done.synchronize()            # the row count is data dependent: one small wait per frame
         M = int(self._num_pinned[0])
-        with torch.cuda.stream(self.stream):
-            out_feats_pinned[:M].copy_(self._last[:M], non_blocking=True)
-            out_coors_pinned[:M].copy_(self.vc[:M], non_blocking=True)
+        sent = self._rows_sent
+        if M > sent:                        # no prediction yet, or it was short: fetch the remainder
+            with torch.cuda.stream(self.stream):
+                out_feats_pinned[sent:M].copy_(self._last[sent:M], non_blocking=True)
+                out_coors_pinned[sent:M].copy_(self.vc[sent:M], non_blocking=True)
+        self.d2h_rows = max(M, sent)
+        self._rows_guess = max(int(M * 1.02) + 64, int(self._rows_guess * 0.98))
         return M

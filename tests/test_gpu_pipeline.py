@@ -87,6 +87,37 @@ def test_engine_matches_oracle(cuda, precision, tol):
     assert err < tol, err
 
 
+def test_engine_host_api_with_predicted_row_count(cuda):
+    """forward_host / submit_host + collect_host on pinned HOST buffers: the D2H of the result is enqueued for a predicted row
+    count; frames with fewer, equal and MORE voxels than predicted all return exactly the rows the device path returns."""
+    from sst_b200 import flagship as fl
+    from sst_b200.engine import SSTEngine
+    cfg = fl.sst_cfg(num_blocks=1)
+    vfe, il, bb = fl.build_sst(cfg)
+    eng = SSTEngine(fl.VOXEL_SIZE, fl.PC_RANGE, vfe.to(cuda), il, bb.to(cuda), max_points=30000, batch_size=1, precision="bf16", device=cuda)
+    out_f = torch.empty((30000, eng.d), dtype=torch.float32).pin_memory()
+    out_c = torch.empty((30000, 4), dtype=torch.int32).pin_memory()
+    seen = []
+    for seed, P in [(1, 8000), (2, 8000), (3, 5000), (4, 30000), (5, 9000)]:   # 4th frame: far more voxels than predicted
+        pts = O.synth_frame(seed, P)
+        offs = torch.tensor([0, P], dtype=torch.int32)
+        eng.load_frames_device(pts.to(cuda), offs.to(cuda))
+        feats, coors, num = eng.run()
+        torch.cuda.synchronize()
+        M_ref = int(num.item())
+        ref_f, ref_c = feats[:M_ref].cpu(), coors[:M_ref].cpu()
+        out_f.fill_(float("nan"))
+        M = eng.forward_host(pts.pin_memory(), offs.pin_memory(), out_f, out_c)
+        eng.stream.synchronize()
+        assert M == M_ref
+        assert torch.equal(out_f[:M], ref_f) and torch.equal(out_c[:M], ref_c)
+        assert eng.d2h_rows >= M
+        seen.append((M, eng.d2h_rows))
+    assert seen[0][1] == seen[0][0]            # no prediction for the first frame: exactly M rows
+    assert seen[1][1] > seen[1][0]             # predicted: a little more than needed
+    assert seen[3][0] > seen[2][1]             # the big frame really exceeded the prediction
+
+
 @pytest.mark.parametrize("mode", ["max", "avg"])
 def test_dynamic_scatter_vfe_wide_input(cuda, mode):
     """FSDv2's virtual-voxel encoder shape (configs/fsdv2: in_channels 67 -> [64, 128], SURVEY config 5): beyond the fused
