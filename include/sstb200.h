@@ -248,6 +248,14 @@ int sstb200_voxelize_frames(sstb200_ctx* ctx, const float* points, int capacity,
                             const int32_t* frame_offsets_dev, int num_frames, const float voxel_size[3],
                             const float coors_range[6], int32_t* coors4);
 
+/* Fork / join of a side branch.  `side` is a second context (own stream, own workspace arena).  fork: side's stream waits for the
+ * point of ctx's stream at which the last sstb200_dynamic_vfe_forward / sstb200_dynamic_scatter_vfe_forward call had produced
+ * voxel_coors and num_dev (the VFE layers that follow in that call keep running on ctx's stream); join: ctx's stream waits for
+ * everything enqueued on side's stream so far.  The engine runs the two sstb200_window_plan calls of a frame on the side branch,
+ * next to the VFE layers.  Valid on plain streams and inside sstb200_graph_begin/end (the side stream joins the capture). */
+int sstb200_branch_fork(sstb200_ctx* ctx, sstb200_ctx* side);
+int sstb200_branch_join(sstb200_ctx* ctx, sstb200_ctx* side);
+
 /* CUDA-graph helpers for callers that chain several entry points per frame (the reference has no
  * counterpart: it launches ~10^3 ATen kernels per frame with >= 8 host syncs).
  * begin: start capturing the context's stream; end: stop, instantiate, return an opaque handle and the number

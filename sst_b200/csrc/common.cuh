@@ -29,6 +29,8 @@ struct sstb200_ctx {
   std::vector<void*> retired;  // old arenas kept alive until destroy (stream-ordered safety)
   std::string err;
   int32_t* pinned_i32 = nullptr;  // small pinned scratch for D2H counters
+  cudaEvent_t ev_coords = nullptr;  // recorded by the VFE entry points once voxel_coors / num_dev are produced (fork point of a side branch)
+  cudaEvent_t ev_done = nullptr;    // recorded by sstb200_branch_join on the side context's stream
 };
 
 inline int sstb_fail(sstb200_ctx* c, int code, const char* fmt, ...) {

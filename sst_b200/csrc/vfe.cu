@@ -834,6 +834,7 @@ static int vfe_forward_impl(sstb200_ctx* c, const sstb200_vfe_cfg* cfg, const fl
   int eg = (int)((k.nwords * 4 + 63) / 64);
   if (eg > c->num_sms * 32) eg = c->num_sms * 32;
   launch_pdl(vfe_emit_kernel<TC>, dim3(eg), dim3(64), (size_t)(0), c->stream, k.bitmap, k.word_prefix, k.nwords, cells_pad, Y, X, q, out_coors, k.total, num_dev);
+  CUDA_TRY(c, cudaEventRecord(c->ev_coords, c->stream));   // voxel_coors / num_dev are final from here on (sstb200_branch_fork)
   Csr r;
   if (inverse) {
     launch_pdl(vfe_map_kernel<TC>, dim3(nb), dim3(256), (size_t)(0), c->stream, k.keys, P, k.bitmap, k.word_prefix, cells_pad, q, inverse, count);

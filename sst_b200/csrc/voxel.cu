@@ -326,7 +326,9 @@ extern "C" sstb200_ctx* sstb200_create(int device) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-  if (cudaMallocHost((void**)&c->pinned_i32, 256) != cudaSuccess) {
+  if (cudaMallocHost((void**)&c->pinned_i32, 256) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_coords, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return nullptr;
   }
@@ -339,6 +341,8 @@ extern "C" void sstb200_destroy(sstb200_ctx* c) {
   if (c->arena) cudaFree(c->arena);
   for (void* p : c->retired) cudaFree(p);
   if (c->pinned_i32) cudaFreeHost(c->pinned_i32);
+  if (c->ev_coords) cudaEventDestroy(c->ev_coords);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   delete c;
 }
 extern "C" int sstb200_set_stream(sstb200_ctx* c, void* s) {
@@ -348,6 +352,23 @@ extern "C" int sstb200_set_stream(sstb200_ctx* c, void* s) {
 }
 extern "C" const char* sstb200_last_error(sstb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" int sstb200_num_sms(sstb200_ctx* c) { return c ? c->num_sms : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// fork / join of a side branch (a second context = second stream + second arena).  The two window plans of a frame need only the
+// voxel coordinates, which the VFE entry point produces in its first third: fork there, run the plans next to the VFE layers,
+// join before the encoder stack.  Works on plain streams and inside a stream capture (the side stream joins the capture).
+// ------------------------------------------------------------------------------------------------
+extern "C" int sstb200_branch_fork(sstb200_ctx* c, sstb200_ctx* side) {
+  CHECK_ARG(c, c && side && side != c && side->device == c->device && side->stream != c->stream);
+  CUDA_TRY(c, cudaStreamWaitEvent(side->stream, c->ev_coords, 0));
+  return SSTB_OK;
+}
+extern "C" int sstb200_branch_join(sstb200_ctx* c, sstb200_ctx* side) {
+  CHECK_ARG(c, c && side && side != c && side->device == c->device);
+  CUDA_TRY(c, cudaEventRecord(side->ev_done, side->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, side->ev_done, 0));
+  return SSTB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // CUDA graph helpers

@@ -16,6 +16,8 @@ from . import ops
 from .sst_modules import PRECISIONS, _SraPlan, SSTInputLayerV2, SSTv2
 from .voxel_modules import DynamicVFE
 
+L.SIGNATURES["sstb200_branch_fork"] = (C.c_int, [L.vp, L.vp])
+L.SIGNATURES["sstb200_branch_join"] = (C.c_int, [L.vp, L.vp])
 L.SIGNATURES["sstb200_graph_begin"] = (C.c_int, [L.vp])
 L.SIGNATURES["sstb200_graph_end"] = (C.c_int, [L.vp, C.POINTER(C.c_void_p), L.P_i32, L.P_i32])
 L.SIGNATURES["sstb200_graph_launch"] = (C.c_int, [L.vp, L.vp])
@@ -78,6 +80,7 @@ class SSTEngine:
         self._build_layer_structs()
         self._vs_arr, self._rng_arr = L.arr(C.c_float, self.vs), L.arr(C.c_float, self.rng)
         self.stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)   # side branch: the two window plans run next to the VFE layers
         self.graph = None
         self.launches_per_frame = None
         with torch.cuda.stream(self.stream):
@@ -130,9 +133,14 @@ class SSTEngine:
                                                self._vs_arr, self._rng_arr, self.coors4.data_ptr()))
         L.check(c, lib.sstb200_dynamic_vfe_forward(c, C.byref(self.vfe_cfg), self.points.data_ptr(), self.coors4.data_ptr(),
                                                    cap, self.vf.data_ptr(), self.vc.data_ptr(), self.num.data_ptr(), None))
+        # fork: the window plans need only the voxel coordinates (final after the first third of the VFE call)
+        with torch.cuda.stream(self.side):
+            cs = L.ctx(self.dev)
+        L.check(c, lib.sstb200_branch_fork(c, cs))
         for s in range(2):
-            L.check(c, lib.sstb200_window_plan_i32(c, self.vc.data_ptr(), cap, self.num.data_ptr(), C.byref(self.wcfg), s,
-                                                   C.byref(self._shift_structs[s])))
+            L.check(cs, lib.sstb200_window_plan_i32(cs, self.vc.data_ptr(), cap, self.num.data_ptr(), C.byref(self.wcfg), s,
+                                                    C.byref(self._shift_structs[s])))
+        L.check(c, lib.sstb200_branch_join(c, cs))
         if self._layers:
             L.check(c, lib.sstb200_sra_stack_forward(c, self._layer_array, len(self._layers), C.byref(self._plan_structs[0]),
                                                      C.byref(self._plan_structs[1]), self.vf.data_ptr(), self.x[0].data_ptr(),
