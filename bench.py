@@ -263,6 +263,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    from sst_b200.dist_utils import pin_to_gpu_numa
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = pin_to_gpu_numa(local)   # host thread + pinned staging buffers on the GPU's NUMA node (None: topology not exposed)
 
     from sst_b200 import build, flagship as fl
     build.build()
@@ -473,6 +476,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again, like the --impl reference arm
         times, threads, _ = cpu_oracle_frames(6, 1, budget_s=30.0)
         cpu = {"value": len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": f"{len(times)} frames of the same workload after 1 warm-up (oracle/sst_oracle.py, torch CPU fp32, "
@@ -487,6 +491,7 @@ def main():
             "dtype": "f32" if precision == "fp32" else "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "precision": precision, "voxels": int(M), "frames_in_flight": S,
+                       "host_cpus": (len(numa_cpus) if numa_cpus else None),
                        "l2": "inputs larger than L2: 80 distinct resident sweeps (144 MB) cycled; latency_ms measured with a 512 MB L2 flush per step",
                        "parallelism": f"dp{world} (frames sharded, no collective)"},
             "clocks": clocks, "gpu_launches": int(eng.launches_per_frame or 0) * args.steps,

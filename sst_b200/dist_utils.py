@@ -1,8 +1,35 @@
 """Host-side helpers for the multi-GPU layout of the path: frames are sharded over ranks with no data-path collective
 in inference; training adds ONE gradient all-reduce per step over a single flat buffer (NCCL over NVLink on the GPU boxes, gloo in
 the CPU tests) and the naiveSyncBN statistics exchange (sst_b200/norm.py).  Pure torch.distributed plumbing - no kernels here."""
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def pin_to_gpu_numa(device_index):
+    """Bind this process to the CPUs that are local to GPU `device_index` (the PCI device's `local_cpulist` in sysfs), so the
+    host thread that feeds the engine and the pinned staging buffers it allocates afterwards live on the GPU's NUMA node.
+    Returns the CPU set, or None when the topology is not exposed (containers without sysfs PCI info): never fatal."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        path = f"/sys/bus/pci/devices/{bdf.lower()}/local_cpulist"
+        if not os.path.exists(path):
+            return None
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def shard_range(num_frames, rank, world):
