@@ -248,6 +248,12 @@ int sstb200_voxelize_frames(sstb200_ctx* ctx, const float* points, int capacity,
                             const int32_t* frame_offsets_dev, int num_frames, const float voxel_size[3],
                             const float coors_range[6], int32_t* coors4);
 
+/* C5  SingleStageFSDV2.voxelize_with_batch_idx (mmdet3d/models/detectors/single_stage_fsd_v2.py:108-123): virtual-voxel coordinates
+ * of the concatenated real + virtual points.  points [n, ldp] fp32 (x,y,z first), batch_idx [n] int64 ->
+ * coors [n,4] int64 (batch, z, y, x) = floor_div(p - range_lo, voxel_size) with torch.div(rounding_mode='floor') semantics, no clamp. */
+int sstb200_voxelize_with_batch_idx(sstb200_ctx* ctx, const float* points, int n, int ldp, const int64_t* batch_idx,
+                                    const float voxel_size[3], const float range_lo[3], int64_t* coors);
+
 /* Fork / join of a side branch.  `side` is a second context (own stream, own workspace arena).  fork: side's stream waits for the
  * point of ctx's stream at which the last sstb200_dynamic_vfe_forward / sstb200_dynamic_scatter_vfe_forward call had produced
  * voxel_coors and num_dev (the VFE layers that follow in that call keep running on ctx's stream); join: ctx's stream waits for

@@ -175,6 +175,87 @@ def dsvfe_fixture(R):
     print("dsvfe_small", f.shape)
 
 
+FSDV2 = dict(vs=(0.5, 0.5, 0.5), rng=[-40, -40, -2, 40, 40, 4], target=[12, 160, 160], C=16,
+             vfe=dict(in_channels=19, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True, rel_dist_scaler=10.0),
+             ms_hiddens=[[24, 32], [16, 32], [16, 32]], ms_shapes=[[12, 160, 160], [6, 80, 80], [3, 40, 40]])
+
+
+def fsdv2_inputs(seed=11, n_ori=4000, n_vir=1500, batch=2):
+    """Synthetic segmentor outputs for the FSDv2 front: real points with features, sampled foreground points with centre votes."""
+    g = torch.Generator().manual_seed(seed)
+    C, rng = FSDV2["C"], FSDV2["rng"]
+    lo, hi = torch.tensor(rng[:3], dtype=torch.float32), torch.tensor(rng[3:], dtype=torch.float32)
+
+    def pts(n):
+        return torch.cat([lo + (hi - lo) * torch.rand(n, 3, generator=g) * 0.98 + 0.01, torch.rand(n, 2, generator=g)], 1)
+    origin = dict(seg_points=pts(n_ori), seg_feats=torch.randn(n_ori, C + 3, generator=g), batch_idx=torch.randint(0, batch, (n_ori,), generator=g))
+    sp = pts(n_vir)
+    centers = sp[:, :3] + torch.randn(n_vir, 3, generator=g) * 1.5   # votes; a few leave the range and get clipped
+    centers[::97] += 100.0
+    sampled = dict(seg_points=sp, center_preds=centers, seg_logits=torch.randn(n_vir, 3, generator=g), seg_feats=torch.randn(n_vir, C, generator=g),
+                   batch_idx=torch.randint(0, batch, (n_vir,), generator=g))
+    levels = []
+    for (fin, _), shp in zip(FSDV2["ms_hiddens"], FSDV2["ms_shapes"]):
+        n = 600
+        cells = torch.randperm(batch * shp[0] * shp[1] * shp[2], generator=g)[:n]
+        b, r = cells // (shp[0] * shp[1] * shp[2]), cells % (shp[0] * shp[1] * shp[2])
+        idx = torch.stack([b, r // (shp[1] * shp[2]), (r // shp[2]) % shp[1], r % shp[2]], 1).int()
+        levels.append((torch.randn(n, fin, generator=g), idx, list(shp)))
+    return sampled, origin, levels
+
+
+def fsdv2_front_fixture(R):
+    """SingleStageFSDV2.extract_feat / multiscale_fusion / voxelize_with_batch_idx / clip_points / ms_coors_proj run from the
+    reference source itself (ref_shim.reference_methods) on a stand-in `self` that carries the reference's own sub-modules; the
+    backbone (sparse-conv mixer) is an identity that records what it is given."""
+    import types
+    torch.manual_seed(0)
+    fns = ref_shim.reference_methods("mmdet3d/models/detectors/single_stage_fsd_v2.py", "SingleStageFSDV2",
+                                     ["extract_feat", "multiscale_fusion", "voxelize_with_batch_idx", "clip_points", "ms_coors_proj"])
+    norm = dict(type='naiveSyncBN1d', eps=1e-5, momentum=0.01)
+    C = FSDV2["C"]
+
+    class Stand(torch.nn.Module):
+        pass
+    for with_ms in (False, True):
+        self = Stand()
+        self.baseline_mode, self.zero_virtual_feature, self.only_virtual, self.as_rpn = False, False, False, False
+        self.virtual_voxel_size, self.point_cloud_range = FSDV2["vs"], FSDV2["rng"]
+        self.virtual_proj = R.sst_ops.build_mlp(C + 3 + 3 + 2, [16, 16], norm)
+        self.ori_proj = R.sst_ops.build_mlp(C + 3, [16, 16], norm)
+        self.voxel_encoder = R.DynamicScatterVFE(voxel_size=FSDV2["vs"], point_cloud_range=FSDV2["rng"],
+                                                 norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), unique_once=True, **FSDV2["vfe"])
+        self.multiscale_cfg = dict(multiscale_levels=[0, 1, 2], projector_hiddens=FSDV2["ms_hiddens"], fusion_mode='avg',
+                                   target_sparse_shape=FSDV2["target"], norm_cfg=norm) if with_ms else None
+        if with_ms:
+            self.ms_projectors = torch.nn.ModuleList([R.sst_ops.build_mlp(h[0], h[1:], norm) for h in FSDV2["ms_hiddens"]])
+        self.eval()
+        _rand_norm(self, 21)
+        seen = {}
+
+        def backbone(vf, vc, bs):
+            seen.update(vf=vf.clone(), vc=vc.clone(), bs=bs)
+            return vf, vc, None
+        self.backbone = backbone
+        for k, f in fns.items():
+            setattr(self, k, types.MethodType(f, self))
+        sampled, origin, levels = fsdv2_inputs()
+        ms = [types.SimpleNamespace(features=f, indices=i, spatial_shape=s) for f, i, s in levels] if with_ms else None
+        with torch.no_grad():
+            out = self.extract_feat({k: v.clone() for k, v in sampled.items()}, {k: v.clone() for k, v in origin.items()}, None, ms)
+            coors = self.voxelize_with_batch_idx(torch.cat([origin["seg_points"][:, :3], self.clip_points(sampled["center_preds"].clone(), FSDV2["rng"])]),
+                                                 torch.cat([origin["batch_idx"], sampled["batch_idx"]]))
+        tag = "ms" if with_ms else "plain"
+        np.savez_compressed(os.path.join(OUT, f"fsdv2_front_{tag}.npz"), coors=coors.numpy(), backbone_feats=seen["vf"].numpy(),
+                            backbone_coors=seen["vc"].numpy(), batch_size=np.array(seen["bs"]), virtual_feats=out["virtual_feats"].numpy(),
+                            virtual_coors=out["virtual_coors"].numpy(), virtual_centers=out["virtual_centers"].numpy(),
+                            **{f"sampled.{k}": v.numpy() for k, v in sampled.items()}, **{f"origin.{k}": v.numpy() for k, v in origin.items()},
+                            **{f"ms{i}.{n}": (np.array(a) if n == "shape" else a.numpy()) for i, lv in enumerate(levels)
+                               for n, a in zip(("features", "indices", "shape"), lv)},
+                            **_sd(self, "w."))
+        print("fsdv2_front", tag, seen["vf"].shape, out["virtual_feats"].shape)
+
+
 def scatter_fixture():
     """Seeded restatement of tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:56-84: expected values are the
     brute-force per-voxel loop the reference test itself uses as ground truth."""
@@ -234,6 +315,7 @@ if __name__ == "__main__":
     vfe_fixture(R)
     sir_fixture(R)
     dsvfe_fixture(R)
+    fsdv2_front_fixture(R)
     scatter_fixture()
     neck_fixture(R)
     hard_voxelize_fixture()

@@ -214,3 +214,27 @@ def load():
     )
     _LOADED = ns
     return ns
+
+
+def reference_methods(relpath, class_name, names, extra_globals=None):
+    """Compile selected METHODS of a reference class straight from its source file, unmodified, without importing the module
+    (detector files import half of mmdet / mmseg / spconv at module level).  Returns {name: function}; decorators are dropped
+    (`force_fp32` / `torch.no_grad` do not change CPU fp32 results).  The functions see the shim's `scatter_v2` / `build_mlp`."""
+    import ast
+    R = load()
+    src = open(os.path.join(REF_ROOT, relpath)).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    g = {"torch": torch, "scatter_v2": R.sst_ops.scatter_v2, "build_mlp": R.sst_ops.build_mlp, "F": torch.nn.functional}
+    g.update(extra_globals or {})
+    out = {}
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, os.path.join(REF_ROOT, relpath), "exec"), g)
+            out[node.name] = g[node.name]
+    missing = set(names) - set(out)
+    assert not missing, f"{class_name} has no method(s) {missing}"
+    return out

@@ -34,6 +34,47 @@ __global__ void dynamic_voxelize_kernel(const float* __restrict__ points, int P,
   coors[(size_t)i * 3 + 2] = cx;
 }
 
+// FSDv2 virtual-voxel coordinates (single_stage_fsd_v2.py:108-123): coors = [batch, floor_div(p - lo, vs) in z,y,x order], NO clamp
+// (the detector clips the predicted centres beforehand).  torch.div(rounding_mode='floor') on floats is c10::div_floor_floating
+// (fmod-based, with a half-way correction), restated here so that the coordinates are bit-identical to the reference's.
+__device__ __forceinline__ float div_floor_f32(float a, float b) {
+  if (b == 0.f) return __fdiv_rn(a, b);
+  const float mod = fmodf(a, b);
+  float div = __fdiv_rn(a - mod, b);
+  if (mod != 0.f && (b < 0.f) != (mod < 0.f)) div -= 1.0f;
+  if (div != 0.f) {
+    float fl = floorf(div);
+    if (div - fl > 0.5f) fl += 1.0f;
+    return fl;
+  }
+  return copysignf(0.f, __fdiv_rn(a, b));
+}
+__global__ void voxelize_batch_idx_kernel(const float* __restrict__ points, int n, int ldp, const long long* __restrict__ batch_idx,
+                                          float vx, float vy, float vz, float x0, float y0, float z0, long long* __restrict__ coors) {
+  pdl_wait();
+  pdl_launch();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = points + (size_t)i * ldp;
+  longlong2 a, b;
+  a.x = batch_idx[i];
+  a.y = (long long)div_floor_f32(p[2] - z0, vz);
+  b.x = (long long)div_floor_f32(p[1] - y0, vy);
+  b.y = (long long)div_floor_f32(p[0] - x0, vx);
+  reinterpret_cast<longlong2*>(coors)[2 * (size_t)i] = a;
+  reinterpret_cast<longlong2*>(coors)[2 * (size_t)i + 1] = b;
+}
+extern "C" int sstb200_voxelize_with_batch_idx(sstb200_ctx* c, const float* points, int n, int ldp, const int64_t* batch_idx,
+                                               const float voxel_size[3], const float range_lo[3], int64_t* coors) {
+  CHECK_ARG(c, c && n >= 0 && ldp >= 3 && voxel_size && range_lo);
+  if (n == 0) return SSTB_OK;
+  CHECK_ARG(c, points && batch_idx && coors && ((uintptr_t)coors & 15) == 0);
+  launch_pdl(voxelize_batch_idx_kernel, dim3((n + 255) / 256), dim3(256), (size_t)0, c->stream, points, n, ldp, (const long long*)batch_idx,
+             voxel_size[0], voxel_size[1], voxel_size[2], range_lo[0], range_lo[1], range_lo[2], (long long*)coors);
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
+}
+
 void sstb_grid_size(const float vs[3], const float r[6], int g[3]) {
   // ceil((max-min)/vs) in float32, voxelization_cuda.cu:355-357
   for (int i = 0; i < 3; i++) g[i] = (int)ceilf((r[3 + i] - r[i]) / vs[i]);

@@ -120,3 +120,60 @@ def test_dynamic_scatter_vfe_reference_golden(cuda):
     f, c, inv = m.to(cuda)(z["points"].to(cuda), z["coors"].to(cuda), return_inv=True)
     assert torch.equal(c.cpu(), z["vcoors"]) and torch.equal(inv.cpu(), z["inv"])
     torch.testing.assert_close(f.cpu(), z["feats"], rtol=1e-4, atol=1e-5)
+
+
+FSDV2 = dict(vs=(0.5, 0.5, 0.5), rng=[-40, -40, -2, 40, 40, 4], target=[12, 160, 160])
+
+
+@pytest.mark.parametrize("tag", ["plain", "ms"])
+def test_fsdv2_front_reference_golden(cuda, tag):
+    """BASELINE config 5 front (sst_b200.fsdv2_modules.VirtualVoxelFront: voxelize_with_batch_idx kernel, DynamicScatterVFE, indicator
+    and multiscale scatter_v2 on one shared voxel index) against the tensors SingleStageFSDV2.extract_feat hands to / takes from its
+    backbone in the unmodified reference: coordinates and masks bit-exact, features to fp32 accuracy."""
+    import types
+    from sst_b200.fsdv2_modules import VirtualVoxelFront
+    z = _load(f"fsdv2_front_{tag}.npz")
+    norm = dict(type='naiveSyncBN1d', eps=1e-5, momentum=0.01)
+    ms_cfg = dict(multiscale_levels=[0, 1, 2], projector_hiddens=[[24, 32], [16, 32], [16, 32]], fusion_mode='avg',
+                  target_sparse_shape=FSDV2["target"], norm_cfg=norm) if tag == "ms" else None
+    m = VirtualVoxelFront(
+        voxel_encoder=dict(type='DynamicScatterVFE', in_channels=19, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True,
+                           voxel_size=FSDV2["vs"], point_cloud_range=FSDV2["rng"], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01),
+                           unique_once=True, rel_dist_scaler=10.0),
+        virtual_point_projector=dict(in_channels=24, hidden_dims=[16, 16], norm_cfg=norm, ori_in_channels=19, ori_hidden_dims=[16, 16]),
+        multiscale_cfg=ms_cfg).eval()
+    missing, unexpected = m.load_state_dict(_w(z, "w."), strict=False)
+    assert not [k for k in missing if "num_batches_tracked" not in k] and not unexpected
+    m = m.to(cuda)
+    sampled = {k[len("sampled."):]: v.to(cuda) for k, v in z.items() if k.startswith("sampled.")}
+    origin = {k[len("origin."):]: v.to(cuda) for k, v in z.items() if k.startswith("origin.")}
+    ms = None
+    if tag == "ms":
+        ms = [types.SimpleNamespace(features=z[f"ms{i}.features"].to(cuda), indices=z[f"ms{i}.indices"].to(cuda),
+                                    spatial_shape=z[f"ms{i}.shape"].tolist()) for i in range(3)]
+    with torch.no_grad():
+        fr = m.front(sampled, origin, ms)
+        out = m.finish(fr, fr["voxel_feats"], fr["voxel_coors"])      # identity in place of the sparse-conv mixer
+    assert torch.equal(fr["coors"].cpu(), z["coors"])
+    assert torch.equal(fr["voxel_coors"].cpu(), z["backbone_coors"])
+    torch.testing.assert_close(fr["voxel_feats"].cpu(), z["backbone_feats"], rtol=1e-4, atol=1e-4)
+    assert torch.equal(out["virtual_coors"].cpu(), z["virtual_coors"])
+    torch.testing.assert_close(out["virtual_feats"].cpu(), z["virtual_feats"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out["virtual_centers"].cpu(), z["virtual_centers"], rtol=0, atol=1e-5)
+
+
+def test_voxelize_with_batch_idx_matches_torch_floor_div(cuda):
+    """The kernel restates c10::div_floor_floating: bit-identical to torch.div(rounding_mode='floor') on adversarial inputs
+    (exact multiples of the voxel size, negatives, tiny offsets, non-representable voxel sizes)."""
+    from sst_b200.fsdv2_modules import voxelize_with_batch_idx
+    g = torch.Generator().manual_seed(0)
+    vs, rng = (0.32, 0.1, 0.3), [-74.88, -10.05, -2.0, 74.88, 10.05, 4.0]
+    n = 200000
+    p = (torch.rand(n, 3, generator=g) - 0.5) * torch.tensor([160.0, 22.0, 7.0])
+    k = torch.randint(-300, 300, (n // 4, 3), generator=g).float()
+    p[: n // 4] = k * torch.tensor(vs) + torch.tensor(rng[:3])            # sit exactly on voxel boundaries
+    p[n // 4: n // 2] = torch.nextafter(p[n // 4: n // 2], torch.full((n // 4, 3), -1e9))
+    bi = torch.randint(0, 4, (n,), generator=g)
+    ref = torch.cat([bi[:, None], torch.div(p - torch.tensor(rng[:3])[None], torch.tensor(vs)[None], rounding_mode="floor").long()[:, [2, 1, 0]]], 1)
+    got = voxelize_with_batch_idx(p.to(cuda), bi.to(cuda), vs, rng).cpu()
+    assert torch.equal(got, ref)

@@ -165,3 +165,35 @@ def test_vfe_small_golden():
     vf, vc = O.dynamic_vfe_forward(z["points"], z["coors"], _w(z, "w."), VS, RNG, 2)
     assert torch.equal(vc, z["vcoors"])
     torch.testing.assert_close(vf, z["feats"], rtol=1e-5, atol=1e-5)
+
+
+FSDV2 = dict(vs=(0.5, 0.5, 0.5), rng=[-40, -40, -2, 40, 40, 4], target=[12, 160, 160],
+             vfe=dict(num_layers=2, with_cluster_center=True, with_voxel_center=True, rel_dist_scaler=10.0, eps=1e-3))
+
+
+def _fsdv2_inputs(z, with_ms):
+    sampled = {k[len("sampled."):]: v for k, v in z.items() if k.startswith("sampled.")}
+    origin = {k[len("origin."):]: v for k, v in z.items() if k.startswith("origin.")}
+    ms = None
+    if with_ms:
+        ms = dict(levels=[(z[f"ms{i}.features"], z[f"ms{i}.indices"], z[f"ms{i}.shape"].tolist()) for i in range(3)],
+                  target_sparse_shape=FSDV2["target"], fusion_mode="avg")
+    return sampled, origin, ms
+
+
+@pytest.mark.parametrize("tag", ["plain", "ms"])
+def test_fsdv2_front_golden(tag):
+    """FSDv2 virtual-voxel front (config 5): the oracle against what SingleStageFSDV2.extract_feat itself hands to its backbone
+    (reference source run through oracle/ref_shim.reference_methods, fixture tests/golden/fsdv2_front_*.npz)."""
+    z = _load(f"fsdv2_front_{tag}.npz")
+    sampled, origin, ms = _fsdv2_inputs(z, tag == "ms")
+    out = O.fsdv2_front(sampled, origin, _w(z, "w."), FSDV2["vs"], FSDV2["rng"], FSDV2["vfe"], ms=ms)
+    assert torch.equal(out["coors"], z["coors"])
+    assert torch.equal(out["voxel_coors"], z["backbone_coors"])
+    torch.testing.assert_close(out["voxel_feats"], z["backbone_feats"], rtol=1e-5, atol=1e-5)
+    # the part after the (identity) backbone: virtual voxels only
+    vf, vc = out["voxel_feats"], out["voxel_coors"]
+    if out["singlescale_mask"] is not None:
+        vf, vc = vf[out["singlescale_mask"]], vc[out["singlescale_mask"]]
+    assert torch.equal(vc[out["virtual_mask"]], z["virtual_coors"])
+    torch.testing.assert_close(vf[out["virtual_mask"]], z["virtual_feats"], rtol=1e-5, atol=1e-5)
