@@ -318,7 +318,13 @@ def main():
     main = torch.cuda.current_stream(dev)
     REPS = int(os.environ.get("SSTB200_BENCH_REPS", "30"))   # the K-step window is repeated and the MEDIAN window reported
     windows = []
+    ncu_range = os.environ.get("SSTB200_NCU_RANGE") == "1"   # `ncu --profile-from-start off`: profile the first timed window only
     for rep in range(REPS):
+        if ncu_range and rep == 0:
+            torch.cuda.profiler.start()
+        if ncu_range and rep == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
         for e in engs:

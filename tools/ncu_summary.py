@@ -80,6 +80,8 @@ def main():
             if vs:
                 e[k] = round(statistics.median(vs), 3)
         e["us_total"] = round(sum(x.get("us", 0) for x in ls), 2)
+        if e.get("us"):
+            e["dram_GBps"] = round((e.get("dram_read_B", 0) + e.get("dram_write_B", 0)) / e["us"] * 1e-3, 1)
         out[name] = e
     json.dump({"note": "ncu --set full --clock-control none; per-launch medians; durations are serialised + cold-cache, use shares not absolutes",
                "kernels": out}, open(a.out, "w"), indent=1)
@@ -95,10 +97,10 @@ def main():
                       open(a.layer_json, "w"), indent=1)
     if a.md:
         with open(a.md, "w") as f:
-            f.write("| kernel | launches | µs (median) | DRAM rd MB | DRAM wr MB | regs | grid×block | SM % | DRAM % | issue % | tensor % |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+            f.write("| kernel | launches | µs (median) | DRAM rd MB | DRAM wr MB | DRAM GB/s | regs | grid×block | SM % | DRAM % | issue % | tensor % |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
             for k, v in out.items():
-                f.write("| `%s` | %d | %.2f | %.3f | %.3f | %d | %d×%d | %.1f | %.1f | %.1f | %.1f |\n" % (
-                    k[:90], v["launches"], v.get("us", 0), v.get("dram_read_B", 0) / 1e6, v.get("dram_write_B", 0) / 1e6, v.get("regs", 0),
+                f.write("| `%s` | %d | %.2f | %.3f | %.3f | %.0f | %d | %d×%d | %.1f | %.1f | %.1f | %.1f |\n" % (
+                    k[:90], v["launches"], v.get("us", 0), v.get("dram_read_B", 0) / 1e6, v.get("dram_write_B", 0) / 1e6, v.get("dram_GBps", 0), v.get("regs", 0),
                     v.get("grid", 0), v.get("block", 0), v.get("sm_pct", 0), v.get("dram_pct", 0), v.get("issue_active_pct", 0), v.get("tensor_pipe_pct", 0)))
     print("kernels:", len(out))
 
