@@ -143,7 +143,7 @@ typedef struct {
                             *       [18] status bits (bit0 token outside the window grid, bit1 window count not covered), [19] spare */
   int32_t* tok_slot;       /* opt [n] position of the token inside tok_perm (inverse permutation) */
   int32_t* win_batch;      /* opt [n+16], 16-byte aligned: one record of 4 ints per batch b = the windows whose first slot lies in
-                              [112b, 112b+112): {first window, end window, first slot, end slot}; at most n/112 + 2 records */
+                              [112b, 112b+112): {first window, end window, first slot, end slot}; at most n/32 + 2 records (fits: 4 (n/32 + 2) <= n + 16) */
 } sstb200_window_shift;
 
 /* status_host (opt, int32[18]): if non-NULL the call synchronises and returns

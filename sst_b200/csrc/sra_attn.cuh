@@ -427,7 +427,7 @@ static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const
 // capacity the window plan was built for (bounds the record array).  out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
                                       const int32_t* win_batch, int n_cap, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
-  const int rec_cap = n_cap / ATT_CHUNK + 2;
+  const int rec_cap = n_cap / 32 + 2;   // bound of the record array for the smallest batch size (csrc/window.cu)
   static int nhl_env = -1;
   if (nhl_env < 0) nhl_env = getenv("SSTB200_ATT_NHL") ? atoi(getenv("SSTB200_ATT_NHL")) : 2;
   if (nhl_env == 4) return sstb_win_attn_batch_t<4>(c, qkv, counters, win_offsets, win_batch, rec_cap, tok_perm, out_v, out_bf16);

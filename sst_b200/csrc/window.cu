@@ -292,9 +292,16 @@ static int window_plan_impl(sstb200_ctx* c, const TC* coors, int n, const int32_
     launch_pdl(tok_finish_kernel, dim3(nb), dim3(256), (size_t)(0), c->stream, n, n_dev, o->tok_win, o->tok_inner, o->win_level, o->win_rank, lv,
                (long long*)o->drop_level, (long long*)o->flat2win_inds, r.offsets, o->tok_slot);
   }
-  if (o->win_batch)
-    launch_pdl(win_batch_kernel, dim3((n / 112 + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
-               112, reinterpret_cast<int4*>(o->win_batch), n / 112 + 2, o->counters, (const int32_t*)k.flags);
+  if (o->win_batch) {
+    static int chunk = 0;   // slots per window batch (tuning knob SSTB200_ATT_CHUNK, 32..112; a batch holds <= chunk - 1 + 144 <= 255 rows)
+    if (!chunk) {
+      const char* e = getenv("SSTB200_ATT_CHUNK");
+      chunk = e ? atoi(e) : 112;
+      if (chunk < 32 || chunk > 112) chunk = 112;
+    }
+    launch_pdl(win_batch_kernel, dim3((n / chunk + 256) / 256), dim3(256), (size_t)0, c->stream, (const uint32_t*)r.offsets, (const int32_t*)nwin,
+               chunk, reinterpret_cast<int4*>(o->win_batch), n / 32 + 2, o->counters, (const int32_t*)k.flags);
+  }
   LAUNCH_CHECK(c);
   if (err_host) {
     CUDA_TRY(c, cudaMemcpyAsync(c->pinned_i32, k.flags, 8, cudaMemcpyDeviceToHost, c->stream));
