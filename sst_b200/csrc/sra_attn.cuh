@@ -197,9 +197,9 @@ __device__ __forceinline__ uint32_t ex2_h2(float a, float b) {
 // m0 / m1: running row maxima in log2 units; o / ol: running numerators / denominators.  kaddr / vaddr: this lane's ldmatrix
 // row addresses for the chunk's first key (shared-memory byte addresses); n = keys of the window inside this chunk
 // (8 * KT - 16 < n <= 8 * KT, so only the last two key tiles can be partial).
-template <int KT, int LD>
-__device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, uint32_t vaddr, int n, int t4, bool ones_lane, float sl2,
-                                           bool first, float& m0, float& m1, float (*o)[4], float* ol) {
+template <int KT, int LD, bool COS>
+__device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, uint32_t vaddr, int n, int t4, bool ones_lane, float sl2_0,
+                                           float sl2_1, const float* invk, bool first, float& m0, float& m1, float (*o)[4], float* ol) {
   float s[KT][4];
 #pragma unroll
   for (int jj = 0; jj < KT / 2; jj++) {
@@ -211,6 +211,13 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
     s[2 * jj + 1][0] = s[2 * jj + 1][1] = s[2 * jj + 1][2] = s[2 * jj + 1][3] = 0.f;
     mma_f16_16816(s[2 * jj], qa, kf[0], kf[1]);
     mma_f16_16816(s[2 * jj + 1], qa, kf[2], kf[3]);
+  }
+  if (COS) {   // cosine attention: the key's 1 / |k| per column (the query's 1 / |q| and 1 / tau ride in the row scales)
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+      const float i0 = invk[j * 8 + 2 * t4], i1 = invk[j * 8 + 2 * t4 + 1];
+      s[j][0] *= i0, s[j][1] *= i1, s[j][2] *= i0, s[j][3] *= i1;
+    }
   }
   // columns past the window hold other windows' keys or zero fill: -inf (only the last two tiles can be affected)
 #pragma unroll
@@ -229,7 +236,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
   c0m = fmaxf(c0m, __shfl_xor_sync(0xffffffffu, c0m, 2));
   c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 1));
   c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 2));
-  const float n0 = fmaxf(m0, c0m * sl2), n1 = fmaxf(m1, c1m * sl2);
+  const float n0 = fmaxf(m0, c0m * sl2_0), n1 = fmaxf(m1, c1m * sl2_1);   // (row scales are positive)
   if (!first) {   // rescale what the earlier chunks accumulated (warp-uniform)
     const float f0 = fast_ex2(m0 - n0), f1 = fast_ex2(m1 - n1);
     o[0][0] *= f0, o[0][1] *= f0, o[1][0] *= f0, o[1][1] *= f0, ol[0] *= f0, ol[1] *= f0;
@@ -241,10 +248,10 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
 #pragma unroll
   for (int kc = 0; kc < KT / 2; kc++) {
     uint32_t pa[4];
-    pa[0] = ex2_h2(fmaf(s[2 * kc][0], sl2, -n0), fmaf(s[2 * kc][1], sl2, -n0));
-    pa[1] = ex2_h2(fmaf(s[2 * kc][2], sl2, -n1), fmaf(s[2 * kc][3], sl2, -n1));
-    pa[2] = ex2_h2(fmaf(s[2 * kc + 1][0], sl2, -n0), fmaf(s[2 * kc + 1][1], sl2, -n0));
-    pa[3] = ex2_h2(fmaf(s[2 * kc + 1][2], sl2, -n1), fmaf(s[2 * kc + 1][3], sl2, -n1));
+    pa[0] = ex2_h2(fmaf(s[2 * kc][0], sl2_0, -n0), fmaf(s[2 * kc][1], sl2_0, -n0));
+    pa[1] = ex2_h2(fmaf(s[2 * kc][2], sl2_1, -n1), fmaf(s[2 * kc][3], sl2_1, -n1));
+    pa[2] = ex2_h2(fmaf(s[2 * kc + 1][0], sl2_0, -n0), fmaf(s[2 * kc + 1][1], sl2_0, -n0));
+    pa[3] = ex2_h2(fmaf(s[2 * kc + 1][2], sl2_1, -n1), fmaf(s[2 * kc + 1][3], sl2_1, -n1));
     uint32_t vb[4];
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                  : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3])
@@ -263,12 +270,16 @@ __device__ __forceinline__ void attn_chunk(const uint32_t* qa, uint32_t kaddr, u
 // BEFORE griddepcontrol.wait, i.e. while the tail of the kernel that produces q|k|v is still running (the plan was written by
 // kernels that completed before that producer started: every kernel of the library waits before it triggers its dependents),
 // (3) Q is staged with K and V by cp.async, so the compute phase never waits on global memory.
-template <int NHL, bool OUT_BF16>
+// COS: cosine attention (models/sst/cosine_msa.py:123-185): logits = (q / |q|) . (k / |k|) / clamp(tau_head, tau_min) instead of
+// q . k / sqrt(dh).  q and k stay as staged; 1 / |q|, 1 / |k| per (row, head) are computed once per batch in fp32 and applied to the
+// fp32 scores (no second rounding of the operands).
+template <int NHL, bool OUT_BF16, bool COS>
 static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __half* __restrict__ qkv,
                                                                        const int32_t* __restrict__ counters,
                                                                        const int32_t* __restrict__ win_offsets,
                                                                        const int4* __restrict__ batch_rec, int rec_cap,
                                                                        const int32_t* __restrict__ tok_perm, float scale,
+                                                                       const float* __restrict__ tau, int tau_n, float tau_min,
                                                                        __half* __restrict__ out, long long* dbg) {
   pdl_launch();
   int dbg_n = 0;
@@ -283,6 +294,7 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
   __shared__ short sTileKb[ATT_BT];    // local key range of its window
   __shared__ short sTileKe[ATT_BT];
   __shared__ int sNumTiles;
+  __shared__ float sInvQ[COS ? NHL * NROW : 1], sInvK[COS ? NHL * NROW : 1];   // [head][row]: 1 / max(|q|, 1e-12), 1 / max(|k|, 1e-12)
   // batch b = the windows whose first slot lies in [b*ATT_CHUNK, (b+1)*ATT_CHUNK) (win_batch_kernel, csrc/window.cu); it holds
   // at most ATT_CHUNK - 1 + 144 <= ATT_BT rows.  record = {first window, end window, first slot, end slot}
   int4 rc = batch_rec[min((int)blockIdx.x / HSPLIT, rec_cap - 1)];
@@ -374,6 +386,22 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     if (dbg && threadIdx.x == 0 && dbg_n < 4) dbg[(blockIdx.x * 4 + dbg_n) * 4 + 2] = clock64();
+    if (COS) {   // F.normalize(q), F.normalize(k) per head (eps 1e-12) as fp32 factors
+      for (int idx = threadIdx.x; idx < nfill * NHL * 2; idx += 256) {
+        const int r = idx / (NHL * 2), rem = idx - r * (NHL * 2), hl = rem >> 1, isk = rem & 1;
+        const uint4* p = reinterpret_cast<const uint4*>((isk ? sK : sQ) + r * LD + hl * DH);
+        const uint4 a = p[0], b4 = p[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+          ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+        }
+        (isk ? sInvK : sInvQ)[hl * NROW + r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      }
+      __syncthreads();
+    }
     const int ntiles = sNumTiles;
 #pragma unroll 1
     for (int item = warp; item < ntiles * NHL; item += 8) {   // (q-tile, head) items, round-robin over the warps
@@ -390,14 +418,23 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float ol[4] = {0.f, 0.f, 0.f, 0.f};
       float m0 = -INFINITY, m1 = -INFINITY;
+      float s0r = sl2, s1r = sl2;   // log2(e) x logit scale of this lane's two query rows
+      if (COS) {
+        const int h = hs * NHL + hl;
+        const float it = 1.4426950408889634f / fmaxf(tau_n > 1 ? tau[h] : tau[0], tau_min);
+        s0r = it * sInvQ[hl * NROW + min(r0, NROW - 1)];
+        s1r = it * sInvQ[hl * NROW + min(r1, NROW - 1)];
+      }
+      const float* ikw = COS ? sInvK + hl * NROW + kb : nullptr;
 #pragma unroll 1
       for (int off = 0; off < n; off += ATT_KCHUNK) {
         const int rem = n - off;   // warp-uniform
         const uint32_t ka = kwin + (uint32_t)(off * LD * 2), va = vwin + (uint32_t)(off * LD * 2);
-        if (rem > 48) attn_chunk<8, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-        else if (rem > 32) attn_chunk<6, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-        else if (rem > 16) attn_chunk<4, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
-        else attn_chunk<2, LD>(qa, ka, va, rem, t4, g4 == 0, sl2, off == 0, m0, m1, o, ol);
+        const float* ik = COS ? ikw + off : nullptr;
+        if (rem > 48) attn_chunk<8, LD, COS>(qa, ka, va, rem, t4, g4 == 0, s0r, s1r, ik, off == 0, m0, m1, o, ol);
+        else if (rem > 32) attn_chunk<6, LD, COS>(qa, ka, va, rem, t4, g4 == 0, s0r, s1r, ik, off == 0, m0, m1, o, ol);
+        else if (rem > 16) attn_chunk<4, LD, COS>(qa, ka, va, rem, t4, g4 == 0, s0r, s1r, ik, off == 0, m0, m1, o, ol);
+        else attn_chunk<2, LD, COS>(qa, ka, va, rem, t4, g4 == 0, s0r, s1r, ik, off == 0, m0, m1, o, ol);
       }
       const float l0 = __shfl_sync(0xffffffffu, ol[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, ol[2], lane & ~3);
       if (tok0 >= 0) {
@@ -420,27 +457,22 @@ static __global__ void __launch_bounds__(256, 3) win_attn_batch_kernel(const __h
   }
 }
 
-template <int NHL>
-static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                        const int32_t* win_batch, int rec_cap, const int32_t* tok_perm, void* out_v, bool out_bf16);
 // win_batch: the per-batch records of win_batch_kernel ({first window, end window, first slot, end slot}), n_cap = the token
-// capacity the window plan was built for (bounds the record array).  out: [n, 128] attention output in flat token order, IEEE fp16 (inference) or bf16 (out_bf16: training path)
+// capacity the window plan was built for (bounds the record array).  out: [n, 128] attention output in flat token order, IEEE fp16
+// (inference) or bf16 (out_bf16: training path).  tau != nullptr: cosine attention with tau_n (1 or 8) temperatures.
 static inline int sstb_win_attn_batch(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                      const int32_t* win_batch, int n_cap, const int32_t* tok_perm, void* out_v, bool out_bf16 = false) {
+                                      const int32_t* win_batch, int n_cap, const int32_t* tok_perm, void* out_v, bool out_bf16 = false,
+                                      const float* tau = nullptr, int tau_n = 0, float tau_min = 0.f) {
+  constexpr int NHL = 2;   // heads per CTA -> 4 CTAs per window batch (4 heads per CTA measured slower on B200)
   const int rec_cap = n_cap / 32 + 2;   // bound of the record array for the smallest batch size (csrc/window.cu)
-  static int nhl_env = -1;
-  if (nhl_env < 0) nhl_env = getenv("SSTB200_ATT_NHL") ? atoi(getenv("SSTB200_ATT_NHL")) : 2;
-  if (nhl_env == 4) return sstb_win_attn_batch_t<4>(c, qkv, counters, win_offsets, win_batch, rec_cap, tok_perm, out_v, out_bf16);
-  return sstb_win_attn_batch_t<2>(c, qkv, counters, win_offsets, win_batch, rec_cap, tok_perm, out_v, out_bf16);
-}
-template <int NHL>   // heads per CTA -> 8 / NHL CTAs per window batch
-static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const int32_t* counters, const int32_t* win_offsets,
-                                        const int32_t* win_batch, int rec_cap, const int32_t* tok_perm, void* out_v, bool out_bf16) {
   __half* out = reinterpret_cast<__half*>(out_v);
   const int4* recs = reinterpret_cast<const int4*>(win_batch);
+  if (tau && out_bf16) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "cosine attention is not built for the training path");
   size_t smem = (size_t)3 * (ATT_BT + 16) * (NHL * 16 + 8) * sizeof(__half);
-  static SmemAttr sa, sb;
-  CUDA_TRY(c, out_bf16 ? ensure_smem(c, sb, win_attn_batch_kernel<NHL, true>, smem) : ensure_smem(c, sa, win_attn_batch_kernel<NHL, false>, smem));
+  static SmemAttr sa, sb, sc;
+  CUDA_TRY(c, out_bf16 ? ensure_smem(c, sb, win_attn_batch_kernel<NHL, true, false>, smem)
+                       : (tau ? ensure_smem(c, sc, win_attn_batch_kernel<NHL, false, true>, smem)
+                              : ensure_smem(c, sa, win_attn_batch_kernel<NHL, false, false>, smem)));
   static int grid_mult = 0;
   if (!grid_mult) {
     const char* e = getenv("SSTB200_ATT_GRID");  // CTAs per SM of the persistent unit loop (tuning knob; default from the B200 sweep)
@@ -452,12 +484,16 @@ static inline int sstb_win_attn_batch_t(sstb200_ctx* c, const __half* qkv, const
   const int grid = c->num_sms * grid_mult;
   if (dbg_on && !dbg_buf) CUDA_TRY(c, cudaMalloc(&dbg_buf, (size_t)4096 * 16 * 8));
   if (dbg_on) CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, (size_t)grid * 16 * 8, c->stream));
+  long long* dbg = dbg_on ? dbg_buf : (long long*)nullptr;
   if (out_bf16)
-    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, true>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
-                           tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, true, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
+                           tok_perm, 0.25f, tau, tau_n, tau_min, out, dbg));
+  else if (tau)
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false, true>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
+                           tok_perm, 0.25f, tau, tau_n, tau_min, out, dbg));
   else
-    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
-                           tok_perm, 0.25f, out, dbg_on ? dbg_buf : (long long*)nullptr));
+    CUDA_TRY(c, launch_pdl(win_attn_batch_kernel<NHL, false, false>, dim3(grid), dim3(256), smem, c->stream, qkv, counters, win_offsets, recs, rec_cap,
+                           tok_perm, 0.25f, tau, tau_n, tau_min, out, dbg));
   if (dbg_on) {
     static int dumps = 0;
     std::vector<long long> h((size_t)grid * 16);

@@ -46,7 +46,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     dbg_skip = e ? atoi(e) : 0;
   }
   // tensor-core attention path: plain scaled-dot-product, 8 heads x 16, windows <= 144 tokens
-  const bool tc_attn = !L->tau && L->nhead == 8 && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
+  const bool tc_attn = L->nhead == 8 && (!L->tau || L->tau_n == 1 || L->tau_n == 8) && P->max_window_tokens > 0 && P->max_window_tokens <= ATT_MAXT &&
                        P->num_windows_dev && P->win_batch;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -74,7 +74,7 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
   if (dbg_skip & 2)
     rc = 0;
   else if (tc_attn)
-    rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att);
+    rc = sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att, false, L->tau, L->tau_n, L->tau_min);
   else  // cosine attention / unbounded windows: SIMT kernel on the bf16 operands
     rc = sstb_win_attn<__half, __half>(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win,
                                                      L->tau, L->tau_n, L->tau_min, att);
@@ -141,7 +141,9 @@ int sstb_sra_layer_bf16(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
 // 2 launches per layer; q/k/v, attention output and the residual stream never take a detour.
 // ------------------------------------------------------------------------------------------------
 static bool layer_supported_tc(const sstb200_sra_layer* L, const sstb200_sra_plan* P) {
-  return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && !L->norm1_mean && L->act == 2 && !L->tau && L->nhead == 8 &&
+  // LayerNorm or eval-mode BatchNorm (use_bn), plain or cosine attention (tau per layer or per head)
+  return L->d_model == 128 && L->dim_ff == 256 && L->post_norm && L->act == 2 && L->nhead == 8 && (!L->tau || L->tau_n == 1 || L->tau_n == 8) &&
+         (!L->norm1_mean || (L->norm1_var && L->norm2_mean && L->norm2_var)) &&
          L->in_proj_w_f16 && L->out_proj_w_f16 && L->lin1_w_f16 && L->lin2_w_f16 && P->max_window_tokens > 0 &&
          P->max_window_tokens <= ATT_MAXT && P->num_windows_dev && P->win_batch && P->pos_table && P->pos_code && P->pos_L % 32 == 0 &&
          P->pos_ndim >= 1 && P->pos_ndim <= 3 && P->pos_ndim * P->pos_maxw <= 32 && P->pos_ndim * P->pos_L <= 128;
@@ -157,7 +159,14 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
   __half* qkv = arena_alloc<__half>(c, (size_t)n_cap * 3 * d);
   __half* att = arena_alloc<__half>(c, (size_t)n_cap * d);
   __half* pos_qk = arena_alloc<__half>(c, (size_t)num_layers * 256 * 64);
-  if (!qkv || !att || !pos_qk) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
+  bool any_bn = false;
+  for (int l = 0; l < num_layers; l++) any_bn |= layers[l].norm1_mean != nullptr;
+  float* bn_fold = any_bn ? arena_alloc<float>(c, (size_t)num_layers * 4 * 128) : nullptr;
+  if (!qkv || !att || !pos_qk || (any_bn && !bn_fold)) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra stack: arena too small");
+  if (any_bn) {
+    int rc = sstb_sra_bn_fold(c, layers, num_layers, bn_fold);
+    if (rc) return rc;
+  }
   // the positional term of every layer's q|k projection, tabulated per (axis, coordinate): B operand of the chain's one-hot K chunk
   // (both shifts share the table: it depends on the window shape only)
   {
@@ -192,14 +201,16 @@ int sstb_sra_stack_bf16(sstb200_ctx* c, const sstb200_sra_layer* layers, int num
   const float* xin = x;
   for (int l = 0; l < num_layers; l++) {
     const sstb200_sra_plan* P = &plans[l & 1];
-    int rc = (skip & 2) ? 0 : sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att);
+    int rc = (skip & 2) ? 0 : sstb_win_attn_batch(c, qkv, P->num_windows_dev, P->win_offsets, P->win_batch, n_cap, P->tok_perm, att, false,
+                                                  layers[l].tau, layers[l].tau_n, layers[l].tau_min);
     if (rc) return rc;
     const bool has_next = l + 1 < num_layers;
     if (skip & 4) continue;
     // the chain reads the residual rows of a tile before it writes the same rows of y: in-place (xin == y) is safe
     rc = sstb_sra_chain2(c, &layers[l], att, xin, y, n_cap, n_dev, has_next ? &layers[l + 1] : nullptr,
                                 has_next ? &plans[(l + 1) & 1] : nullptr, has_next ? qkv : nullptr,
-                                has_next ? pos_qk + (size_t)(l + 1) * 256 * 64 : nullptr);
+                                has_next ? pos_qk + (size_t)(l + 1) * 256 * 64 : nullptr,
+                                layers[l].norm1_mean ? bn_fold + (size_t)l * 4 * 128 : nullptr);
     if (rc) return rc;
     xin = y;
   }

@@ -71,6 +71,7 @@ struct Chain2Args {
   int M_cap;
   const int32_t* M_dev;
   int has_tail;                  // GEMM4: q|k|v of the next layer
+  // norm: LayerNorm (g1/be1/g2/be2 = weight, bias) or eval-mode BatchNorm (layer_cfg use_bn: g* = folded scale, be* = folded shift)
   const float* bqkv;             // [384]
   const int32_t* next_pos_code;  // [tokens]
   int pos_maxw, pos_ndim;        // one-hot column of (axis, in-window coordinate) = axis * maxw + coordinate (< 32)
@@ -178,7 +179,7 @@ __device__ __forceinline__ void mma_steps(uint32_t d_tmem, u64 adesc, u64 bdesc,
     else mma1<0>(d_tmem, adesc + ao, bdesc + bo, idesc);
   }
 }
-template <bool TAIL>
+template <bool TAIL, bool BN>
 __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Args g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -452,30 +453,36 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           sq2 = fma2(a, a, sq2);
           sq2 = fma2(b, b, sq2);
         }
-        float s0, s1, q0, q1;
-        up2(sum2, s0, s1);
-        up2(sq2, q0, q1);
-        *stat_own = make_float2(s0 + s1, q0 + q1);
+        if (!BN) {
+          float s0, s1, q0, q1;
+          up2(sum2, s0, s1);
+          up2(sq2, q0, q1);
+          *stat_own = make_float2(s0 + s1, q0 + q1);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 8; q++) ga[q] = __ldg(reinterpret_cast<const float4*>(g.g1 + c0) + q);
-      named_bar_sync(2 + qd, 128);
+      if (!BN) named_bar_sync(2 + qd, 128);
       DBG_E(3);
       {
-        const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
-        const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
-        const float2 s2 = *reinterpret_cast<const float2*>(rowC + 2 * 16384 + (sw << 4));
-        const float2 s3 = *reinterpret_cast<const float2*>(rowC + 3 * 16384 + (sw << 4));
-        const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
-        const float mean = sum * (1.0f / D);
-        const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
-        const u64 rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+        u64 rs2 = 0ull, nm2 = 0ull;
+        if (!BN) {
+          const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
+          const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
+          const float2 s2 = *reinterpret_cast<const float2*>(rowC + 2 * 16384 + (sw << 4));
+          const float2 s3 = *reinterpret_cast<const float2*>(rowC + 3 * 16384 + (sw << 4));
+          const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
+          const float mean = sum * (1.0f / D);
+          const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
+          rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+        }
         uint32_t xo[32];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float4 e4 = __ldg(reinterpret_cast<const float4*>(g.be1 + c0) + q);
-          const u64 a = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
-          const u64 b = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
+          // LayerNorm: ((t - mean) rstd) w + b; eval BatchNorm: t s + t0 with the folded per-channel scale / shift
+          const u64 a = fma2(BN ? t2[2 * q] : fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
+          const u64 b = fma2(BN ? t2[2 * q + 1] : fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
           t2[2 * q] = a;
           t2[2 * q + 1] = b;
           up2u(a, xo[4 * q], xo[4 * q + 1]);
@@ -568,31 +575,36 @@ __global__ void __launch_bounds__(NTHR, 1) sra_chain2_kernel(const __grid_consta
           sq2 = fma2(a, a, sq2);
           sq2 = fma2(b, b, sq2);
         }
-        float s0, s1, q0, q1;
-        up2(sum2, s0, s1);
-        up2(sq2, q0, q1);
-        *stat_own = make_float2(s0 + s1, q0 + q1);
+        if (!BN) {
+          float s0, s1, q0, q1;
+          up2(sum2, s0, s1);
+          up2(sq2, q0, q1);
+          *stat_own = make_float2(s0 + s1, q0 + q1);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 8; q++) ga[q] = __ldg(reinterpret_cast<const float4*>(g.g2 + c0) + q);
-      named_bar_sync(2 + qd, 128);
+      if (!BN) named_bar_sync(2 + qd, 128);
       DBG_E(10);
       {
-        const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
-        const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
-        const float2 s2 = *reinterpret_cast<const float2*>(rowC + 2 * 16384 + (sw << 4));
-        const float2 s3 = *reinterpret_cast<const float2*>(rowC + 3 * 16384 + (sw << 4));
-        const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
-        const float mean = sum * (1.0f / D);
-        const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
-        const u64 rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
-        named_bar_sync(2 + qd, 128);   // every statistic of this quadrant has been read: C may now receive the operands
+        u64 rs2 = 0ull, nm2 = 0ull;
+        if (!BN) {
+          const float2 s0 = *reinterpret_cast<const float2*>(rowC + 0 * 16384 + (sw << 4));
+          const float2 s1 = *reinterpret_cast<const float2*>(rowC + 1 * 16384 + (sw << 4));
+          const float2 s2 = *reinterpret_cast<const float2*>(rowC + 2 * 16384 + (sw << 4));
+          const float2 s3 = *reinterpret_cast<const float2*>(rowC + 3 * 16384 + (sw << 4));
+          const float sum = (s0.x + s1.x) + (s2.x + s3.x), sq = (s0.y + s1.y) + (s2.y + s3.y);
+          const float mean = sum * (1.0f / D);
+          const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + g.eps);
+          rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+          named_bar_sync(2 + qd, 128);   // every statistic of this quadrant has been read: C may now receive the operands
+        }
         // (global loads are kept out of the loops that store to shared memory: the compiler will not move them across the stores)
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const float4 e4 = __ldg(reinterpret_cast<const float4*>(g.be2 + c0) + q);
-          t2[2 * q] = fma2(fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
-          t2[2 * q + 1] = fma2(fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
+          t2[2 * q] = fma2(BN ? t2[2 * q] : fma2(t2[2 * q], rs2, nm2), pk2(ga[q].x, ga[q].y), pk2(e4.x, e4.y));
+          t2[2 * q + 1] = fma2(BN ? t2[2 * q + 1] : fma2(t2[2 * q + 1], rs2, nm2), pk2(ga[q].z, ga[q].w), pk2(e4.z, e4.w));
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -718,6 +730,25 @@ __global__ void __launch_bounds__(256) pos_qk_kernel(PosQkArgs a, const float* _
   o[32 + lane] = __float2half_rn(0.f);
 }
 
+// eval-mode BatchNorm of layer_cfg use_bn folded to y = x s + t per channel: out[l][4][128] = {s1, t1, s2, t2}
+struct BnFoldArgs {
+  const float* p[8][8];   // per layer: norm1 w, b, mean, var, norm2 w, b, mean, var
+  float eps[8];
+};
+__global__ void __launch_bounds__(128) bn_fold_kernel(BnFoldArgs a, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int l = blockIdx.x, c = threadIdx.x;
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const float* const* q = a.p[l] + 4 * n;
+    if (!q[2]) continue;   // LayerNorm layer
+    const float sc = q[0][c] * rsqrtf(q[3][c] + a.eps[l]);
+    out[((size_t)l * 4 + 2 * n) * 128 + c] = sc;
+    out[((size_t)l * 4 + 2 * n + 1) * 128 + c] = q[1][c] - q[2][c] * sc;
+  }
+}
+
 }  // namespace
 
 int sstb_sra_pos_qk(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, const sstb200_sra_plan* plan, __half* out) {
@@ -731,8 +762,25 @@ int sstb_sra_pos_qk(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_lay
   return SSTB_OK;
 }
 
+int sstb_sra_bn_fold(sstb200_ctx* c, const sstb200_sra_layer* layers, int num_layers, float* out) {
+  for (int l0 = 0; l0 < num_layers; l0 += 8) {
+    BnFoldArgs a;
+    memset(&a, 0, sizeof(a));
+    const int nl = num_layers - l0 < 8 ? num_layers - l0 : 8;
+    for (int l = 0; l < nl; l++) {
+      const sstb200_sra_layer* L = &layers[l0 + l];
+      const float* src[8] = {L->norm1_w, L->norm1_b, L->norm1_mean, L->norm1_var, L->norm2_w, L->norm2_b, L->norm2_mean, L->norm2_var};
+      for (int i = 0; i < 8; i++) a.p[l][i] = src[i];
+      a.eps[l] = L->norm_eps;
+    }
+    CUDA_TRY(c, launch_pdl(bn_fold_kernel, dim3(nl), dim3(128), (size_t)0, c->stream, a, out + (size_t)l0 * 4 * 128));
+  }
+  return SSTB_OK;
+}
+
 int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* att, const float* x, float* y, int n_cap, const int32_t* n_dev,
-                    const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv, const __half* next_pos_qk) {
+                    const sstb200_sra_layer* next, const sstb200_sra_plan* next_plan, void* next_qkv, const __half* next_pos_qk,
+                    const float* bn_fold) {
   Chain2Maps maps;
   Chain2Args g;
   memset(&g, 0, sizeof(g));
@@ -763,15 +811,19 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
   g.bo = L->out_proj_b;
   g.b1 = L->lin1_b;
   g.b2 = L->lin2_b;
-  g.g1 = L->norm1_w;
-  g.be1 = L->norm1_b;
-  g.g2 = L->norm2_w;
-  g.be2 = L->norm2_b;
+  const bool bn = L->norm1_mean != nullptr;
+  if (bn && !bn_fold) return sstb_fail(c, SSTB_ERR_ARG, "BatchNorm layer without folded scale / shift (sstb_sra_bn_fold)");
+  g.g1 = bn ? bn_fold : L->norm1_w;
+  g.be1 = bn ? bn_fold + 128 : L->norm1_b;
+  g.g2 = bn ? bn_fold + 256 : L->norm2_w;
+  g.be2 = bn ? bn_fold + 384 : L->norm2_b;
   g.eps = L->norm_eps;
   g.M_cap = n_cap;
   g.M_dev = n_dev;
-  static SmemAttr sa0, sa1;
-  CUDA_TRY(c, tail ? ensure_smem(c, sa1, sra_chain2_kernel<true>, (size_t)SMEM_BYTES) : ensure_smem(c, sa0, sra_chain2_kernel<false>, (size_t)SMEM_BYTES));
+  static SmemAttr sa[4];
+  void (*kern)(const Chain2Maps, const Chain2Args) = tail ? (bn ? sra_chain2_kernel<true, true> : sra_chain2_kernel<true, false>)
+                                                          : (bn ? sra_chain2_kernel<false, true> : sra_chain2_kernel<false, false>);
+  CUDA_TRY(c, ensure_smem(c, sa[(tail ? 2 : 0) + (bn ? 1 : 0)], kern, (size_t)SMEM_BYTES));
   const int tiles_cap = (n_cap + TM - 1) / TM;
   const int grid = c->num_sms < tiles_cap ? c->num_sms : tiles_cap;
   static int dbg_on = -1;
@@ -783,8 +835,7 @@ int sstb_sra_chain2(sstb200_ctx* c, const sstb200_sra_layer* L, const __half* at
     CUDA_TRY(c, cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, c->stream));
     g.dbg = dbg_buf;
   }
-  if (tail) CUDA_TRY(c, launch_pdl(sra_chain2_kernel<true>, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
-  else CUDA_TRY(c, launch_pdl(sra_chain2_kernel<false>, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
+  CUDA_TRY(c, launch_pdl(kern, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, c->stream, maps, g));
   if (dbg_on) {
     std::vector<long long> h(dbg_n);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));

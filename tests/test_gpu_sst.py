@@ -171,31 +171,57 @@ def test_sstv2_bf16_parity(cuda, P, blocks):
     assert (got32 - ref).abs().max().item() / ref.abs().max().item() < 1e-3
 
 
-def test_sstv2_tensor_path_cosine_variant(cuda):
-    """precision='bf16' with cosine attention (learned tau): tcgen05 GEMMs + the SIMT cosine window attention on fp16 q|k|v;
-    same <= 1e-2 bound as the plain path."""
+@pytest.mark.parametrize("name,lc,P,blocks", [
+    ("cosine, one tau per layer", dict(cosine=True, tau_min=0.01), 6000, 1),
+    ("cosine, tau per head", dict(cosine=True, non_shared_tau=True, tau_min=0.01), 20000, 2),
+    ("eval BatchNorm", dict(use_bn=True), 20000, 2),
+    ("configs/fsd SST encoder: BatchNorm + cosine", dict(use_bn=True, cosine=True, tau_min=0.01), 150000, 4),
+])
+def test_sstv2_tensor_path_variants(cuda, name, lc, P, blocks):
+    """precision='bf16' on the FUSED path (2 launches per layer) for the layer_cfg variants the reference's configs use with the
+    SST-6 shape: cosine attention (sst_waymoD5_1x_3class_centerhead.py:75: 1/|q|, 1/|k| and 1/tau applied to the fp32 scores of the
+    tensor-core kernel), eval-mode BatchNorm (folded scale / shift in the chain epilogues) and both together
+    (configs/fsd/fsd_waymoD1_1x_sst_encoder.py:70).  Same <= 1e-2 bound as the plain path, max-norm and element-wise."""
     from sst_b200.sst_modules import SSTInputLayerV2
-    feats, coors = _voxels((1000,), 6000, C=128)
-    lc = dict(cosine=True, tau_min=0.01)
-    m = _sst_pair(128, 8, 256, 1, lc)
+    feats, coors = _voxels((1000,), P, C=128)
+    m = _sst_pair(128, 8, 256, blocks, lc)
     il = SSTInputLayerV2((DROP_TRAIN, DROP_TEST), (12, 12, 1), (468, 468, 1), shuffle_voxels=False, mute=True).eval()
     w = {k: v.clone() for k, v in m.state_dict().items()}
     info_o = O.input_layer_v2(feats, coors, DROP_TEST, (12, 12, 1), (468, 468, 1))
-    ref = O.sstv2_forward(info_o, w, [8], 1, "gelu", lc)
+    ref = O.sstv2_forward(info_o, w, [8] * blocks, blocks, "gelu", lc)
     m = m.to(cuda)
     m.precision = "bf16"
     with torch.no_grad():
         got = m(il(feats.to(cuda), coors.to(cuda), 1))[0]["voxel_feats"].cpu()
+    assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 1e-2, err
+    assert err < 1e-2, (name, err)
     torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+
+
+def test_sstv2_tensor_path_variants_run_fused(cuda):
+    """The variants above really take the fused stack path (2 kernels per layer): the frame graph of an engine built with cosine
+    attention has exactly as many kernel nodes as the plain one, BatchNorm + cosine one more (the per-frame BatchNorm fold); the
+    unfused fallback would add 3 launches per layer."""
+    from sst_b200 import flagship as fl
+    from sst_b200.engine import SSTEngine
+    counts = {}
+    for name, lc in (("plain", {}), ("cosine", dict(cosine=True, tau_min=0.01)), ("bn_cosine", dict(use_bn=True, cosine=True, tau_min=0.01))):
+        cfg = fl.sst_cfg(num_blocks=2)
+        cfg["backbone"]["layer_cfg"] = lc
+        vfe, il, bb = fl.build_sst(cfg)
+        eng = SSTEngine(fl.VOXEL_SIZE, fl.PC_RANGE, vfe.to(cuda), il, bb.to(cuda), max_points=20000, batch_size=1, precision="bf16", device=cuda)
+        counts[name] = eng.launches_per_frame
+    assert counts["cosine"] == counts["plain"], counts
+    assert counts["bn_cosine"] == counts["plain"] + 1, counts
 
 
 @pytest.mark.parametrize("layer_cfg,act,d,ff", [(dict(use_bn=True), "relu", 128, 256), (dict(post_norm=False), "gelu", 128, 256),
                                                 ({}, "gelu", 64, 128)])
 def test_sstv2_tensor_path_refuses_other_variants(cuda, layer_cfg, act, d, ff):
-    """The tensor-core path is built for the reference's shipped shape (d_model 128, dim_ff 256, post-norm LayerNorm, gelu).
-    Asking for it with BatchNorm / pre-norm / another width fails loudly - it never silently runs the fp32 kernels instead."""
+    """The tensor-core path is built for the reference's shipped shape (d_model 128, dim_ff 256, post-norm, gelu; LayerNorm or
+    BatchNorm, plain or cosine attention).  Asking for it with relu / pre-norm / another width fails loudly - it never silently runs
+    the fp32 kernels instead."""
     from sst_b200._lib import SSTB200Error
     from sst_b200.sst_modules import SSTInputLayerV2
     feats, coors = _voxels((1000,), 3000, C=d)
