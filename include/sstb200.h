@@ -368,6 +368,41 @@ int sstb200_sra_stack_backward(sstb200_ctx* ctx, const sstb200_sra_layer* layers
 int sstb200_adamw_step(sstb200_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale);
 
+/* ---- next-1: sparse 3-D convolution of the reference's sparse U-Nets (SimpleSparseUNet / VirtualVoxelMixer,
+ * mmdet3d/models/middle_encoders/sparse_unet.py:15-505; SparseBasicBlock / make_sparse_convmodule, mmdet3d/ops/sparse_block.py:81-289),
+ * which the reference delegates to spconv.  The three entry points replace spconv's native interface as vendored in the tree
+ * (mmdet3d/ops/spconv/src/all.cc:21-33): get_indice_pairs_3d (ops.py:47-107 -> include/spconv/spconv_ops.h:25-93, geometry.h:25-301)
+ * and indice_conv_fp32 / fused_indice_conv_fp32 (ops.py:110-137 -> spconv_ops.h:95-260, fused_spconv_ops.h).
+ * Coordinates are int32 rows (batch, z, y, x); spatial shapes / kernel sizes / strides / paddings are (z, y, x) triples; kernel
+ * offset k = (dz * ky + dy) * kx + dx reads the input cell  out * stride - padding + (dz, dy, dx)  (geometry.h:60-67).
+ * The rulebook is OUTPUT-STATIONARY: nbr[o][k] = input row feeding output row o through offset k, or -1. */
+
+/* Active output cells of SparseConv3d (non-submanifold): every output cell with at least one active input in its receptive field,
+ * emitted in lexicographic (b,z,y,x) order (spconv's order is hash-insertion order; features are compared per coordinate).
+ * out_cap >= min(n_in * prod(ceil(k/s)), batch * prod(out_shape)).  num_out_host != NULL: one stream sync, and an input coordinate
+ * outside batch_size / in_shape is reported as an error. */
+int sstb200_spconv_out_coors(sstb200_ctx* ctx, const int32_t* in_coors, int n_in, int batch_size, const int32_t in_shape[3],
+                             const int32_t out_shape[3], const int32_t ksize[3], const int32_t stride[3], const int32_t padding[3],
+                             int32_t* out_coors, int out_cap, int32_t* num_out_dev, int32_t* num_out_host);
+
+/* Neighbour tables between two coordinate sets (rows unique).  SubMConv3d: out_coors = in_coors, stride 1, out_shape = in_shape.
+ * nbr [n_out, KV] (may be NULL): input row at  out * stride - padding + delta_k.  nbr_inv [n_in, KV] (may be NULL): the transposed
+ * table = output row that input row i feeds through offset k - the table SparseInverseConv3d runs on (indice pairs of its couple
+ * conv with in / out swapped, mmdet3d/ops/spconv/conv.py:147-153).  status_host != NULL: one stream sync, coordinates outside the
+ * grids are an error. */
+int sstb200_spconv_table(sstb200_ctx* ctx, const int32_t* in_coors, int n_in, const int32_t* out_coors, int n_out, int batch_size,
+                         const int32_t in_shape[3], const int32_t out_shape[3], const int32_t ksize[3], const int32_t stride[3],
+                         const int32_t padding[3], int32_t* nbr, int32_t* nbr_inv, int32_t* status_host);
+
+/* out[o, :] = act( (sum_k feats[nbr[o][k], :] . W[k]) * scale + shift + residual[o, :] )   - one launch for conv + folded
+ * BatchNorm1d (+ residual add) (+ ReLU).  feats [*, c_in] fp32, weight [KV, c_in, c_out] fp32 = the reference's parameter layout
+ * (D,H,W,in,out; mmdet3d/ops/spconv/conv.py:97-98), scale / shift [c_out] or NULL (1 / 0), residual [n_out, c_out] or NULL.
+ * precision FP32: FFMA implicit GEMM (c_in, c_out multiples of 4).  precision BF16 (16-bit operands, fp32 accumulation in TMEM):
+ * tcgen05 implicit GEMM over weight_h16 = IEEE fp16 copy laid out [KV, c_out, c_in]; needs c_in, c_out multiples of 64, KV <= 32. */
+int sstb200_spconv_forward(sstb200_ctx* ctx, const float* feats, int c_in, const int32_t* nbr, int n_out, int kernel_volume,
+                           const float* weight, const void* weight_h16, int c_out, const float* scale, const float* shift,
+                           const float* residual, int relu, int precision, float* out);
+
 #ifdef __cplusplus
 }
 #endif

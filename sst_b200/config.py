@@ -47,11 +47,13 @@ class Config(dict):
 
 
 # every type name the reference registers from a hot-path file - voxel_encoders/voxel_encoder.py,
-# middle_encoders/sst_input_layer{,_v2}.py, backbones/{sst,sst_v1,sst_v2,sir}.py, necks/voxel2point_neck.py, ops/norm.py.
+# middle_encoders/sst_input_layer{,_v2}.py, middle_encoders/sparse_unet.py, backbones/{sst,sst_v1,sst_v2,sir}.py, necks/voxel2point_neck.py, ops/norm.py.
 # A config that names one of these must find it in this package: "configs load unchanged" cannot pass by skipping.
 REFERENCE_HOT_PATH_TYPES = frozenset((
     "DynamicVFE", "DynamicScatterVFE", "SIRLayer", "SSTInputLayer", "SSTInputLayerV2", "PseudoMiddleEncoderForSpconvFSD",
-    "SST", "SSTv1", "SSTv2", "SIR", "Voxel2PointScatterNeck", "naiveSyncBN1d", "naiveSyncBN2d", "naiveSyncBN3d"))
+    "SST", "SSTv1", "SSTv2", "SIR", "Voxel2PointScatterNeck", "naiveSyncBN1d", "naiveSyncBN2d", "naiveSyncBN3d",
+    # middle_encoders/sparse_unet.py
+    "SparseUNet", "SimpleSparseUNet", "VirtualVoxelMixer"))
 
 
 def find_hot_path_modules(cfg, registry, strict=True):

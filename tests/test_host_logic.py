@@ -84,7 +84,8 @@ def test_reference_configs_load_and_build_unchanged():
             built.setdefault(node["type"], 0)
             built[node["type"]] += 1
             assert sum(p.numel() for p in m.parameters()) >= 0
-    for t in ("DynamicVFE", "SSTInputLayer", "SSTv1", "SSTInputLayerV2", "SSTv2", "DynamicScatterVFE", "SIR", "Voxel2PointScatterNeck"):
+    for t in ("DynamicVFE", "SSTInputLayer", "SSTv1", "SSTInputLayerV2", "SSTv2", "DynamicScatterVFE", "SIR", "Voxel2PointScatterNeck",
+              "SimpleSparseUNet", "VirtualVoxelMixer"):
         assert built.get(t, 0) >= 1, f"no config exercised {t}: {built}"
     assert not built.get("unsupported"), built.get("unsupported")
 
