@@ -307,8 +307,88 @@ def hard_voxelize_fixture():
     print("hard_voxelize", out["voxels_roomy"].shape, out["voxels_capped"].shape)
 
 
+def _rand_bn(m, seed):
+    """BatchNorm statistics / affine parameters that keep the signal alive through ~25 layers (weights in [0.5, 1.5])"""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.2)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.weight.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.2)
+        for p in m.parameters():
+            if p.dim() == 5:   # spconv's default init (kaiming_uniform, a = sqrt 5) shrinks the signal ~3x per layer
+                p.mul_(2.0)
+
+
+def _sort_rows(feats, coors):
+    c = coors.long()
+    order = torch.argsort(((c[:, 0] * 4096 + c[:, 1]) * 4096 + c[:, 2]) * 4096 + c[:, 3])
+    return feats[order], coors[order]
+
+
+def spconv_fixture():
+    """the reference's vendored spconv v1 layers (mmdet3d/ops/spconv/conv.py over oracle/_ref/sparse_conv_ext_ref*.so,
+    built from its own C++ sources) and its SimpleSparseUNet / VirtualVoxelMixer classes (middle_encoders/sparse_unet.py), eval mode.
+    Rows of strided-conv outputs are stored sorted by coordinate (spconv's own order is hash-insertion order)."""
+    from oracle import spconv_oracle as SO
+    S = ref_shim.load_spconv()
+    out = {}
+    feats, coors = SO.synth_sparse(11, 2, (9, 20, 24), 400, 8)
+    out["l_feats"], out["l_coors"], out["l_shape"] = feats.numpy(), coors.numpy(), np.array([9, 20, 24])
+    torch.manual_seed(21)
+    for name, (ks, st, pd) in {"a": (3, 2, 1), "b": (3, 2, (0, 1, 1)), "c": ((3, 1, 1), (2, 1, 1), 0)}.items():
+        conv = S.SparseConv3d(8, 12, ks, stride=st, padding=pd, bias=False, indice_key="k")
+        inv = S.SparseInverseConv3d(12, 8, ks, indice_key="k", bias=False)
+        with torch.no_grad():
+            y = conv(S.SparseConvTensor(feats, coors, [9, 20, 24], 2))
+            z = inv(y)
+        yf, yc = _sort_rows(y.features, y.indices)
+        out[f"conv_{name}_cfg"] = np.array(list(conv.kernel_size) + list(conv.stride) + list(conv.padding))
+        out[f"conv_{name}_w"], out[f"conv_{name}_out"], out[f"conv_{name}_coors"] = conv.weight.detach().numpy(), yf.numpy(), yc.numpy()
+        out[f"conv_{name}_shape"] = np.array(list(y.spatial_shape))
+        out[f"inv_{name}_w"], out[f"inv_{name}_out"] = inv.weight.detach().numpy(), z.features.numpy()
+        assert torch.equal(z.indices, coors)
+    sub = S.SubMConv3d(8, 12, 3, padding=0, bias=True, indice_key="s")
+    with torch.no_grad():
+        y = sub(S.SparseConvTensor(feats, coors, [9, 20, 24], 2))
+    out["subm_w"], out["subm_b"], out["subm_out"] = sub.weight.detach().numpy(), sub.bias.detach().numpy(), y.features.numpy()
+    np.savez_compressed(os.path.join(OUT, "spconv_layers.npz"), **out)
+
+    out = {}
+    torch.manual_seed(3)
+    net = S.SimpleSparseUNet(**SO.SP_UNET, return_multiscale_features=True).eval()
+    _rand_bn(net, 5)
+    feats, coors = SO.synth_sparse(4, 2, (9, 32, 32), 500, 8)
+    with torch.no_grad():
+        r = net(dict(voxel_feats=feats, voxel_coors=coors))[0]
+    assert torch.equal(r["voxel_coors"], coors)
+    out["unet_feats"], out["unet_coors"], out["unet_out"] = feats.numpy(), coors.numpy(), r["voxel_feats"].numpy()
+    for i, d in enumerate(r["decoder_features"]):
+        f, c = _sort_rows(d.features, d.indices)
+        out[f"unet_ms{i}_f"], out[f"unet_ms{i}_c"] = f.numpy(), c.numpy()
+    for k, v in net.state_dict().items():
+        out["unet_sd." + k] = v.numpy()
+    torch.manual_seed(7)
+    mix = S.VirtualVoxelMixer(**SO.SP_MIXER).eval()
+    _rand_bn(mix, 9)
+    feats, coors = SO.synth_sparse(8, 3, (8, 24, 24), 300, 8)
+    with torch.no_grad():
+        rf, rc, _ = mix(feats, coors, 3)
+    assert torch.equal(rc, coors)
+    out["mixer_feats"], out["mixer_coors"], out["mixer_out"] = feats.numpy(), coors.numpy(), rf.numpy()
+    for k, v in mix.state_dict().items():
+        out["mixer_sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "spconv_unet.npz"), **out)
+    print("spconv", out["unet_out"].shape, out["mixer_out"].shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "spconv" in sys.argv[1:]:   # only the next-1 fixtures
+        spconv_fixture()
+        sys.exit(0)
     R = ref_shim.load()
     sst_fixture(R)
     sst_v1_fixture(R)
@@ -319,3 +399,4 @@ if __name__ == "__main__":
     scatter_fixture()
     neck_fixture(R)
     hard_voxelize_fixture()
+    spconv_fixture()

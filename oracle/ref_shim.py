@@ -103,7 +103,7 @@ def _build_norm_layer(cfg, num_features, postfix=""):
     if t == "LN":
         return "ln", nn.LayerNorm(num_features, **cfg)
     if t in ("BN1d", "naiveSyncBN1d", "BN"):
-        return "bn", nn.BatchNorm1d(num_features, **cfg)
+        return f"bn{postfix}", nn.BatchNorm1d(num_features, **cfg)
     if t in ("BN2d", "naiveSyncBN2d"):
         return "bn", nn.BatchNorm2d(num_features, **cfg)
     raise NotImplementedError(t)
@@ -114,6 +114,13 @@ def _build_conv_layer(cfg, *args, **kwargs):
     t = cfg.pop("type")
     assert t in ("Conv2d", "Conv")
     return nn.Conv2d(*args, **kwargs, **cfg)
+
+
+class _BaseModule(nn.Module):
+    """mmcv.runner.BaseModule: nn.Module whose constructor takes init_cfg"""
+
+    def __init__(self, init_cfg=None):
+        super().__init__()
 
 
 def _passthrough_deco(*dargs, **dkwargs):
@@ -141,7 +148,7 @@ def load():
 
     mod("ipdb", set_trace=lambda *a, **k: None)
     mod("mmcv")
-    mod("mmcv.runner", auto_fp16=_passthrough_deco, force_fp32=_passthrough_deco, BaseModule=nn.Module)
+    mod("mmcv.runner", auto_fp16=_passthrough_deco, force_fp32=_passthrough_deco, BaseModule=_BaseModule)
     mod("mmcv.cnn", build_norm_layer=_build_norm_layer, build_conv_layer=_build_conv_layer,
         NORM_LAYERS=_Registry(), ConvModule=None)
     mod("mmdet")
@@ -214,6 +221,93 @@ def load():
     )
     _LOADED = ns
     return ns
+
+
+class _RefBasicBlock(nn.Module):
+    """mmdet.models.backbones.resnet.BasicBlock (mmdet 2.x, absent from this image) restated as far as
+    mmdet3d/ops/sparse_block.py:81-143 uses it: attribute / state-dict names conv1, bn1, conv2, bn2, relu, downsample."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, style="pytorch", with_cp=False, conv_cfg=None,
+                 norm_cfg=dict(type="BN"), dcn=None, plugins=None, init_cfg=None):
+        super().__init__()
+        build_norm, build_conv = sys.modules["mmcv.cnn"].build_norm_layer, sys.modules["mmcv.cnn"].build_conv_layer
+        self.norm1_name, norm1 = build_norm(norm_cfg, planes, postfix=1)
+        self.norm2_name, norm2 = build_norm(norm_cfg, planes, postfix=2)
+        self.conv1 = build_conv(conv_cfg, inplanes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.add_module(self.norm1_name, norm1)
+        self.conv2 = build_conv(conv_cfg, planes, planes, 3, padding=1, bias=False)
+        self.add_module(self.norm2_name, norm2)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride, self.dilation, self.with_cp = stride, dilation, with_cp
+
+    @property
+    def norm1(self):
+        return getattr(self, self.norm1_name)
+
+    @property
+    def norm2(self):
+        return getattr(self, self.norm2_name)
+
+
+_SPCONV = None
+
+
+def load_spconv():
+    """The reference's vendored spconv v1 (mmdet3d/ops/spconv/*.py, imported unmodified, over oracle/_ref/sparse_conv_ext_ref*.so =
+    its own C++/CUDA sources compiled by oracle/build_ref.py), its sparse_block.py and its sparse U-Nets."""
+    global _SPCONV
+    if _SPCONV is not None:
+        return _SPCONV
+    R = load()
+    from oracle import build_ref
+    ext = build_ref.load_module("sparse_conv_ext_ref")
+    assert ext is not None, "oracle/_ref/sparse_conv_ext_ref*.so not built (python -m oracle.build_ref)"
+    cnn = sys.modules["mmcv.cnn"]
+    conv_reg = _Registry()
+    cnn.CONV_LAYERS = conv_reg
+    dense_build = cnn.build_conv_layer
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        c = dict(cfg or dict(type="Conv2d"))
+        if c.get("type") in conv_reg.d:
+            return conv_reg.d[c.pop("type")](*args, **kwargs, **c)
+        return dense_build(cfg, *args, **kwargs)
+
+    cnn.build_conv_layer = build_conv_layer
+    sp = sys.modules["mmdet3d.ops.spconv"]
+    sp.sparse_conv_ext = ext
+    sys.modules["mmdet3d.ops.spconv.sparse_conv_ext"] = ext
+    structure = importlib.import_module("mmdet3d.ops.spconv.structure")
+    modules = importlib.import_module("mmdet3d.ops.spconv.modules")
+    conv = importlib.import_module("mmdet3d.ops.spconv.conv")
+    if not hasattr(structure.SparseConvTensor, "replace_feature"):
+        # sparse_unet.py:181-186 calls x.replace_feature (spconv 2.x API); on the v1 tensor it is a plain re-wrap
+        def replace_feature(self, feature):
+            t = structure.SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid)
+            t.indice_dict = self.indice_dict
+            return t
+        structure.SparseConvTensor.replace_feature = replace_feature
+    m = types.ModuleType("mmcv.ops")
+    m.SparseConvTensor, m.SparseSequential, m.SparseModule = structure.SparseConvTensor, modules.SparseSequential, modules.SparseModule
+    sys.modules["mmcv.ops"] = m
+    for name in ("mmdet.models.backbones", "mmdet.models.backbones.resnet"):
+        mm = types.ModuleType(name)
+        sys.modules[name] = mm
+    sys.modules["mmdet.models.backbones.resnet"].BasicBlock = _RefBasicBlock
+    sys.modules["mmdet.models.backbones.resnet"].Bottleneck = _RefBasicBlock
+    sb = importlib.import_module("mmdet3d.ops.sparse_block")
+    ops = sys.modules["mmdet3d.ops"]
+    ops.SparseBasicBlock, ops.make_sparse_convmodule = sb.SparseBasicBlock, sb.make_sparse_convmodule
+    ops.SparseBottleneck = sb.SparseBottleneck
+    unet = importlib.import_module("mmdet3d.models.middle_encoders.sparse_unet")
+    _SPCONV = types.SimpleNamespace(ext=ext, structure=structure, modules=modules, conv=conv, sparse_block=sb, sparse_unet=unet,
+                                    SparseConvTensor=structure.SparseConvTensor, SubMConv3d=conv.SubMConv3d,
+                                    SparseConv3d=conv.SparseConv3d, SparseInverseConv3d=conv.SparseInverseConv3d,
+                                    SimpleSparseUNet=unet.SimpleSparseUNet, VirtualVoxelMixer=unet.VirtualVoxelMixer,
+                                    SparseBasicBlock=sb.SparseBasicBlock, make_sparse_convmodule=sb.make_sparse_convmodule)
+    return _SPCONV
 
 
 def reference_methods(relpath, class_name, names, extra_globals=None):

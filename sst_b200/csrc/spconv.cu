@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) spconv_gemm_f32_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int SPU_TM = 128;
 constexpr int SPU_A_BYTES = SPU_TM * 128;
-#define SPU_MAX_KV 32
+#define SPU_MAX_KV 27
 
 __device__ __forceinline__ uint32_t sp_pack_f16(float a, float b) {
   a = fminf(fmaxf(a, -65504.f), 65504.f);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) spconv_umma_kernel(const float* __restric
   __shared__ __align__(8) uint64_t mbar[NS];
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t used_mask;
-  __shared__ int sNbr[SPU_TM][SPU_MAX_KV + 1];
+  __shared__ int sNbr[SPU_TM][SPU_MAX_KV];   // odd row pitch: conflict-free column reads
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * SPU_TM, n0 = blockIdx.y * NT;

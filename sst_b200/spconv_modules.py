@@ -12,9 +12,9 @@ residual tail of SparseBasicBlock are folded into that launch's epilogue.
 Weights keep the reference's checkpoint layout (kD, kH, kW, in, out) (write_spconv2.py:44-60 converts spconv2's to it on save).
 There is no CPU / PyTorch fallback; the backward pass of the sparse convolutions is not built (declared in DESIGN.md section 7).
 
-Sub-manifold index semantics: spconv 2.x (the version the reference pins) generates SubM pairs centred on the kernel and ignores
-`padding`; the vendored v1 honours `padding` (geometry.h:25-86), which differs only for VirtualVoxelMixer.conv_out (kernel 3,
-padding 0).  SUBM_IGNORES_PADDING selects the behaviour (default: spconv 2.x)."""
+Sub-manifold convolutions are always centred: spconv forces stride 1 / padding k//2 in the SubM index generation whatever the layer
+was built with (vendored v1: include/spconv/spconv_ops.h:74-78; spconv 2.x: generate_subm_conv_inds takes no padding), so e.g.
+VirtualVoxelMixer.conv_out (kernel 3, padding 0) is a centred 3x3x3 convolution."""
 import ctypes as C
 import math
 
@@ -33,8 +33,8 @@ L.SIGNATURES["sstb200_spconv_table"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c
 L.SIGNATURES["sstb200_spconv_forward"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c_int, C.c_int, L.vp, L.vp, C.c_int, L.vp, L.vp, L.vp,
                                                    C.c_int, C.c_int, L.vp])
 
-SUBM_IGNORES_PADDING = True
 PREC = {"fp32": 0, "bf16": 1}
+FUSE_EPILOGUE = True   # eval mode: fold BatchNorm1d / residual / ReLU into the convolution launch (False = conv launch + torch modules)
 
 
 def _triple(v, ndim):
@@ -235,9 +235,10 @@ class SparseSequential(SparseModule):
         while i < len(mods):
             m = mods[i]
             if isinstance(m, SparseConvolution):
-                bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) and not mods[i + 1].training else None
+                bn = mods[i + 1] if (FUSE_EPILOGUE and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)
+                                     and not mods[i + 1].training) else None
                 relu = bn is not None and i + 2 < len(mods) and _is_relu(mods[i + 2])
-                if bn is None and i + 1 < len(mods) and _is_relu(mods[i + 1]) and m.bias is None:
+                if FUSE_EPILOGUE and bn is None and i + 1 < len(mods) and _is_relu(mods[i + 1]):
                     input = m(input, relu=True)
                     i += 2
                     continue
@@ -315,10 +316,8 @@ class SparseConvolution(SparseModule):
         nd = self.ndim
         ks, st, pd = _triple(self.kernel_size, nd), _triple(self.stride, nd), _triple(self.padding, nd)
         in_shape = _triple(spatial_shape, nd)
-        if self.subm:
-            if SUBM_IGNORES_PADDING:
-                pd = [k // 2 for k in ks]
-            return in_shape, in_shape, ks, [1, 1, 1], pd
+        if self.subm:   # spconv_ops.h:74-78: stride 1, padding k//2, whatever the layer says
+            return in_shape, in_shape, ks, [1, 1, 1], [k // 2 for k in ks]
         out_shape = get_conv_output_size(in_shape, ks, st, pd, [1, 1, 1])
         return in_shape, out_shape, ks, st, pd
 
@@ -452,7 +451,7 @@ class SparseBasicBlock(SparseModule):
     def forward(self, x):
         identity = x.features
         assert x.features.dim() == 2, f"x.features.dim()={x.features.dim()}"
-        fused = _is_relu(self.relu) and not self.bn1.training and not self.bn2.training
+        fused = FUSE_EPILOGUE and _is_relu(self.relu) and not self.bn1.training and not self.bn2.training
         if fused:
             out = self.conv1(x, bn=self.bn1, relu=True)
             return self.conv2(out, bn=self.bn2, relu=True, residual=identity)

@@ -1,0 +1,119 @@
+"""CPU: host-side logic of sst_b200/spconv_modules.py (container / layer glue, indice_key reuse, BN folding, fused vs unfused
+epilogues, state-dict keys) with the three C-ABI calls replaced by the oracle's restatements - no compute call reaches the library.
+The real kernels are checked on the GPU in tests/test_gpu_spconv.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spconv_oracle as SO
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture()
+def SP(monkeypatch):
+    from sst_b200 import spconv_modules as SP
+
+    def conv_out_coors(indices, batch_size, in_shape, out_shape, ksize, stride, padding):
+        return SO.out_coors(SP._coors4(indices), batch_size, in_shape, ksize, stride, padding)
+
+    def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, stride, padding, want_nbr=True, want_inv=False):
+        ci, co = SP._coors4(in_indices), SP._coors4(out_indices)
+        nbr = SO.neighbour_table(ci, co, batch_size, in_shape, ksize, stride, padding)
+        inv = None
+        if want_inv:
+            inv = torch.full((ci.shape[0], nbr.shape[1]), -1, dtype=torch.int32)
+            o, k = torch.nonzero(nbr >= 0, as_tuple=True)
+            inv[nbr[o, k].long(), k] = o.int()
+        return (nbr if want_nbr else None), inv
+
+    def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, residual=None, relu=False, precision="fp32"):
+        return SO.indice_conv(features, nbr, weight.detach(), scale, shift, residual, relu)
+
+    monkeypatch.setattr(SP, "conv_out_coors", conv_out_coors)
+    monkeypatch.setattr(SP, "conv_table", conv_table)
+    monkeypatch.setattr(SP, "indice_conv", indice_conv)
+    return SP
+
+
+def _sorted(f, c):
+    c = c.long()
+    order = torch.argsort(((c[:, 0] * 4096 + c[:, 1]) * 4096 + c[:, 2]) * 4096 + c[:, 3])
+    return f[order], c[order].int()
+
+
+def test_unet_and_mixer_glue_against_reference_golden(SP):
+    from sst_b200 import registry
+    z = np.load(os.path.join(G, "spconv_unet.npz"))
+    net = registry.MODELS.build(dict(type="SimpleSparseUNet", **SO.SP_UNET, return_multiscale_features=True))
+    sd = {k[len("unet_sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("unet_sd.")}
+    assert set(sd) == set(net.state_dict()), "state-dict keys differ from the reference's SimpleSparseUNet"
+    net.load_state_dict(sd)
+    net.eval()
+    feats, coors = torch.from_numpy(z["unet_feats"]), torch.from_numpy(z["unet_coors"])
+    with torch.no_grad():
+        out = net(dict(voxel_feats=feats, voxel_coors=coors))[0]
+        SP.FUSE_EPILOGUE = False
+        try:
+            out2 = net(dict(voxel_feats=feats, voxel_coors=coors))[0]
+        finally:
+            SP.FUSE_EPILOGUE = True
+    for o in (out, out2):
+        assert torch.equal(o["voxel_coors"], coors)
+        torch.testing.assert_close(o["voxel_feats"], torch.from_numpy(z["unet_out"]), rtol=1e-3, atol=1e-4)
+        for i, d in enumerate(o["decoder_features"]):
+            f, c = _sorted(d.features, d.indices)
+            assert torch.equal(c, torch.from_numpy(z[f"unet_ms{i}_c"]).int())
+            torch.testing.assert_close(f, torch.from_numpy(z[f"unet_ms{i}_f"]), rtol=1e-3, atol=1e-4)
+    mix = registry.MODELS.build(dict(type="VirtualVoxelMixer", **SO.SP_MIXER))
+    sd = {k[len("mixer_sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("mixer_sd.")}
+    assert set(sd) == set(mix.state_dict())
+    mix.load_state_dict(sd)
+    mix.eval()
+    with torch.no_grad():
+        f, c, shape = mix(torch.from_numpy(z["mixer_feats"]), torch.from_numpy(z["mixer_coors"]), 3)
+    assert list(shape) == SO.SP_MIXER["sparse_shape"]
+    torch.testing.assert_close(f, torch.from_numpy(z["mixer_out"]), rtol=1e-3, atol=1e-4)
+
+
+def test_layer_glue_against_reference_golden(SP):
+    z = np.load(os.path.join(G, "spconv_layers.npz"))
+    feats, coors, shape = torch.from_numpy(z["l_feats"]), torch.from_numpy(z["l_coors"]), z["l_shape"].tolist()
+    with torch.no_grad():
+        for name in "abc":
+            cfg = z[f"conv_{name}_cfg"].tolist()
+            conv = SP.SparseConv3d(8, 12, cfg[0:3], stride=cfg[3:6], padding=cfg[6:9], bias=False, indice_key="k")
+            inv = SP.SparseInverseConv3d(12, 8, cfg[0:3], indice_key="k", bias=False)
+            conv.weight.copy_(torch.from_numpy(z[f"conv_{name}_w"]))
+            inv.weight.copy_(torch.from_numpy(z[f"inv_{name}_w"]))
+            y = conv(SP.SparseConvTensor(feats, coors, shape, 2))
+            assert y.spatial_shape == z[f"conv_{name}_shape"].tolist()
+            assert torch.equal(y.indices, torch.from_numpy(z[f"conv_{name}_coors"]).int())
+            torch.testing.assert_close(y.features, torch.from_numpy(z[f"conv_{name}_out"]), rtol=1e-4, atol=1e-5)
+            back = inv(y)
+            assert torch.equal(back.indices, coors) and back.spatial_shape == shape
+            torch.testing.assert_close(back.features, torch.from_numpy(z[f"inv_{name}_out"]), rtol=1e-4, atol=1e-5)
+        sub = SP.SubMConv3d(8, 12, 3, padding=0, bias=True, indice_key="s")
+        sub.weight.copy_(torch.from_numpy(z["subm_w"]))
+        sub.bias.copy_(torch.from_numpy(z["subm_b"]))
+        torch.testing.assert_close(sub(SP.SparseConvTensor(feats, coors, shape, 2)).features, torch.from_numpy(z["subm_out"]), rtol=1e-4, atol=1e-5)
+
+
+def test_2d_layers_and_dense(SP):
+    """ndim = 2 layers ride on the 3-D tables with a unit z axis; dense() matches the reference layout [B, C, *spatial]"""
+    g = torch.Generator().manual_seed(0)
+    yx = torch.unique(torch.randint(0, 12, (60, 2), generator=g), dim=0)
+    coors = torch.cat([torch.zeros((yx.shape[0], 1), dtype=torch.long), yx], 1).int()
+    feats = torch.randn((coors.shape[0], 4), generator=g)
+    conv = SP.SparseConv2d(4, 8, 3, stride=2, padding=1, bias=True)
+    with torch.no_grad():
+        y = conv(SP.SparseConvTensor(feats, coors, [12, 12], 1))
+        dense_in = SP.SparseConvTensor(feats, coors, [12, 12], 1).dense()
+        ref = torch.nn.functional.conv2d(dense_in, conv.weight.permute(3, 2, 0, 1), conv.bias, stride=2, padding=1)
+    assert y.indices.shape[1] == 3 and y.spatial_shape == [6, 6]
+    d = y.dense()
+    assert d.shape == ref.shape
+    mask = (d != 0).any(1, keepdim=True)
+    torch.testing.assert_close(d, ref * mask, rtol=1e-4, atol=1e-5)

@@ -197,3 +197,50 @@ def test_fsdv2_front_golden(tag):
         vf, vc = vf[out["singlescale_mask"]], vc[out["singlescale_mask"]]
     assert torch.equal(vc[out["virtual_mask"]], z["virtual_coors"])
     torch.testing.assert_close(vf[out["virtual_mask"]], z["virtual_feats"], rtol=1e-5, atol=1e-5)
+
+
+# ---- sparse convolution fixtures produced by the reference's vendored spconv v1 (oracle/make_golden.py spconv) ------
+def _sp_sorted(f, c):
+    c = c.long()
+    order = torch.argsort(((c[:, 0] * 4096 + c[:, 1]) * 4096 + c[:, 2]) * 4096 + c[:, 3])
+    return f[order], c[order].int()
+
+
+def test_spconv_layers_golden():
+    from oracle import spconv_oracle as SO
+    z = np.load(os.path.join(G, "spconv_layers.npz"))
+    feats, coors, shape = torch.from_numpy(z["l_feats"]), torch.from_numpy(z["l_coors"]), z["l_shape"].tolist()
+    for name in "abc":
+        cfg = z[f"conv_{name}_cfg"].tolist()
+        ks, st, pd = cfg[0:3], cfg[3:6], cfg[6:9]
+        w = torch.from_numpy(z[f"conv_{name}_w"])
+        of, oc, oshape = SO.sparse_conv(feats, coors, 2, shape, w, st, pd)
+        assert oshape == z[f"conv_{name}_shape"].tolist()
+        assert torch.equal(oc, torch.from_numpy(z[f"conv_{name}_coors"]).int())
+        torch.testing.assert_close(of, torch.from_numpy(z[f"conv_{name}_out"]), rtol=1e-4, atol=1e-5)
+        nbr = SO.neighbour_table(coors, oc, 2, shape, ks, st, pd)
+        torch.testing.assert_close(SO.indice_conv(feats, nbr, w), of, rtol=1e-4, atol=1e-5)
+        zi = SO.inverse_conv(of, oc, 2, oshape, coors, shape, torch.from_numpy(z[f"inv_{name}_w"]), st, pd)
+        torch.testing.assert_close(zi, torch.from_numpy(z[f"inv_{name}_out"]), rtol=1e-4, atol=1e-5)
+    o = SO.subm_conv(feats, coors, 2, shape, torch.from_numpy(z["subm_w"]), torch.from_numpy(z["subm_b"]))
+    torch.testing.assert_close(o, torch.from_numpy(z["subm_out"]), rtol=1e-4, atol=1e-5)
+
+
+def test_spconv_unet_golden():
+    from oracle import spconv_oracle as SO
+    z = np.load(os.path.join(G, "spconv_unet.npz"))
+    sd = {k[len("unet_sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("unet_sd.")}
+    feats, coors = torch.from_numpy(z["unet_feats"]), torch.from_numpy(z["unet_coors"])
+    U = SO.SP_UNET
+    f, c, ms = SO.sparse_unet_forward(sd, feats, coors, 2, U["sparse_shape"], U["encoder_channels"], U["encoder_paddings"], U["decoder_channels"],
+                                      U["decoder_paddings"], return_multiscale=True)
+    torch.testing.assert_close(f, torch.from_numpy(z["unet_out"]), rtol=1e-3, atol=1e-4)
+    for i, (mf, mc) in enumerate(ms):
+        mf, mc = _sp_sorted(mf, mc)
+        assert torch.equal(mc, torch.from_numpy(z[f"unet_ms{i}_c"]).int())
+        torch.testing.assert_close(mf, torch.from_numpy(z[f"unet_ms{i}_f"]), rtol=1e-3, atol=1e-4)
+    sd = {k[len("mixer_sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("mixer_sd.")}
+    M = SO.SP_MIXER
+    f, c = SO.sparse_unet_forward(sd, torch.from_numpy(z["mixer_feats"]), torch.from_numpy(z["mixer_coors"]), 3, M["sparse_shape"],
+                                  M["encoder_channels"], M["encoder_paddings"], M["decoder_channels"], M["decoder_paddings"], mixer_out=True)
+    torch.testing.assert_close(f, torch.from_numpy(z["mixer_out"]), rtol=1e-3, atol=1e-4)
