@@ -403,6 +403,17 @@ int sstb200_spconv_forward(sstb200_ctx* ctx, const float* feats, int c_in, const
                            const float* weight, const void* weight_h16, int c_out, const float* scale, const float* shift,
                            const float* residual, int relu, int precision, float* out);
 
+/* ---- next-3: FSD instance grouping.  find_connected_componets / _single_batch / _gpu
+ * (mmdet3d/models/detectors/single_stage_fsd.py:37-81; TorchEx connected_components at :20,39-45): two centres of the same sample are
+ * adjacent when sqrt(dx^2 + dy^2) < dist (xy only, fp32); labels [n] = component number, components numbered sample by sample (batch
+ * index ascending) and, inside a sample, by their first centre in input order - scipy.sparse.csgraph.connected_components' numbering
+ * with the reference's running `base`.  centers [n, stride >= 2] fp32 (x, y first), batch_idx [n] int32 in [0, batch_size) or NULL
+ * (one sample).  xy_min / xy_max bound the binning grid (centres outside are binned into the border cells: still exact).
+ * num_components_host != NULL: one stream sync; a batch index outside [0, batch_size) is then reported as an error (label -1). */
+int sstb200_connected_components(sstb200_ctx* ctx, const float* centers, int stride, const int32_t* batch_idx, int n, int batch_size,
+                                 float dist, const float xy_min[2], const float xy_max[2], int32_t* labels,
+                                 int32_t* num_components_dev, int32_t* num_components_host);
+
 #ifdef __cplusplus
 }
 #endif

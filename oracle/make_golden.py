@@ -384,10 +384,49 @@ def spconv_fixture():
     print("spconv", out["unet_out"].shape, out["mixer_out"].shape)
 
 
+
+def fsd_cluster_fixture():
+    """find_connected_componets / ClusterAssigner from the reference's own source (single_stage_fsd.py:47-81, 922-999)."""
+    from oracle import fsd_oracle as FO
+    RF = ref_shim.reference_functions("mmdet3d/models/detectors/single_stage_fsd.py",
+                                      ["filter_almost_empty", "find_connected_componets", "modify_cluster_by_class", "ClusterAssigner"])
+    out = {}
+    pts, bidx = FO.synth_centres(3, 3, 700)
+    g = torch.Generator().manual_seed(1)
+    perm = torch.randperm(pts.shape[0], generator=g)   # samples interleaved: the numbering still goes sample by sample
+    out["cc_points"], out["cc_batch"] = pts.numpy(), bidx.numpy()
+    out["cc_points_mixed"], out["cc_batch_mixed"] = pts[perm].numpy(), bidx[perm].numpy()
+    for d in (0.1, 0.6, 2.0):
+        out[f"cc_labels_{d}"] = RF["find_connected_componets"](pts, bidx, d).numpy()
+        out[f"cc_labels_mixed_{d}"] = RF["find_connected_componets"](pts[perm], bidx[perm], d).numpy()
+    cfg = dict(cluster_voxel_size=dict(Car=(0.3, 0.3, 6), Cyclist=(0.2, 0.2, 6), Pedestrian=(0.05, 0.05, 6)), min_points=2,
+               point_cloud_range=[-80, -80, -2, 80, 80, 4], connected_dist=dict(Car=0.6, Cyclist=0.4, Pedestrian=0.1),
+               class_names=['Car', 'Cyclist', 'Pedestrian'])
+    ca = RF["ClusterAssigner"](**cfg)
+    ca.num_classes = 3
+    ca.train()
+    pts_l, b_l = [], []
+    for i, blob in enumerate((0.5, 0.3, 0.08)):
+        p, b = FO.synth_centres(10 + i, 2, 1500, blob=blob)
+        # coordinates on a 1/64 m lattice: per-voxel sums are then exact in fp32 and fp64 alike, so the voxel centres (scatter_v2 'avg')
+        # do not depend on the summation order / accumulator width of the implementation under test
+        pts_l.append(torch.round(p * 64) / 64)
+        b_l.append(b)
+    inds, masks = ca(pts_l, b_l, origin_points=[None] * 3)
+    for i in range(3):
+        out[f"ca_points{i}"], out[f"ca_batch{i}"] = pts_l[i].numpy(), b_l[i].numpy()
+        out[f"ca_inds{i}"], out[f"ca_mask{i}"] = inds[i].numpy(), masks[i].numpy()
+    np.savez_compressed(os.path.join(OUT, "fsd_cluster.npz"), **out)
+    print("fsd_cluster", {k: int(out[k].max()) + 1 for k in out if k.startswith("cc_labels_")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "spconv" in sys.argv[1:]:   # only the next-1 fixtures
-        spconv_fixture()
+    if "spconv" in sys.argv[1:] or "fsd" in sys.argv[1:]:   # only the next-1 / next-3 fixtures
+        if "spconv" in sys.argv[1:]:
+            spconv_fixture()
+        if "fsd" in sys.argv[1:]:
+            fsd_cluster_fixture()
         sys.exit(0)
     R = ref_shim.load()
     sst_fixture(R)
@@ -400,3 +439,4 @@ if __name__ == "__main__":
     neck_fixture(R)
     hard_voxelize_fixture()
     spconv_fixture()
+    fsd_cluster_fixture()

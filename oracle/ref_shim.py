@@ -332,3 +332,33 @@ def reference_methods(relpath, class_name, names, extra_globals=None):
     missing = set(names) - set(out)
     assert not missing, f"{class_name} has no method(s) {missing}"
     return out
+
+
+def reference_functions(relpath, names, extra_globals=None):
+    """Compile selected MODULE-LEVEL functions / classes of a reference file straight from its source, unmodified, without importing the
+    module (detector files import half of mmdet / mmseg / spconv at module level).  Returns a dict name -> object; the objects see
+    torch, scipy's connected_components, the shim's scatter_v2 and a restated mmdet.core.multi_apply."""
+    import ast
+    from functools import partial
+    R = load()
+    src = open(os.path.join(REF_ROOT, relpath)).read()
+    tree = ast.parse(src)
+
+    def multi_apply(func, *args, **kwargs):   # mmdet/core/utils/misc.py
+        pfunc = partial(func, **kwargs) if kwargs else func
+        return tuple(map(list, zip(*map(pfunc, *args))))
+
+    from scipy.sparse.csgraph import connected_components
+    g = {"torch": torch, "nn": nn, "scatter_v2": R.sst_ops.scatter_v2, "connected_components": connected_components,
+         "multi_apply": multi_apply, "F": torch.nn.functional, "cc_gpu": None}
+    g.update(extra_globals or {})
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    missing = set(names) - {n.name for n in body}
+    assert not missing, f"{relpath} has no top-level {missing}"
+    for node in body:
+        if isinstance(node, ast.ClassDef):
+            node.decorator_list = []
+    mod = ast.Module(body=body, type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, os.path.join(REF_ROOT, relpath), "exec"), g)
+    return {n: g[n] for n in names}

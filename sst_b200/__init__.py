@@ -6,12 +6,13 @@ from . import registry
 from .registry import BACKBONES, MIDDLE_ENCODERS, MODELS, VOXEL_ENCODERS, build_backbone, build_middle_encoder, build_voxel_encoder  # noqa: F401
 from . import norm  # noqa: F401
 from . import ops  # noqa: F401
-from . import sst_modules, voxel_modules, sir_modules, neck_modules, fsdv2_modules, spconv_modules  # noqa: F401
+from . import sst_modules, voxel_modules, sir_modules, neck_modules, fsdv2_modules, spconv_modules, fsd_modules  # noqa: F401
 from .sst_modules import SSTInputLayer, SSTInputLayerV2, SSTv1, SSTv2, SST, PseudoMiddleEncoderForSpconvFSD  # noqa: F401
 from .voxel_modules import DynamicVFE, DynamicScatterVFE  # noqa: F401
 from .sir_modules import SIR, SIRLayer  # noqa: F401
 from .neck_modules import Voxel2PointScatterNeck  # noqa: F401
 from .fsdv2_modules import VirtualVoxelFront  # noqa: F401
+from .fsd_modules import ClusterAssigner  # noqa: F401
 from .spconv_modules import SimpleSparseUNet, SparseUNet, VirtualVoxelMixer, SparseConvTensor  # noqa: F401
 from . import train  # noqa: F401  (training entry points: autograd bridge, FlatAdamW)
 

@@ -163,7 +163,7 @@ def test_tensor_path_refuses_unsupported_shapes(cuda):
         SP.indice_conv(feats, nbr.cpu(), torch.randn(27, 16, 16))
 
 
-UNET64 = dict(in_channels=64, sparse_shape=[8, 40, 40], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), base_channels=64,
+UNET64 = dict(in_channels=64, sparse_shape=[16, 40, 40], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), base_channels=64,
               output_channels=128, encoder_channels=((64,), (64, 64, 64), (64, 64, 64), (128, 128, 128)),
               encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)),
               decoder_channels=((128, 128, 64), (64, 64, 64), (64, 64, 64), (64, 64, 64)), decoder_paddings=((1, 1), (1, 0), (0, 0), (0, 1)))

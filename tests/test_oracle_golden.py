@@ -244,3 +244,22 @@ def test_spconv_unet_golden():
     f, c = SO.sparse_unet_forward(sd, torch.from_numpy(z["mixer_feats"]), torch.from_numpy(z["mixer_coors"]), 3, M["sparse_shape"],
                                   M["encoder_channels"], M["encoder_paddings"], M["decoder_channels"], M["decoder_paddings"], mixer_out=True)
     torch.testing.assert_close(f, torch.from_numpy(z["mixer_out"]), rtol=1e-3, atol=1e-4)
+
+
+def test_fsd_cluster_golden():
+    """the grouping oracle against outputs of the reference's own source (oracle/make_golden.py fsd)"""
+    from oracle import fsd_oracle as FO
+    z = np.load(os.path.join(G, "fsd_cluster.npz"))
+    for tag in ("", "_mixed"):
+        pts, bidx = torch.from_numpy(z["cc_points" + tag]), torch.from_numpy(z["cc_batch" + tag])
+        for d in (0.1, 0.6, 2.0):
+            ref = torch.from_numpy(z[f"cc_labels{tag}_{d}"])
+            assert torch.equal(FO.find_connected_components(pts, bidx, d), ref)
+            assert torch.equal(FO.connected_components_large(pts, bidx, d), ref)
+    vs = dict(Car=(0.3, 0.3, 6), Cyclist=(0.2, 0.2, 6), Pedestrian=(0.05, 0.05, 6))
+    dist = dict(Car=0.6, Cyclist=0.4, Pedestrian=0.1)
+    for i, name in enumerate(('Car', 'Cyclist', 'Pedestrian')):
+        inds, mask = FO.cluster_assigner_single_class(torch.from_numpy(z[f"ca_points{i}"]), torch.from_numpy(z[f"ca_batch{i}"]), vs[name], 2,
+                                                      [-80, -80, -2, 80, 80, 4], dist[name])
+        assert torch.equal(mask, torch.from_numpy(z[f"ca_mask{i}"]))
+        assert torch.equal(inds.long(), torch.from_numpy(z[f"ca_inds{i}"])[:, 1:].long())
