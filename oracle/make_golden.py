@@ -217,7 +217,7 @@ def fsdv2_front_fixture(R):
 
     class Stand(torch.nn.Module):
         pass
-    for with_ms in (False, True):
+    for with_ms, with_mixer in ((False, False), (True, False), (True, True)):
         self = Stand()
         self.baseline_mode, self.zero_virtual_feature, self.only_virtual, self.as_rpn = False, False, False, False
         self.virtual_voxel_size, self.point_cloud_range = FSDV2["vs"], FSDV2["rng"]
@@ -237,6 +237,16 @@ def fsdv2_front_fixture(R):
             seen.update(vf=vf.clone(), vc=vc.clone(), bs=bs)
             return vf, vc, None
         self.backbone = backbone
+        if with_mixer:   # the reference's own VirtualVoxelMixer over its vendored spconv v1: config 5 end to end
+            from oracle import spconv_oracle as SO_
+            torch.manual_seed(5)
+            mixer = ref_shim.load_spconv().VirtualVoxelMixer(**SO_.FSDV2_MIXER).eval()
+            _rand_bn(mixer, 33, wmul=5.0)   # the fused voxels are almost isolated (7k in 600k cells): little neighbour signal
+
+            def backbone_mixer(vf, vc, bs):
+                seen.update(vf=vf.clone(), vc=vc.clone(), bs=bs)
+                return mixer(vf, vc, bs)
+            self.backbone = backbone_mixer
         for k, f in fns.items():
             setattr(self, k, types.MethodType(f, self))
         sampled, origin, levels = fsdv2_inputs()
@@ -245,8 +255,9 @@ def fsdv2_front_fixture(R):
             out = self.extract_feat({k: v.clone() for k, v in sampled.items()}, {k: v.clone() for k, v in origin.items()}, None, ms)
             coors = self.voxelize_with_batch_idx(torch.cat([origin["seg_points"][:, :3], self.clip_points(sampled["center_preds"].clone(), FSDV2["rng"])]),
                                                  torch.cat([origin["batch_idx"], sampled["batch_idx"]]))
-        tag = "ms" if with_ms else "plain"
-        np.savez_compressed(os.path.join(OUT, f"fsdv2_front_{tag}.npz"), coors=coors.numpy(), backbone_feats=seen["vf"].numpy(),
+        tag = "mixer" if with_mixer else ("ms" if with_ms else "plain")
+        extra = {"mix." + k: v.numpy() for k, v in mixer.state_dict().items()} if with_mixer else {}
+        np.savez_compressed(os.path.join(OUT, f"fsdv2_front_{tag}.npz"), **extra, coors=coors.numpy(), backbone_feats=seen["vf"].numpy(),
                             backbone_coors=seen["vc"].numpy(), batch_size=np.array(seen["bs"]), virtual_feats=out["virtual_feats"].numpy(),
                             virtual_coors=out["virtual_coors"].numpy(), virtual_centers=out["virtual_centers"].numpy(),
                             **{f"sampled.{k}": v.numpy() for k, v in sampled.items()}, **{f"origin.{k}": v.numpy() for k, v in origin.items()},
@@ -307,7 +318,7 @@ def hard_voxelize_fixture():
     print("hard_voxelize", out["voxels_roomy"].shape, out["voxels_capped"].shape)
 
 
-def _rand_bn(m, seed):
+def _rand_bn(m, seed, wmul=2.0):
     """BatchNorm statistics / affine parameters that keep the signal alive through ~25 layers (weights in [0.5, 1.5])"""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
@@ -319,7 +330,7 @@ def _rand_bn(m, seed):
                 mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.2)
         for p in m.parameters():
             if p.dim() == 5:   # spconv's default init (kaiming_uniform, a = sqrt 5) shrinks the signal ~3x per layer
-                p.mul_(2.0)
+                p.mul_(wmul)
 
 
 def _sort_rows(feats, coors):
@@ -422,6 +433,9 @@ def fsd_cluster_fixture():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "fsdv2" in sys.argv[1:]:
+        fsdv2_front_fixture(ref_shim.load())
+        sys.exit(0)
     if "spconv" in sys.argv[1:] or "fsd" in sys.argv[1:]:   # only the next-1 / next-3 fixtures
         if "spconv" in sys.argv[1:]:
             spconv_fixture()

@@ -239,6 +239,11 @@ SP_MIXER = dict(in_channels=8, sparse_shape=[8, 24, 24], norm_cfg=dict(type='nai
                 output_channels=12, encoder_channels=((8,), (8, 8), (8, 8)), encoder_paddings=((1,), (1, 1), (1, 1)),
                 decoder_channels=((8, 8, 8), (8, 8, 8), (8, 8, 8)), decoder_paddings=((1, 1), (1, 1), (1, 1)))
 
+# the mixer of the config-5 fixture (tests/golden/fsdv2_front_mixer.npz)
+FSDV2_MIXER = dict(in_channels=32, sparse_shape=[12, 160, 160], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), base_channels=8,
+                   output_channels=16, encoder_channels=((8,), (8, 8), (16, 16)), encoder_paddings=((1,), (1, 1), (1, 1)),
+                   decoder_channels=((16, 16, 8), (8, 8, 8), (8, 8, 8)), decoder_paddings=((1, 1), (1, 1), (1, 1)))
+
 
 def synth_sparse(seed, batch_size, shape, n_per_sample, channels, clustered=True):
     """Deterministic sparse tensor for tests: unique (b,z,y,x) int32 rows in random order + fp32 features."""

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .registry import build_voxel_encoder
+from .registry import build_backbone, build_voxel_encoder
 
 L.SIGNATURES["sstb200_voxelize_with_batch_idx"] = (C.c_int, [L.vp, L.vp, C.c_int, C.c_int, L.vp, L.P_f32, L.P_f32, L.vp])
 
@@ -38,9 +38,10 @@ class VirtualVoxelFront(nn.Module):
     """Constructor kwargs = the corresponding kwargs of SingleStageFSDV2 (configs/fsdv2/*.py): `voxel_encoder` (a DynamicScatterVFE
     config), `virtual_point_projector`, `multiscale_cfg`, `point_cloud_range`."""
 
-    def __init__(self, voxel_encoder, virtual_point_projector, point_cloud_range=None, multiscale_cfg=None, as_rpn=False):
+    def __init__(self, voxel_encoder, virtual_point_projector, point_cloud_range=None, multiscale_cfg=None, as_rpn=False, backbone=None):
         super().__init__()
         self.voxel_encoder = build_voxel_encoder(voxel_encoder)
+        self.backbone = build_backbone(backbone) if backbone is not None else None   # VirtualVoxelMixer (spconv_modules.py)
         self.virtual_voxel_size = voxel_encoder["voxel_size"]
         self.point_cloud_range = voxel_encoder["point_cloud_range"] if point_cloud_range is None else point_cloud_range
         vpp = virtual_point_projector
@@ -127,7 +128,15 @@ class VirtualVoxelFront(nn.Module):
             out["voxel_coors"] = out["voxel_coors"][virtual_mask]
         return out
 
-    # ---- single_stage_fsd_v2.py:217-242, 262-269: after the backbone (the sparse-conv mixer: SURVEY 8f next-1, not built here)
+    # ---- single_stage_fsd_v2.py:157-271: front -> sparse-conv mixer -> bookkeeping, eval mode
+    def extract_feat(self, sampled_dict, origin_dict, gt_bboxes_3d=None, multiscale_features=None):
+        assert self.backbone is not None, "built without a backbone: call front() / finish() around your own mixer"
+        fr = self.front(sampled_dict, origin_dict, multiscale_features)
+        batch_size = int(fr["coors"][:, 0].max().item()) + 1
+        out_voxel_feats, out_coors, sparse_shape = self.backbone(fr["voxel_feats"], fr["voxel_coors"], batch_size)
+        return self.finish(fr, out_voxel_feats, out_coors, sparse_shape)
+
+    # ---- single_stage_fsd_v2.py:217-242, 262-269: after the backbone
     def finish(self, front_out, out_voxel_feats, out_coors, sparse_shape=None):
         virtual_mask = front_out["virtual_mask"]
         ssm = front_out["singlescale_mask"]

@@ -162,6 +162,40 @@ def test_fsdv2_front_reference_golden(cuda, tag):
     torch.testing.assert_close(out["virtual_centers"].cpu(), z["virtual_centers"], rtol=0, atol=1e-5)
 
 
+def test_fsdv2_extract_feat_with_mixer_reference_golden(cuda):
+    """BASELINE config 5 end to end on the GPU: VirtualVoxelFront.extract_feat = front kernels -> VirtualVoxelMixer (sparse-conv U-Net,
+    SURVEY 8f next-1) -> virtual-voxel bookkeeping, against the reference's own extract_feat running its own VirtualVoxelMixer over its
+    vendored spconv (fixture fsdv2_front_mixer.npz): coordinates bit-exact, features to fp32 accuracy."""
+    import types
+    from oracle import spconv_oracle as SO
+    from sst_b200.fsdv2_modules import VirtualVoxelFront
+    z = _load("fsdv2_front_mixer.npz")
+    norm = dict(type='naiveSyncBN1d', eps=1e-5, momentum=0.01)
+    m = VirtualVoxelFront(
+        voxel_encoder=dict(type='DynamicScatterVFE', in_channels=19, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True,
+                           voxel_size=FSDV2["vs"], point_cloud_range=FSDV2["rng"], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01),
+                           unique_once=True, rel_dist_scaler=10.0),
+        virtual_point_projector=dict(in_channels=24, hidden_dims=[16, 16], norm_cfg=norm, ori_in_channels=19, ori_hidden_dims=[16, 16]),
+        multiscale_cfg=dict(multiscale_levels=[0, 1, 2], projector_hiddens=[[24, 32], [16, 32], [16, 32]], fusion_mode='avg',
+                            target_sparse_shape=FSDV2["target"], norm_cfg=norm),
+        backbone=dict(type='VirtualVoxelMixer', **SO.FSDV2_MIXER)).eval()
+    sd = dict(_w(z, "w."))
+    sd.update({"backbone." + k: v for k, v in _w(z, "mix.").items()})
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "num_batches_tracked" not in k] and not unexpected
+    m = m.to(cuda)
+    sampled = {k[len("sampled."):]: v.to(cuda) for k, v in z.items() if k.startswith("sampled.")}
+    origin = {k[len("origin."):]: v.to(cuda) for k, v in z.items() if k.startswith("origin.")}
+    ms = [types.SimpleNamespace(features=z[f"ms{i}.features"].to(cuda), indices=z[f"ms{i}.indices"].to(cuda),
+                                spatial_shape=z[f"ms{i}.shape"].tolist()) for i in range(3)]
+    with torch.no_grad():
+        out = m.extract_feat(sampled, origin, None, ms)
+    assert list(out["sparse_shape"]) == SO.FSDV2_MIXER["sparse_shape"]
+    assert torch.equal(out["virtual_coors"].cpu().long(), z["virtual_coors"].long())
+    torch.testing.assert_close(out["virtual_feats"].cpu(), z["virtual_feats"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(out["virtual_centers"].cpu(), z["virtual_centers"], rtol=0, atol=1e-5)
+
+
 def test_voxelize_with_batch_idx_matches_torch_floor_div(cuda):
     """The kernel restates c10::div_floor_floating: bit-identical to torch.div(rounding_mode='floor') on adversarial inputs
     (exact multiples of the voxel size, negatives, tiny offsets, non-representable voxel sizes)."""

@@ -263,3 +263,19 @@ def test_fsd_cluster_golden():
                                                       [-80, -80, -2, 80, 80, 4], dist[name])
         assert torch.equal(mask, torch.from_numpy(z[f"ca_mask{i}"]))
         assert torch.equal(inds.long(), torch.from_numpy(z[f"ca_inds{i}"])[:, 1:].long())
+
+
+def test_fsdv2_extract_feat_with_mixer_golden():
+    """BASELINE config 5 end to end: front (oracle) -> VirtualVoxelMixer (spconv oracle) -> virtual voxels, against the reference's own
+    extract_feat running its own VirtualVoxelMixer over its vendored spconv (fixture fsdv2_front_mixer.npz)."""
+    from oracle import spconv_oracle as SO
+    z = _load("fsdv2_front_mixer.npz")
+    sampled, origin, ms = _fsdv2_inputs(z, True)
+    out = O.fsdv2_front(sampled, origin, _w(z, "w."), FSDV2["vs"], FSDV2["rng"], FSDV2["vfe"], ms=ms)
+    torch.testing.assert_close(out["voxel_feats"], z["backbone_feats"], rtol=1e-5, atol=1e-5)
+    M = SO.FSDV2_MIXER
+    f, c = SO.sparse_unet_forward(_w(z, "mix."), out["voxel_feats"], out["voxel_coors"].int(), int(z["batch_size"]), M["sparse_shape"],
+                                  M["encoder_channels"], M["encoder_paddings"], M["decoder_channels"], M["decoder_paddings"], mixer_out=True)
+    f, c = f[out["singlescale_mask"]], c[out["singlescale_mask"]]
+    assert torch.equal(c[out["virtual_mask"]].long(), z["virtual_coors"].long())
+    torch.testing.assert_close(f[out["virtual_mask"]], z["virtual_feats"], rtol=1e-3, atol=1e-4)

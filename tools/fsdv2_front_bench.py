@@ -1,9 +1,10 @@
 """BASELINE config 5 (front part): FSDv2 virtual-voxel front at nuScenes shape - 30k real points x batch 16 (+ 2k voted centres per
 sample), 67-dim point features into DynamicScatterVFE [64,128], multiscale fusion with three coarse levels - through
-sst_b200.fsdv2_modules.VirtualVoxelFront on one B200.  The sparse-conv mixer that follows is not built, so this
-times everything `SingleStageFSDV2.extract_feat` does before and after its `self.backbone(...)` call.
+sst_b200.fsdv2_modules.VirtualVoxelFront on one B200: first everything `SingleStageFSDV2.extract_feat` does before and after its
+`self.backbone(...)` call (identity mixer), then the whole extract_feat with the configs/fsdv2 VirtualVoxelMixer (sparse-conv U-Net,
+SURVEY 8f next-1; spconv_modules.py) in both precisions.
 
-    python tools/fsdv2_front_bench.py > profiles/r02_fsdv2_front.json     (GPU box)"""
+    python tools/fsdv2_front_bench.py > profiles/r02_fsdv2_config5.json     (GPU box)"""
 import json
 import os
 import sys
@@ -13,6 +14,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sst_b200.fsdv2_modules import VirtualVoxelFront  # noqa: E402
+from sst_b200 import spconv_modules as SP  # noqa: E402
 
 dev = torch.device("cuda:0")
 B, P, V = 16, 30000, 2000
@@ -23,7 +25,11 @@ m = VirtualVoxelFront(
                        voxel_size=VS, point_cloud_range=RNG, norm_cfg=norm, unique_once=True, rel_dist_scaler=10.0),
     virtual_point_projector=dict(in_channels=75 + 64, hidden_dims=[64, 64], norm_cfg=norm, ori_in_channels=67 + 64, ori_hidden_dims=[64, 64]),
     multiscale_cfg=dict(multiscale_levels=[0, 1, 2], projector_hiddens=[[256, 128], [128, 128], [128, 128]], fusion_mode="avg",
-                        target_sparse_shape=TGT, norm_cfg=norm)).eval().to(dev)
+                        target_sparse_shape=TGT, norm_cfg=norm),
+    # configs/fsdv2/fsdv2_nusc_1x.py:142-154 (sparse_shape follows this bench's 0.4 m grid)
+    backbone=dict(type="VirtualVoxelMixer", in_channels=128, sparse_shape=TGT, order=("conv", "norm", "act"), norm_cfg=norm, base_channels=64,
+                  output_channels=128, encoder_channels=((64,), (64, 64), (64, 64)), encoder_paddings=((1,), (1, 1), (1, 1)),
+                  decoder_channels=((64, 64, 64), (64, 64, 64), (64, 64, 64)), decoder_paddings=((1, 1), (1, 1), (1, 1)))).eval().to(dev)
 g = torch.Generator().manual_seed(0)
 lo, hi = torch.tensor(RNG[:3]), torch.tensor(RNG[3:])
 
@@ -58,20 +64,37 @@ def step():
         return m.finish(fr, fr["voxel_feats"], fr["voxel_coors"]), fr
 
 
-for _ in range(3):
-    out, fr = step()
-torch.cuda.synchronize()
-times = []
-for _ in range(10):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    out, fr = step()
-    b.record()
+def full():
+    with torch.no_grad():
+        return m.extract_feat({k: v.clone() for k, v in sampled.items()}, origin, None, levels)
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        r = fn()
     torch.cuda.synchronize()
-    times.append(a.elapsed_time(b))
-times.sort()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return r, ts
+
+
+(out, fr), times = timed(step)
+e2e = {}
+for prec in ("fp32", "bf16"):
+    SP.set_spconv_precision(m, prec)
+    o, ts = timed(full)
+    e2e[prec] = {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "frames_per_s": B / (ts[len(ts) // 2] * 1e-3),
+                 "virtual_voxels": int(o["virtual_coors"].shape[0])}
 print(json.dumps({"workload": "config 5 front: FSDv2 extract_feat without the sparse-conv mixer, 16 x (30k points + 2k votes), 0.4 m voxels, "
                               "67-dim VFE input, 3-level multiscale fusion", "ms_median": times[len(times) // 2], "ms_min": times[0],
                   "points": B * (P + V), "voxels": int(fr["voxel_coors"].shape[0]), "virtual_voxels": int(out["virtual_coors"].shape[0]),
                   "frames_per_s": B / (times[len(times) // 2] * 1e-3),
+                  "with_mixer": dict(workload="config 5 end to end: extract_feat incl. VirtualVoxelMixer (configs/fsdv2 channels, 3 stages)", **e2e),
                   "note": "module API (stream launches, torch cat / projector MLPs through cuBLAS); not graph-captured"}))

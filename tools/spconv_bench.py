@@ -21,15 +21,16 @@ FSD_UNET = dict(type="SimpleSparseUNet", in_channels=64, sparse_shape=[32, 640, 
                 decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1)))
 
 
-def sweep_voxels(dev, seed=1000, points=150000):
+def sweep_voxels(dev, seed=1000, points=150000, shuffle=False):
     from sst_b200 import flagship as fl
     pts = fl.synth_frame(seed, points)
     vs, lo = 0.2, torch.tensor([-64.0, -64.0, -3.2])
     c = ((pts[:, :3] - lo) / vs).floor().long()[:, [2, 1, 0]]
     ok = (c[:, 0] >= 0) & (c[:, 0] < 32) & (c[:, 1] >= 0) & (c[:, 1] < 640) & (c[:, 2] >= 0) & (c[:, 2] < 640)
-    c = torch.unique(c[ok], dim=0)
+    c = torch.unique(c[ok], dim=0)   # lexicographic (z,y,x) order = the order the voxel encoder (scatter_v2 / unique) hands over
     g = torch.Generator().manual_seed(seed)
-    c = c[torch.randperm(c.shape[0], generator=g)]
+    if shuffle:
+        c = c[torch.randperm(c.shape[0], generator=g)]
     coors = torch.cat([torch.zeros((c.shape[0], 1), dtype=torch.long), c], 1).int()
     return torch.randn((coors.shape[0], 64), generator=g).to(dev), coors.to(dev)
 
@@ -39,12 +40,13 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--once", default=None)
+    ap.add_argument("--shuffle", action="store_true", help="rows in random order instead of the voxel encoder's sorted order")
     a = ap.parse_args()
     from sst_b200 import registry, spconv_modules as SP
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = registry.MODELS.build(dict(FSD_UNET)).to(dev).eval()
-    feats, coors = sweep_voxels(dev)
+    feats, coors = sweep_voxels(dev, shuffle=a.shuffle)
     info = dict(voxel_feats=feats, voxel_coors=coors)
 
     # per-convolution work: record (n_out, pairs, cin, cout) of every launch
@@ -86,7 +88,7 @@ def main():
         return e0.elapsed_time(e1) / reps
 
     res = dict(workload="SimpleSparseUNet configs/fsd shape, 150k-point sweep -> %d voxels, grid 32x640x640, eval" % coors.shape[0],
-               voxels=int(coors.shape[0]), conv_launches=len(launches), pair_gflop=flops / 1e9, dense_tile_gflop=dense_flops / 1e9,
+               row_order="shuffled" if a.shuffle else "sorted (z,y,x)", voxels=int(coors.shape[0]), conv_launches=len(launches), pair_gflop=flops / 1e9, dense_tile_gflop=dense_flops / 1e9,
                algorithmic_mb=byts / 1e6)
     with torch.no_grad():
         for prec in ("fp32", "bf16"):
