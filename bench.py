@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-tolerance sub-record")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE config 4)")
+    ap.add_argument("--no-fsd", action="store_true", help="skip the FSD sparse U-Net sub-record (SURVEY 8f next-1)")
     ap.add_argument("--train-frames", type=int, default=4, help="frames per GPU and training step (config 4: 32 frames / 8 GPUs)")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SSTB200_STREAMS", "8")),
                     help="frames in flight per GPU (independent engines on their own CUDA streams); 1 = strictly serial")
@@ -480,6 +481,14 @@ def main():
         except Exception as e:   # the inference record must not be lost to a training-side failure; say so loudly instead
             train = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- FSD sparse U-Net, rank 0 only: one sweep through SimpleSparseUNet, both precisions ---------------------
+    fsd = None
+    if rank == 0 and not args.no_fsd:
+        try:
+            fsd = fl.fsd_unet_bench(dev)
+        except Exception as e:
+            fsd = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again, like the --impl reference arm
@@ -504,7 +513,7 @@ def main():
             "gpu_graph_other_nodes_per_step": int(getattr(eng, "other_nodes_per_frame", 0) or 0),
             "gpu_launches_per_step": int(eng.launches_per_frame or 0),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roof, "cpu_baseline": cpu, "fp32": fp32_rec, "train": train,
+            "roofline": roof, "cpu_baseline": cpu, "fp32": fp32_rec, "train": train, "fsd_unet": fsd,
         }
         print(json.dumps(line))
     if world > 1:

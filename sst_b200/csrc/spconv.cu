@@ -229,27 +229,34 @@ __global__ void __launch_bounds__(256) spconv_gemm_f32_kernel(const float* __res
 // tensor-core implicit GEMM (precision 'bf16' = 16-bit operands, fp32 accumulation): 128-row output tile x NT output channels per
 // CTA, accumulators [128, NT] fp32 in TMEM across ALL kernel offsets, operands IEEE fp16 in the K-major SWIZZLE_128B layout (same
 // staging / descriptors as umma_gemm.cuh).  K is walked in stages of (kernel offset, 64 input channels): the 256 threads gather the
-// 128 neighbour rows (fp32 -> fp16 on the fly, absent neighbours = zero rows) and the [NT, 64] weight slab into one of NS operand
-// buffers, one thread issues 4 tcgen05.mma (K = 16 each) and commits to the buffer's mbarrier; the global loads of stage s+1 are
-// issued into registers before the MMAs of stage s, and a buffer is rewritten only after its commit has fired.  Offsets no row of
-// the tile uses are skipped.  Epilogue: thread-per-row out of TMEM, y = acc * scale + shift (+ residual) (ReLU), fp32 rows.
+// 128 neighbour rows (fp32 -> fp16 on the fly, absent neighbours = zero rows that are neither loaded nor converted) and the [NT, 64]
+// weight slab into one of NS operand buffers, one thread issues 4 tcgen05.mma (K = 16 each) and commits to the buffer's mbarrier; the
+// global loads run TWO stages ahead in two register sets (the deep levels of a U-Net are a few CTAs walking 100-200 stages each:
+// pure load latency), and a buffer is rewritten only after its commit has fired.  Offsets no row of the tile uses are skipped.  Epilogue: thread-per-row out of TMEM, y = acc * scale + shift (+ residual) (ReLU), fp32 rows.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int SPU_TM = 128;
 constexpr int SPU_A_BYTES = SPU_TM * 128;
 #define SPU_MAX_KV 27
 
+// fp32 pair -> fp16x2 with saturation to +-65504 in ONE instruction (F2FP.SATFINITE.F16.F32.PACK_AB); a = low half
 __device__ __forceinline__ uint32_t sp_pack_f16(float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
+template <int BU>
+struct SpStageRegs {
+  float4 a0[4], a1[4];   // 4 pieces of 8 gathered channels each
+  int4 b[BU];            // weight pieces
+  uint32_t valid;        // bit u: piece u has a source row (absent neighbours are neither loaded nor converted)
+};
+
 template <int NT, int NS>
-__global__ void __launch_bounds__(256) spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __restrict__ nbr, int n_out,
-                                                         int KV, const __half* __restrict__ W16 /* [KV][Cout][Cin] */, int Cout,
-                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         const float* __restrict__ residual, int relu, float* __restrict__ out) {
+__global__ void __launch_bounds__(256, NT == 64 ? 2 : 1)
+spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __restrict__ nbr, int n_out, int KV,
+                   const __half* __restrict__ W16 /* [KV][Cout][Cin] */, int Cout, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ residual, int relu, float* __restrict__ out) {
   pdl_wait();
   pdl_launch();
   extern __shared__ uint8_t sp_smem_raw[];
@@ -288,65 +295,62 @@ __global__ void __launch_bounds__(256) spconv_umma_kernel(const float* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  uint32_t mask = used_mask;
   const int nch = Cin >> 6;
-  const int nst = __popc(mask) * nch;
+  const int nst = __popc(used_mask) * nch;
 
-  float4 ra0[4], ra1[4];
-  int4 rb[BU];
-  auto load_stage = [&](int k, int c) {
+  // stage iterator of the loader (stages are visited in order: used offsets ascending, 64-channel chunks inside)
+  uint32_t ld_mask = used_mask;
+  int ld_c = 0, loaded = 0;
+  const int my_r = tid >> 3, my_jj = tid & 7;   // piece u of this thread: row my_r + 32 u, 16-byte column my_jj
+  auto load_next = [&](SpStageRegs<BU>& R) {
+    if (loaded >= nst) return;
+    const int k = __ffs(ld_mask) - 1, c = ld_c;
+    R.valid = 0u;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int p = tid + u * 256, r = p >> 3, jj = p & 7;
-      const int src = sNbr[r][k];
-      ra0[u] = ra1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int src = sNbr[my_r + 32 * u][k];
       if (src >= 0) {
-        const float* ap = feats + (size_t)src * Cin + c * 64 + jj * 8;
-        ra0[u] = *reinterpret_cast<const float4*>(ap);
-        ra1[u] = *reinterpret_cast<const float4*>(ap + 4);
+        R.valid |= 1u << u;
+        const float* ap = feats + (size_t)src * Cin + c * 64 + my_jj * 8;
+        R.a0[u] = *reinterpret_cast<const float4*>(ap);
+        R.a1[u] = *reinterpret_cast<const float4*>(ap + 4);
       }
     }
+    const __half* wp = W16 + ((size_t)k * Cout + n0 + my_r) * Cin + c * 64 + my_jj * 8;
 #pragma unroll
-    for (int u = 0; u < BU; u++) {
-      const int p = tid + u * 256, r = p >> 3, jj = p & 7;
-      rb[u] = __ldg(reinterpret_cast<const int4*>(W16 + ((size_t)k * Cout + n0 + r) * Cin + c * 64 + jj * 8));
+    for (int u = 0; u < BU; u++) R.b[u] = __ldg(reinterpret_cast<const int4*>(wp + (size_t)32 * u * Cin));
+    loaded++;
+    if (++ld_c == nch) {
+      ld_c = 0;
+      ld_mask &= ld_mask - 1u;
     }
   };
-  auto store_stage = [&](uint8_t* sA, uint8_t* sB) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int p = tid + u * 256, r = p >> 3, jj = p & 7;
-      int4 v;
-      v.x = (int)sp_pack_f16(ra0[u].x, ra0[u].y);
-      v.y = (int)sp_pack_f16(ra0[u].z, ra0[u].w);
-      v.z = (int)sp_pack_f16(ra1[u].x, ra1[u].y);
-      v.w = (int)sp_pack_f16(ra1[u].z, ra1[u].w);
-      *reinterpret_cast<int4*>(sA + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
-    }
-#pragma unroll
-    for (int u = 0; u < BU; u++) {
-      const int p = tid + u * 256, r = p >> 3, jj = p & 7;
-      *reinterpret_cast<int4*>(sB + r * 128 + ((jj ^ (r & 7)) << 4)) = rb[u];
-    }
-  };
-
-  int k_cur = mask ? __ffs(mask) - 1 : 0, c_cur = 0;
-  if (nst > 0) load_stage(k_cur, c_cur);
-  for (int s = 0; s < nst; s++) {
-    const int b = s % NS, u = s / NS;
+  auto run_stage = [&](int s, SpStageRegs<BU>& R) {
+    const int b = s % NS, u_ = s / NS;
     uint8_t* sA = base + (size_t)b * ST_BYTES;
     uint8_t* sB = sA + SPU_A_BYTES;
-    if (u >= 1) {  // the MMAs that read this buffer NS stages ago have completed
-      mbar_wait(smem_u32(&mbar[b]), (uint32_t)((u - 1) & 1));
+    if (u_ >= 1) {  // the MMAs that read this buffer NS stages ago have completed
+      mbar_wait(smem_u32(&mbar[b]), (uint32_t)((u_ - 1) & 1));
       tc_fence_after();
     }
-    store_stage(sA, sB);
-    if (++c_cur == nch) {
-      c_cur = 0;
-      mask &= mask - 1u;
-      k_cur = mask ? __ffs(mask) - 1 : 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = my_r + 32 * u;
+      int4 v = make_int4(0, 0, 0, 0);
+      if ((R.valid >> u) & 1u) {
+        v.x = (int)sp_pack_f16(R.a0[u].x, R.a0[u].y);
+        v.y = (int)sp_pack_f16(R.a0[u].z, R.a0[u].w);
+        v.z = (int)sp_pack_f16(R.a1[u].x, R.a1[u].y);
+        v.w = (int)sp_pack_f16(R.a1[u].z, R.a1[u].w);
+      }
+      *reinterpret_cast<int4*>(sA + r * 128 + ((my_jj ^ (r & 7)) << 4)) = v;
     }
-    if (s + 1 < nst) load_stage(k_cur, c_cur);
+#pragma unroll
+    for (int u = 0; u < BU; u++) {
+      const int r = my_r + 32 * u;
+      *reinterpret_cast<int4*>(sB + r * 128 + ((my_jj ^ (r & 7)) << 4)) = R.b[u];
+    }
+    load_next(R);         // the register set is free again: fetch the stage two ahead while this one is multiplied
     fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -359,6 +363,15 @@ __global__ void __launch_bounds__(256) spconv_umma_kernel(const float* __restric
         umma_f16(tmem, umma_desc_sw128(a0 + q * 32), umma_desc_sw128(b0 + q * 32), idesc, (s | q) ? 1u : 0u);
       umma_commit(smem_u32(&mbar[b]));  // implicit tcgen05.fence::before_thread_sync
     }
+  };
+
+  SpStageRegs<BU> R0, R1;
+  R0.valid = R1.valid = 0u;
+  load_next(R0);
+  load_next(R1);
+  for (int s = 0; s < nst; s += 2) {
+    run_stage(s, R0);
+    if (s + 1 < nst) run_stage(s + 1, R1);
   }
   if (nst > 0) {
     const int s = nst - 1;

@@ -63,3 +63,52 @@ def synth_frame(seed, P=150000, extra_dims=0, sigma=0.04):
     z = torch.rand(P, generator=g) * 6.0 - 2.0
     cols = [r * torch.cos(th), r * torch.sin(th), z] + [torch.rand(P, generator=g) for _ in range(extra_dims)]
     return torch.stack(cols, dim=1).contiguous()
+
+
+# ---- the FSD segmentation backbone (configs/fsd/fsd_waymoD1_1x.py:39-51) ---------------------------------------
+FSD_UNET = dict(type="SimpleSparseUNet", in_channels=64, sparse_shape=[32, 640, 640], order=("conv", "norm", "act"),
+                norm_cfg=dict(type="naiveSyncBN1d", eps=1e-3, momentum=0.01), base_channels=64, output_channels=128,
+                encoder_channels=((64,), (64, 64, 64), (64, 64, 64), (128, 128, 128), (256, 256, 256)),
+                encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1), (1, 1, 1)),
+                decoder_channels=((256, 256, 128), (128, 128, 64), (64, 64, 64), (64, 64, 64), (64, 64, 64)),
+                decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1)))
+
+
+def fsd_sweep_voxels(seed=1000, points=150000, channels=64, shuffle=False):
+    """A synthetic sweep voxelised on the configs/fsd segmentation grid (0.2 m, [32, 640, 640]): ([M, channels] fp32, [M, 4] int32
+    (b,z,y,x)) on the CPU, rows in lexicographic order (what the voxel encoder hands over) unless shuffled."""
+    pts = synth_frame(seed, points)
+    lo = torch.tensor([-64.0, -64.0, -3.2])
+    c = ((pts[:, :3] - lo) / 0.2).floor().long()[:, [2, 1, 0]]
+    ok = (c[:, 0] >= 0) & (c[:, 0] < 32) & (c[:, 1] >= 0) & (c[:, 1] < 640) & (c[:, 2] >= 0) & (c[:, 2] < 640)
+    c = torch.unique(c[ok], dim=0)
+    g = torch.Generator().manual_seed(seed)
+    if shuffle:
+        c = c[torch.randperm(c.shape[0], generator=g)]
+    coors = torch.cat([torch.zeros((c.shape[0], 1), dtype=torch.long), c], 1).int()
+    return torch.randn((coors.shape[0], channels), generator=g), coors
+
+
+def fsd_unet_bench(dev, reps=5, precisions=("bf16", "fp32")):
+    """SimpleSparseUNet forward (tables + 34 convolution launches + glue) on one sweep, CUDA events on the current stream."""
+    from . import spconv_modules as SP
+    torch.manual_seed(0)
+    net = build_backbone(dict(FSD_UNET)).to(dev).eval()
+    feats, coors = fsd_sweep_voxels()
+    info = dict(voxel_feats=feats.to(dev), voxel_coors=coors.to(dev))
+    rec = {"workload": "SimpleSparseUNet, configs/fsd backbone shape, 150k-point sweep at 0.2 m, eval, batch 1", "voxels": int(coors.shape[0])}
+    with torch.no_grad():
+        for prec in precisions:
+            SP.set_spconv_precision(net, prec)
+            for _ in range(2):
+                net(info)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                net(info)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / reps
+            rec["f16_tcgen05" if prec == "bf16" else "fp32_ffma"] = {"ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms}
+    return rec

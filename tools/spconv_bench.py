@@ -13,26 +13,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-FSD_UNET = dict(type="SimpleSparseUNet", in_channels=64, sparse_shape=[32, 640, 640], order=("conv", "norm", "act"),
-                norm_cfg=dict(type="naiveSyncBN1d", eps=1e-3, momentum=0.01), base_channels=64, output_channels=128,
-                encoder_channels=((64,), (64, 64, 64), (64, 64, 64), (128, 128, 128), (256, 256, 256)),
-                encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1), (1, 1, 1)),
-                decoder_channels=((256, 256, 128), (128, 128, 64), (64, 64, 64), (64, 64, 64), (64, 64, 64)),
-                decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1)))
+from sst_b200.flagship import FSD_UNET, fsd_sweep_voxels  # noqa: E402
 
 
-def sweep_voxels(dev, seed=1000, points=150000, shuffle=False):
-    from sst_b200 import flagship as fl
-    pts = fl.synth_frame(seed, points)
-    vs, lo = 0.2, torch.tensor([-64.0, -64.0, -3.2])
-    c = ((pts[:, :3] - lo) / vs).floor().long()[:, [2, 1, 0]]
-    ok = (c[:, 0] >= 0) & (c[:, 0] < 32) & (c[:, 1] >= 0) & (c[:, 1] < 640) & (c[:, 2] >= 0) & (c[:, 2] < 640)
-    c = torch.unique(c[ok], dim=0)   # lexicographic (z,y,x) order = the order the voxel encoder (scatter_v2 / unique) hands over
-    g = torch.Generator().manual_seed(seed)
-    if shuffle:
-        c = c[torch.randperm(c.shape[0], generator=g)]
-    coors = torch.cat([torch.zeros((c.shape[0], 1), dtype=torch.long), c], 1).int()
-    return torch.randn((coors.shape[0], 64), generator=g).to(dev), coors.to(dev)
+def sweep_voxels(dev, shuffle=False):
+    feats, coors = fsd_sweep_voxels(shuffle=shuffle)
+    return feats.to(dev), coors.to(dev)
 
 
 def main():
