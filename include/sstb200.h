@@ -403,6 +403,14 @@ int sstb200_spconv_forward(sstb200_ctx* ctx, const float* feats, int c_in, const
                            const float* weight, const void* weight_h16, int c_out, const float* scale, const float* shift,
                            const float* residual, int relu, int precision, float* out);
 
+/* Backward of sstb200_spconv_forward without epilogue (indice_conv_backward_fp32, mmdet3d/ops/spconv/src/all.cc:34-35 ->
+ * spconv_ops.h:262-420).  The input gradient needs no entry point of its own: dX = sstb200_spconv_forward(dY, nbr_T, W^T) on the
+ * TRANSPOSED table (nbr_inv of sstb200_spconv_table; the table SparseInverseConv3d runs on).  This call computes the weight gradient
+ * grad_weight [KV, c_in, c_out] fp32 (fully written) = sum over pairs of feats[nbr[o][k]]^T . grad_out[o]; fp32 atomics across row
+ * chunks, so the last bits depend on the launch like the reference's backward. */
+int sstb200_spconv_backward_weight(sstb200_ctx* ctx, const float* feats, int c_in, const int32_t* nbr, int n_out, int kernel_volume,
+                                   const float* grad_out, int c_out, float* grad_weight);
+
 /* ---- next-3: FSD instance grouping.  find_connected_componets / _single_batch / _gpu
  * (mmdet3d/models/detectors/single_stage_fsd.py:37-81; TorchEx connected_components at :20,39-45): two centres of the same sample are
  * adjacent when sqrt(dx^2 + dy^2) < dist (xy only, fp32); labels [n] = component number, components numbered sample by sample (batch

@@ -226,6 +226,84 @@ __global__ void __launch_bounds__(256) spconv_gemm_f32_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
+// weight gradient:  dW[k] += sum over output rows o with nbr[o][k] >= 0 of  X[nbr[o][k]]^T . dY[o]      (fp32, FFMA)
+// CTA = (chunk of SPW_ROWS output rows, kernel offset k, 64 x 64 tile of dW[k]).  The rows of the chunk that actually have a neighbour
+// at offset k (17 % on a LiDAR sweep) are compacted into shared memory first, so the reduction only walks real pairs; the partial
+// tile is added to dW with fp32 atomics (summation order across chunks is not fixed, like the reference's atomics-based backward).
+// ------------------------------------------------------------------------------------------------------------------------------
+#define SPW_ROWS 1024
+__global__ void __launch_bounds__(256) spconv_dw_kernel(const float* __restrict__ X, int Cin, const int32_t* __restrict__ nbr, int n_out, int KV,
+                                                       const float* __restrict__ dY, int Cout, float* __restrict__ dW) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ int sIn[SPW_ROWS], sOut[SPW_ROWS];
+  __shared__ int sCount;
+  __shared__ __align__(16) float sA[16][64];
+  __shared__ __align__(16) float sB[16][64];
+  const int tid = threadIdx.x;
+  const int k = blockIdx.y;
+  const int ncot = (Cout + 63) / 64;
+  const int ci0 = ((int)blockIdx.z / ncot) * 64, co0 = ((int)blockIdx.z % ncot) * 64;
+  const int r0 = blockIdx.x * SPW_ROWS;
+  if (tid == 0) sCount = 0;
+  __syncthreads();
+  for (int j = tid; j < SPW_ROWS; j += 256) {
+    const int o = r0 + j;
+    if (o < n_out) {
+      const int v = nbr[(size_t)o * KV + k];
+      if (v >= 0) {
+        const int pos = atomicAdd(&sCount, 1);
+        sIn[pos] = v;
+        sOut[pos] = o;
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = sCount;
+  if (cnt == 0) return;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int q0 = 0; q0 < cnt; q0 += 16) {
+    {
+      const int r = tid >> 4, c4 = (tid & 15) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < cnt) {
+        if (ci0 + c4 < Cin) a = *reinterpret_cast<const float4*>(X + (size_t)sIn[q0 + r] * Cin + ci0 + c4);
+        if (co0 + c4 < Cout) b = *reinterpret_cast<const float4*>(dY + (size_t)sOut[q0 + r] * Cout + co0 + c4);
+      }
+      *reinterpret_cast<float4*>(&sA[r][c4]) = a;
+      *reinterpret_cast<float4*>(&sB[r][c4]) = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[r][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[r][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int co = co0 + tx * 4 + j;
+      if (co < Cout) atomicAdd(&dW[((size_t)k * Cin + ci) * Cout + co], acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
 // tensor-core implicit GEMM (precision 'bf16' = 16-bit operands, fp32 accumulation): 128-row output tile x NT output channels per
 // CTA, accumulators [128, NT] fp32 in TMEM across ALL kernel offsets, operands IEEE fp16 in the K-major SWIZZLE_128B layout (same
 // staging / descriptors as umma_gemm.cuh).  K is walked in stages of (kernel offset, 64 input channels): the 256 threads gather the
@@ -589,4 +667,21 @@ extern "C" int sstb200_spconv_forward(sstb200_ctx* c, const float* feats, int c_
   if (c_out % 128 == 0)
     return launch_spconv_umma<128, 3>(c, feats, c_in, nbr, n_out, kernel_volume, w16, c_out, scale, shift, residual, relu, out);
   return launch_spconv_umma<64, 3>(c, feats, c_in, nbr, n_out, kernel_volume, w16, c_out, scale, shift, residual, relu, out);
+}
+
+extern "C" int sstb200_spconv_backward_weight(sstb200_ctx* c, const float* feats, int c_in, const int32_t* nbr, int n_out, int kernel_volume,
+                                              const float* grad_out, int c_out, float* grad_weight) {
+  CHECK_ARG(c, c && n_out >= 0 && c_in >= 1 && c_out >= 1 && kernel_volume >= 1 && grad_weight);
+  CUDA_TRY(c, cudaMemsetAsync(grad_weight, 0, (size_t)kernel_volume * c_in * c_out * 4, c->stream));
+  if (n_out == 0) return SSTB_OK;
+  CHECK_ARG(c, feats && nbr && grad_out);
+  CHECK_ARG(c, ((uintptr_t)feats & 15) == 0 && ((uintptr_t)grad_out & 15) == 0);
+  if ((c_in & 3) || (c_out & 3))
+    return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "spconv_backward_weight: channel counts must be multiples of 4 (got %d -> %d)", c_in, c_out);
+  const int tiles = ((c_in + 63) / 64) * ((c_out + 63) / 64);
+  if (kernel_volume > 65535 || tiles > 65535) return sstb_fail(c, SSTB_ERR_UNSUPPORTED, "spconv_backward_weight: grid too large");
+  dim3 grid((n_out + SPW_ROWS - 1) / SPW_ROWS, kernel_volume, tiles);
+  launch_pdl(spconv_dw_kernel, grid, dim3(256), (size_t)0, c->stream, feats, c_in, nbr, n_out, kernel_volume, grad_out, c_out, grad_weight);
+  LAUNCH_CHECK(c);
+  return SSTB_OK;
 }

@@ -10,7 +10,9 @@ sstb200_spconv_table from the bitmap-rank index.  In eval mode `conv -> BatchNor
 residual tail of SparseBasicBlock are folded into that launch's epilogue.
 
 Weights keep the reference's checkpoint layout (kD, kH, kW, in, out) (write_spconv2.py:44-60 converts spconv2's to it on save).
-There is no CPU / PyTorch fallback; the backward pass of the sparse convolutions is not built (declared in DESIGN.md section 7).
+There is no CPU / PyTorch fallback.  Gradients: a convolution whose input or weight requires grad runs epilogue-free through
+_IndiceConvFunction (dX = the same kernel on the transposed table with W^T, dW = sstb200_spconv_backward_weight) and the containers
+compose BatchNorm / activation / residual with torch modules, as the reference does.
 
 Sub-manifold convolutions are always centred: spconv forces stride 1 / padding k//2 in the SubM index generation whatever the layer
 was built with (vendored v1: include/spconv/spconv_ops.h:74-78; spconv 2.x: generate_subm_conv_inds takes no padding), so e.g.
@@ -30,6 +32,7 @@ L.SIGNATURES["sstb200_spconv_out_coors"] = (C.c_int, [L.vp, L.vp, C.c_int, C.c_i
                                                      C.c_int, L.vp, L.P_i32])
 L.SIGNATURES["sstb200_spconv_table"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c_int, C.c_int, L.P_i32, L.P_i32, L.P_i32, L.P_i32,
                                                  L.P_i32, L.vp, L.vp, L.P_i32])
+L.SIGNATURES["sstb200_spconv_backward_weight"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c_int, C.c_int, L.vp, C.c_int, L.vp])
 L.SIGNATURES["sstb200_spconv_forward"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c_int, C.c_int, L.vp, L.vp, C.c_int, L.vp, L.vp, L.vp,
                                                    C.c_int, C.c_int, L.vp])
 
@@ -85,8 +88,9 @@ def conv_out_coors(indices, batch_size, in_shape, out_shape, ksize, stride, padd
     return out[:num_host.value]
 
 
-def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, stride, padding, want_nbr=True, want_inv=False):
-    """(nbr [n_out, KV], nbr_inv [n_in, KV]) int32 neighbour tables (None when not asked for)."""
+def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, stride, padding, want_nbr=True, want_inv=False, check=True):
+    """(nbr [n_out, KV], nbr_inv [n_in, KV]) int32 neighbour tables (None when not asked for).  check: read the status word back (one
+    host sync) and raise on coordinates outside the grid; callers pass False for coordinate sets this package produced itself."""
     ci, co = _coors4(in_indices), _coors4(out_indices)
     if not ci.is_cuda:
         raise L.SSTB200Error("sst_b200 spconv needs CUDA tensors (no CPU fallback)")
@@ -97,19 +101,15 @@ def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, 
     c = L.ctx(ci.device)
     L.check(c, L.lib().sstb200_spconv_table(c, ci.data_ptr(), ci.shape[0], co.data_ptr(), co.shape[0], int(batch_size), _i3(in_shape),
                                             _i3(out_shape), _i3(ksize), _i3(stride), _i3(padding), L.ptr(nbr), L.ptr(inv),
-                                            C.byref(status)))
+                                            C.byref(status) if check else None))
     return nbr, inv
 
 
-def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, residual=None, relu=False, precision="fp32"):
-    """out[o] = act((sum_k features[nbr[o,k]] @ weight[k]) * scale + shift + residual[o]); weight [KV, Cin, Cout] fp32."""
-    if not features.is_cuda:
-        raise L.SSTB200Error("sst_b200 spconv needs CUDA tensors (no CPU fallback)")
-    if torch.is_grad_enabled() and (features.requires_grad or weight.requires_grad):
-        raise NotImplementedError("backward of the sparse convolution is not built; run under torch.no_grad()")
+def _indice_conv_launch(features, nbr, weight, weight_h16, scale, shift, residual, relu, precision):
     feats = features.float().contiguous()
     kv, cin, cout = weight.shape
     assert feats.shape[1] == cin and nbr.shape[1] == kv and nbr.dtype == torch.int32 and nbr.is_contiguous()
+    weight = weight.detach().contiguous()
     n_out = nbr.shape[0]
     out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
     if residual is not None:
@@ -117,15 +117,77 @@ def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, 
         assert residual.shape == out.shape
     prec = PREC[precision]
     if prec == 1 and weight_h16 is None:
-        weight_h16 = weight.detach().permute(0, 2, 1).contiguous().half()
+        weight_h16 = weight.permute(0, 2, 1).contiguous().half()
     c = L.ctx(feats.device)
     L.check(c, L.lib().sstb200_spconv_forward(c, feats.data_ptr(), cin, nbr.data_ptr(), n_out, kv, weight.data_ptr(), L.ptr(weight_h16), cout,
                                               L.ptr(scale), L.ptr(shift), L.ptr(residual), int(bool(relu)), prec, out.data_ptr()))
     return out
 
 
-def fold_bn(bn):
-    """eval-mode BatchNorm1d -> (scale, shift) fp32 [C]"""
+def indice_conv_backward_weight(features, nbr, grad_out, kv, cin, cout):
+    """dW [KV, Cin, Cout] = sum over pairs of features[nbr[o,k]]^T grad_out[o]"""
+    feats, g = features.float().contiguous(), grad_out.float().contiguous()
+    dw = torch.empty((kv, cin, cout), dtype=torch.float32, device=feats.device)
+    c = L.ctx(feats.device)
+    L.check(c, L.lib().sstb200_spconv_backward_weight(c, feats.data_ptr(), cin, nbr.data_ptr(), nbr.shape[0], kv, g.data_ptr(), cout,
+                                                      dw.data_ptr()))
+    return dw
+
+
+class _IndiceConvFunction(torch.autograd.Function):
+    """autograd bridge of a convolution without epilogue (the reference: spconv's SparseConvFunction / SubMConvFunction /
+    SparseInverseConvFunction, mmdet3d/ops/spconv/functional.py:20-98).  dX is the same kernel on the transposed table with W^T."""
+
+    @staticmethod
+    def forward(ctx, features, weight, nbr, transposed_table, precision):
+        ctx.save_for_backward(features, weight, nbr)
+        ctx.transposed_table, ctx.precision = transposed_table, precision
+        return _indice_conv_launch(features, nbr, weight, None, None, None, None, False, precision)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, weight, nbr = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            nbr_t = ctx.transposed_table()
+            assert nbr_t.shape[0] == features.shape[0]
+            dx = _indice_conv_launch(grad_out, nbr_t, weight.detach().transpose(1, 2).contiguous(), None, None, None, None, False, ctx.precision)
+        if ctx.needs_input_grad[1]:
+            dw = indice_conv_backward_weight(features, nbr, grad_out, *weight.shape)
+        return dx, dw, None, None, None
+
+
+def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, residual=None, relu=False, precision="fp32",
+                transposed_table=None):
+    """out[o] = act((sum_k features[nbr[o,k]] @ weight[k]) * scale + shift + residual[o]); weight [KV, Cin, Cout] fp32.
+    With gradients enabled the call must be epilogue-free and name its transposed table (a callable returning nbr_T [n_in, KV])."""
+    if not features.is_cuda:
+        raise L.SSTB200Error("sst_b200 spconv needs CUDA tensors (no CPU fallback)")
+    if torch.is_grad_enabled() and (features.requires_grad or weight.requires_grad):
+        if scale is not None or shift is not None or residual is not None or relu or transposed_table is None:
+            raise NotImplementedError("gradients flow through epilogue-free sparse convolutions only (the modules compose BatchNorm / "
+                                      "activation / residual with torch ops when a gradient is needed)")
+        return _IndiceConvFunction.apply(features, weight, nbr, transposed_table, precision)
+    return _indice_conv_launch(features, nbr, weight, weight_h16, scale, shift, residual, relu, precision)
+
+
+def fold_bn(bn, conv_bias=None):
+    """eval-mode BatchNorm1d (+ the bias of the convolution in front of it) -> (scale, shift) fp32 [C]; cached on the module until a
+    parameter / buffer changes (34 convolutions x 6 tiny torch kernels per U-Net forward otherwise)"""
+    ts = (bn.running_mean, bn.running_var, bn.weight, bn.bias, conv_bias)
+    key = tuple((t._version, t.data_ptr()) for t in ts if t is not None)
+    hit = getattr(bn, "_sstb200_fold", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    scale, shift = _fold_bn(bn)
+    if conv_bias is not None:
+        shift = (shift + conv_bias.detach().float() * scale).contiguous()
+    bn._sstb200_fold = (key, scale, shift)
+    return scale, shift
+
+
+def _fold_bn(bn):
     var = bn.running_var.float()
     inv = torch.rsqrt(var + bn.eps)
     w = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(var)
@@ -190,12 +252,16 @@ class IndiceData:
     def inverse_table(self):
         if self._inv is None:
             _, self._inv = conv_table(self.in_indices, self.out_indices, self.batch_size, self.in_shape, self.out_shape, self.ksize,
-                                      self.stride, self.padding, want_nbr=False, want_inv=True)
+                                      self.stride, self.padding, want_nbr=False, want_inv=True, check=False)
         return self._inv
 
 
 class SparseModule(nn.Module):
     """marker base class: SparseSequential hands these the SparseConvTensor itself (modules.py:45-48)"""
+
+
+def _wants_grad(x, conv):
+    return torch.is_grad_enabled() and (x.features.requires_grad or conv.weight.requires_grad)
 
 
 def _is_relu(m):
@@ -235,10 +301,11 @@ class SparseSequential(SparseModule):
         while i < len(mods):
             m = mods[i]
             if isinstance(m, SparseConvolution):
-                bn = mods[i + 1] if (FUSE_EPILOGUE and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)
+                fuse = FUSE_EPILOGUE and not _wants_grad(input, m)
+                bn = mods[i + 1] if (fuse and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)
                                      and not mods[i + 1].training) else None
                 relu = bn is not None and i + 2 < len(mods) and _is_relu(mods[i + 2])
-                if FUSE_EPILOGUE and bn is None and i + 1 < len(mods) and _is_relu(mods[i + 1]):
+                if fuse and bn is None and i + 1 < len(mods) and _is_relu(mods[i + 1]):
                     input = m(input, relu=True)
                     i += 2
                     continue
@@ -327,16 +394,20 @@ class SparseConvolution(SparseModule):
         indices = input.indices
         kv = int(np.prod(self.kernel_size))
         w = self.weight.reshape(kv, self.in_channels, self.out_channels)
-        if bn is not None:
-            scale, shift = fold_bn(bn)
-            if self.bias is not None:
-                shift = shift + self.bias.detach().float() * scale
+        grad = _wants_grad(input, self)
+        if grad:
+            assert bn is None and not relu and residual is None, "fused epilogues carry no gradient (SparseSequential composes them)"
+            scale = shift = None
+        elif bn is not None:
+            scale, shift = fold_bn(bn, self.bias)
         else:
             scale, shift = None, (self.bias.detach().float().contiguous() if self.bias is not None else None)
-        h16 = self._weight_h16() if self.precision == "bf16" else None
+        h16 = self._weight_h16() if self.precision == "bf16" and not grad else None
         if self.conv1x1:
             nbr = torch.arange(feats.shape[0], dtype=torch.int32, device=feats.device).view(-1, 1)
-            out = indice_conv(feats, nbr, w, h16, scale, shift, residual, relu, self.precision)
+            out = indice_conv(feats, nbr, w, h16, scale, shift, residual, relu, self.precision, transposed_table=lambda: nbr)
+            if grad and self.bias is not None:
+                out = out + self.bias
             t = SparseConvTensor(out, indices, input.spatial_shape, input.batch_size, input.grid)
             t.indice_dict = input.indice_dict
             return t
@@ -346,13 +417,17 @@ class SparseConvolution(SparseModule):
             assert datas.nbr.shape[1] == kv, "inverse conv must have same kernel size as its couple conv"
             nbr, out_indices = datas.inverse_table(), datas.in_indices
             out_shape = datas.in_shape[3 - self.ndim:]
+            transposed = lambda d=datas: d.nbr
         else:
             if self.indice_key is not None and datas is not None:
                 assert datas.nbr.shape[1] == kv
             else:
                 in_shape, oshape, ks, st, pd = self._geometry(input.spatial_shape)
+                # conv_out_coors validates the input coordinates; rows this package produced (output of an earlier conv: the tensor
+                # already carries tables) need no second status round trip
+                derived = bool(input.indice_dict)
                 out_ids = indices if self.subm else conv_out_coors(indices, input.batch_size, in_shape, oshape, ks, st, pd)
-                nbr_, _ = conv_table(indices, out_ids, input.batch_size, in_shape, oshape, ks, st, pd)
+                nbr_, _ = conv_table(indices, out_ids, input.batch_size, in_shape, oshape, ks, st, pd, check=self.subm and not derived)
                 if not self.subm and self.ndim == 2:
                     out_ids = out_ids[:, [0, 2, 3]].contiguous()
                 datas = IndiceData(out_ids, indices, nbr_, input.batch_size, in_shape, oshape, ks, st, pd)
@@ -360,7 +435,10 @@ class SparseConvolution(SparseModule):
                     input.indice_dict[self.indice_key] = datas
             nbr, out_indices = datas.nbr, datas.out_indices
             out_shape = datas.out_shape[3 - self.ndim:]
-        out = indice_conv(feats, nbr, w, h16, scale, shift, residual, relu, self.precision)
+            transposed = datas.inverse_table
+        out = indice_conv(feats, nbr, w, h16, scale, shift, residual, relu, self.precision, transposed_table=transposed)
+        if grad and self.bias is not None:
+            out = out + self.bias
         t = SparseConvTensor(out, out_indices, out_shape, input.batch_size, input.grid)
         t.indice_dict = input.indice_dict
         return t
@@ -451,7 +529,8 @@ class SparseBasicBlock(SparseModule):
     def forward(self, x):
         identity = x.features
         assert x.features.dim() == 2, f"x.features.dim()={x.features.dim()}"
-        fused = FUSE_EPILOGUE and _is_relu(self.relu) and not self.bn1.training and not self.bn2.training
+        fused = (FUSE_EPILOGUE and _is_relu(self.relu) and not self.bn1.training and not self.bn2.training
+                 and not _wants_grad(x, self.conv1) and not _wants_grad(x, self.conv2))
         if fused:
             out = self.conv1(x, bn=self.bn1, relu=True)
             return self.conv2(out, bn=self.bn2, relu=True, residual=identity)

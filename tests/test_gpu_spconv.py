@@ -289,3 +289,67 @@ def test_vs_reference_cuda_spconv(cuda):
     _close(out16, ref, 5e-3)
     print(f"\n[spconv SubM 3x3x3 64->64, {coors.shape[0]} voxels, pairs {pairs_ref} / {pairs_here}] reference CUDA: pairs {t_ref_pairs:.0f} us + conv {t_ref_conv:.0f} us | "
           f"sst_b200: table {t_tab:.0f} us + conv fp32 {t32:.0f} us / tcgen05 {t16:.0f} us")
+
+
+def _gclose(a, b, tol):
+    a, b = a.float().cpu(), b.float().cpu()
+    torch.testing.assert_close(a, b, rtol=tol, atol=tol * float(b.abs().max()) + 1e-7)
+
+
+@pytest.mark.parametrize("cin,cmid,prec,tol", [(8, 12, "fp32", 2e-4), (64, 128, "fp32", 2e-4), (64, 128, "bf16", 1e-2)])
+def test_layer_gradients(cuda, cin, cmid, prec, tol):
+    """SubM -> strided conv -> inverse conv: input and weight gradients (dX = the forward kernel on the transposed table with W^T,
+    dW = spconv_dw_kernel) against autograd through the oracle's dense restatement"""
+    from sst_b200 import spconv_modules as SP
+    shape = [9, 20, 24]
+    feats, coors = SO.synth_sparse(41, 2, shape, 400, cin)
+    torch.manual_seed(5)
+    sub = SP.SubMConv3d(cin, cmid, 3, padding=1, bias=True, indice_key="s")
+    conv = SP.SparseConv3d(cmid, cmid, 3, stride=2, padding=(0, 1, 1), bias=False, indice_key="k")
+    inv = SP.SparseInverseConv3d(cmid, cin, 3, indice_key="k", bias=False)
+    # oracle (CPU, dense, differentiable)
+    ws = [p.detach().clone().requires_grad_(True) for p in (sub.weight, sub.bias, conv.weight, inv.weight)]
+    x_ref = feats.clone().requires_grad_(True)
+    y = SO.subm_conv(x_ref, coors, 2, shape, ws[0], ws[1])
+    y2, oc, oshape = SO.sparse_conv(y, coors, 2, shape, ws[2], [2, 2, 2], [0, 1, 1])
+    z_ref = SO.inverse_conv(y2, oc, 2, oshape, coors, shape, ws[3], [2, 2, 2], [0, 1, 1])
+    probe = torch.randn(z_ref.shape, generator=torch.Generator().manual_seed(1))
+    (z_ref * probe).sum().backward()
+    for m in (sub, conv, inv):
+        m.to(cuda)
+        m.precision = prec
+    x = feats.to(cuda).requires_grad_(True)
+    z = inv(conv(sub(SP.SparseConvTensor(x, coors.to(cuda), shape, 2))))
+    _gclose(z.features.detach(), z_ref.detach(), tol)
+    (z.features * probe.to(cuda)).sum().backward()
+    _gclose(x.grad, x_ref.grad, tol)
+    for p, r in zip((sub.weight, sub.bias, conv.weight, inv.weight), ws):
+        _gclose(p.grad, r.grad, tol)
+
+
+def test_unet_gradients(cuda):
+    """SimpleSparseUNet with gradients enabled (frozen BatchNorm statistics): the loss gradient w.r.t. the input features and every
+    parameter against autograd through the oracle"""
+    from sst_b200 import registry
+    cfg = dict(SO.SP_UNET)
+    torch.manual_seed(2)
+    net = registry.MODELS.build(dict(type="SimpleSparseUNet", **cfg)).eval()
+    _live_init(net, 4)
+    feats, coors = SO.synth_sparse(6, 2, cfg["sparse_shape"], 300, 8)
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in net.state_dict().items()}
+    x_ref = feats.clone().requires_grad_(True)
+    ref = SO.sparse_unet_forward(sd, x_ref, coors, 2, cfg["sparse_shape"], cfg["encoder_channels"], cfg["encoder_paddings"], cfg["decoder_channels"],
+                                 cfg["decoder_paddings"])[0]
+    probe = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+    (ref * probe).sum().backward()
+    net = net.to(cuda)
+    x = feats.to(cuda).requires_grad_(True)
+    out = net(dict(voxel_feats=x, voxel_coors=coors.to(cuda)))[0]["voxel_feats"]
+    _gclose(out.detach(), ref.detach(), 2e-4)
+    (out * probe.to(cuda)).sum().backward()
+    _gclose(x.grad, x_ref.grad, 1e-3)
+    n = 0
+    for name, p in net.named_parameters():
+        _gclose(p.grad, sd[name].grad, 1e-3)
+        n += 1
+    assert n > 60

@@ -19,7 +19,7 @@ def SP(monkeypatch):
     def conv_out_coors(indices, batch_size, in_shape, out_shape, ksize, stride, padding):
         return SO.out_coors(SP._coors4(indices), batch_size, in_shape, ksize, stride, padding)
 
-    def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, stride, padding, want_nbr=True, want_inv=False):
+    def conv_table(in_indices, out_indices, batch_size, in_shape, out_shape, ksize, stride, padding, want_nbr=True, want_inv=False, check=True):
         ci, co = SP._coors4(in_indices), SP._coors4(out_indices)
         nbr = SO.neighbour_table(ci, co, batch_size, in_shape, ksize, stride, padding)
         inv = None
@@ -29,7 +29,15 @@ def SP(monkeypatch):
             inv[nbr[o, k].long(), k] = o.int()
         return (nbr if want_nbr else None), inv
 
-    def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, residual=None, relu=False, precision="fp32"):
+    def indice_conv(features, nbr, weight, weight_h16=None, scale=None, shift=None, residual=None, relu=False, precision="fp32",
+                    transposed_table=None):
+        if torch.is_grad_enabled() and (features.requires_grad or weight.requires_grad):
+            assert scale is None and shift is None and residual is None and not relu and transposed_table is not None
+            nt = transposed_table()   # the table the dX launch would run on: same pairs, transposed
+            assert nt.shape == (features.shape[0], nbr.shape[1])
+            o, k = torch.nonzero(nbr >= 0, as_tuple=True)
+            assert torch.equal(nt[nbr[o, k].long(), k].long(), o) and int((nt >= 0).sum()) == o.numel()
+            return SO.indice_conv(features, nbr, weight)   # torch ops: differentiable
         return SO.indice_conv(features, nbr, weight.detach(), scale, shift, residual, relu)
 
     monkeypatch.setattr(SP, "conv_out_coors", conv_out_coors)
@@ -117,3 +125,42 @@ def test_2d_layers_and_dense(SP):
     assert d.shape == ref.shape
     mask = (d != 0).any(1, keepdim=True)
     torch.testing.assert_close(d, ref * mask, rtol=1e-4, atol=1e-5)
+
+
+def test_gradient_composition_matches_dense_autograd(SP):
+    """with gradients enabled the containers run epilogue-free convolutions + torch BatchNorm / ReLU / residual; the gradient of that
+    composition (table form) equals autograd through the oracle's dense restatement, for the input and every parameter"""
+    from sst_b200 import registry
+    cfg = dict(SO.SP_UNET)
+    torch.manual_seed(2)
+    net = registry.MODELS.build(dict(type="SimpleSparseUNet", **cfg)).eval()   # frozen-BN fine-tuning: eval statistics, grads on
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+        for p in net.parameters():
+            if p.dim() == 5:
+                p.mul_(2.0)
+    feats, coors = SO.synth_sparse(6, 2, cfg["sparse_shape"], 300, 8)
+    x = feats.clone().requires_grad_(True)
+    out = net(dict(voxel_feats=x, voxel_coors=coors))[0]["voxel_feats"]
+    probe = torch.randn(out.shape, generator=g)
+    (out * probe).sum().backward()
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in net.state_dict().items()}
+    x2 = feats.clone().requires_grad_(True)
+    ref = SO.sparse_unet_forward(sd, x2, coors, 2, cfg["sparse_shape"], cfg["encoder_channels"], cfg["encoder_paddings"],
+                                 cfg["decoder_channels"], cfg["decoder_paddings"])[0]
+    torch.testing.assert_close(out.detach(), ref.detach(), rtol=1e-3, atol=1e-5)
+    (ref * probe).sum().backward()
+
+    def close(a, b):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-4 * float(b.abs().max()) + 1e-7)
+    close(x.grad, x2.grad)
+    n = 0
+    for name, p in net.named_parameters():
+        assert sd[name].grad is not None, name
+        close(p.grad, sd[name].grad)
+        n += 1
+    assert n > 60
