@@ -66,42 +66,86 @@ class ClockSampler:
         self.windows[-1][1] = time.time()
 
     def start(self):
+        """NVML in-process (ready when start() returns; a fresh box can take > 1 s to bring up an `nvidia-smi -lms` child, longer than
+        the whole timed region); the nvidia-smi loop stays as the fallback."""
+        self.mode, self.proc, self.running = None, None, False
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+                self.h = N.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                self.h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+            self.N, self.mode, self.running = N, "nvml", True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "10"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        N = self.N
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}   # nvmlClocksEventReason*
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                sm, mx = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM), N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+                r = int(get_reasons(self.h))
+                row = ["", str(sm), str(mx), "", ""] + ["Active" if r & bits[k] else "Not Active"
+                                                        for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append((time.time(), row))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ts, r in self.rows:
-            if self.windows and not any(a <= ts <= (b if b is not None else ts) for a, b in self.windows):
-                continue
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (pynvml / nvidia-smi unavailable)"], "samples": 0}
+        self.running = False
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.proc.wait(timeout=2)
             except Exception:
-                pass
+                self.proc.kill()
+
+        def collect(inside_only):
+            sm, mx, reasons = [], [], set()
+            for ts, r in self.rows:
+                if inside_only and self.windows and not any(a <= ts <= (b if b is not None else ts) for a, b in self.windows):
+                    continue
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    pass
+            return sm, mx, reasons
+        sm, mx, reasons = collect(True)
+        where = "inside the timed windows"
+        if not sm:   # the source delivered nothing while the windows were open: report what it saw around them, and say so
+            sm, mx, reasons = collect(False)
+            where = "around the timed windows (none fell inside)"
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": f"{self.mode}, samples {where}"}
 
 
 _BEST_THREADS = None

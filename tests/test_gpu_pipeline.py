@@ -141,3 +141,56 @@ def test_dynamic_scatter_vfe_wide_input(cuda, mode):
     assert torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[2].cpu(), ref[2])
     err = (got[0].cpu() - ref[0]).abs().max().item() / ref[0].abs().max().item()
     assert err < 1e-3, err
+
+
+def test_fsd_segmentation_front_pipeline(cuda):
+    """VoteSegmentor.extract_feat (mmdet3d/models/detectors/single_stage_fsd.py:227-249) through the registered modules with the configs/fsd
+    type names - DynamicScatterVFE -> PseudoMiddleEncoderForSpconvFSD -> SimpleSparseUNet -> Voxel2PointScatterNeck - then the grouping
+    stage (ClusterAssigner) on the per-point output: every hand-over matches the oracle chain (coordinates / masks / cluster ids exact)."""
+    from oracle import fsd_oracle as FO, spconv_oracle as SO
+    from sst_b200 import ops, registry
+    vs, rng = (0.5, 0.5, 0.375), [-40, -40, -2, 40, 40, 4]         # grid 160 x 160 x 16
+    norm = dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)
+    unet_cfg = dict(in_channels=16, sparse_shape=[16, 160, 160], norm_cfg=norm, base_channels=16, output_channels=16,
+                    encoder_channels=((16,), (16, 16, 16), (32, 32, 32)), encoder_paddings=((1,), (1, 1, 1), (1, 1, 1)),
+                    decoder_channels=((32, 32, 16), (16, 16, 16), (16, 16, 16)), decoder_paddings=((1, 1), (1, 0), (0, 1)))
+    torch.manual_seed(1)
+    vfe = registry.MODELS.build(dict(type='DynamicScatterVFE', in_channels=5, feat_channels=[16, 16], with_cluster_center=True,
+                                     with_voxel_center=True, voxel_size=vs, point_cloud_range=rng, norm_cfg=norm, unique_once=True)).eval()
+    me = registry.MODELS.build(dict(type='PseudoMiddleEncoderForSpconvFSD'))
+    bb = registry.MODELS.build(dict(type='SimpleSparseUNet', **unet_cfg)).eval()
+    neck = registry.MODELS.build(dict(type='Voxel2PointScatterNeck', voxel_size=vs, point_cloud_range=rng))
+    g = torch.Generator().manual_seed(3)
+    for m in list(vfe.modules()) + list(bb.modules()):
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    P = 6000
+    pts = torch.cat([torch.cat([O.synth_frame(7 + b, P) * torch.tensor([0.5, 0.5, 1.0]), torch.rand(P, 2, generator=g)], 1) for b in range(2)])
+    co = torch.cat([torch.nn.functional.pad(O.dynamic_voxelize(pts[b * P:(b + 1) * P], vs, rng), (1, 0), value=b) for b in range(2)]).long()
+    # oracle chain (CPU)
+    vf_r, vc_r, inv_r = O.dynamic_scatter_vfe_forward(pts, co, dict(vfe.state_dict()), vs, rng, 2)
+    uf_r, uc_r = SO.sparse_unet_forward(bb.state_dict(), vf_r, vc_r.int(), 2, unet_cfg["sparse_shape"], unet_cfg["encoder_channels"],
+                                        unet_cfg["encoder_paddings"], unet_cfg["decoder_channels"], unet_cfg["decoder_paddings"])
+    out_r, mask_r = O.voxel2point_neck(pts, co, uf_r, inv_r, vs, rng)
+    # product chain (GPU)
+    vfe, bb = vfe.to(cuda), bb.to(cuda)
+    with torch.no_grad():
+        vf, vc, inv = vfe(pts.to(cuda), co.to(cuda), return_inv=True)
+        x = bb(me(vf, vc))[0]
+        out, mask = neck(pts.to(cuda), co.to(cuda), x['voxel_feats'], inv, -1)
+    assert torch.equal(vc.cpu(), vc_r) and torch.equal(inv.cpu(), inv_r)
+    assert torch.equal(x['voxel_coors'].cpu().long(), vc_r) and x['batch_size'] == 2
+    torch.testing.assert_close(x['voxel_feats'].cpu(), uf_r, rtol=1e-3, atol=1e-4)
+    assert torch.equal(mask.cpu(), mask_r)
+    torch.testing.assert_close(out.cpu(), out_r, rtol=1e-3, atol=1e-4)
+    # grouping on the points that survived (their xyz stand in for the voted centres; lattice coordinates keep the voxel means exact)
+    from sst_b200.fsd_modules import ClusterAssigner
+    ca = ClusterAssigner(cluster_voxel_size=dict(Car=(0.3, 0.3, 6)), min_points=2, point_cloud_range=rng, connected_dist=dict(Car=0.6),
+                         class_names=['Car']).train()
+    centres = torch.round(pts[mask_r][:, :3] * 64) / 64
+    bidx = co[mask_r][:, 0].int()
+    inds, valid = ca([centres.to(cuda)], [bidx.to(cuda)])
+    ref_inds, ref_valid = FO.cluster_assigner_single_class(centres, bidx, (0.3, 0.3, 6), 2, rng, 0.6)
+    assert torch.equal(valid[0].cpu(), ref_valid)
+    assert torch.equal(inds[0][:, 1:].cpu().int(), ref_inds) and int(inds[0][:, 0].abs().sum()) == 0

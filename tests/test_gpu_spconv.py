@@ -353,3 +353,37 @@ def test_unet_gradients(cuda):
         _gclose(p.grad, sd[name].grad, 1e-3)
         n += 1
     assert n > 60
+
+
+def test_sparse_unet_dense_branch(cuda):
+    """SparseUNet.forward (PartA2's middle encoder, sparse_unet.py:114-165): the detection branch = SparseConv (3,1,1) / stride (2,1,1) on
+    the last encoder stage, densified to [N, C*D, H, W]; the segmentation branch = the decoder output"""
+    from sst_b200 import registry
+    cfg = dict(in_channels=8, sparse_shape=[41, 32, 32], norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), base_channels=8,
+               output_channels=16, encoder_channels=((8,), (8, 8, 8), (16, 16, 16), (16, 16, 16)),
+               encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)),
+               decoder_channels=((16, 16, 16), (16, 16, 8), (8, 8, 8), (8, 8, 8)), decoder_paddings=((1, 0), (1, 0), (0, 0), (0, 1)))
+    torch.manual_seed(4)
+    net = registry.MODELS.build(dict(type="SparseUNet", **cfg)).eval()
+    _live_init(net, 6)
+    feats, coors = SO.synth_sparse(12, 2, cfg["sparse_shape"], 600, 8)
+    sd = {k: v.float() for k, v in net.state_dict().items()}
+    seg_ref, _ = SO.sparse_unet_forward(sd, feats, coors, 2, cfg["sparse_shape"], cfg["encoder_channels"], cfg["encoder_paddings"],
+                                        cfg["decoder_channels"], cfg["decoder_paddings"])
+    # detection branch from the oracle's pieces: encoder up to the last stage, then conv_out + BN + ReLU, densified
+    x = SO._block(SO._T(feats, coors, cfg["sparse_shape"], 2), sd, "conv_input.", "subm", "subm1", 1e-3, padding=1)
+    for i, blocks in enumerate(cfg["encoder_channels"]):
+        for j in range(len(blocks)):
+            pad = tuple(cfg["encoder_paddings"][i])[j]
+            p = f"encoder_layers.encoder_layer{i + 1}.{j}."
+            x = SO._block(x, sd, p, "conv", f"spconv{i + 1}", 1e-3, stride=2, padding=pad) if (i != 0 and j == 0) else \
+                SO._block(x, sd, p, "subm", f"subm{i + 1}", 1e-3, padding=pad)
+    y = SO._block(x, sd, "conv_out.", "conv", "spconv_down2", 1e-3, stride=(2, 1, 1), padding=0)
+    dense_ref = SO._dense(y.f, y.c, 2, y.shape)
+    net = net.to(cuda)
+    with torch.no_grad():
+        out = net(feats.to(cuda), coors.to(cuda), 2)
+    _close(out["seg_features"], seg_ref, 1e-4)
+    N, C, D, H, W = dense_ref.shape
+    assert list(out["spatial_features"].shape) == [N, C * D, H, W]
+    _close(out["spatial_features"], dense_ref.reshape(N, C * D, H, W), 1e-4)
