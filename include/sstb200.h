@@ -38,6 +38,8 @@ typedef struct sstb200_ctx sstb200_ctx;
                              * IEEE fp16 operands (the reference's own mixed-precision mode, `fp16 = dict(loss_scale=32.0)`), the
                              * VFE / SIR tensor paths bf16; the API name of the mode stays 'bf16'. */
 #define SSTB200_PREC_F16 1
+#define SSTB200_PREC_FP32_TC 2 /* sstb200_spconv_forward only: fp32 tolerance on the tensor core - every operand carried as two fp16 numbers
+                                * (hi + residue, 22 significant bits), three tcgen05 products per stage, fp32 accumulation in TMEM */
 
 int sstb200_version(void);
 sstb200_ctx* sstb200_create(int device);
@@ -398,7 +400,9 @@ int sstb200_spconv_table(sstb200_ctx* ctx, const int32_t* in_coors, int n_in, co
  * BatchNorm1d (+ residual add) (+ ReLU).  feats [*, c_in] fp32, weight [KV, c_in, c_out] fp32 = the reference's parameter layout
  * (D,H,W,in,out; mmdet3d/ops/spconv/conv.py:97-98), scale / shift [c_out] or NULL (1 / 0), residual [n_out, c_out] or NULL.
  * precision FP32: FFMA implicit GEMM (c_in, c_out multiples of 4).  precision BF16 (16-bit operands, fp32 accumulation in TMEM):
- * tcgen05 implicit GEMM over weight_h16 = IEEE fp16 copy laid out [KV, c_out, c_in]; needs c_in, c_out multiples of 64, KV <= 27. */
+ * tcgen05 implicit GEMM over weight_h16 = IEEE fp16 copy laid out [KV, c_out, c_in]; needs c_in, c_out multiples of 64, KV <= 27.
+ * precision FP32_TC: the same kernel in split mode; weight_h16 = [2][KV, c_out, c_in]: the fp16 copy followed by the fp16 residue
+ * (w - float(half(w))). */
 int sstb200_spconv_forward(sstb200_ctx* ctx, const float* feats, int c_in, const int32_t* nbr, int n_out, int kernel_volume,
                            const float* weight, const void* weight_h16, int c_out, const float* scale, const float* shift,
                            const float* residual, int relu, int precision, float* out);

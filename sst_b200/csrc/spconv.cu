@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 #include "index.cuh"
 #include "umma.cuh"
+#include "sra.cuh"
 
 namespace {
 
@@ -323,23 +324,42 @@ __device__ __forceinline__ uint32_t sp_pack_f16(float a, float b) {
   return r;
 }
 
-template <int BU>
-struct SpStageRegs {
-  float4 a0[4], a1[4];   // 4 pieces of 8 gathered channels each
-  int4 b[BU];            // weight pieces
-  uint32_t valid;        // bit u: piece u has a source row (absent neighbours are neither loaded nor converted)
+struct SpArgs {
+  const float* feats;      // [*, lda] fp32 rows (gathered through nbr, or row o itself when nbr == nullptr)
+  int lda, Cin;
+  const int32_t* nbr;      // [n_out, KV] or nullptr (KV must be 1: a plain row GEMM)
+  int n_out;
+  const int32_t* n_dev;    // optional device-side row count (<= n_out)
+  int KV;
+  const __half* Whi;       // [KV][Cout][Cin] fp16
+  const __half* Wlo;       // SPLIT: the fp16 residue  W - float(Whi)
+  int Cout;
+  const float *scale, *shift, *residual;
+  int ldr, act;            // act: 0 none, 1 ReLU, 2 GELU (erf form)
+  float* out;
+  int ldo;
 };
 
-template <int NT, int NS>
-__global__ void __launch_bounds__(256, NT == 64 ? 2 : 1)
-spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __restrict__ nbr, int n_out, int KV,
-                   const __half* __restrict__ W16 /* [KV][Cout][Cin] */, int Cout, const float* __restrict__ scale,
-                   const float* __restrict__ shift, const float* __restrict__ residual, int relu, float* __restrict__ out) {
+template <int BU, bool SPLIT>
+struct SpStageRegs {
+  float4 a0[4], a1[4];            // 4 pieces of 8 gathered channels each
+  int4 b[BU];                     // weight pieces
+  int4 blo[SPLIT ? BU : 1];       // SPLIT: residue pieces
+  uint32_t valid;                 // bit u: piece u has a source row (absent neighbours are neither loaded nor converted)
+};
+
+// SPLIT = the fp32-tolerance mode on the tensor core: every fp32 operand is carried as two fp16 numbers (hi = rn(x), lo = rn(x - hi):
+// 22 significant bits), and a stage issues the three products hi.hi + lo.hi + hi.lo into the same fp32 TMEM accumulator (the
+// dropped lo.lo term is 2^-22 relative).  Same staging, same epilogue; 3x the MMAs, 2x the operand bytes.
+template <int NT, int NS, bool SPLIT>
+__global__ void __launch_bounds__(256, (NT == 64 && !SPLIT) ? 2 : 1) spconv_umma_kernel(SpArgs g) {
   pdl_wait();
   pdl_launch();
   extern __shared__ uint8_t sp_smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)sp_smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int B_BYTES = NT * 128, ST_BYTES = SPU_A_BYTES + B_BYTES;
+  constexpr int B_BYTES = NT * 128;
+  constexpr int ST_BYTES = (SPLIT ? 2 : 1) * (SPU_A_BYTES + B_BYTES);   // [A_hi][A_lo][B_hi][B_lo] or [A][B]
+  constexpr int OFF_ALO = SPU_A_BYTES, OFF_B = (SPLIT ? 2 : 1) * SPU_A_BYTES, OFF_BLO = OFF_B + B_BYTES;
   constexpr int BU = NT / 32;  // 16-byte weight pieces per thread and stage
   __shared__ __align__(8) uint64_t mbar[NS];
   __shared__ uint32_t tmem_slot;
@@ -348,6 +368,9 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * SPU_TM, n0 = blockIdx.y * NT;
+  const int n_out = g.n_dev ? min(g.n_out, *g.n_dev) : g.n_out;
+  if (row0 >= n_out) return;   // uniform per CTA, nothing allocated yet
+  const int KV = g.KV, Cin = g.Cin, Cout = g.Cout;
   if (warp == 0) tmem_alloc(&tmem_slot, NT);
   if (tid == 0) {
 #pragma unroll
@@ -361,7 +384,7 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
     for (int idx = tid; idx < SPU_TM * KV; idx += 256) {
       const int r = idx / KV, k = idx - r * KV;
       const int o = row0 + r;
-      const int v = o < n_out ? nbr[(size_t)o * KV + k] : -1;
+      const int v = o < n_out ? (g.nbr ? g.nbr[(size_t)o * KV + k] : o) : -1;
       sNbr[r][k] = v;
       if (v >= 0) m |= 1u << k;
     }
@@ -380,7 +403,7 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
   uint32_t ld_mask = used_mask;
   int ld_c = 0, loaded = 0;
   const int my_r = tid >> 3, my_jj = tid & 7;   // piece u of this thread: row my_r + 32 u, 16-byte column my_jj
-  auto load_next = [&](SpStageRegs<BU>& R) {
+  auto load_next = [&](SpStageRegs<BU, SPLIT>& R) {
     if (loaded >= nst) return;
     const int k = __ffs(ld_mask) - 1, c = ld_c;
     R.valid = 0u;
@@ -389,24 +412,27 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
       const int src = sNbr[my_r + 32 * u][k];
       if (src >= 0) {
         R.valid |= 1u << u;
-        const float* ap = feats + (size_t)src * Cin + c * 64 + my_jj * 8;
+        const float* ap = g.feats + (size_t)src * g.lda + c * 64 + my_jj * 8;
         R.a0[u] = *reinterpret_cast<const float4*>(ap);
         R.a1[u] = *reinterpret_cast<const float4*>(ap + 4);
       }
     }
-    const __half* wp = W16 + ((size_t)k * Cout + n0 + my_r) * Cin + c * 64 + my_jj * 8;
+    const size_t woff = ((size_t)k * Cout + n0 + my_r) * Cin + c * 64 + my_jj * 8;
 #pragma unroll
-    for (int u = 0; u < BU; u++) R.b[u] = __ldg(reinterpret_cast<const int4*>(wp + (size_t)32 * u * Cin));
+    for (int u = 0; u < BU; u++) {
+      R.b[u] = __ldg(reinterpret_cast<const int4*>(g.Whi + woff + (size_t)32 * u * Cin));
+      if (SPLIT) R.blo[u] = __ldg(reinterpret_cast<const int4*>(g.Wlo + woff + (size_t)32 * u * Cin));
+    }
     loaded++;
     if (++ld_c == nch) {
       ld_c = 0;
       ld_mask &= ld_mask - 1u;
     }
   };
-  auto run_stage = [&](int s, SpStageRegs<BU>& R) {
+  auto run_stage = [&](int s, SpStageRegs<BU, SPLIT>& R) {
     const int b = s % NS, u_ = s / NS;
     uint8_t* sA = base + (size_t)b * ST_BYTES;
-    uint8_t* sB = sA + SPU_A_BYTES;
+    uint8_t* sB = sA + OFF_B;
     if (u_ >= 1) {  // the MMAs that read this buffer NS stages ago have completed
       mbar_wait(smem_u32(&mbar[b]), (uint32_t)((u_ - 1) & 1));
       tc_fence_after();
@@ -414,19 +440,31 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int r = my_r + 32 * u;
-      int4 v = make_int4(0, 0, 0, 0);
+      const int off = r * 128 + ((my_jj ^ (r & 7)) << 4);
+      int4 v = make_int4(0, 0, 0, 0), vl = make_int4(0, 0, 0, 0);
       if ((R.valid >> u) & 1u) {
-        v.x = (int)sp_pack_f16(R.a0[u].x, R.a0[u].y);
-        v.y = (int)sp_pack_f16(R.a0[u].z, R.a0[u].w);
-        v.z = (int)sp_pack_f16(R.a1[u].x, R.a1[u].y);
-        v.w = (int)sp_pack_f16(R.a1[u].z, R.a1[u].w);
+        const float f[8] = {R.a0[u].x, R.a0[u].y, R.a0[u].z, R.a0[u].w, R.a1[u].x, R.a1[u].y, R.a1[u].z, R.a1[u].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          hi[e] = sp_pack_f16(f[2 * e], f[2 * e + 1]);
+          if (SPLIT) {
+            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+            lo[e] = sp_pack_f16(f[2 * e] - h.x, f[2 * e + 1] - h.y);
+          }
+        }
+        v = make_int4((int)hi[0], (int)hi[1], (int)hi[2], (int)hi[3]);
+        if (SPLIT) vl = make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]);
       }
-      *reinterpret_cast<int4*>(sA + r * 128 + ((my_jj ^ (r & 7)) << 4)) = v;
+      *reinterpret_cast<int4*>(sA + off) = v;
+      if (SPLIT) *reinterpret_cast<int4*>(sA + OFF_ALO + off) = vl;
     }
 #pragma unroll
     for (int u = 0; u < BU; u++) {
       const int r = my_r + 32 * u;
-      *reinterpret_cast<int4*>(sB + r * 128 + ((my_jj ^ (r & 7)) << 4)) = R.b[u];
+      const int off = r * 128 + ((my_jj ^ (r & 7)) << 4);
+      *reinterpret_cast<int4*>(sB + off) = R.b[u];
+      if (SPLIT) *reinterpret_cast<int4*>(sA + OFF_BLO + off) = R.blo[u];
     }
     load_next(R);         // the register set is free again: fetch the stage two ahead while this one is multiplied
     fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -439,11 +477,18 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
 #pragma unroll
       for (int q = 0; q < 4; q++)
         umma_f16(tmem, umma_desc_sw128(a0 + q * 32), umma_desc_sw128(b0 + q * 32), idesc, (s | q) ? 1u : 0u);
+      if (SPLIT) {
+        const uint32_t al = a0 + OFF_ALO, bl = a0 + OFF_BLO;
+#pragma unroll
+        for (int q = 0; q < 4; q++) umma_f16(tmem, umma_desc_sw128(al + q * 32), umma_desc_sw128(b0 + q * 32), idesc, 1u);   // lo . hi
+#pragma unroll
+        for (int q = 0; q < 4; q++) umma_f16(tmem, umma_desc_sw128(a0 + q * 32), umma_desc_sw128(bl + q * 32), idesc, 1u);   // hi . lo
+      }
       umma_commit(smem_u32(&mbar[b]));  // implicit tcgen05.fence::before_thread_sync
     }
   };
 
-  SpStageRegs<BU> R0, R1;
+  SpStageRegs<BU, SPLIT> R0, R1;
   R0.valid = R1.valid = 0u;
   load_next(R0);
   load_next(R1);
@@ -474,23 +519,24 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
     }
     if (o < n_out) {
       const int col = n0 + c0;
-      float* op = out + (size_t)o * Cout + col;
-      const float* rp = residual ? residual + (size_t)o * Cout + col : nullptr;
+      float* op = g.out + (size_t)o * g.ldo + col;
+      const float* rp = g.residual ? g.residual + (size_t)o * g.ldr + col : nullptr;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + col) + q);
-        if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + col) + q);
+        if (g.scale) sc = __ldg(reinterpret_cast<const float4*>(g.scale + col) + q);
+        if (g.shift) sh = __ldg(reinterpret_cast<const float4*>(g.shift + col) + q);
         float4 y;
         y.x = fmaf(v[4 * q], sc.x, sh.x);
         y.y = fmaf(v[4 * q + 1], sc.y, sh.y);
         y.z = fmaf(v[4 * q + 2], sc.z, sh.z);
         y.w = fmaf(v[4 * q + 3], sc.w, sh.w);
+        if (g.act == 2) y.x = gelu_erf(y.x), y.y = gelu_erf(y.y), y.z = gelu_erf(y.z), y.w = gelu_erf(y.w);   // Linear -> GELU (-> + residual)
         if (rp) {
           const float4 r4 = *(reinterpret_cast<const float4*>(rp) + q);
           y.x += r4.x, y.y += r4.y, y.z += r4.z, y.w += r4.w;
         }
-        if (relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+        if (g.act == 1) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);  // conv + BN + res -> ReLU
         *(reinterpret_cast<float4*>(op) + q) = y;
       }
     }
@@ -500,17 +546,39 @@ spconv_umma_kernel(const float* __restrict__ feats, int Cin, const int32_t* __re
   if (warp == 0) tmem_dealloc(tmem, NT);
 }
 
-template <int NT, int NS>
-static int launch_spconv_umma(sstb200_ctx* c, const float* feats, int Cin, const int32_t* nbr, int n_out, int KV, const __half* W16,
-                              int Cout, const float* scale, const float* shift, const float* residual, int relu, float* out) {
-  auto kern = spconv_umma_kernel<NT, NS>;
+template <int NT, int NS, bool SPLIT>
+static int launch_spconv_umma(sstb200_ctx* c, const SpArgs& g) {
+  auto kern = spconv_umma_kernel<NT, NS, SPLIT>;
   static SmemAttr sa;
-  const size_t smem = (size_t)NS * (SPU_A_BYTES + NT * 128) + 1024;
+  const size_t smem = (size_t)NS * (SPLIT ? 2 : 1) * (SPU_A_BYTES + NT * 128) + 1024;
   CUDA_TRY(c, ensure_smem(c, sa, kern, smem));
-  dim3 grid((n_out + SPU_TM - 1) / SPU_TM, Cout / NT);
-  launch_pdl(kern, grid, dim3(256), smem, c->stream, feats, Cin, nbr, n_out, KV, W16, Cout, scale, shift, residual, relu, out);
+  dim3 grid((g.n_out + SPU_TM - 1) / SPU_TM, g.Cout / NT);
+  launch_pdl(kern, grid, dim3(256), smem, c->stream, g);
   LAUNCH_CHECK(c);
   return SSTB_OK;
+}
+
+static int dispatch_spconv_umma(sstb200_ctx* c, const SpArgs& g, bool split) {
+  if (split) {
+    if (g.Cout % 256 == 0) return launch_spconv_umma<256, 2, true>(c, g);
+    if (g.Cout % 128 == 0) return launch_spconv_umma<128, 2, true>(c, g);
+    return launch_spconv_umma<64, 3, true>(c, g);
+  }
+  if (g.Cout % 256 == 0) return launch_spconv_umma<256, 2, false>(c, g);
+  if (g.Cout % 128 == 0) return launch_spconv_umma<128, 3, false>(c, g);
+  return launch_spconv_umma<64, 3, false>(c, g);
+}
+
+// W fp32 -> (hi, lo) fp16, elementwise
+__global__ void split_f16_kernel(const float* __restrict__ w, size_t n, __half* __restrict__ hi, __half* __restrict__ lo) {
+  pdl_wait();
+  pdl_launch();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+  hi[i] = h;
+  lo[i] = __float2half_rn(x - __half2float(h));
 }
 
 }  // namespace
@@ -656,17 +724,35 @@ extern "C" int sstb200_spconv_forward(sstb200_ctx* c, const float* feats, int c_
     LAUNCH_CHECK(c);
     return SSTB_OK;
   }
+  CHECK_ARG(c, precision == SSTB200_PREC_BF16 || precision == SSTB200_PREC_FP32_TC);
   CHECK_ARG(c, weight_h16 != nullptr && ((uintptr_t)weight_h16 & 15) == 0);
   if ((c_in & 63) || (c_out & 63) || kernel_volume > SPU_MAX_KV)
     return sstb_fail(c, SSTB_ERR_UNSUPPORTED,
                      "spconv_forward: the tensor-core path needs c_in, c_out multiples of 64 and kernel volume <= %d (got %d -> %d, %d); "
                      "use precision fp32", SPU_MAX_KV, c_in, c_out, kernel_volume);
-  const __half* w16 = (const __half*)weight_h16;
-  if (c_out % 256 == 0)
-    return launch_spconv_umma<256, 2>(c, feats, c_in, nbr, n_out, kernel_volume, w16, c_out, scale, shift, residual, relu, out);
-  if (c_out % 128 == 0)
-    return launch_spconv_umma<128, 3>(c, feats, c_in, nbr, n_out, kernel_volume, w16, c_out, scale, shift, residual, relu, out);
-  return launch_spconv_umma<64, 3>(c, feats, c_in, nbr, n_out, kernel_volume, w16, c_out, scale, shift, residual, relu, out);
+  SpArgs g;
+  g.feats = feats, g.lda = c_in, g.Cin = c_in, g.nbr = nbr, g.n_out = n_out, g.n_dev = nullptr, g.KV = kernel_volume;
+  g.Whi = (const __half*)weight_h16;
+  g.Wlo = g.Whi + (size_t)kernel_volume * c_out * c_in;   // FP32_TC: the residue copy follows the hi copy
+  g.Cout = c_out, g.scale = scale, g.shift = shift, g.residual = residual, g.ldr = c_out, g.act = relu ? 1 : 0, g.out = out, g.ldo = c_out;
+  return dispatch_spconv_umma(c, g, precision == SSTB200_PREC_FP32_TC);
+}
+
+// fp32-tolerance row GEMM on the tensor core (used by the fp32 mode of the SRA encoder, csrc/sra_fp32.cu):
+//   out[r, :N] = act(A[r, :K] . W[N, K]^T + bias) + res[r]      with every operand split into two fp16 numbers (see SPLIT above)
+int sstb_gemm_rows_x3(sstb200_ctx* c, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr, float* out,
+                      int ldo, int M_cap, const int32_t* M_dev, int N, int K, int act) {
+  if (M_cap <= 0) return SSTB_OK;
+  if ((K & 63) || (N & 63) || (lda & 3) || (ldo & 3) || (ldr & 3) || (act == 1 && res)) return SSTB_ERR_UNSUPPORTED;
+  __half* hi = arena_alloc<__half>(c, (size_t)N * K);
+  __half* lo = arena_alloc<__half>(c, (size_t)N * K);
+  if (!hi || !lo) return sstb_fail(c, SSTB_ERR_WORKSPACE, "gemm_rows_x3: arena too small");
+  const size_t n = (size_t)N * K;
+  launch_pdl(split_f16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, c->stream, W, n, hi, lo);
+  SpArgs g;
+  g.feats = A, g.lda = lda, g.Cin = K, g.nbr = nullptr, g.n_out = M_cap, g.n_dev = M_dev, g.KV = 1, g.Whi = hi, g.Wlo = lo, g.Cout = N;
+  g.scale = nullptr, g.shift = bias, g.residual = res, g.ldr = ldr, g.act = act, g.out = out, g.ldo = ldo;
+  return dispatch_spconv_umma(c, g, true);
 }
 
 extern "C" int sstb200_spconv_backward_weight(sstb200_ctx* c, const float* feats, int c_in, const int32_t* nbr, int n_out, int kernel_volume,

@@ -191,6 +191,40 @@ void sstb_add_norm(cudaStream_t st, const float* a, const float* b, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32-tolerance GEMMs on the tensor core (SSTB200_FP32_TC, default on): every Linear of the layer runs through sstb_gemm_rows_x3
+// (split-fp16 operands: hi.hi + lo.hi + hi.lo in one fp32 TMEM accumulator, ~2^-22 relative) instead of the FFMA kernel above; the
+// positional term of q|k is added to a copy of the input first.  Shapes that do not fit fall back to the FFMA kernel.
+// ------------------------------------------------------------------------------------------------
+static int fp32_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSTB200_FP32_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+__global__ void add_pos_kernel(const float* __restrict__ x, int d, PosTab pos, float* __restrict__ out, int n, const int32_t* __restrict__ n_dev) {
+  pdl_wait();
+  pdl_launch();
+  if (n_dev) n = *n_dev;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * d) return;
+  const int r = (int)(i / d), k = (int)(i % d);
+  out[i] = x[i] + pos_value(pos, pos.code[r], k);
+}
+
+static int linear_fp32(sstb200_ctx* c, const float* A, int lda, const float* W, const float* bias, const float* res, int ldr, float* out,
+                       int ldo, int n_cap, const int32_t* n_dev, int N, int K, int act) {
+  if (fp32_tc_enabled()) {
+    const int rc = sstb_gemm_rows_x3(c, A, lda, W, bias, res, ldr, out, ldo, n_cap, n_dev, N, K, act);
+    if (rc != SSTB_ERR_UNSUPPORTED) return rc;
+  }
+  sstb_gemm_rows_ex(c->stream, A, lda, W, K, bias, res, ldr, nullptr, out, ldo, n_cap, n_dev, N, K, act, nullptr, nullptr, 0, 0, 0, 0);
+  return SSTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // one encoder layer, fp32
 // ------------------------------------------------------------------------------------------------
 int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb200_sra_plan* P, const float* x, float* y,
@@ -210,23 +244,40 @@ int sstb_sra_layer_fp32(sstb200_ctx* c, const sstb200_sra_layer* L, const sstb20
     xin = x1;
   }
   // q,k from (x + pos); v from x
-  sstb_gemm_rows(st, xin, d, L->in_proj_w, L->in_proj_b, nullptr, 0, qkv, 3 * d, n_cap, n_dev, 3 * d, d, 0, P->pos_table,
-                 P->pos_code, P->pos_L, P->pos_maxw, P->pos_ndim, 2 * d);
-  int rc = sstb_win_attn_fp32(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win, L->tau, L->tau_n,
+  int rc = SSTB_OK;
+  if (fp32_tc_enabled() && d % 64 == 0 && ff % 64 == 0) {
+    const float* xqk = xin;
+    if (P->pos_table) {
+      float* xpos = arena_alloc<float>(c, (size_t)n_cap * d);
+      if (!xpos) return sstb_fail(c, SSTB_ERR_WORKSPACE, "sra layer: arena too small");
+      PosTab pt{P->pos_table, P->pos_code, P->pos_L, P->pos_maxw, P->pos_ndim};
+      const size_t tot = (size_t)n_cap * d;
+      launch_pdl(add_pos_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), (size_t)0, st, xin, d, pt, xpos, n_cap, n_dev);
+      xqk = xpos;
+    }
+    rc = linear_fp32(c, xqk, d, L->in_proj_w, L->in_proj_b, nullptr, 0, qkv, 3 * d, n_cap, n_dev, 2 * d, d, 0);
+    if (rc) return rc;
+    rc = linear_fp32(c, xin, d, L->in_proj_w + (size_t)2 * d * d, L->in_proj_b + 2 * d, nullptr, 0, qkv + 2 * d, 3 * d, n_cap, n_dev, d, d, 0);
+    if (rc) return rc;
+  } else {
+    sstb_gemm_rows(st, xin, d, L->in_proj_w, L->in_proj_b, nullptr, 0, qkv, 3 * d, n_cap, n_dev, 3 * d, d, 0, P->pos_table,
+                   P->pos_code, P->pos_L, P->pos_maxw, P->pos_ndim, 2 * d);
+  }
+  rc = sstb_win_attn_fp32(c, qkv, d, L->nhead, n_cap, n_dev, P->win_offsets, P->tok_perm, P->tok_win, L->tau, L->tau_n,
                               L->tau_min, att);
   if (rc) return rc;
   if (L->post_norm) {
-    sstb_gemm_rows(st, att, d, L->out_proj_w, L->out_proj_b, nullptr, 0, t1, d, n_cap, n_dev, d, d, 0, nullptr, nullptr, 0, 0, 0, 0);
+    if ((rc = linear_fp32(c, att, d, L->out_proj_w, L->out_proj_b, nullptr, 0, t1, d, n_cap, n_dev, d, d, 0))) return rc;
     sstb_add_norm(st, x, t1, L->norm1_w, L->norm1_b, L->norm1_mean, L->norm1_var, L->norm_eps, x1, n_cap, n_dev, d);
-    sstb_gemm_rows(st, x1, d, L->lin1_w, L->lin1_b, nullptr, 0, hid, ff, n_cap, n_dev, ff, d, L->act, nullptr, nullptr, 0, 0, 0, 0);
-    sstb_gemm_rows(st, hid, ff, L->lin2_w, L->lin2_b, nullptr, 0, t1, d, n_cap, n_dev, d, ff, 0, nullptr, nullptr, 0, 0, 0, 0);
+    if ((rc = linear_fp32(c, x1, d, L->lin1_w, L->lin1_b, nullptr, 0, hid, ff, n_cap, n_dev, ff, d, L->act))) return rc;
+    if ((rc = linear_fp32(c, hid, ff, L->lin2_w, L->lin2_b, nullptr, 0, t1, d, n_cap, n_dev, d, ff, 0))) return rc;
     sstb_add_norm(st, x1, t1, L->norm2_w, L->norm2_b, L->norm2_mean, L->norm2_var, L->norm_eps, y, n_cap, n_dev, d);
   } else {
     // src = src + attn ; src = src + ffn(norm2(src))
-    sstb_gemm_rows(st, att, d, L->out_proj_w, L->out_proj_b, x, d, t1, d, n_cap, n_dev, d, d, 0, nullptr, nullptr, 0, 0, 0, 0);
+    if ((rc = linear_fp32(c, att, d, L->out_proj_w, L->out_proj_b, x, d, t1, d, n_cap, n_dev, d, d, 0))) return rc;
     sstb_add_norm(st, t1, nullptr, L->norm2_w, L->norm2_b, L->norm2_mean, L->norm2_var, L->norm_eps, x1, n_cap, n_dev, d);
-    sstb_gemm_rows(st, x1, d, L->lin1_w, L->lin1_b, nullptr, 0, hid, ff, n_cap, n_dev, ff, d, L->act, nullptr, nullptr, 0, 0, 0, 0);
-    sstb_gemm_rows(st, hid, ff, L->lin2_w, L->lin2_b, t1, d, y, d, n_cap, n_dev, d, ff, 0, nullptr, nullptr, 0, 0, 0, 0);
+    if ((rc = linear_fp32(c, x1, d, L->lin1_w, L->lin1_b, nullptr, 0, hid, ff, n_cap, n_dev, ff, d, L->act))) return rc;
+    if ((rc = linear_fp32(c, hid, ff, L->lin2_w, L->lin2_b, t1, d, y, d, n_cap, n_dev, d, ff, 0))) return rc;
   }
   CUDA_TRY(c, cudaGetLastError());
   return SSTB_OK;

@@ -89,7 +89,7 @@ def fsd_sweep_voxels(seed=1000, points=150000, channels=64, shuffle=False):
     return torch.randn((coors.shape[0], channels), generator=g), coors
 
 
-def fsd_unet_bench(dev, reps=5, precisions=("bf16", "fp32")):
+def fsd_unet_bench(dev, reps=5, precisions=("bf16", "fp32_tc", "fp32")):
     """SimpleSparseUNet forward (tables + 34 convolution launches + glue) on one sweep, CUDA events on the current stream."""
     from . import spconv_modules as SP
     torch.manual_seed(0)
@@ -110,5 +110,5 @@ def fsd_unet_bench(dev, reps=5, precisions=("bf16", "fp32")):
             b.record()
             torch.cuda.synchronize(dev)
             ms = a.elapsed_time(b) / reps
-            rec["f16_tcgen05" if prec == "bf16" else "fp32_ffma"] = {"ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms}
+            rec[{"bf16": "f16_tcgen05", "fp32_tc": "fp32_split_tcgen05", "fp32": "fp32_ffma"}[prec]] = {"ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms}
     return rec

@@ -36,7 +36,15 @@ L.SIGNATURES["sstb200_spconv_backward_weight"] = (C.c_int, [L.vp, L.vp, C.c_int,
 L.SIGNATURES["sstb200_spconv_forward"] = (C.c_int, [L.vp, L.vp, C.c_int, L.vp, C.c_int, C.c_int, L.vp, L.vp, C.c_int, L.vp, L.vp, L.vp,
                                                    C.c_int, C.c_int, L.vp])
 
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "fp32_tc": 2}   # fp32_tc: fp32 tolerance on the tensor core (split-fp16 operands, 3 products per stage)
+
+
+def split_h16(weight):
+    """[KV, Cin, Cout] fp32 -> the 16-bit operand copy of the tensor-core paths, laid out [KV, Cout, Cin]; with residue=True the fp16
+    residue  w - float(half(w))  follows the hi copy ([2 KV, Cout, Cin]) as SSTB200_PREC_FP32_TC expects."""
+    w = weight.detach().permute(0, 2, 1).contiguous().float()
+    hi = w.half()
+    return hi, (w - hi.float()).half()
 FUSE_EPILOGUE = True   # eval mode: fold BatchNorm1d / residual / ReLU into the convolution launch (False = conv launch + torch modules)
 
 
@@ -116,8 +124,9 @@ def _indice_conv_launch(features, nbr, weight, weight_h16, scale, shift, residua
         residual = residual.float().contiguous()
         assert residual.shape == out.shape
     prec = PREC[precision]
-    if prec == 1 and weight_h16 is None:
-        weight_h16 = weight.permute(0, 2, 1).contiguous().half()
+    if prec != 0 and weight_h16 is None:
+        hi, lo = split_h16(weight)
+        weight_h16 = hi if prec == 1 else torch.cat([hi, lo], 0)
     c = L.ctx(feats.device)
     L.check(c, L.lib().sstb200_spconv_forward(c, feats.data_ptr(), cin, nbr.data_ptr(), n_out, kv, weight.data_ptr(), L.ptr(weight_h16), cout,
                                               L.ptr(scale), L.ptr(shift), L.ptr(residual), int(bool(relu)), prec, out.data_ptr()))
@@ -333,8 +342,9 @@ class ToDense(SparseModule):
 # convolution layers
 # ------------------------------------------------------------------------------------------------------------------------
 class SparseConvolution(SparseModule):
-    """conv.py:45-206.  precision: 'fp32' (FFMA, exact path) or 'bf16' (tcgen05, 16-bit operands) - module attribute, also settable
-    for a whole model with set_spconv_precision()."""
+    """conv.py:45-206.  precision: 'fp32' (FFMA, exact path), 'bf16' (tcgen05, 16-bit operands) or 'fp32_tc' (tcgen05 with split-fp16
+    operands: fp32 tolerance at tensor-core speed; channels % 64) - module attribute, also settable for a whole model with
+    set_spconv_precision()."""
 
     def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1, bias=True, subm=False,
                  output_padding=0, transposed=False, inverse=False, indice_key=None, fused_bn=False):
@@ -372,11 +382,11 @@ class SparseConvolution(SparseModule):
                 self.bias.uniform_(-b, b)
 
     def _weight_h16(self):
-        key = (self.weight._version, self.weight.data_ptr())
+        key = (self.weight._version, self.weight.data_ptr(), self.precision)
         if self._h16 is None or self._h16[0] != key:
             kv = int(np.prod(self.kernel_size))
-            w = self.weight.detach().reshape(kv, self.in_channels, self.out_channels)
-            self._h16 = (key, w.permute(0, 2, 1).contiguous().half())
+            hi, lo = split_h16(self.weight.reshape(kv, self.in_channels, self.out_channels))
+            self._h16 = (key, hi if self.precision == "bf16" else torch.cat([hi, lo], 0))
         return self._h16[1]
 
     def _geometry(self, spatial_shape):
@@ -402,7 +412,7 @@ class SparseConvolution(SparseModule):
             scale, shift = fold_bn(bn, self.bias)
         else:
             scale, shift = None, (self.bias.detach().float().contiguous() if self.bias is not None else None)
-        h16 = self._weight_h16() if self.precision == "bf16" and not grad else None
+        h16 = self._weight_h16() if self.precision != "fp32" and not grad else None
         if self.conv1x1:
             nbr = torch.arange(feats.shape[0], dtype=torch.int32, device=feats.device).view(-1, 1)
             out = indice_conv(feats, nbr, w, h16, scale, shift, residual, relu, self.precision, transposed_table=lambda: nbr)

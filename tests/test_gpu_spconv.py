@@ -147,7 +147,7 @@ def test_conv_epilogue_both_precisions(cuda, cin, cout):
     nbr, _ = SP.conv_table(coors.to(cuda), coors.to(cuda), 2, shape, shape, [3, 3, 3], [1, 1, 1], [1, 1, 1])
     for relu, use_res, use_aff in ((True, True, True), (False, False, False)):
         ref = SO.indice_conv(feats, nbr_ref, w, scale if use_aff else None, shift if use_aff else None, res if use_res else None, relu)
-        for prec, tol in (("fp32", 1e-4), ("bf16", 5e-3)):
+        for prec, tol in (("fp32", 1e-4), ("bf16", 5e-3), ("fp32_tc", 2e-5)):
             out = SP.indice_conv(feats.to(cuda), nbr, w.to(cuda), None, scale.to(cuda) if use_aff else None,
                                  shift.to(cuda) if use_aff else None, res.to(cuda) if use_res else None, relu, prec)
             _close(out, ref, tol)
@@ -194,7 +194,7 @@ def test_unet_fsd_channels_both_precisions(cuda):
                                      UNET64["encoder_paddings"], UNET64["decoder_channels"], UNET64["decoder_paddings"])
     net = net.to(cuda)
     with torch.no_grad():
-        for prec, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        for prec, tol in (("fp32", 1e-4), ("bf16", 1e-2), ("fp32_tc", 1e-4)):
             SP.set_spconv_precision(net, prec)
             out = net(dict(voxel_feats=feats.to(cuda), voxel_coors=coors.to(cuda)))[0]
             assert torch.equal(out["voxel_coors"].cpu(), coors)
@@ -233,11 +233,13 @@ def test_full_size_properties(cuda):
     w[13] = torch.eye(64, device=cuda)
     assert torch.equal(SP.indice_conv(feats, nbr, w), feats)                       # identity kernel, fp32 path: exact
     _close(SP.indice_conv(feats, nbr, w, precision="bf16"), feats, 1e-3)            # fp16 operand rounding only
+    _close(SP.indice_conv(feats, nbr, w, precision="fp32_tc"), feats, 1e-6)         # split operands: 22 significant bits
     g = torch.Generator().manual_seed(3)
     w = (torch.randn((27, 64, 64), generator=g) / (27 * 64) ** 0.5 * 2).to(cuda)
     a = SP.indice_conv(feats, nbr, w, precision="fp32")
     b = SP.indice_conv(feats, nbr, w, precision="bf16")
     _close(b, a, 5e-3)
+    _close(SP.indice_conv(feats, nbr, w, precision="fp32_tc"), a, 2e-5)
     oshape = SO.conv_output_size(shape, [3, 3, 3], [2, 2, 2], [1, 1, 1])
     oc = SP.conv_out_coors(coors, 1, shape, oshape, [3, 3, 3], [2, 2, 2], [1, 1, 1])
     key = (oc[:, 1].long() * oshape[1] + oc[:, 2]) * oshape[2] + oc[:, 3]

@@ -87,7 +87,7 @@ def timed(fn, reps=10):
 
 (out, fr), times = timed(step)
 e2e = {}
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "bf16", "fp32_tc"):
     SP.set_spconv_precision(m, prec)
     o, ts = timed(full)
     e2e[prec] = {"ms_median": ts[len(ts) // 2], "ms_min": ts[0], "frames_per_s": B / (ts[len(ts) // 2] * 1e-3),

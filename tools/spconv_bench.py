@@ -77,7 +77,7 @@ def main():
                row_order="shuffled" if a.shuffle else "sorted (z,y,x)", voxels=int(coors.shape[0]), conv_launches=len(launches), pair_gflop=flops / 1e9, dense_tile_gflop=dense_flops / 1e9,
                algorithmic_mb=byts / 1e6)
     with torch.no_grad():
-        for prec in ("fp32", "bf16"):
+        for prec in ("fp32", "bf16", "fp32_tc"):
             SP.set_spconv_precision(net, prec)
             ms = timed(lambda: net(info), a.reps)
             res[prec] = dict(ms_forward_incl_tables=ms, tflops_pairs=flops / ms / 1e9)
@@ -91,7 +91,9 @@ def main():
         w = torch.randn((27, 64, 64), device=dev) * 0.02
         w16 = w.permute(0, 2, 1).contiguous().half()
         pairs = int((nbr >= 0).sum())
-        for prec in ("fp32", "bf16"):
+        hi, lo = SP.split_h16(w)
+        for prec in ("fp32", "bf16", "fp32_tc"):
+            w16 = hi if prec != "fp32_tc" else torch.cat([hi, lo], 0)
             ms = timed(lambda: SP.indice_conv(feats, nbr, w, w16, precision=prec), a.reps * 3)
             res[f"subm64_{prec}"] = dict(us=ms * 1e3, pairs=pairs, tflops_pairs=2 * pairs * 64 * 64 / ms / 1e9,
                                          tflops_dense_tile=2 * coors.shape[0] * 27 * 64 * 64 / ms / 1e9,
