@@ -514,7 +514,7 @@ def main():
             dist.all_reduce(t32, op=dist.ReduceOp.MAX)
         ms32 = float(t32[len(ws) // 2])
         fp32_rec = {"value": world * K32 / (ms32 / 1e3), "unit": "frames/s", "steps": K32, "ms_per_step": ms32 / K32,
-                    "frames_in_flight": len(e32), "tolerance": "1e-3 (FFMA path, csrc/sra_fp32.cu)"}
+                    "frames_in_flight": len(e32), "tolerance": "1e-3 (fp32-tolerance mode, csrc/sra_fp32.cu: Linear layers as split-fp16 tcgen05 GEMMs with fp32 accumulation, fp32 SIMT window attention / LayerNorm)"}
         del e32
 
     # ---- training step (BASELINE config 4): fwd + bwd + ONE flat NCCL gradient all-reduce + fused AdamW, weak scaling ----

@@ -151,11 +151,11 @@ def test_fsd_segmentation_front_pipeline(cuda):
     from sst_b200 import ops, registry
     vs, rng = (0.5, 0.5, 0.375), [-40, -40, -2, 40, 40, 4]         # grid 160 x 160 x 16
     norm = dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)
-    unet_cfg = dict(in_channels=16, sparse_shape=[16, 160, 160], norm_cfg=norm, base_channels=16, output_channels=16,
+    unet_cfg = dict(in_channels=32, sparse_shape=[16, 160, 160], norm_cfg=norm, base_channels=16, output_channels=16,
                     encoder_channels=((16,), (16, 16, 16), (32, 32, 32)), encoder_paddings=((1,), (1, 1, 1), (1, 1, 1)),
                     decoder_channels=((32, 32, 16), (16, 16, 16), (16, 16, 16)), decoder_paddings=((1, 1), (1, 0), (0, 1)))
     torch.manual_seed(1)
-    vfe = registry.MODELS.build(dict(type='DynamicScatterVFE', in_channels=5, feat_channels=[16, 16], with_cluster_center=True,
+    vfe = registry.MODELS.build(dict(type='DynamicScatterVFE', in_channels=5, feat_channels=[32, 32], with_cluster_center=True,
                                      with_voxel_center=True, voxel_size=vs, point_cloud_range=rng, norm_cfg=norm, unique_once=True)).eval()
     me = registry.MODELS.build(dict(type='PseudoMiddleEncoderForSpconvFSD'))
     bb = registry.MODELS.build(dict(type='SimpleSparseUNet', **unet_cfg)).eval()

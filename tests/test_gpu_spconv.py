@@ -147,7 +147,7 @@ def test_conv_epilogue_both_precisions(cuda, cin, cout):
     nbr, _ = SP.conv_table(coors.to(cuda), coors.to(cuda), 2, shape, shape, [3, 3, 3], [1, 1, 1], [1, 1, 1])
     for relu, use_res, use_aff in ((True, True, True), (False, False, False)):
         ref = SO.indice_conv(feats, nbr_ref, w, scale if use_aff else None, shift if use_aff else None, res if use_res else None, relu)
-        for prec, tol in (("fp32", 1e-4), ("bf16", 5e-3), ("fp32_tc", 2e-5)):
+        for prec, tol in (("fp32", 1e-4), ("bf16", 5e-3), ("fp32_tc", 1e-4)):
             out = SP.indice_conv(feats.to(cuda), nbr, w.to(cuda), None, scale.to(cuda) if use_aff else None,
                                  shift.to(cuda) if use_aff else None, res.to(cuda) if use_res else None, relu, prec)
             _close(out, ref, tol)
@@ -239,7 +239,7 @@ def test_full_size_properties(cuda):
     a = SP.indice_conv(feats, nbr, w, precision="fp32")
     b = SP.indice_conv(feats, nbr, w, precision="bf16")
     _close(b, a, 5e-3)
-    _close(SP.indice_conv(feats, nbr, w, precision="fp32_tc"), a, 2e-5)
+    _close(SP.indice_conv(feats, nbr, w, precision="fp32_tc"), a, 1e-4)
     oshape = SO.conv_output_size(shape, [3, 3, 3], [2, 2, 2], [1, 1, 1])
     oc = SP.conv_out_coors(coors, 1, shape, oshape, [3, 3, 3], [2, 2, 2], [1, 1, 1])
     key = (oc[:, 1].long() * oshape[1] + oc[:, 2]) * oshape[2] + oc[:, 3]
