@@ -69,3 +69,28 @@ def test_connected_components_large_and_edge_cases(cuda):
         FM.connected_components(far, torch.full((1000,), 3, dtype=torch.int32, device=cuda), 0.6, batch_size=2)
     with pytest.raises(L.SSTB200Error):   # no CPU fallback
         FM.connected_components(far.cpu(), None, 0.6)
+
+
+def test_grouping_speed_vs_reference_cpu_path(cuda):
+    """the reference labels the voted centres on the CPU (dense n x n distance matrix + scipy, single_stage_fsd.py:47-68) - timed here through
+    the oracle's restatement of exactly that, beside sstb200_connected_components on the same centres (FSD scale: 3 classes x ~8k voxel
+    centres of one sweep); labels identical, timings printed for profiles/"""
+    import time
+    from sst_b200 import fsd_modules as FM
+    pts, bidx = FO.synth_centres(5, 1, 8000, spread=70.0, blob=0.5, blobs=400)
+    t0 = time.perf_counter()
+    ref = FO.find_connected_components(pts, bidx, 0.6)
+    t_cpu = time.perf_counter() - t0
+    p, b = pts.to(cuda), bidx.to(cuda)
+    bounds = ([-80.0, -80.0], [80.0, 80.0])
+    FM.connected_components(p, b, 0.6, batch_size=1, xy_bounds=bounds)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        labels, num = FM.connected_components(p, b, 0.6, batch_size=1, xy_bounds=bounds)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.equal(labels.cpu(), ref.int())
+    print(f"\n[FSD grouping, {pts.shape[0]} centres, dist 0.6 -> {num} components] reference CPU path (n x n matrix + scipy): {t_cpu * 1e3:.1f} ms | "
+          f"sst_b200: {e0.elapsed_time(e1) / 10 * 1e3:.0f} us per call incl. the host round trip for the component count")
