@@ -14,6 +14,8 @@ from .neck_modules import Voxel2PointScatterNeck  # noqa: F401
 from .fsdv2_modules import VirtualVoxelFront  # noqa: F401
 from .fsd_modules import ClusterAssigner  # noqa: F401
 from .spconv_modules import SimpleSparseUNet, SparseUNet, VirtualVoxelMixer, SparseConvTensor  # noqa: F401
+# `from mmdet3d.ops import SparseBasicBlock, make_sparse_convmodule` (mmdet3d/ops/__init__.py:21-22) resolves on the op namespace too
+ops.SparseBasicBlock, ops.make_sparse_convmodule = spconv_modules.SparseBasicBlock, spconv_modules.make_sparse_convmodule
 from . import train  # noqa: F401  (training entry points: autograd bridge, FlatAdamW)
 
 __version__ = "0.1.0"
