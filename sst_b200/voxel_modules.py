@@ -213,6 +213,35 @@ class DynamicVFE(nn.Module):
         return vf[:num.value], vc[:num.value]
 
 
+def _scatter_vfe_train(self, features, coors, return_inv):
+    """voxel_encoder.py:551-612 as a composition: ONE voxel index (`ops.unique_rows`; unique_once or not gives the same result), segmented
+    reductions with their backward kernels (`ops.segment_reduce`: mean / sum gradients gathered, max gradient to the arg-max row),
+    torch Linear + (naiveSync)BatchNorm + ReLU in between - batch statistics and autograd like the reference's training mode."""
+    if self.return_point_feats:
+        raise NotImplementedError("return_point_feats in training mode")
+    new_coors, inv = ops.unique_rows(coors)
+    M = new_coors.shape[0]
+    mode = "mean" if self.mode == "avg" else self.mode
+    feats = [features]
+    if self._with_cluster_center:
+        voxel_mean, _ = ops.segment_reduce(features[:, :3].contiguous(), inv, "mean", M, want_argmax=False)
+        feats.append((features[:, :3] - voxel_mean[inv]) / self.rel_dist_scaler)
+    if self._with_voxel_center:
+        centre = torch.stack([coors[:, 3].type_as(features) * self.vx + self.x_offset, coors[:, 2].type_as(features) * self.vy + self.y_offset,
+                              coors[:, 1].type_as(features) * self.vz + self.z_offset], 1)
+        feats.append(features[:, :3] - centre)
+    if self._with_distance:
+        feats.append(torch.norm(features[:, :3], 2, 1, keepdim=True))
+    x = torch.cat(feats, dim=-1)
+    voxel_feats = None
+    for i, vfe in enumerate(self.vfe_layers):
+        point_feats = torch.relu(vfe.norm(vfe.linear(x)))          # utils.py:147-189 (act = relu, dropout 0)
+        voxel_feats, _ = ops.segment_reduce(point_feats, inv, mode, M)
+        if i != len(self.vfe_layers) - 1:
+            x = torch.cat([point_feats, voxel_feats[inv]], dim=1)
+    return (voxel_feats, new_coors, inv) if return_inv else (voxel_feats, new_coors)
+
+
 @VOXEL_ENCODERS.register_module()
 class DynamicScatterVFE(DynamicVFE):
     """voxel_encoder.py:502-612 (torch.unique based: no voxel is dropped; int64 coors; returns unq_inv)."""
@@ -227,10 +256,12 @@ class DynamicScatterVFE(DynamicVFE):
         self.rel_dist_scaler = rel_dist_scaler
         self.unique_once = unique_once
 
+    _forward_train_scatter = _scatter_vfe_train
+
     def forward(self, features, coors, points=None, img_feats=None, img_metas=None, return_inv=False):
         self._check(features, coors)
-        if self.training:
-            raise NotImplementedError("DynamicScatterVFE training mode (FSD) is not built; BASELINE config 4 trains the SST path")
+        if self.training or (torch.is_grad_enabled() and features.requires_grad):
+            return self._forward_train_scatter(features.contiguous(), coors.long().contiguous(), return_inv)
         features, coors = features.contiguous(), coors.long().contiguous()
         P, dev = features.shape[0], features.device
         if P == 0:

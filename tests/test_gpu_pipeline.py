@@ -194,3 +194,46 @@ def test_fsd_segmentation_front_pipeline(cuda):
     ref_inds, ref_valid = FO.cluster_assigner_single_class(centres, bidx, (0.3, 0.3, 6), 2, rng, 0.6)
     assert torch.equal(valid[0].cpu(), ref_valid)
     assert torch.equal(inds[0][:, 1:].cpu().int(), ref_inds) and int(inds[0][:, 0].abs().sum()) == 0
+
+
+def test_dynamic_scatter_vfe_training_gradients(cuda):
+    """DynamicScatterVFE.train(): the composition over ops.unique_rows / ops.segment_reduce (forward + backward kernels) and torch Linear /
+    naiveSyncBN matches the oracle's training=True restatement (pinned to the reference class in train mode): outputs, the input gradient
+    and every parameter gradient; then the FSD trainable chain DynamicScatterVFE -> SimpleSparseUNet takes one optimiser step"""
+    from sst_b200 import registry
+    vs, rng = (0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4]
+    norm = dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)
+    torch.manual_seed(0)
+    m = registry.MODELS.build(dict(type='DynamicScatterVFE', in_channels=5, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True,
+                                   voxel_size=vs, point_cloud_range=rng, norm_cfg=norm, unique_once=True, rel_dist_scaler=10.0)).train()
+    pts = torch.cat([torch.cat([O.synth_frame(3 + b, 3000), torch.rand(3000, 2)], 1) for b in range(2)])
+    co = torch.cat([torch.nn.functional.pad(O.dynamic_voxelize(pts[b * 3000:(b + 1) * 3000], vs, rng), (1, 0), value=b) for b in range(2)]).long()
+    w = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in m.state_dict().items()}
+    x_ref = pts.clone().requires_grad_(True)
+    of, oc, oinv = O.dynamic_scatter_vfe_forward(x_ref, co, w, vs, rng, 2, rel_dist_scaler=10.0, training=True)
+    probe = torch.randn(of.shape, generator=torch.Generator().manual_seed(1))
+    (of * probe).sum().backward()
+    m = m.to(cuda)
+    x = pts.to(cuda).requires_grad_(True)
+    vf, vc, inv = m(x, co.to(cuda), return_inv=True)
+    assert torch.equal(vc.cpu(), oc) and torch.equal(inv.cpu(), oinv)
+    torch.testing.assert_close(vf.detach().cpu(), of.detach(), rtol=1e-4, atol=1e-4)
+    (vf * probe.to(cuda)).sum().backward()
+    torch.testing.assert_close(x.grad.cpu(), x_ref.grad, rtol=1e-3, atol=1e-4 * float(x_ref.grad.abs().max()))
+    for name, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), w[name].grad, rtol=1e-3, atol=2e-4 * float(w[name].grad.abs().max()) + 1e-7)
+    # one training step of the FSD segmentation chain (voxel encoder -> sparse U-Net), every parameter receives a finite gradient
+    unet = registry.MODELS.build(dict(type='SimpleSparseUNet', in_channels=32, sparse_shape=[32, 640, 640], norm_cfg=norm, base_channels=16,
+                                      output_channels=16, encoder_channels=((16,), (16, 16), (32, 32)), encoder_paddings=((1,), (1, 1), (1, 1)),
+                                      decoder_channels=((32, 32, 16), (16, 16, 16), (16, 16, 16)),
+                                      decoder_paddings=((1, 1), (1, 0), (0, 1)))).to(cuda).train()
+    params = list(m.parameters()) + list(unet.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    opt.zero_grad()
+    vf, vc, inv = m(pts.to(cuda), co.to(cuda), return_inv=True)
+    out = unet(dict(voxel_feats=vf, voxel_coors=vc))[0]["voxel_feats"]
+    loss = out.float().square().mean()
+    loss.backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in params)
+    assert sum(float(p.grad.abs().sum()) for p in unet.parameters()) > 0 and float(m.vfe_layers[0].linear.weight.grad.abs().sum()) > 0
+    opt.step()

@@ -164,3 +164,32 @@ def test_gradient_composition_matches_dense_autograd(SP):
         close(p.grad, sd[name].grad)
         n += 1
     assert n > 60
+
+
+def test_dynamic_scatter_vfe_training_composition(monkeypatch):
+    """host logic of DynamicScatterVFE's training composition with the two library calls replaced by the oracle's restatements:
+    same outputs and gradients as the oracle's training=True forward (pinned to the reference class in train mode)"""
+    from oracle import sst_oracle as O
+    from sst_b200 import ops, registry
+    monkeypatch.setattr(ops, "unique_rows", lambda coors, return_counts=False, bounds=None: torch.unique(coors, return_inverse=True, dim=0))
+    monkeypatch.setattr(ops, "segment_reduce", lambda src, index, mode, num_segments=None, want_argmax=True: (O.segment_reduce(src, index, mode, num_segments), None))
+    vs, rng = (0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4]
+    torch.manual_seed(0)
+    m = registry.MODELS.build(dict(type='DynamicScatterVFE', in_channels=5, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True,
+                                   voxel_size=vs, point_cloud_range=rng, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01),
+                                   unique_once=True, rel_dist_scaler=10.0)).train()
+    monkeypatch.setattr(type(m), "_check", lambda self, f, c: None)   # the CUDA-tensor guard: nothing reaches the library in this test
+    pts = torch.cat([torch.cat([O.synth_frame(3 + b, 2000), torch.rand(2000, 2)], 1) for b in range(2)])
+    co = torch.cat([torch.nn.functional.pad(O.dynamic_voxelize(pts[b * 2000:(b + 1) * 2000], vs, rng), (1, 0), value=b) for b in range(2)]).long()
+    w = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in m.state_dict().items()}
+    x_ref = pts.clone().requires_grad_(True)
+    of, oc, oinv = O.dynamic_scatter_vfe_forward(x_ref, co, w, vs, rng, 2, rel_dist_scaler=10.0, training=True)
+    (of.square()).sum().backward()
+    x = pts.clone().requires_grad_(True)
+    vf, vc, inv = m(x, co, return_inv=True)
+    assert torch.equal(vc, oc) and torch.equal(inv, oinv)
+    torch.testing.assert_close(vf, of, rtol=1e-5, atol=1e-6)
+    (vf.square()).sum().backward()
+    torch.testing.assert_close(x.grad, x_ref.grad, rtol=1e-4, atol=1e-6)
+    for name, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, w[name].grad, rtol=1e-4, atol=1e-5 * float(w[name].grad.abs().max()) + 1e-8)

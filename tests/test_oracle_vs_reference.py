@@ -166,3 +166,28 @@ def test_training_mode_vfe_matches_reference(R):
     sd = vfe.state_dict()
     torch.testing.assert_close(rm, sd["vfe_layers.0.norm.running_mean"], rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(rv, sd["vfe_layers.0.norm.running_var"], rtol=1e-5, atol=1e-7)
+
+
+def test_dynamic_scatter_vfe_training_mode_matches_reference(R):
+    """DynamicScatterVFE in train() (batch-statistics BatchNorm, autograd through scatter_v2): outputs and gradients of the oracle's
+    training=True restatement against the reference class - the checker of the product's training composition"""
+    vs, rng = (0.25, 0.25, 0.2), [-80, -80, -2, 80, 80, 4]
+    torch.manual_seed(0)
+    m = R.DynamicScatterVFE(in_channels=5, feat_channels=[32, 32], with_cluster_center=True, with_voxel_center=True, voxel_size=vs,
+                            point_cloud_range=rng, norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01), unique_once=True,
+                            rel_dist_scaler=10.0).train()
+    pts = torch.cat([torch.cat([O.synth_frame(3 + b, 3000), torch.rand(3000, 2)], 1) for b in range(2)])
+    co = torch.cat([torch.nn.functional.pad(O.dynamic_voxelize(pts[b * 3000:(b + 1) * 3000], vs, rng), (1, 0), value=b) for b in range(2)]).long()
+    x = pts.clone().requires_grad_(True)
+    vf, vc, inv = m(x, co, return_inv=True)
+    probe = torch.randn(vf.shape, generator=torch.Generator().manual_seed(1))
+    (vf * probe).sum().backward()
+    w = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in m.state_dict().items()}
+    x2 = pts.clone().requires_grad_(True)
+    of, oc, oinv = O.dynamic_scatter_vfe_forward(x2, co, w, vs, rng, 2, rel_dist_scaler=10.0, training=True)
+    assert torch.equal(oc, vc) and torch.equal(oinv, inv)
+    torch.testing.assert_close(of, vf, rtol=1e-4, atol=1e-5)
+    (of * probe).sum().backward()
+    torch.testing.assert_close(x2.grad, x.grad, rtol=1e-3, atol=1e-5)
+    for name, p in m.named_parameters():
+        torch.testing.assert_close(w[name].grad, p.grad, rtol=1e-3, atol=1e-4 * float(p.grad.abs().max()) + 1e-7)
