@@ -117,14 +117,56 @@ class SIRLayer(nn.Module):
 
     precision = "fp32"  # 'bf16': rel-MLP layer 3 and both VFE layers on tcgen05 (bf16 operands, fp32 accumulate / LN / pooling)
 
+    def _forward_composed(self, features, coors, f_cluster, return_inv, return_both, unq_inv_once, new_coors_once):
+        """voxel_encoder.py:696-764 as a composition when a gradient is needed: torch Linear / LayerNorm / activation modules (autograd)
+        around `ops.segment_reduce` (segmented max / mean with their backward kernels) on ONE group index.  The fused kernels above
+        are the eval()/no_grad() path."""
+        features = features.float()
+        if unq_inv_once is None:
+            new_coors, unq_inv = ops.unique_rows(coors.long())
+        else:
+            new_coors, unq_inv = new_coors_once, unq_inv_once
+        G = new_coors.shape[0]
+        nz = features.new_tensor(self.xyz_normalizer)
+        x0 = torch.cat([features[:, :3] / nz[None, :], features[:, 3:]], dim=1)
+        shortcut = features[:, 3:]
+        if f_cluster is None:
+            mean, _ = ops.segment_reduce(features[:, :3].contiguous(), unq_inv, "mean", G, want_argmax=False)
+            f_cluster = (features[:, :3] - mean[unq_inv]) / self.rel_dist_scaler
+        else:
+            f_cluster = f_cluster.float() / self.rel_dist_scaler
+        if self._with_rel_mlp:
+            x0 = x0 * self.rel_mlp(f_cluster)
+        act = ops.get_activation(self.act)
+        mode = "mean" if self.mode == "avg" else self.mode
+        x, groups, point_feats = x0, [], None
+        for i, vfe in enumerate(self.vfe_layers):
+            if getattr(vfe, "dropout", None) is not None:
+                x = vfe.dropout(x)
+            point_feats = act(vfe.norm(vfe.linear(x)))
+            g, _ = ops.segment_reduce(point_feats.contiguous(), unq_inv, mode, G)
+            groups.append(g)
+            if i != len(self.vfe_layers) - 1:
+                x = torch.cat([point_feats, g[unq_inv]], dim=1)
+        voxel_feats = torch.cat(groups, dim=1)
+        if (return_both or self.return_point_feats) and self.with_shortcut and point_feats.shape == shortcut.shape:
+            point_feats = point_feats + shortcut
+        if return_both:
+            return point_feats, voxel_feats, new_coors
+        if self.return_point_feats:
+            return point_feats, voxel_feats
+        if return_inv:
+            return voxel_feats, new_coors, unq_inv
+        return voxel_feats, new_coors
+
     def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_inv=False,
                 return_both=False, unq_inv_once=None, new_coors_once=None, csr_once=None, point_feats_out=None, feat_gap=None):
         """`csr_once` = group_csr(unq_inv, G) shared between blocks; `point_feats_out` = a [N, >=C] fp32 view (last dim
         contiguous) that receives the point features in place of a fresh tensor (bf16 path; SIR.forward uses it to write
         block i's output straight into block i+1's [points || feats] input).  `feat_gap` = (at, width): `features` is that
         hand-over buffer, whose columns >= at sit `width` floats further right (bf16 path)."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("SIRLayer backward is not built yet; run under eval()/no_grad()")
+        if torch.is_grad_enabled() and (self.training or features.requires_grad or (f_cluster is not None and f_cluster.requires_grad)):
+            return self._forward_composed(features, coors, f_cluster, return_inv, return_both, unq_inv_once, new_coors_once)
         ops._need_cuda(features, coors)
         features = features.float().contiguous()
         if unq_inv_once is None:
@@ -188,11 +230,12 @@ class SIR(nn.Module):
     def forward(self, points, features, coors, f_cluster=None):
         # unique + group CSR once regardless of the flag: the result is identical and both are reused by every block
         new_coors, unq_inv = ops.unique_rows(coors.long())
-        csr = group_csr(unq_inv, new_coors.shape[0]) if points.shape[0] and new_coors.shape[0] else None
+        csr = group_csr(unq_inv, new_coors.shape[0]) if points.shape[0] and new_coors.shape[0] and points.is_cuda else None
         out_feats = features
         cluster_feat_list = []
         out_coors = new_coors
         in_feats = torch.cat([points, out_feats], 1)
+        grad = torch.is_grad_enabled() and (self.training or features.requires_grad or points.requires_grad)
         npt = points.shape[1]
         pad = (-npt) % 8  # the feature block of the hand-over buffer starts on a 32-byte boundary
         gap = None
@@ -202,7 +245,7 @@ class SIR(nn.Module):
             kw = dict(unq_inv_once=unq_inv, new_coors_once=new_coors, csr_once=csr, feat_gap=gap)
             nxt = None
             Cb = block.feat_channels[-1]
-            if (not last and self.precision == "bf16" and Cb + npt == self.block_list[i + 1].in_channels and Cb % 4 == 0
+            if (not last and not grad and self.precision == "bf16" and Cb + npt == self.block_list[i + 1].in_channels and Cb % 4 == 0
                     and not (block.with_shortcut and block.in_channels - 3 == Cb)):
                 # this block's point features land next to the raw points: no torch.cat between blocks.  Block i >= 1 reads
                 # and writes the same buffer (its kernel A has consumed the input before kernel B writes the output).

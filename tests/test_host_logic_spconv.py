@@ -193,3 +193,40 @@ def test_dynamic_scatter_vfe_training_composition(monkeypatch):
     torch.testing.assert_close(x.grad, x_ref.grad, rtol=1e-4, atol=1e-6)
     for name, p in m.named_parameters():
         torch.testing.assert_close(p.grad, w[name].grad, rtol=1e-4, atol=1e-5 * float(w[name].grad.abs().max()) + 1e-8)
+
+
+def test_sir_training_composition(monkeypatch):
+    """host logic of SIR / SIRLayer when a gradient is needed (composition over ops.segment_reduce + torch Linear / LayerNorm / GELU) with
+    the library calls replaced by the oracle's restatements: outputs and gradients equal autograd through the oracle's sir_forward, which
+    tests/test_oracle_vs_reference.py pins to the reference's own autograd"""
+    from oracle import sst_oracle as O
+    from sst_b200 import ops
+    from sst_b200.sir_modules import SIR
+    monkeypatch.setattr(ops, "unique_rows", lambda coors, return_counts=False, bounds=None: torch.unique(coors, return_inverse=True, dim=0))
+    monkeypatch.setattr(ops, "segment_reduce", lambda src, index, mode, num_segments=None, want_argmax=True: (O.segment_reduce(src, index, mode, num_segments), None))
+    torch.manual_seed(0)
+    m = SIR(num_blocks=3, in_channels=[20, 37, 37], feat_channels=[[32, 32]] * 3, rel_mlp_hidden_dims=[[16, 32]] * 3, norm_cfg=dict(type='LN', eps=1e-3),
+            mode='max', xyz_normalizer=[20, 20, 4], act='gelu', unique_once=True).train()
+    g = torch.Generator().manual_seed(1)
+    N, G = 1500, 40
+    points = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1)
+    feats = torch.randn(N, 15, generator=g)
+    gid = torch.randint(0, G, (N,), generator=g)
+    coors = torch.stack([gid % 3, torch.zeros_like(gid), gid], 1)
+    fcl = torch.randn(N, 3, generator=g) * 2
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    f_ref = feats.clone().requires_grad_(True)
+    ref = O.sir_forward(points, f_ref, coors, fcl, w, 3, 3, 2, [20, 20, 4])
+    (ref[0].square().sum() + ref[1].square().sum()).backward()
+    f = feats.clone().requires_grad_(True)
+    a, b, c = m(points, f, coors, fcl)
+    assert torch.equal(c, ref[2])
+    torch.testing.assert_close(a, ref[0], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(b, ref[1], rtol=1e-5, atol=1e-5)
+    (a.square().sum() + b.square().sum()).backward()
+    torch.testing.assert_close(f.grad, f_ref.grad, rtol=1e-4, atol=1e-5 * float(f_ref.grad.abs().max()))
+    n = 0
+    for name, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, w[name].grad, rtol=1e-4, atol=1e-5 * float(w[name].grad.abs().max()) + 1e-8)
+        n += 1
+    assert n >= 30
