@@ -135,3 +135,30 @@ def test_sir_empty_input(cuda, precision):
         a, b, c = m(torch.zeros(0, 5, device=cuda), torch.zeros(0, 79, device=cuda), torch.zeros(0, 3, dtype=torch.long, device=cuda),
                     torch.zeros(0, 3, device=cuda))
     assert a.shape == (0, 128) and b.shape == (0, 768) and c.shape == (0, 3)
+
+
+def test_sir_training_gradients(cuda):
+    """SIR with gradients enabled (composition over the segmented-reduction forward / backward kernels): outputs, the feature gradient and
+    every parameter gradient against autograd through the oracle (pinned to the reference's autograd)"""
+    m = _sir([20, 37, 37], 32, 3).train()
+    g = torch.Generator().manual_seed(1)
+    N, G = 3000, 60
+    points = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1)
+    feats = torch.randn(N, 15, generator=g)
+    gid = torch.randint(0, G, (N,), generator=g)
+    coors = torch.stack([gid % 3, torch.zeros_like(gid), gid], 1)
+    fcl = torch.randn(N, 3, generator=g) * 2
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    f_ref = feats.clone().requires_grad_(True)
+    ref = O.sir_forward(points, f_ref, coors, fcl, w, 3, 3, 2, [20, 20, 4])
+    (ref[0].square().sum() + ref[1].square().sum()).backward()
+    m = m.to(cuda)
+    f = feats.to(cuda).requires_grad_(True)
+    a, b, c = m(points.to(cuda), f, coors.to(cuda), fcl.to(cuda))
+    assert torch.equal(c.cpu(), ref[2])
+    torch.testing.assert_close(a.detach().cpu(), ref[0].detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(b.detach().cpu(), ref[1].detach(), rtol=1e-4, atol=1e-4)
+    (a.square().sum() + b.square().sum()).backward()
+    torch.testing.assert_close(f.grad.cpu(), f_ref.grad, rtol=1e-3, atol=1e-4 * float(f_ref.grad.abs().max()))
+    for name, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), w[name].grad, rtol=1e-3, atol=2e-4 * float(w[name].grad.abs().max()) + 1e-7)
