@@ -279,3 +279,39 @@ def test_fsdv2_extract_feat_with_mixer_golden():
     f, c = f[out["singlescale_mask"]], c[out["singlescale_mask"]]
     assert torch.equal(c[out["virtual_mask"]].long(), z["virtual_coors"].long())
     torch.testing.assert_close(f[out["virtual_mask"]], z["virtual_feats"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_spconv_oracle_table_form_equals_dense_form(seed):
+    """the two independent forms of the sparse-convolution checker agree on random geometries (kernel 1-3, stride 1-2, asymmetric padding,
+    ragged batches): the neighbour-table form (what the CUDA path is compared with launch by launch) and the dense conv3d /
+    conv_transpose3d form (what is pinned to the reference's spconv)"""
+    from oracle import spconv_oracle as SO
+    g = torch.Generator().manual_seed(100 + seed)
+    shape = [int(v) for v in torch.randint(5, 14, (3,), generator=g)]
+    ks = [int(v) for v in torch.randint(1, 4, (3,), generator=g)]
+    st = [int(v) for v in torch.randint(1, 3, (3,), generator=g)]
+    pd = [int(torch.randint(0, k, (1,), generator=g)) for k in ks]
+    B = 1 + seed % 3
+    feats, coors = SO.synth_sparse(seed, B, shape, 40 + 25 * seed, 4, clustered=bool(seed % 2))
+    if seed == 5:   # one empty sample in the middle of the batch
+        keep = coors[:, 0] != 1
+        feats, coors = feats[keep], coors[keep]
+    cin, cout = 4, 6
+    w = torch.randn((*ks, cin, cout), generator=g)
+    of, oc, oshape = SO.sparse_conv(feats, coors, B, shape, w, st, pd)
+    nbr = SO.neighbour_table(coors, oc, B, shape, ks, st, pd)
+    torch.testing.assert_close(SO.indice_conv(feats, nbr, w), of, rtol=1e-4, atol=1e-5)
+    assert bool((nbr >= 0).any(1).all()), "every active output cell has at least one contributing input"
+    # inverse conv through the transposed table
+    kv = nbr.shape[1]
+    inv = torch.full((coors.shape[0], kv), -1, dtype=torch.int32)
+    o, k = torch.nonzero(nbr >= 0, as_tuple=True)
+    inv[nbr[o, k].long(), k] = o.int()
+    wi = torch.randn((*ks, cout, cin), generator=g)
+    torch.testing.assert_close(SO.indice_conv(of, inv, wi), SO.inverse_conv(of, oc, B, oshape, coors, shape, wi, st, pd), rtol=1e-4, atol=1e-5)
+    # SubM (odd kernels only: spconv centres them)
+    ko = [k | 1 for k in ks]
+    ws = torch.randn((*ko, cin, cout), generator=g)
+    nb = SO.neighbour_table(coors, coors, B, shape, ko, [1, 1, 1], [k // 2 for k in ko])
+    torch.testing.assert_close(SO.indice_conv(feats, nb, ws), SO.subm_conv(feats, coors, B, shape, ws), rtol=1e-4, atol=1e-5)
