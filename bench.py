@@ -525,9 +525,10 @@ def main():
         except Exception as e:   # the inference record must not be lost to a training-side failure; say so loudly instead
             train = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- FSD sparse U-Net, rank 0 only: one sweep through SimpleSparseUNet, both precisions ---------------------
+    # ---- FSD sparse U-Net, single-GPU runs only (like the CPU baseline: no rank-0-only work between the
+    # collectives of a multi-rank run and its process-group teardown): one sweep through SimpleSparseUNet, three precisions ----------
     fsd = None
-    if rank == 0 and not args.no_fsd:
+    if rank == 0 and world == 1 and not args.no_fsd:
         try:
             fsd = fl.fsd_unet_bench(dev)
         except Exception as e:
