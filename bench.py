@@ -534,6 +534,13 @@ def main():
         except Exception as e:
             fsd = {"error": f"{type(e).__name__}: {e}"}
 
+    sir = None
+    if rank == 0 and world == 1 and not args.no_fsd:   # BASELINE config 3 beside it (same flag), never allowed to cost the main line
+        try:
+            sir = fl.sir_bench(dev)
+        except Exception as e:
+            sir = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again, like the --impl reference arm
@@ -558,7 +565,7 @@ def main():
             "gpu_graph_other_nodes_per_step": int(getattr(eng, "other_nodes_per_frame", 0) or 0),
             "gpu_launches_per_step": int(eng.launches_per_frame or 0),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roof, "cpu_baseline": cpu, "fp32": fp32_rec, "train": train, "fsd_unet": fsd,
+            "roofline": roof, "cpu_baseline": cpu, "fp32": fp32_rec, "train": train, "fsd_unet": fsd, "fsd_sir": sir,
         }
         print(json.dumps(line))
     if world > 1:

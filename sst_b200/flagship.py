@@ -112,3 +112,36 @@ def fsd_unet_bench(dev, reps=5, precisions=("bf16", "fp32_tc", "fp32")):
             ms = a.elapsed_time(b) / reps
             rec[{"bf16": "f16_tcgen05", "fp32_tc": "fp32_split_tcgen05", "fp32": "fp32_ffma"}[prec]] = {"ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms}
     return rec
+
+
+def sir_bench(dev, reps=5, precisions=("bf16", "fp32")):
+    """BASELINE config 3: FSD `SIR` (3 blocks, 150k points, 256 groups; configs/fsd/fsd_waymoD1_1x.py:92-103) forward, CUDA events on the
+    current stream.  Same synthetic inputs as tools/sir_kernels.py / SURVEY 8(d)."""
+    from .sir_modules import SIR
+    N, G = 150000, 256
+    g = torch.Generator().manual_seed(3)
+    sp = torch.cat([torch.randn(N, 3, generator=g) * 10, torch.rand(N, 2, generator=g)], 1).to(dev)
+    sf = torch.randn(N, 79, generator=g).to(dev)
+    gid = torch.randint(0, G, (N,), generator=g)
+    sc = torch.stack([gid % 3, torch.zeros_like(gid), gid], 1).to(dev)
+    fcl = (torch.randn(N, 3, generator=g) * 2).to(dev)
+    torch.manual_seed(0)
+    sir = SIR(num_blocks=3, in_channels=[84, 133, 133], feat_channels=[[128, 128]] * 3, rel_mlp_hidden_dims=[[16, 32]] * 3,
+              norm_cfg=dict(type="LN", eps=1e-3), mode="max", xyz_normalizer=[20, 20, 4], act="gelu", unique_once=True).eval().to(dev)
+    flops = sum(2 * N * (3 * 16 + 16 * 32 + 32 * c + c * 128 + 256 * 128) for c in (84, 133, 133))   # SURVEY 8(d)
+    rec = {"workload": "config3: FSD SIR, 3 blocks, 150k points, 256 groups, forward", "gflop": flops / 1e9}
+    with torch.no_grad():
+        for prec in precisions:
+            sir.precision = prec
+            for _ in range(2):
+                sir(sp, sf, sc, fcl)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                sir(sp, sf, sc, fcl)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / reps
+            rec["bf16_tcgen05" if prec == "bf16" else "fp32_ffma"] = {"ms": ms, "tflops": flops / ms / 1e9}
+    return rec
